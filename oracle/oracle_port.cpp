@@ -1,0 +1,657 @@
+// TEST INFRASTRUCTURE ONLY — never linked, imported or executed by the product
+// path (libigl_b200/).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load the library built from this.
+//
+// CPU restatement (plain C++17, no Eigen, no reference headers) of the parts of
+// libigl's point-vs-mesh query path that cannot be compiled in this image
+// because they need Eigen 5.0.1 (cmake/recipes/external/eigen.cmake:8-13, not
+// vendored).  Each function cites the reference file:line whose algorithm it
+// follows.  The soup fast-winding-number core is NOT restated: the genuine
+// header is compiled into oracle/_ref/libref_fwn.so (oracle/ref_fwn.cpp).
+//
+// Pinning (see tests/test_oracle_*.py):
+//  * closest point: cross-checked against the O(nP*nF) brute force below
+//    (the result is topology independent) and the reference's known-answer
+//    tests (tests/include/igl/AABB.cpp:100-113, signed_distance.cpp:4-43);
+//  * point-cloud FWN: reference golden vector
+//    tests/include/igl/fast_winding_number.cpp:17-53 (1e-15) pins the dipole
+//    term; the order-1/2 Taylor terms are pinned by no reference test
+//    ("parity unpinned" for those terms) and are cross-checked against the
+//    brute-force dipole sum at large beta.
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <numeric>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// igl::parallel_for  (parallel_for.h:140-204) + default_num_threads
+// (default_num_threads.cpp:38-59): static slices, fresh std::threads per call,
+// serial below min_parallel.
+// ---------------------------------------------------------------------------
+unsigned port_num_threads() {
+  static unsigned n = [] {
+    if (const char *e = std::getenv("IGL_NUM_THREADS")) {
+      int v = std::atoi(e);
+      if (v > 0) return (unsigned)v;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    return hw ? hw : 8u;
+  }();
+  return n;
+}
+
+template <class F>
+void port_parallel_for(int64_t n, const F &f, int64_t min_parallel) {
+  if (n <= 0) return;
+  const int64_t nt = port_num_threads();
+  if (n < min_parallel || nt <= 1) {
+    for (int64_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  const int64_t slice = std::max<int64_t>((int64_t)std::llround((n + 1) / (double)nt), 1);
+  std::vector<std::thread> pool;
+  pool.reserve(nt);
+  int64_t i1 = 0, i2 = std::min(slice, n);
+  int64_t t = 0;
+  auto range = [&f](int64_t a, int64_t b) {
+    for (int64_t k = a; k < b; ++k) f(k);
+  };
+  for (; t + 1 < nt && i1 < n; ++t) {
+    pool.emplace_back(range, i1, i2);
+    i1 = i2;
+    i2 = std::min(i2 + slice, n);
+  }
+  if (i1 < n) pool.emplace_back(range, i1, n);
+  for (auto &th : pool) th.join();
+}
+
+struct V3 {
+  double x, y, z;
+};
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline bool same(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+
+// ---------------------------------------------------------------------------
+// Ericson closest point on triangle, point_simplex_squared_distance.cpp:45-110
+// and sqr_d = |p-c|^2 (:134).  Degenerate [i j j]/[i i i] rows act as
+// segments/points through the same code (a!=b guard at :70).
+// ---------------------------------------------------------------------------
+inline V3 closest_on_triangle(V3 p, V3 a, V3 b, V3 c) {
+  const V3 ab = b - a, ac = c - a, ap = p - a;
+  const double d1 = dot(ab, ap), d2 = dot(ac, ap);
+  if (d1 <= 0.0 && d2 <= 0.0) return a;
+  const V3 bp = p - b;
+  const double d3 = dot(ab, bp), d4 = dot(ac, bp);
+  if (d3 >= 0.0 && d4 <= d3) return b;
+  const double vc = d1 * d4 - d3 * d2;
+  if (!same(a, b)) {
+    if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+      const double v = d1 / (d1 - d3);
+      return a + ab * v;
+    }
+  }
+  const V3 cp = p - c;
+  const double d5 = dot(ab, cp), d6 = dot(ac, cp);
+  if (d6 >= 0.0 && d5 <= d6) return c;
+  const double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+    const double w = d2 / (d2 - d6);
+    return a + ac * w;
+  }
+  const double va = d3 * d6 - d5 * d4;
+  if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+    const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    return b + (c - b) * w;
+  }
+  const double denom = 1.0 / (va + vb + vc);
+  const double v = vb * denom, w = vc * denom;
+  return (a + ab * v) + ac * w;
+}
+
+// ---------------------------------------------------------------------------
+// igl::AABB<MatrixXd,3>: init (AABB.cpp:845-871, 890-978) and squared_distance
+// (AABB.cpp:1135-1218, leaf :1413-1432, set_min :787-802).  Nodes live in one
+// vector in creation (depth-first) order instead of individual `new`s.
+// Eigen::AlignedBox semantics: contains() inclusive; squaredExteriorDistance =
+// sum over axes of max(min-p, p-max, 0)^2.
+// ---------------------------------------------------------------------------
+struct Node {
+  double lo[3], hi[3];
+  int left, right, prim;
+};
+
+struct CpTree {
+  const double *V;  // nV x 3 row-major (caller memory)
+  const int *F;     // nF x 3 row-major
+  int64_t nV, nF;
+  std::vector<Node> nodes;
+  std::vector<int> SI;  // nF x 3 ranks
+};
+
+V3 vtx(const CpTree &t, int f, int k) {
+  const double *v = t.V + 3 * (int64_t)t.F[3 * (int64_t)f + k];
+  return {v[0], v[1], v[2]};
+}
+
+int build_rec(CpTree &t, std::vector<int> &I) {
+  const int id = (int)t.nodes.size();
+  t.nodes.push_back(Node());
+  {
+    Node &n = t.nodes[id];
+    for (int d = 0; d < 3; ++d) {
+      n.lo[d] = std::numeric_limits<double>::max();
+      n.hi[d] = std::numeric_limits<double>::lowest();
+    }
+    for (int f : I)
+      for (int k = 0; k < 3; ++k) {
+        const double *v = t.V + 3 * (int64_t)t.F[3 * (int64_t)f + k];
+        for (int d = 0; d < 3; ++d) {
+          n.lo[d] = std::min(n.lo[d], v[d]);
+          n.hi[d] = std::max(n.hi[d], v[d]);
+        }
+      }
+    n.left = n.right = -1;
+    n.prim = -1;
+  }
+  if (I.size() == 1) {
+    t.nodes[id].prim = I[0];
+    return id;
+  }
+  int max_d = 0;
+  {
+    const Node &n = t.nodes[id];
+    double best = n.hi[0] - n.lo[0];
+    for (int d = 1; d < 3; ++d)
+      if (n.hi[d] - n.lo[d] > best) {  // maxCoeff: first maximum
+        best = n.hi[d] - n.lo[d];
+        max_d = d;
+      }
+  }
+  std::vector<int> key(I.size());
+  for (size_t i = 0; i < I.size(); ++i) key[i] = t.SI[3 * (int64_t)I[i] + max_d];
+  int med;
+  {
+    std::vector<int> A(key);
+    const size_t n = (A.size() - 1) / 2;
+    std::nth_element(A.begin(), A.begin() + n, A.end());
+    med = A[n];
+  }
+  std::vector<int> LI, RI;
+  LI.reserve((I.size() + 1) / 2);
+  RI.reserve(I.size() / 2);
+  for (size_t i = 0; i < I.size(); ++i) (key[i] <= med ? LI : RI).push_back(I[i]);
+  std::vector<int>().swap(key);
+  std::vector<int>().swap(I);  // the reference keeps I alive; freeing it changes nothing
+  if (!LI.empty()) {
+    const int l = build_rec(t, LI);
+    t.nodes[id].left = l;
+  }
+  if (!RI.empty()) {
+    const int r = build_rec(t, RI);
+    t.nodes[id].right = r;
+  }
+  return id;
+}
+
+inline bool box_contains(const Node &n, V3 p) {
+  return n.lo[0] <= p.x && p.x <= n.hi[0] && n.lo[1] <= p.y && p.y <= n.hi[1] &&
+         n.lo[2] <= p.z && p.z <= n.hi[2];
+}
+inline double box_ext_d2(const Node &n, V3 p) {
+  const double q[3] = {p.x, p.y, p.z};
+  double s = 0;
+  for (int d = 0; d < 3; ++d) {
+    if (n.lo[d] > q[d]) {
+      const double a = n.lo[d] - q[d];
+      s += a * a;
+    } else if (q[d] > n.hi[d]) {
+      const double a = q[d] - n.hi[d];
+      s += a * a;
+    }
+  }
+  return s;
+}
+
+struct Counters {
+  int64_t nodes = 0, tris = 0;
+};
+
+template <bool COUNT>
+double sqd_rec(const CpTree &t, int id, V3 p, double low, double up, int &i, V3 &c,
+               Counters *cnt) {
+  if (low > up) return low;  // AABB.cpp:1145-1148
+  double sqr_d = up;
+  const Node &n = t.nodes[id];
+  if (COUNT) cnt->nodes++;
+  if (n.prim != -1) {
+    // leaf_squared_distance, AABB.cpp:1413-1432
+    if (low > sqr_d) return low;
+    if (COUNT) cnt->tris++;
+    const V3 cc = closest_on_triangle(p, vtx(t, n.prim, 0), vtx(t, n.prim, 1), vtx(t, n.prim, 2));
+    const V3 d = p - cc;
+    const double dd = dot(d, d);
+    if (dd < sqr_d) {  // set_min, strict
+      i = n.prim;
+      c = cc;
+      sqr_d = dd;
+    }
+    return sqr_d;
+  }
+  bool looked_left = false, looked_right = false;
+  auto look = [&](int child, bool &flag) {
+    int ic = -1;
+    V3 cchild = c;
+    const double d = sqd_rec<COUNT>(t, child, p, low, sqr_d, ic, cchild, cnt);
+    if (d < sqr_d) {
+      i = ic;
+      c = cchild;
+      sqr_d = d;
+    }
+    flag = true;
+  };
+  const Node &L = t.nodes[n.left];
+  const Node &R = t.nodes[n.right];
+  if (box_contains(L, p)) look(n.left, looked_left);
+  if (box_contains(R, p)) look(n.right, looked_right);
+  const double dl = box_ext_d2(L, p), dr = box_ext_d2(R, p);
+  if (dl < dr) {
+    if (!looked_left && dl < sqr_d) look(n.left, looked_left);
+    if (!looked_right && dr < sqr_d) look(n.right, looked_right);
+  } else {
+    if (!looked_right && dr < sqr_d) look(n.right, looked_right);
+    if (!looked_left && dl < sqr_d) look(n.left, looked_left);
+  }
+  return sqr_d;
+}
+
+// ---------------------------------------------------------------------------
+// igl::octree (octree.cpp:16-168) and point-cloud fast winding number
+// (fast_winding_number.cpp:28-124 precompute, :152-311 evaluation), double.
+// ---------------------------------------------------------------------------
+struct Cloud {
+  const double *P, *N, *A;  // caller memory, n x 3 / n x 3 / n
+  int64_t n;
+  int order;
+  std::vector<std::vector<int>> pts;   // point_indices
+  std::vector<std::array<int, 8>> CH;  // children, -1 = leaf
+  std::vector<std::array<double, 3>> CN;
+  std::vector<double> Wd;
+  std::vector<std::array<double, 3>> CM;
+  std::vector<double> R;
+  std::vector<double> EC;  // ncells x nterms
+  int nterms;
+};
+
+void octree_rec(Cloud &c, int index, int depth, int &m) {
+  const int MAX_DEPTH = 30000;
+  if (c.pts[index].size() > 1 && depth < MAX_DEPTH) {
+    for (int k = 0; k < 8; ++k) c.CH[index][k] = m + k;
+    const double h = c.Wd[index] / 2;
+    const std::array<double, 3> cen = c.CN[index];
+    for (int k = 0; k < 8; ++k) {
+      c.CH.push_back({-1, -1, -1, -1, -1, -1, -1, -1});
+      c.pts.emplace_back();
+      const double q = h / 2;
+      std::array<double, 3> cc = {cen[0] + ((k & 1) ? q : -q), cen[1] + ((k & 2) ? q : -q),
+                                  cen[2] + ((k & 4) ? q : -q)};
+      c.CN.push_back(cc);
+      c.Wd.push_back(h);
+    }
+    for (size_t j = 0; j < c.pts[index].size(); ++j) {
+      const int pi = c.pts[index][j];
+      const double *p = c.P + 3 * (int64_t)pi;
+      int oct = 0;
+      if (p[0] >= cen[0]) oct += 1;
+      if (p[1] >= cen[1]) oct += 2;
+      if (p[2] >= cen[2]) oct += 4;
+      c.pts[m + oct].push_back(pi);
+    }
+    const int first = m;
+    m += 8;
+    for (int k = 0; k < 8; ++k) octree_rec(c, first + k, depth + 1, m);
+  }
+}
+
+void cloud_precompute_rec(Cloud &c, int index) {
+  double mc[3] = {0, 0, 0}, z[3] = {0, 0, 0}, areatotal = 0.0;
+  const std::vector<int> &L = c.pts[index];
+  for (int pi : L) {
+    const double a = c.A[pi];
+    areatotal += a;
+    for (int d = 0; d < 3; ++d) {
+      mc[d] += a * c.P[3 * (int64_t)pi + d];
+      z[d] += a * c.N[3 * (int64_t)pi + d];
+    }
+  }
+  if (!L.empty()) {
+    for (int d = 0; d < 3; ++d) mc[d] = mc[d] / areatotal;
+  } else {
+    for (int d = 0; d < 3; ++d) mc[d] = std::numeric_limits<double>::quiet_NaN();
+  }
+  c.CM[index] = {mc[0], mc[1], mc[2]};
+  double *ec = c.EC.data() + (int64_t)index * c.nterms;
+  for (int d = 0; d < 3; ++d) ec[d] = z[d];
+  double max_norm = 0;
+  for (int pi : L) {
+    double pt[3];
+    for (int d = 0; d < 3; ++d) pt[d] = c.P[3 * (int64_t)pi + d] - mc[d];
+    const double nrm = std::sqrt(pt[0] * pt[0] + pt[1] * pt[1] + pt[2] * pt[2]);
+    if (nrm > max_norm) max_norm = nrm;
+    const double a = c.A[pi];
+    const double *nn = c.N + 3 * (int64_t)pi;
+    if (c.nterms >= 12) {
+      // column-major Map of the 3x3 temporary: data()[k] = T(k%3, k/3)
+      for (int k = 0; k < 9; ++k) ec[3 + k] += a * pt[k % 3] * nn[k / 3];
+    }
+    if (c.nterms == 39) {
+      for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 9; ++k)
+          ec[12 + 9 * i + k] += 0.5 * pt[i] * (a * pt[k % 3] * nn[k / 3]);
+    }
+  }
+  c.R[index] = max_norm;
+  if (c.CH[index][0] != -1)
+    for (int k = 0; k < 8; ++k) cloud_precompute_rec(c, c.CH[index][k]);
+}
+
+const double PI_4 = 4.0 * 3.1415926535897932384626433832795;  // igl/PI.h
+
+inline double direct_eval(const double loc[3], const double an[3]) {
+  const double ln = std::sqrt(loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2]);
+  if (ln == 0) return 0.5;
+  return (loc[0] * an[0] + loc[1] * an[1] + loc[2] * an[2]) / (PI_4 * (ln * ln * ln));
+}
+
+double expansion_eval(const Cloud &c, const double loc[3], int child) {
+  const double *ec = c.EC.data() + (int64_t)child * c.nterms;
+  double wn = direct_eval(loc, ec);
+  const double r = std::sqrt(loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2]);
+  double r3 = 0, r5 = 0;
+  if (c.nterms > 3) {
+    r3 = PI_4 * r * r * r;
+    r5 = r3 * r * r;
+    const double d = 1.0 / r3;
+    const double s = -3.0 / r5;
+    double acc = 0;
+    for (int k = 0; k < 9; ++k) {
+      const int u = k % 3, v = k / 3;
+      double sd = loc[u] * loc[v] * s;
+      if (u == v) sd += d;
+      acc += sd * ec[3 + k];
+    }
+    wn += acc;
+  }
+  if (c.nterms > 12) {
+    const double r7 = r5 * r * r;
+    for (int i = 0; i < 3; ++i) {
+      double acc = 0;
+      for (int k = 0; k < 9; ++k) {
+        const int u = k % 3, v = k / 3;
+        double rcd = 0;
+        if (u == v) rcd += loc[i];
+        if (u == i) rcd += loc[v];
+        if (v == i) rcd += loc[u];
+        const double td = 15.0 * loc[i] * (loc[u] * (loc[v] / r7)) + (-3.0 / r5) * rcd;
+        acc += td * ec[12 + 9 * i + k];
+      }
+      wn += acc;
+    }
+  }
+  return wn;
+}
+
+double cloud_eval_rec(const Cloud &c, const double q[3], const std::vector<int> &near, double beta) {
+  double wn = 0;
+  std::vector<int> next;
+  next.reserve(8);
+  auto leaf_sum = [&](int cell) {
+    for (int pi : c.pts[cell]) {
+      double loc[3], an[3];
+      for (int d = 0; d < 3; ++d) {
+        loc[d] = c.P[3 * (int64_t)pi + d] - q[d];
+        an[d] = c.N[3 * (int64_t)pi + d] * c.A[pi];
+      }
+      wn += direct_eval(loc, an);
+    }
+  };
+  for (int index : near) {
+    if (c.CH[index][0] == -1) {
+      leaf_sum(index);
+    } else {
+      for (int k = 0; k < 8; ++k) {
+        const int ch = c.CH[index][k];
+        if (c.pts[ch].empty()) continue;
+        double loc[3];
+        for (int d = 0; d < 3; ++d) loc[d] = c.CM[ch][d] - q[d];
+        const double nrm = std::sqrt(loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2]);
+        if (nrm > beta * c.R[ch]) {
+          if (c.CH[ch][0] == -1)
+            leaf_sum(ch);
+          else
+            wn += expansion_eval(c, loc, ch);
+        } else {
+          next.push_back(ch);
+        }
+      }
+    }
+  }
+  if (!next.empty()) wn += cloud_eval_rec(c, q, next, beta);
+  return wn;
+}
+
+}  // namespace
+
+extern "C" {
+
+int port_threads() { return (int)port_num_threads(); }
+
+// ---- closest point -------------------------------------------------------
+void *port_cp_create(const double *V, int64_t nV, const int *F, int64_t nF) {
+  CpTree *t = new CpTree;
+  t->V = V;
+  t->F = F;
+  t->nV = nV;
+  t->nF = nF;
+  if (nF == 0) return t;
+  // barycenters + per-axis sort ranks, AABB.cpp:845-871
+  std::vector<double> BC(3 * nF);
+  for (int64_t f = 0; f < nF; ++f)
+    for (int d = 0; d < 3; ++d)
+      BC[3 * f + d] = (V[3 * (int64_t)F[3 * f] + d] + V[3 * (int64_t)F[3 * f + 1] + d] +
+                       V[3 * (int64_t)F[3 * f + 2] + d]) /
+                      3.0;
+  t->SI.resize(3 * nF);
+  std::vector<int> order(nF);
+  for (int d = 0; d < 3; ++d) {
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return BC[3 * (int64_t)a + d] < BC[3 * (int64_t)b + d]; });
+    for (int64_t i = 0; i < nF; ++i) t->SI[3 * (int64_t)order[i] + d] = (int)i;
+  }
+  std::vector<int> all(nF);
+  std::iota(all.begin(), all.end(), 0);
+  t->nodes.reserve(2 * nF);
+  build_rec(*t, all);
+  std::vector<int>().swap(t->SI);
+  return t;
+}
+void port_cp_destroy(void *p) { delete (CpTree *)p; }
+int64_t port_cp_num_nodes(void *p) { return (int64_t)((CpTree *)p)->nodes.size(); }
+
+// batch squared distance with bounds (AABB.cpp:1241-1265 when low=0, up=inf).
+// P n x 3 row-major.  Rows that find nothing keep I=-1 and sqrD=up.
+void port_cp_query(void *p, const double *P, int64_t n, double low, double up, double *sqrD,
+                   int *I, double *C, int64_t *counters /* [2] or null */) {
+  const CpTree &t = *(CpTree *)p;
+  std::atomic<int64_t> cn{0}, ct{0};
+  port_parallel_for(
+      n,
+      [&](int64_t k) {
+        const V3 q = {P[3 * k], P[3 * k + 1], P[3 * k + 2]};
+        int i = -1;
+        V3 c = {0, 0, 0};
+        double d;
+        if (counters) {
+          Counters cc;
+          d = sqd_rec<true>(t, 0, q, low, up, i, c, &cc);
+          cn += cc.nodes;
+          ct += cc.tris;
+        } else {
+          d = sqd_rec<false>(t, 0, q, low, up, i, c, nullptr);
+        }
+        sqrD[k] = d;
+        I[k] = i;
+        C[3 * k] = c.x;
+        C[3 * k + 1] = c.y;
+        C[3 * k + 2] = c.z;
+      },
+      10000);
+  if (counters) {
+    counters[0] = cn;
+    counters[1] = ct;
+  }
+}
+
+// O(nP*nF) brute force, lowest-index tie-break (strict <)
+void port_cp_brute(const double *V, const int *F, int64_t nF, const double *P, int64_t n,
+                   double *sqrD, int *I, double *C) {
+  port_parallel_for(
+      n,
+      [&](int64_t k) {
+        const V3 q = {P[3 * k], P[3 * k + 1], P[3 * k + 2]};
+        double best = std::numeric_limits<double>::infinity();
+        int bi = -1;
+        V3 bc = {0, 0, 0};
+        for (int64_t f = 0; f < nF; ++f) {
+          const double *a = V + 3 * (int64_t)F[3 * f], *b = V + 3 * (int64_t)F[3 * f + 1],
+                       *c = V + 3 * (int64_t)F[3 * f + 2];
+          const V3 cc = closest_on_triangle(q, {a[0], a[1], a[2]}, {b[0], b[1], b[2]},
+                                            {c[0], c[1], c[2]});
+          const V3 d = q - cc;
+          const double dd = dot(d, d);
+          if (dd < best) {
+            best = dd;
+            bi = (int)f;
+            bc = cc;
+          }
+        }
+        sqrD[k] = best;
+        I[k] = bi;
+        C[3 * k] = bc.x;
+        C[3 * k + 1] = bc.y;
+        C[3 * k + 2] = bc.z;
+      },
+      1);
+}
+
+// squared distance of each P[k] to the single face faces[k]
+void port_cp_face_distance(const double *V, const int *F, const double *P, const int *faces,
+                           int64_t n, double *sqrD, double *C) {
+  port_parallel_for(
+      n,
+      [&](int64_t k) {
+        const V3 q = {P[3 * k], P[3 * k + 1], P[3 * k + 2]};
+        const int64_t f = faces[k];
+        const double *a = V + 3 * (int64_t)F[3 * f], *b = V + 3 * (int64_t)F[3 * f + 1],
+                     *c = V + 3 * (int64_t)F[3 * f + 2];
+        const V3 cc =
+            closest_on_triangle(q, {a[0], a[1], a[2]}, {b[0], b[1], b[2]}, {c[0], c[1], c[2]});
+        const V3 d = q - cc;
+        sqrD[k] = dot(d, d);
+        if (C) {
+          C[3 * k] = cc.x;
+          C[3 * k + 1] = cc.y;
+          C[3 * k + 2] = cc.z;
+        }
+      },
+      10000);
+}
+
+// ---- point cloud FWN -----------------------------------------------------
+void *port_cloud_create(const double *P, const double *N, const double *A, int64_t n, int order) {
+  Cloud *c = new Cloud;
+  c->P = P;
+  c->N = N;
+  c->A = A;
+  c->n = n;
+  c->order = order;
+  c->nterms = order == 0 ? 3 : (order == 1 ? 12 : 39);
+  std::vector<int> all(n);
+  std::iota(all.begin(), all.end(), 0);
+  c->pts.push_back(all);
+  c->CH.push_back({-1, -1, -1, -1, -1, -1, -1, -1});
+  double lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = std::numeric_limits<double>::infinity();
+    hi[d] = -std::numeric_limits<double>::infinity();
+  }
+  for (int64_t i = 0; i < n; ++i)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], P[3 * i + d]);
+      hi[d] = std::max(hi[d], P[3 * i + d]);
+    }
+  c->CN.push_back({(lo[0] + hi[0]) / 2.0, (lo[1] + hi[1]) / 2.0, (lo[2] + hi[2]) / 2.0});
+  c->Wd.push_back(std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2])));
+  int m = 1;
+  octree_rec(*c, 0, 0, m);
+  const size_t nc = c->CH.size();
+  c->CM.resize(nc);
+  c->R.resize(nc);
+  c->EC.assign(nc * c->nterms, 0.0);
+  cloud_precompute_rec(*c, 0);
+  return c;
+}
+void port_cloud_destroy(void *p) { delete (Cloud *)p; }
+int64_t port_cloud_num_cells(void *p) { return (int64_t)((Cloud *)p)->CH.size(); }
+void port_cloud_cells(void *p, int *CH, double *CN, double *W, double *CM, double *R, double *EC,
+                      int *counts) {
+  const Cloud &c = *(Cloud *)p;
+  for (size_t i = 0; i < c.CH.size(); ++i) {
+    if (CH) std::memcpy(CH + 8 * i, c.CH[i].data(), 8 * sizeof(int));
+    if (CN) std::memcpy(CN + 3 * i, c.CN[i].data(), 3 * sizeof(double));
+    if (W) W[i] = c.Wd[i];
+    if (CM) std::memcpy(CM + 3 * i, c.CM[i].data(), 3 * sizeof(double));
+    if (R) R[i] = c.R[i];
+    if (counts) counts[i] = (int)c.pts[i].size();
+  }
+  if (EC) std::memcpy(EC, c.EC.data(), c.EC.size() * sizeof(double));
+}
+void port_cloud_eval(void *p, const double *Q, int64_t m, double beta, double *WN) {
+  const Cloud &c = *(Cloud *)p;
+  if (beta > 0) {
+    const std::vector<int> start = {0};
+    port_parallel_for(
+        m, [&](int64_t k) { WN[k] = cloud_eval_rec(c, Q + 3 * k, start, beta); }, 1000);
+  } else {
+    port_parallel_for(
+        m,
+        [&](int64_t k) {
+          double wn = 0;
+          for (int64_t j = 0; j < c.n; ++j) {
+            double loc[3], an[3];
+            for (int d = 0; d < 3; ++d) {
+              loc[d] = c.P[3 * j + d] - Q[3 * k + d];
+              an[d] = c.N[3 * j + d] * c.A[j];
+            }
+            wn += direct_eval(loc, an);
+          }
+          WN[k] = wn;
+        },
+        1000);
+  }
+}
+
+}  // extern "C"
