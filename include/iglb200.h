@@ -1,0 +1,146 @@
+/* iglb200 — C ABI of the B200-native point-vs-mesh query path.
+ *
+ * This is the whole drop-in boundary: plain pointers and sizes, no C++/torch
+ * types.  libigl itself has no FFI for this path — its interface is the set of
+ * C++ function templates cited beside each entry point below (paths relative to
+ * /root/reference/include/igl/).  include/iglb200/ *.h re-creates those
+ * templates on top of this ABI; INTEGRATION.md shows the few lines a libigl
+ * maintainer would add to route igl::signed_distance through it.
+ *
+ * Conventions
+ *  - Matrices are passed as (pointer, is_f64, rows, row_stride, col_stride),
+ *    strides in ELEMENTS, which covers Eigen column-major (rs=1, cs=rows),
+ *    row-major (rs=cols, cs=1) and Map<..., Stride<>> views.
+ *  - All pointers in the non-_dev entry points are HOST pointers (pageable or
+ *    pinned); the library copies to/from the current CUDA device.
+ *  - The caller owns every array (AABB.h:20-21: "The mesh (V,Ele) is stored and
+ *    managed by the caller").  A mesh handle COPIES V and F at creation, so the
+ *    inputs may be freed afterwards (unlike UT_SolidAngle, which keeps raw
+ *    pointers: FastWindingNumberForSoups.h:6232-6234).
+ *  - Return value 0 = ok, negative = error; iglb200_last_error() gives the
+ *    message (thread local).  There is NO CPU fallback: without a CUDA device
+ *    every compute entry point returns IGLB200_ERR_CUDA.
+ *  - Handles are immutable after creation and may be queried from several
+ *    host threads at once (the reference structures are const-queried from
+ *    igl::parallel_for threads: AABB.h:569-574).
+ */
+#ifndef IGLB200_H
+#define IGLB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGLB200_OK 0
+#define IGLB200_ERR_ARG (-1)
+#define IGLB200_ERR_CUDA (-2)
+#define IGLB200_ERR_OOM (-3)
+#define IGLB200_ERR_UNSUPPORTED (-4)
+#define IGLB200_ERR_INTERNAL (-5)
+
+/* igl::SignedDistanceType, signed_distance.h:20-34.  Only UNSIGNED and
+ * FAST_WINDING_NUMBER are implemented; the others return
+ * IGLB200_ERR_UNSUPPORTED (no silent fallback). */
+#define IGLB200_SIGN_PSEUDONORMAL 0
+#define IGLB200_SIGN_WINDING_NUMBER 1
+#define IGLB200_SIGN_DEFAULT 2
+#define IGLB200_SIGN_UNSIGNED 3
+#define IGLB200_SIGN_FAST_WINDING_NUMBER 4
+
+typedef struct iglb200_mesh iglb200_mesh;   /* AABB<MatrixXd,3> + FastWindingNumberBVH in one */
+typedef struct iglb200_cloud iglb200_cloud; /* octree + CM/R/EC of the point-cloud FWN */
+
+const char *iglb200_last_error(void);
+const char *iglb200_version(void);
+int iglb200_device_count(void);          /* <0 on error, 0 when no GPU */
+int iglb200_set_device(int device);      /* device used by the calling thread */
+
+/* pinned host memory for fast transfers (optional; any host pointer works) */
+int iglb200_host_alloc(void **out, uint64_t bytes);
+int iglb200_host_free(void *p);
+
+/* ---- mesh: replaces AABB::init (AABB.h:494-496, AABB.cpp:877-883) and
+ *      fast_winding_number(V,F,order,bvh) (fast_winding_number.h:160-170,
+ *      fast_winding_number.cpp:383-416).  Both trees are built on the device. */
+int iglb200_mesh_create(const void *V, int v_is_f64, int64_t nV, int64_t v_row_stride, int64_t v_col_stride,
+                        const int32_t *F, int64_t nF, int64_t f_row_stride, int64_t f_col_stride,
+                        int fwn_order, iglb200_mesh **out);
+int iglb200_mesh_destroy(iglb200_mesh *m);
+/* info[0]=#faces, [1]=#tree nodes, [2]=#levels, [3]=device bytes, [4]=#faces excluded (NaN/Inf boxes) */
+int iglb200_mesh_info(const iglb200_mesh *m, int64_t info[8]);
+/* device build time of the last create on this handle, milliseconds (CUDA events) */
+double iglb200_mesh_build_ms(const iglb200_mesh *m);
+
+/* Flat, position-independent image of the built trees, for replication to
+ * other GPUs (ncclBroadcast of one byte range) or caching.  The arena is one
+ * device allocation owned by the handle. */
+int iglb200_mesh_arena(const iglb200_mesh *m, void **device_ptr, uint64_t *bytes);
+/* Copy the arena to host memory (serialisation; AABB::serialize is the
+ * reference's analogue, AABB.cpp:1089-1116). `bytes` must equal the arena size. */
+int iglb200_mesh_arena_download(const iglb200_mesh *m, void *host_dst, uint64_t bytes);
+/* Adopt an arena that already sits in device memory of the current device.
+ * copy!=0: the handle makes its own copy; copy==0: the caller keeps `device_ptr`
+ * alive for the lifetime of the handle. */
+int iglb200_mesh_from_arena(const void *device_ptr, uint64_t bytes, int copy, iglb200_mesh **out);
+
+/* ---- igl::signed_distance(P,V,F,sign_type,lower,upper,S,I,C,N)
+ *      signed_distance.h:61-89, signed_distance.cpp:28-139, 372-416.
+ *      N is not written for these sign types (as in the reference).
+ *      W (optional, may be NULL) receives the winding number the sign was made
+ *      from — an extension.  Out-of-bounds rows: S=NaN, I=#F+1, C=0, W=NaN
+ *      (signed_distance.cpp:99-105).  #F==0: S=NaN, I=-1, C=NaN (:398-405). */
+int iglb200_signed_distance(const iglb200_mesh *m,
+                            const void *P, int p_is_f64, int64_t nP, int64_t p_row_stride, int64_t p_col_stride,
+                            int sign_type, double lower_bound, double upper_bound,
+                            void *S, int s_is_f64, int32_t *I,
+                            void *C, int c_is_f64, int64_t c_row_stride, int64_t c_col_stride,
+                            void *W, int w_is_f64);
+
+/* ---- AABB::squared_distance(V,Ele,P,sqrD,I,C) batch, AABB.h:722-728,
+ *      AABB.cpp:1241-1265; also point_mesh_squared_distance.h:54-60. */
+int iglb200_squared_distance(const iglb200_mesh *m,
+                             const void *P, int p_is_f64, int64_t nP, int64_t p_row_stride, int64_t p_col_stride,
+                             void *sqrD, int d_is_f64, int32_t *I,
+                             void *C, int c_is_f64, int64_t c_row_stride, int64_t c_col_stride);
+
+/* ---- fast_winding_number(fwn_bvh, accuracy_scale, Q, W)
+ *      fast_winding_number.h:172-187, fast_winding_number.cpp:421-437. */
+int iglb200_fwn_eval(const iglb200_mesh *m,
+                     const void *Q, int q_is_f64, int64_t nQ, int64_t q_row_stride, int64_t q_col_stride,
+                     float accuracy_scale, void *W, int w_is_f64);
+
+/* ---- device-resident variants: every pointer is a DEVICE pointer on the
+ *      current device, canonical layout (P/C column-major doubles, rs=1,
+ *      cs=nP; S,W doubles; I int32), `stream` is a cudaStream_t (NULL = default
+ *      stream).  Asynchronous: the call returns after enqueueing.  `scratch`
+ *      must hold iglb200_query_scratch_bytes(nP) bytes.  sort_queries!=0 groups
+ *      queries in Morton order before traversal. */
+uint64_t iglb200_query_scratch_bytes(int64_t nP);
+int iglb200_signed_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP,
+                                int sign_type, double lower_bound, double upper_bound,
+                                double *S, int32_t *I, double *C, double *W,
+                                void *scratch, int sort_queries, void *stream);
+int iglb200_squared_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP,
+                                 double *sqrD, int32_t *I, double *C,
+                                 void *scratch, int sort_queries, void *stream);
+int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, float accuracy_scale,
+                         double *W, void *scratch, int sort_queries, void *stream);
+/* number of kernels the last *_dev / host call on this thread enqueued */
+int iglb200_last_launch_count(void);
+
+/* ---- point cloud: fast_winding_number(P,N,A,Q,order,beta,WN)
+ *      fast_winding_number.h:44-53,88-131; octree.h; fast_winding_number.cpp:17-344 */
+int iglb200_cloud_create(const void *P, const void *N, const void *A, int is_f64, int64_t nP,
+                         int expansion_order, iglb200_cloud **out);
+int iglb200_cloud_destroy(iglb200_cloud *c);
+int iglb200_cloud_info(const iglb200_cloud *c, int64_t info[8]);
+int iglb200_cloud_eval(const iglb200_cloud *c,
+                       const void *Q, int q_is_f64, int64_t nQ, int64_t q_row_stride, int64_t q_col_stride,
+                       double beta, void *WN, int w_is_f64);
+int iglb200_cloud_eval_dev(const iglb200_cloud *c, const double *Q, int64_t nQ, double beta, double *WN,
+                           void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

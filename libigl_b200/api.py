@@ -1,0 +1,331 @@
+"""Host-side mirror of the reference interface for the point-vs-mesh query path,
+on top of the C ABI in include/iglb200.h (ctypes; no torch, no CPU compute).
+
+Names and argument meaning follow libigl (paths under /root/reference/include/igl):
+  signed_distance                signed_distance.h:61-89
+  signed_distance_fast_winding_number  signed_distance.h:283-312
+  AABB.init / AABB.squared_distance    AABB.h:494-496, 722-728
+  point_mesh_squared_distance    point_mesh_squared_distance.h:54-60
+  fast_winding_number (soup)     fast_winding_number.h:160-206
+  fast_winding_number (cloud)    fast_winding_number.h:44-53, 88-131
+Outputs are returned instead of being written through reference arguments, as
+the libigl python bindings do.  numpy arrays are passed by pointer with their
+own strides (row- or column-major, float32 or float64) — nothing is copied on
+the host unless the dtype is unsupported.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+SIGNED_DISTANCE_TYPE_PSEUDONORMAL = 0
+SIGNED_DISTANCE_TYPE_WINDING_NUMBER = 1
+SIGNED_DISTANCE_TYPE_DEFAULT = 2
+SIGNED_DISTANCE_TYPE_UNSIGNED = 3
+SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER = 4
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+_dbl = C.c_double
+
+
+class IglB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"iglb200 error {code}: {msg}")
+        self.code = code
+
+
+def _mat(a, name):
+    """(array kept alive, pointer, is_f64, rows, row_stride, col_stride) of an n x 3 matrix."""
+    a = np.asarray(a)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError(f"{name} must be #x3, got {a.shape}")
+    if a.dtype not in (np.float64, np.float32):
+        a = a.astype(np.float64)
+    es = a.dtype.itemsize
+    if a.shape[0] > 0 and (a.strides[0] <= 0 or a.strides[1] <= 0 or a.strides[0] % es or a.strides[1] % es):
+        a = np.ascontiguousarray(a)
+    return a, a.ctypes.data_as(_vp), int(a.dtype == np.float64), a.shape[0], a.strides[0] // es, a.strides[1] // es
+
+
+class Api:
+    """Bound C ABI.  The product instance is created by libigl_b200/__init__.py from
+    libigl_b200/libiglb200.so; nothing here knows about any other library."""
+
+    SYMBOLS = [
+        "iglb200_last_error", "iglb200_version", "iglb200_device_count", "iglb200_set_device",
+        "iglb200_host_alloc", "iglb200_host_free",
+        "iglb200_mesh_create", "iglb200_mesh_destroy", "iglb200_mesh_info", "iglb200_mesh_build_ms",
+        "iglb200_mesh_arena", "iglb200_mesh_arena_download", "iglb200_mesh_from_arena",
+        "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
+        "iglb200_query_scratch_bytes", "iglb200_signed_distance_dev", "iglb200_squared_distance_dev",
+        "iglb200_fwn_eval_dev", "iglb200_last_launch_count",
+        "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
+        "iglb200_cloud_eval_dev",
+    ]
+
+    def __init__(self, lib: C.CDLL):
+        self.lib = L = lib
+        for s in self.SYMBOLS:
+            getattr(L, s)  # AttributeError if the library does not export it
+        L.iglb200_last_error.restype = C.c_char_p
+        L.iglb200_version.restype = C.c_char_p
+        L.iglb200_host_alloc.argtypes = [C.POINTER(_vp), C.c_uint64]
+        L.iglb200_host_free.argtypes = [_vp]
+        L.iglb200_mesh_create.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, C.POINTER(_vp)]
+        L.iglb200_mesh_destroy.argtypes = [_vp]
+        L.iglb200_mesh_info.argtypes = [_vp, C.POINTER(_i64)]
+        L.iglb200_mesh_build_ms.argtypes = [_vp]
+        L.iglb200_mesh_build_ms.restype = _dbl
+        L.iglb200_mesh_arena.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64)]
+        L.iglb200_mesh_arena_download.argtypes = [_vp, _vp, C.c_uint64]
+        L.iglb200_mesh_from_arena.argtypes = [_vp, C.c_uint64, _int, C.POINTER(_vp)]
+        L.iglb200_signed_distance.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _int, _dbl, _dbl,
+                                              _vp, _int, _vp, _vp, _int, _i64, _i64, _vp, _int]
+        L.iglb200_squared_distance.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _int, _i64, _i64]
+        L.iglb200_fwn_eval.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, C.c_float, _vp, _int]
+        L.iglb200_query_scratch_bytes.argtypes = [_i64]
+        L.iglb200_query_scratch_bytes.restype = C.c_uint64
+        L.iglb200_signed_distance_dev.argtypes = [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _int, _vp]
+        L.iglb200_squared_distance_dev.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _vp]
+        L.iglb200_fwn_eval_dev.argtypes = [_vp, _vp, _i64, C.c_float, _vp, _vp, _int, _vp]
+        L.iglb200_cloud_create.argtypes = [_vp, _vp, _vp, _int, _i64, _int, C.POINTER(_vp)]
+        L.iglb200_cloud_destroy.argtypes = [_vp]
+        L.iglb200_cloud_info.argtypes = [_vp, C.POINTER(_i64)]
+        L.iglb200_cloud_eval.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _dbl, _vp, _int]
+        L.iglb200_cloud_eval_dev.argtypes = [_vp, _vp, _i64, _dbl, _vp, _vp]
+
+    # -- plumbing ---------------------------------------------------------
+    def check(self, rc):
+        if rc != 0:
+            raise IglB200Error(rc, self.lib.iglb200_last_error().decode())
+
+    def version(self):
+        return self.lib.iglb200_version().decode()
+
+    def device_count(self):
+        return int(self.lib.iglb200_device_count())
+
+    def set_device(self, d):
+        self.check(self.lib.iglb200_set_device(int(d)))
+
+    def last_launch_count(self):
+        return int(self.lib.iglb200_last_launch_count())
+
+    # -- handles ----------------------------------------------------------
+    def Mesh(self, V, F, order=2):
+        return Mesh(self, V, F, order)
+
+    def Cloud(self, P, N, A, order=2):
+        return Cloud(self, P, N, A, order)
+
+    # -- reference-named free functions -------------------------------------
+    def signed_distance(self, P, V, F, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER,
+                        lower_bound=None, upper_bound=None, return_W=False):
+        """igl::signed_distance: returns S, I, C (and W if asked).  N is not produced for
+        the supported sign types, exactly as in the reference."""
+        F = np.asarray(F)
+        if F.shape[0] == 0:  # signed_distance.cpp:398-405
+            n = np.asarray(P).shape[0]
+            out = (np.full(n, np.nan), np.full(n, -1, np.int32), np.full((n, 3), np.nan))
+            return out + (np.full(n, np.nan),) if return_W else out
+        m = Mesh(self, V, F, 2)
+        try:
+            return m.signed_distance(P, sign_type, lower_bound, upper_bound, return_W)
+        finally:
+            m.close()
+
+    def point_mesh_squared_distance(self, P, V, Ele):
+        m = Mesh(self, V, Ele, 0)
+        try:
+            return m.squared_distance(P)
+        finally:
+            m.close()
+
+    def fast_winding_number(self, *args, **kw):
+        """Overloads of igl::fast_winding_number:
+        (V, F, Q) -> W                         soup one-shot (fast_winding_number.cpp:367-378)
+        (P, N, A, Q[, order, beta]) -> WN      point cloud (fast_winding_number.cpp:320-365)"""
+        if len(args) == 3:
+            V, F, Q = args
+            m = Mesh(self, V, F, 2)
+            try:
+                return m.fast_winding_number(Q, 2.0)
+            finally:
+                m.close()
+        if len(args) in (4, 6):
+            P, N, A, Q = args[:4]
+            order, beta = (args[4], args[5]) if len(args) == 6 else (kw.get("expansion_order", 2), kw.get("beta", 2.0))
+            c = Cloud(self, P, N, A, order)
+            try:
+                return c.eval(Q, beta)
+            finally:
+                c.close()
+        raise TypeError("fast_winding_number(V,F,Q) or fast_winding_number(P,N,A,Q[,order,beta])")
+
+
+class Mesh:
+    """AABB<MatrixXd,3> + FastWindingNumberBVH built on the device (one handle)."""
+
+    def __init__(self, api: Api, V, F, order=2, _handle=None):
+        self.api = api
+        self.h = _vp()
+        if _handle is not None:
+            self.h = _handle
+            return
+        Vk, vp, vf64, nV, vrs, vcs = _mat(V, "V")
+        F = np.asarray(F)
+        if F.ndim != 2 or F.shape[1] != 3:
+            raise ValueError(f"F must be #Fx3, got {F.shape}")
+        if F.dtype != np.int32:
+            F = F.astype(np.int32)
+        if F.shape[0] and (F.strides[0] <= 0 or F.strides[1] <= 0):
+            F = np.ascontiguousarray(F)
+        api.check(api.lib.iglb200_mesh_create(vp, vf64, nV, vrs, vcs, F.ctypes.data_as(_vp), F.shape[0],
+                                              F.strides[0] // 4 if F.shape[0] else 3, F.strides[1] // 4 if F.shape[0] else 1,
+                                              int(order), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.api.lib.iglb200_mesh_destroy(self.h)
+            self.h = _vp()
+
+    __del__ = close
+
+    def info(self):
+        a = (_i64 * 8)()
+        self.api.check(self.api.lib.iglb200_mesh_info(self.h, a))
+        return dict(n_faces=a[0], n_nodes=a[1], n_levels=a[2], device_bytes=a[3], n_excluded=a[4], order=a[5],
+                    build_ms=float(self.api.lib.iglb200_mesh_build_ms(self.h)))
+
+    def arena(self):
+        p = _vp()
+        b = C.c_uint64()
+        self.api.check(self.api.lib.iglb200_mesh_arena(self.h, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def download(self):
+        """Host copy of the flat tree image, parsed into numpy views (inspection / caching)."""
+        _, nbytes = self.arena()
+        buf = np.empty(nbytes, np.uint8)
+        self.api.check(self.api.lib.iglb200_mesh_arena_download(self.h, buf.ctypes.data_as(_vp), nbytes))
+        return parse_arena(buf)
+
+    @staticmethod
+    def from_arena(api: Api, device_ptr: int, nbytes: int, copy: bool = True):
+        h = _vp()
+        api.check(api.lib.iglb200_mesh_from_arena(_vp(device_ptr), nbytes, int(copy), C.byref(h)))
+        return Mesh(api, None, None, _handle=h)
+
+    # igl::signed_distance with prebuilt structures
+    def signed_distance(self, P, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower_bound=None,
+                        upper_bound=None, return_W=False):
+        Pk, pp, pf64, n, prs, pcs = _mat(P, "P")
+        if lower_bound is None:  # signed_distance.cpp:436-439
+            lower_bound = np.finfo(np.float64).tiny
+        if upper_bound is None:
+            upper_bound = np.finfo(np.float64).max
+        S = np.empty(n, np.float64)
+        I = np.empty(n, np.int32)
+        Cc = np.empty((n, 3), np.float64, order="F")
+        W = np.empty(n, np.float64) if return_W else None
+        self.api.check(self.api.lib.iglb200_signed_distance(
+            self.h, pp, pf64, n, prs, pcs, int(sign_type), float(lower_bound), float(upper_bound),
+            S.ctypes.data_as(_vp), 1, I.ctypes.data_as(_vp), Cc.ctypes.data_as(_vp), 1, 1, max(n, 1),
+            W.ctypes.data_as(_vp) if return_W else None, 1))
+        return (S, I, Cc, W) if return_W else (S, I, Cc)
+
+    # igl::signed_distance_fast_winding_number(P,V,F,tree,fwn_bvh,S): S only
+    def signed_distance_fast_winding_number(self, P):
+        return self.signed_distance(P)[0]
+
+    # AABB::squared_distance(V,Ele,P,sqrD,I,C)
+    def squared_distance(self, P):
+        Pk, pp, pf64, n, prs, pcs = _mat(P, "P")
+        D = np.empty(n, np.float64)
+        I = np.empty(n, np.int32)
+        Cc = np.empty((n, 3), np.float64, order="F")
+        self.api.check(self.api.lib.iglb200_squared_distance(
+            self.h, pp, pf64, n, prs, pcs, D.ctypes.data_as(_vp), 1, I.ctypes.data_as(_vp),
+            Cc.ctypes.data_as(_vp), 1, 1, max(n, 1)))
+        return D, I, Cc
+
+    # fast_winding_number(fwn_bvh, accuracy_scale, Q, W)
+    def fast_winding_number(self, Q, accuracy_scale=2.0):
+        Qk, qp, qf64, n, qrs, qcs = _mat(Q, "Q")
+        W = np.empty(n, np.float64)
+        self.api.check(self.api.lib.iglb200_fwn_eval(self.h, qp, qf64, n, qrs, qcs, float(accuracy_scale),
+                                                     W.ctypes.data_as(_vp), 1))
+        return W
+
+
+class AABB:
+    """igl::AABB<DerivedV,3> subset: init + squared_distance."""
+
+    def __init__(self, api: Api):
+        self.api = api
+        self.mesh = None
+
+    def init(self, V, Ele):
+        self.mesh = Mesh(self.api, V, Ele, 0)
+
+    def squared_distance(self, V, Ele, P):
+        if self.mesh is None:
+            raise IglB200Error(-1, "AABB.init was not called")
+        return self.mesh.squared_distance(P)
+
+
+class Cloud:
+    """octree + CM/R/EC of fast_winding_number(P,N,A,...) kept on the device."""
+
+    def __init__(self, api: Api, P, N, A, order=2):
+        self.api = api
+        self.h = _vp()
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        N = np.ascontiguousarray(N, dtype=np.float64)
+        A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1)
+        if P.ndim != 2 or P.shape[1] != 3 or N.shape != P.shape or A.shape[0] != P.shape[0]:
+            raise ValueError("P, N must be #Px3 and A #P")
+        api.check(api.lib.iglb200_cloud_create(P.ctypes.data_as(_vp), N.ctypes.data_as(_vp), A.ctypes.data_as(_vp), 1,
+                                               P.shape[0], int(order), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.api.lib.iglb200_cloud_destroy(self.h)
+            self.h = _vp()
+
+    __del__ = close
+
+    def info(self):
+        a = (_i64 * 8)()
+        self.api.check(self.api.lib.iglb200_cloud_info(self.h, a))
+        return dict(n_points=a[0], n_cells=a[1], n_levels=a[2], device_bytes=a[3], order=a[4])
+
+    def eval(self, Q, beta=2.0):
+        Qk, qp, qf64, n, qrs, qcs = _mat(Q, "Q")
+        W = np.empty(n, np.float64)
+        self.api.check(self.api.lib.iglb200_cloud_eval(self.h, qp, qf64, n, qrs, qcs, float(beta),
+                                                       W.ctypes.data_as(_vp), 1))
+        return W
+
+
+def parse_arena(buf: np.ndarray):
+    """Decode the arena layout of libigl_b200/csrc/mesh.h (ArenaHeader + four arrays)."""
+    hdr = np.dtype([("magic", "<u8"), ("bytes", "<u8"), ("nF", "<i8"), ("nV", "<i8"), ("nnodes", "<i8"),
+                    ("nlevels", "<i8"), ("nexcluded", "<i8"), ("order", "<i4"), ("pad", "<i4"),
+                    ("bbox_lo", "<f8", 3), ("bbox_hi", "<f8", 3), ("absmax", "<f4"), ("padf", "<f4"),
+                    ("off_tri64", "<u8"), ("off_tri32", "<u8"), ("off_fnodes", "<u8"), ("off_cnodes", "<u8"),
+                    ("reserved", "<u8", 8)])
+    h = buf[:hdr.itemsize].view(hdr)[0]
+    nF, nn = int(h["nF"]), int(h["nnodes"])
+    tri64 = buf[int(h["off_tri64"]):int(h["off_tri64"]) + 72 * nF].view(np.float64).reshape(nF, 3, 3)
+    tri32 = buf[int(h["off_tri32"]):int(h["off_tri32"]) + 48 * nF].view(np.float32).reshape(nF, 3, 4)
+    fn = buf[int(h["off_fnodes"]):int(h["off_fnodes"]) + 384 * nn]
+    fchild = fn.view(np.uint32).reshape(nn, 96)[:, :4].copy()
+    fdata = fn.view(np.float32).reshape(nn, 96)[:, 4:].reshape(nn, 23, 4).copy()
+    cn = buf[int(h["off_cnodes"]):int(h["off_cnodes"]) + 128 * nn]
+    cbox = cn.view(np.float32).reshape(nn, 32)[:, :24].reshape(nn, 6, 4).copy()
+    cchild = cn.view(np.uint32).reshape(nn, 32)[:, 24:28].copy()
+    return dict(header=h, tri64=tri64, tri32=tri32, fwn_child=fchild, fwn_data=fdata, cp_box=cbox, cp_child=cchild)

@@ -1,0 +1,120 @@
+// Device build of the mesh handle: gather faces, 4-ary cluster tree
+// (fwn_build.h), bottom-up moments and closest-point boxes (moments.h).
+// Compiled with -fmad=false: every fp32 value that feeds a branch in the
+// reference must be reproduced bit for bit.
+#include "mesh.h"
+
+namespace fwn {
+
+// V (any stride, f32 or f64) + F -> per-face fp64 and fp32 vertices.
+// fp32 = (float)fp64, the reference's V.cast<float>() (signed_distance.cpp:66).
+template <class VT> struct GatherFaces {
+  const VT *V;
+  int64_t nV, v_rs, v_cs;
+  const int32_t *F;
+  int64_t f_rs, f_cs;
+  double *tri64;
+  float4 *tri32;
+  uint32_t *err;      // [0] = out-of-range index seen
+  uint32_t *absacc;   // order-encoded max |coordinate|
+  uint32_t *bbacc;    // [6] order-encoded fp32 hull (rounded outward) of the geometry
+  DEVFN void operator()(int64_t f) const {
+    float amax = 0.f;
+    for (int k = 0; k < 3; ++k) {
+      int64_t vi = F[f * f_rs + k * f_cs];
+      if (vi < 0 || vi >= nV) { plat::atomic_max(err, 1u); vi = 0; }
+      double x[3];
+      for (int d = 0; d < 3; ++d) x[d] = (double)V[vi * v_rs + d * v_cs];
+      for (int d = 0; d < 3; ++d) tri64[9 * f + 3 * k + d] = x[d];
+      tri32[3 * f + k] = make_float4((float)x[0], (float)x[1], (float)x[2], 0.f);
+      for (int d = 0; d < 3; ++d) {
+        const float up = f_round_up(fabs(x[d]));
+        if (up == up) amax = fmaxf(amax, up);
+        const float lo = f_round_down(x[d]), hi = f_round_up(x[d]);
+        if (lo == lo && hi == hi) { plat::atomic_min(&bbacc[d], plat::f2ord(lo)); plat::atomic_max(&bbacc[3 + d], plat::f2ord(hi)); }
+      }
+    }
+    plat::atomic_max(absacc, plat::f2ord(amax));
+  }
+};
+
+static int tree_levels(const Tree &t) { return (int)t.level_start.size() - 1; }
+
+iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F,
+                          int64_t nF, int64_t f_rs, int64_t f_cs, int order, stream_t s) {
+  using plat::DevBuf;
+  iglb200_mesh *m = new iglb200_mesh;
+  std::memset(&m->h, 0, sizeof(m->h));
+  m->h.magic = IGLB200_ARENA_MAGIC;
+  m->h.nF = nF; m->h.nV = nV; m->h.order = order;
+  try {
+    // raw uploads.  Only the bytes actually spanned by the strided views are copied.
+    const size_t vsz = v_is_f64 ? 8 : 4;
+    const size_t v_span = (nV > 0) ? (size_t)((nV - 1) * v_rs + 2 * v_cs + 1) : 0;
+    const size_t f_span = (nF > 0) ? (size_t)((nF - 1) * f_rs + 2 * f_cs + 1) : 0;
+    DevBuf<char> dV(v_span * vsz);
+    DevBuf<int32_t> dF(f_span);
+    plat::h2d(dV.p, V, v_span * vsz, s);
+    plat::h2d(dF.p, F, f_span * 4, s);
+    DevBuf<double> tri64((size_t)9 * nF);
+    DevBuf<float4> tri32((size_t)3 * nF);
+    DevBuf<uint32_t> acc(8);
+    {
+      const uint32_t init[8] = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+      plat::h2d(acc.p, init, sizeof(init), s);
+    }
+    if (v_is_f64)
+      plat::for_n(nF, GatherFaces<double>{(const double *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, acc.p, acc.p + 1, acc.p + 2}, s);
+    else
+      plat::for_n(nF, GatherFaces<float>{(const float *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, acc.p, acc.p + 1, acc.p + 2}, s);
+    uint32_t hacc[8];
+    plat::d2h(hacc, acc.p, sizeof(hacc), s);
+    plat::sync(s);
+    if (hacc[0]) throw std::invalid_argument("F contains a vertex index outside [0, #V)");
+    m->h.absmax = nF ? plat::ord2f(hacc[1]) : 0.f;
+    for (int d = 0; d < 3; ++d) {
+      m->h.bbox_lo[d] = nF ? (double)plat::ord2f(hacc[2 + d]) : 0.0;
+      m->h.bbox_hi[d] = nF ? (double)plat::ord2f(hacc[5 + d]) : 0.0;
+    }
+    dV.release();
+    dF.release();
+
+    DevBuf<TriBox> boxes;
+    Tree tree;
+    build_tree(tri32.p, (uint32_t)nF, boxes, tree, s);
+    const int64_t nn = tree.nnodes;
+    m->h.nnodes = nn;
+    m->h.nexcluded = tree.nexcluded;
+    m->h.nlevels = nn ? tree_levels(tree) : 0;
+
+    auto align = [](uint64_t x) { return (x + 255) & ~uint64_t(255); };
+    uint64_t off = align(sizeof(ArenaHeader));
+    m->h.off_tri64 = off; off = align(off + (uint64_t)72 * nF);
+    m->h.off_tri32 = off; off = align(off + (uint64_t)48 * nF);
+    m->h.off_fnodes = off; off = align(off + (uint64_t)sizeof(FwnNode) * nn);
+    m->h.off_cnodes = off; off = align(off + (uint64_t)sizeof(CpNode) * nn);
+    m->h.bytes = off;
+    m->arena = (char *)plat::dev_alloc(off);
+    plat::d2d(m->arena + m->h.off_tri64, tri64.p, (size_t)72 * nF, s);
+    plat::d2d(m->arena + m->h.off_tri32, tri32.p, (size_t)48 * nF, s);
+    if (nn) {
+      DevBuf<Local> locals((size_t)nn);
+      for (int l = tree_levels(tree) - 1; l >= 0; --l) {
+        const uint32_t first = tree.level_start[l], cnt = tree.level_start[l + 1] - first;
+        plat::for_n(cnt, NodeMoments{tree.nodes.p, (const float4 *)(m->arena + m->h.off_tri32), (const double *)(m->arena + m->h.off_tri64),
+                                     boxes.p, locals.p, (FwnNode *)(m->arena + m->h.off_fnodes), (CpNode *)(m->arena + m->h.off_cnodes), first, order}, s);
+      }
+      // faces dropped by the NaN/Inf filter = faces not referenced by any node
+      plat::sync(s);
+    }
+    plat::h2d(m->arena, &m->h, sizeof(ArenaHeader), s);
+    plat::sync(s);
+  } catch (...) {
+    if (m->arena) plat::dev_free(m->arena);
+    delete m;
+    throw;
+  }
+  return m;
+}
+
+}  // namespace fwn

@@ -1,0 +1,557 @@
+// extern "C" boundary (include/iglb200.h) and the query kernels.
+#include "../../include/iglb200.h"
+#include "mesh.h"
+#include "cloud.h"
+#include <chrono>
+
+using plat::DevBuf;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#ifdef IGLB200_EMUL
+void require_device() {}
+struct Timer {
+  std::chrono::steady_clock::time_point t0;
+  void start(stream_t) { t0 = std::chrono::steady_clock::now(); }
+  double stop(stream_t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+#else
+void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) throw plat::CudaError("no CUDA device available (this library has no CPU fallback)");
+}
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  void start(stream_t s) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+  double stop(stream_t s) {
+    cudaEventRecord(b, s); cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms;
+  }
+};
+#endif
+
+#define API_BEGIN try {
+#define API_END                                                                     \
+  }                                                                                 \
+  catch (const std::invalid_argument &e) { return fail(IGLB200_ERR_ARG, e.what()); } \
+  catch (const std::domain_error &e) { return fail(IGLB200_ERR_UNSUPPORTED, e.what()); } \
+  catch (const std::bad_alloc &e) { return fail(IGLB200_ERR_OOM, e.what()); }        \
+  catch (const std::exception &e) {                                                 \
+    const std::string w = e.what();                                                 \
+    return fail(w.find("out of memory") != std::string::npos ? IGLB200_ERR_OOM : IGLB200_ERR_CUDA, w); \
+  }                                                                                 \
+  catch (...) { return fail(IGLB200_ERR_INTERNAL, "unknown error"); }
+
+// ---------------------------------------------------------------- layout shims
+template <class T> struct ToCanon3 {  // strided n x 3 of T -> column-major doubles
+  const T *src; int64_t rs, cs, n; double *dst;
+  DEVFN void operator()(int64_t i) const { for (int j = 0; j < 3; ++j) dst[j * n + i] = (double)src[i * rs + j * cs]; }
+};
+template <class T> struct FromCanon3 {
+  const double *src; int64_t n; T *dst; int64_t rs, cs;
+  DEVFN void operator()(int64_t i) const { for (int j = 0; j < 3; ++j) dst[i * rs + j * cs] = (T)src[j * n + i]; }
+};
+struct ToFloat1 { const double *src; float *dst; DEVFN void operator()(int64_t i) const { dst[i] = (float)src[i]; } };
+
+// ---------------------------------------------------------------- query kernels
+struct MortonKeys {  // 30-bit Morton code of each query inside the doubled scene box
+  const double *P; int64_t n;
+  double lo[3], inv[3];
+  uint32_t *keys, *vals;
+  static DEVFN uint32_t spread(uint32_t v) {
+    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+    return v;
+  }
+  DEVFN void operator()(int64_t i) const {
+    uint32_t c[3];
+    for (int d = 0; d < 3; ++d) {
+      double t = (P[d * n + i] - lo[d]) * inv[d];
+      t = t < 0.0 ? 0.0 : (t > 1023.0 ? 1023.0 : t);
+      if (!(t == t)) t = 0.0;
+      c[d] = (uint32_t)t;
+    }
+    keys[i] = spread(c[0]) | (spread(c[1]) << 1) | (spread(c[2]) << 2);
+    vals[i] = (uint32_t)i;
+  }
+};
+
+struct ClosestQuery {  // one thread per query (AABB.cpp:1135-1218 semantics)
+  const fwn::CpNode *nodes; const double *tri64;
+  const double *P; int64_t n; const uint32_t *perm;
+  double up, low; float absmax;
+  double *sqrD; int32_t *I; double *C;
+  DEVFN void operator()(int64_t t) const {
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    const fwn::D3 p = {P[i], P[n + i], P[2 * n + i]};
+    uint32_t sn[fwn::CP_STACK]; float sd[fwn::CP_STACK];
+    fwn::CpResult r;
+    const float M = fmaxf(fmaxf(fabsf((float)p.x), fabsf((float)p.y)), fmaxf(fabsf((float)p.z), absmax));
+    if (low > up) { r.sqr_d = low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
+    else fwn::closest_triangle(nodes, tri64, p, up, low, M * 2.3841858e-7f, r, sn, sd);
+    sqrD[i] = r.sqr_d; I[i] = r.face;
+    C[i] = r.c.x; C[n + i] = r.c.y; C[2 * n + i] = r.c.z;
+  }
+};
+
+// winding number and, optionally, the fused epilogue of signed_distance.cpp:99-135
+struct WindingQuery {
+  const fwn::FwnNode *nodes; const float4 *tri32;
+  const double *P; int64_t n; const uint32_t *perm;
+  float acc2; int order;
+  int mode;  // 0: W only (fast_winding_number.cpp:435); 1: signed distance FWN; 2: unsigned
+  double up, low; int32_t nF;
+  double *W; double *S; int32_t *I; double *C;  // S holds sqrD on entry when mode!=0
+  DEVFN void operator()(int64_t t) const {
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    const double FOUR_PI = 4.0 * 3.1415926535897932384626433832795;
+    if (mode != 0) {
+      const double sqrd = S[i];
+      if (sqrd >= up || sqrd < low) {
+        S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
+        if (W) W[i] = NAN;
+        return;
+      }
+      if (mode == 2) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return; }
+    }
+    uint32_t stack[fwn::FWN_STACK];
+    const float om = fwn::winding_solid_angle(nodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], acc2, order, stack, nullptr);
+    const double w = (double)om / FOUR_PI;
+    if (mode == 0) { W[i] = w; return; }
+    const double wf = (double)(float)w;  // narrowed to float by fast_winding_number.cpp:452
+    if (W) W[i] = wf;
+    S[i] = (1.0 - 2.0 * fabs(wf)) * sqrt(S[i]);
+  }
+};
+
+struct FillConst { double *S; int32_t *I; double *C; double *W; int64_t n; double sv; int32_t iv; double cv;
+  DEVFN void operator()(int64_t i) const { if (S) S[i] = sv; if (I) I[i] = iv; if (C) { C[i] = cv; C[n + i] = cv; C[2 * n + i] = cv; } if (W) W[i] = sv; } };
+
+// scratch layout: [keys_in | keys_out | vals_in | vals_out(perm) | cub temp]
+struct Scratch {
+  uint32_t *kin, *kout, *vin, *perm; void *temp; size_t temp_bytes;
+};
+Scratch carve(void *scratch, int64_t n) {
+  Scratch s;
+  const size_t a = ((size_t)n * 4 + 255) & ~size_t(255);
+  char *p = (char *)scratch;
+  s.kin = (uint32_t *)p; s.kout = (uint32_t *)(p + a); s.vin = (uint32_t *)(p + 2 * a); s.perm = (uint32_t *)(p + 3 * a);
+  s.temp = p + 4 * a; s.temp_bytes = plat::sort_pairs_temp_bytes(n);
+  return s;
+}
+
+const uint32_t *morton_perm(const iglb200_mesh *m, const double *P, int64_t n, void *scratch, int sort_queries, stream_t s) {
+  if (!sort_queries || !scratch || n < 2) return nullptr;
+  Scratch sc = carve(scratch, n);
+  MortonKeys mk;
+  mk.P = P; mk.n = n; mk.keys = sc.kin; mk.vals = sc.vin;
+  for (int d = 0; d < 3; ++d) {
+    const double c = 0.5 * (m->h.bbox_lo[d] + m->h.bbox_hi[d]);
+    double ext = (m->h.bbox_hi[d] - m->h.bbox_lo[d]);
+    if (!(ext > 0.0)) ext = 1.0;
+    mk.lo[d] = c - ext;           // box doubled about its centre
+    mk.inv[d] = 1024.0 / (2.0 * ext);
+  }
+  plat::for_n(n, mk, s);
+  plat::sort_pairs_u32(sc.temp, sc.temp_bytes, sc.kin, sc.kout, sc.vin, sc.perm, n, 30, s);
+  return sc.perm;
+}
+
+void check_mesh(const iglb200_mesh *m) {
+  if (!m || m->h.magic != IGLB200_ARENA_MAGIC) throw std::invalid_argument("invalid mesh handle");
+}
+
+void bounds_to_sqr(double lower, double upper, double &low, double &up) {  // signed_distance.cpp:81-84
+  const double max_abs = std::max(std::fabs(lower), std::fabs(upper));
+  up = std::pow(max_abs, 2.0);
+  low = std::pow(std::max(max_abs - (upper - lower), 0.0), 2.0);
+}
+
+void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int sign_type, double lower, double upper,
+                         double *S, int32_t *I, double *C, double *W, void *scratch, int sort_queries, stream_t s) {
+  if (sign_type != IGLB200_SIGN_FAST_WINDING_NUMBER && sign_type != IGLB200_SIGN_UNSIGNED) {
+    throw std::domain_error("sign type not implemented on the device (only UNSIGNED and FAST_WINDING_NUMBER); no CPU fallback");
+  }
+  if (n == 0) return;
+  if (m->h.nF == 0) {  // signed_distance.cpp:398-405
+    plat::for_n(n, FillConst{S, I, C, W, n, NAN, -1, NAN}, s);
+    return;
+  }
+  if (m->h.nnodes == 0) {  // every face excluded: nothing to be close to
+    plat::for_n(n, FillConst{S, I, C, W, n, NAN, (int32_t)m->h.nF + 1, 0.0}, s);
+    return;
+  }
+  double low, up;
+  bounds_to_sqr(lower, upper, low, up);
+  const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
+  plat::for_n(n, ClosestQuery{m->cnodes(), m->tri64(), P, n, perm, up, low, m->h.absmax, S, I, C}, s);
+  plat::for_n(n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
+                              sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s);
+}
+
+void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, double *sqrD, int32_t *I, double *C,
+                          void *scratch, int sort_queries, stream_t s) {
+  if (n == 0) return;
+  if (m->h.nnodes == 0) {  // empty tree: the reference returns the initial bound (+inf) and leaves I/C unset
+    plat::for_n(n, FillConst{sqrD, I, C, nullptr, n, INFINITY, -1, 0.0}, s);
+    return;
+  }
+  const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
+  plat::for_n(n, ClosestQuery{m->cnodes(), m->tri64(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C}, s);
+}
+
+void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_scale, double *W, void *scratch,
+             int sort_queries, stream_t s) {
+  if (n == 0) return;
+  if (m->h.nnodes == 0) { plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, 0.0, 0, 0.0}, s); return; }
+  const uint32_t *perm = morton_perm(m, Q, n, scratch, sort_queries, s);
+  plat::for_n(n, WindingQuery{m->fnodes(), m->tri32(), Q, n, perm, accuracy_scale * accuracy_scale, m->h.order, 0, 0.0, 0.0,
+                              (int32_t)m->h.nF, W, nullptr, nullptr, nullptr}, s);
+}
+
+// upload a strided host matrix n x 3 as canonical column-major doubles
+void upload_points(const void *P, int is_f64, int64_t n, int64_t rs, int64_t cs, DevBuf<double> &out, stream_t s) {
+  out.alloc((size_t)3 * n);
+  if (n == 0) return;
+  if (rs <= 0 || cs <= 0) throw std::invalid_argument("strides must be positive");
+  if (is_f64 && rs == 1 && cs == n) { plat::h2d(out.p, P, (size_t)24 * n, s); return; }
+  const size_t span = (size_t)((n - 1) * rs + 2 * cs + 1);
+  const size_t esz = is_f64 ? 8 : 4;
+  DevBuf<char> raw(span * esz);
+  plat::h2d(raw.p, P, span * esz, s);
+  if (is_f64) plat::for_n(n, ToCanon3<double>{(const double *)raw.p, rs, cs, n, out.p}, s);
+  else plat::for_n(n, ToCanon3<float>{(const float *)raw.p, rs, cs, n, out.p}, s);
+  plat::sync(s);  // raw is released on return
+}
+void download_points(const DevBuf<double> &src, int64_t n, void *C, int is_f64, int64_t rs, int64_t cs, stream_t s) {
+  if (n == 0 || !C) return;
+  if (is_f64 && rs == 1 && cs == n) { plat::d2h(C, src.p, (size_t)24 * n, s); plat::sync(s); return; }
+  const size_t span = (size_t)((n - 1) * rs + 2 * cs + 1);
+  const size_t esz = is_f64 ? 8 : 4;
+  // strided destination: only elements of the view may be written, so stage on the host
+  std::vector<double> h((size_t)3 * n);
+  plat::d2h(h.data(), src.p, (size_t)24 * n, s);
+  plat::sync(s);
+  (void)span; (void)esz;
+  if (is_f64) { double *d = (double *)C; for (int64_t i = 0; i < n; ++i) for (int j = 0; j < 3; ++j) d[i * rs + j * cs] = h[j * n + i]; }
+  else { float *d = (float *)C; for (int64_t i = 0; i < n; ++i) for (int j = 0; j < 3; ++j) d[i * rs + j * cs] = (float)h[j * n + i]; }
+}
+void download_scalar(const DevBuf<double> &src, int64_t n, void *dst, int is_f64, stream_t s) {
+  if (n == 0 || !dst) return;
+  if (is_f64) { plat::d2h(dst, src.p, (size_t)8 * n, s); plat::sync(s); return; }
+  DevBuf<float> f((size_t)n);
+  plat::for_n(n, ToFloat1{src.p, f.p}, s);
+  plat::d2h(dst, f.p, (size_t)4 * n, s);
+  plat::sync(s);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *iglb200_last_error(void) { return g_err.c_str(); }
+const char *iglb200_version(void) {
+#ifdef IGLB200_EMUL
+  return "iglb200 0.1 (HOST EMULATION BUILD - tests only)";
+#else
+  return "iglb200 0.1 (sm_100a)";
+#endif
+}
+
+int iglb200_device_count(void) {
+#ifdef IGLB200_EMUL
+  return 0;
+#else
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) return fail(IGLB200_ERR_CUDA, cudaGetErrorString(e));
+  return n;
+#endif
+}
+int iglb200_set_device(int device) {
+#ifdef IGLB200_EMUL
+  (void)device; return IGLB200_OK;
+#else
+  API_BEGIN
+  require_device();
+  PLAT_CHECK(cudaSetDevice(device));
+  return IGLB200_OK;
+  API_END
+#endif
+}
+int iglb200_host_alloc(void **out, uint64_t bytes) {
+  if (!out) return fail(IGLB200_ERR_ARG, "null out");
+#ifdef IGLB200_EMUL
+  *out = std::malloc(bytes ? bytes : 1); return *out ? IGLB200_OK : fail(IGLB200_ERR_OOM, "malloc");
+#else
+  API_BEGIN
+  require_device();
+  PLAT_CHECK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return IGLB200_OK;
+  API_END
+#endif
+}
+int iglb200_host_free(void *p) {
+#ifdef IGLB200_EMUL
+  std::free(p); return IGLB200_OK;
+#else
+  API_BEGIN
+  if (p) PLAT_CHECK(cudaFreeHost(p));
+  return IGLB200_OK;
+  API_END
+#endif
+}
+
+int iglb200_mesh_create(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F, int64_t nF,
+                        int64_t f_rs, int64_t f_cs, int fwn_order, iglb200_mesh **out) {
+  API_BEGIN
+  if (!out) throw std::invalid_argument("null out");
+  *out = nullptr;
+  if (nV < 0 || nF < 0 || (nV > 0 && !V) || (nF > 0 && !F)) throw std::invalid_argument("null or negative-sized input");
+  if (nF > 0 && nV == 0) throw std::invalid_argument("faces without vertices");
+  if ((nV > 0 && (v_rs <= 0 || v_cs <= 0)) || (nF > 0 && (f_rs <= 0 || f_cs <= 0))) throw std::invalid_argument("strides must be positive");
+  if (fwn_order < 0 || fwn_order > 2) throw std::invalid_argument("fwn_order must be 0, 1 or 2");
+  if (nF >= (int64_t)0x7FFFFFF0) throw std::invalid_argument("too many faces");
+  require_device();
+  plat::launch_counter() = 0;
+  Timer t;
+  t.start(nullptr);
+  iglb200_mesh *m = fwn::create_mesh(V, v_is_f64, nV, v_rs, v_cs, F, nF, f_rs, f_cs, fwn_order, nullptr);
+  m->build_ms = t.stop(nullptr);
+#ifndef IGLB200_EMUL
+  cudaGetDevice(&m->device);
+#endif
+  *out = m;
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_mesh_destroy(iglb200_mesh *m) {
+  API_BEGIN
+  if (!m) return IGLB200_OK;
+  check_mesh(m);
+  if (m->owns && m->arena) plat::dev_free(m->arena);
+  m->h.magic = 0;
+  delete m;
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_mesh_info(const iglb200_mesh *m, int64_t info[8]) {
+  API_BEGIN
+  check_mesh(m);
+  info[0] = m->h.nF; info[1] = m->h.nnodes; info[2] = m->h.nlevels; info[3] = (int64_t)m->h.bytes; info[4] = m->h.nexcluded;
+  info[5] = m->h.order; info[6] = 0; info[7] = 0;
+  return IGLB200_OK;
+  API_END
+}
+double iglb200_mesh_build_ms(const iglb200_mesh *m) { return m ? m->build_ms : 0.0; }
+
+int iglb200_mesh_arena(const iglb200_mesh *m, void **device_ptr, uint64_t *bytes) {
+  API_BEGIN
+  check_mesh(m);
+  if (device_ptr) *device_ptr = m->arena;
+  if (bytes) *bytes = m->h.bytes;
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_mesh_arena_download(const iglb200_mesh *m, void *host_dst, uint64_t bytes) {
+  API_BEGIN
+  check_mesh(m);
+  if (!host_dst || bytes != m->h.bytes) throw std::invalid_argument("destination size must equal the arena size");
+  plat::d2h(host_dst, m->arena, bytes, nullptr);
+  plat::sync(nullptr);
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_mesh_from_arena(const void *device_ptr, uint64_t bytes, int copy, iglb200_mesh **out) {
+  API_BEGIN
+  if (!out || !device_ptr || bytes < sizeof(ArenaHeader)) throw std::invalid_argument("bad arena");
+  require_device();
+  iglb200_mesh *m = new iglb200_mesh;
+  plat::d2h(&m->h, device_ptr, sizeof(ArenaHeader), nullptr);
+  plat::sync(nullptr);
+  if (m->h.magic != IGLB200_ARENA_MAGIC || m->h.bytes != bytes) { delete m; throw std::invalid_argument("arena header mismatch"); }
+  if (copy) {
+    m->arena = (char *)plat::dev_alloc(bytes);
+    plat::d2d(m->arena, device_ptr, bytes, nullptr);
+    plat::sync(nullptr);
+    m->owns = true;
+  } else {
+    m->arena = (char *)device_ptr;
+    m->owns = false;
+  }
+  *out = m;
+  return IGLB200_OK;
+  API_END
+}
+
+uint64_t iglb200_query_scratch_bytes(int64_t nP) {
+  if (nP <= 0) return 256;
+  const size_t a = ((size_t)nP * 4 + 255) & ~size_t(255);
+  return 4 * a + plat::sort_pairs_temp_bytes(nP) + 256;
+}
+
+int iglb200_last_launch_count(void) { return plat::launch_counter(); }
+
+int iglb200_signed_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP, int sign_type, double lower, double upper,
+                                double *S, int32_t *I, double *C, double *W, void *scratch, int sort_queries, void *stream) {
+  API_BEGIN
+  check_mesh(m);
+  if (nP < 0 || (nP > 0 && (!P || !S || !I || !C))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  run_signed_distance(m, P, nP, sign_type, lower, upper, S, I, C, W, scratch, sort_queries, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_squared_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP, double *sqrD, int32_t *I, double *C,
+                                 void *scratch, int sort_queries, void *stream) {
+  API_BEGIN
+  check_mesh(m);
+  if (nP < 0 || (nP > 0 && (!P || !sqrD || !I || !C))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  run_squared_distance(m, P, nP, sqrD, I, C, scratch, sort_queries, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, float accuracy_scale, double *W, void *scratch,
+                         int sort_queries, void *stream) {
+  API_BEGIN
+  check_mesh(m);
+  if (nQ < 0 || (nQ > 0 && (!Q || !W))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  run_fwn(m, Q, nQ, accuracy_scale, W, scratch, sort_queries, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
+                            int sign_type, double lower, double upper, void *S, int s_is_f64, int32_t *I, void *C, int c_is_f64,
+                            int64_t c_rs, int64_t c_cs, void *W, int w_is_f64) {
+  API_BEGIN
+  check_mesh(m);
+  if (nP < 0 || (nP > 0 && (!P || !S || !I || !C))) throw std::invalid_argument("null pointer");
+  if (nP > 0 && (c_rs <= 0 || c_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  require_device();
+  plat::launch_counter() = 0;
+  stream_t s = nullptr;
+  DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP), dW(W ? (size_t)nP : 0);
+  DevBuf<int32_t> dI((size_t)nP);
+  DevBuf<char> scratch(iglb200_query_scratch_bytes(nP));
+  upload_points(P, p_is_f64, nP, p_rs, p_cs, dP, s);
+  run_signed_distance(m, dP.p, nP, sign_type, lower, upper, dS.p, dI.p, dC.p, W ? dW.p : nullptr, scratch.p, 1, s);
+  download_scalar(dS, nP, S, s_is_f64, s);
+  plat::d2h(I, dI.p, (size_t)4 * nP, s);
+  download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);
+  if (W) download_scalar(dW, nP, W, w_is_f64, s);
+  plat::sync(s);
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_squared_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
+                             void *sqrD, int d_is_f64, int32_t *I, void *C, int c_is_f64, int64_t c_rs, int64_t c_cs) {
+  API_BEGIN
+  check_mesh(m);
+  if (nP < 0 || (nP > 0 && (!P || !sqrD || !I || !C))) throw std::invalid_argument("null pointer");
+  if (nP > 0 && (c_rs <= 0 || c_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  require_device();
+  plat::launch_counter() = 0;
+  stream_t s = nullptr;
+  DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP);
+  DevBuf<int32_t> dI((size_t)nP);
+  DevBuf<char> scratch(iglb200_query_scratch_bytes(nP));
+  upload_points(P, p_is_f64, nP, p_rs, p_cs, dP, s);
+  run_squared_distance(m, dP.p, nP, dS.p, dI.p, dC.p, scratch.p, 1, s);
+  download_scalar(dS, nP, sqrD, d_is_f64, s);
+  plat::d2h(I, dI.p, (size_t)4 * nP, s);
+  download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);
+  plat::sync(s);
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_fwn_eval(const iglb200_mesh *m, const void *Q, int q_is_f64, int64_t nQ, int64_t q_rs, int64_t q_cs,
+                     float accuracy_scale, void *W, int w_is_f64) {
+  API_BEGIN
+  check_mesh(m);
+  if (nQ < 0 || (nQ > 0 && (!Q || !W))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  stream_t s = nullptr;
+  DevBuf<double> dQ, dW((size_t)nQ);
+  DevBuf<char> scratch(iglb200_query_scratch_bytes(nQ));
+  upload_points(Q, q_is_f64, nQ, q_rs, q_cs, dQ, s);
+  run_fwn(m, dQ.p, nQ, accuracy_scale, dW.p, scratch.p, 1, s);
+  download_scalar(dW, nQ, W, w_is_f64, s);
+  plat::sync(s);
+  return IGLB200_OK;
+  API_END
+}
+
+// ---- point cloud ----------------------------------------------------------
+int iglb200_cloud_create(const void *P, const void *N, const void *A, int is_f64, int64_t nP, int expansion_order,
+                         iglb200_cloud **out) {
+  API_BEGIN
+  if (!out) throw std::invalid_argument("null out");
+  *out = nullptr;
+  if (nP < 0 || (nP > 0 && (!P || !N || !A))) throw std::invalid_argument("null or negative-sized input");
+  if (expansion_order < 0 || expansion_order > 2) throw std::invalid_argument("expansion_order must be 0, 1 or 2");
+  require_device();
+  plat::launch_counter() = 0;
+  *out = cloud::create(P, N, A, is_f64, nP, expansion_order, nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_cloud_destroy(iglb200_cloud *c) {
+  API_BEGIN
+  cloud::destroy(c);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_cloud_info(const iglb200_cloud *c, int64_t info[8]) {
+  API_BEGIN
+  if (!c) throw std::invalid_argument("invalid cloud handle");
+  cloud::info(c, info);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_cloud_eval_dev(const iglb200_cloud *c, const double *Q, int64_t nQ, double beta, double *WN, void *stream) {
+  API_BEGIN
+  if (!c) throw std::invalid_argument("invalid cloud handle");
+  if (nQ < 0 || (nQ > 0 && (!Q || !WN))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  cloud::eval(c, Q, nQ, beta, WN, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_cloud_eval(const iglb200_cloud *c, const void *Q, int q_is_f64, int64_t nQ, int64_t q_rs, int64_t q_cs, double beta,
+                       void *WN, int w_is_f64) {
+  API_BEGIN
+  if (!c) throw std::invalid_argument("invalid cloud handle");
+  if (nQ < 0 || (nQ > 0 && (!Q || !WN))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  stream_t s = nullptr;
+  DevBuf<double> dQ, dW((size_t)nQ);
+  upload_points(Q, q_is_f64, nQ, q_rs, q_cs, dQ, s);
+  cloud::eval(c, dQ.p, nQ, beta, dW.p, s);
+  download_scalar(dW, nQ, WN, w_is_f64, s);
+  plat::sync(s);
+  return IGLB200_OK;
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// The mesh handle: one position-independent device arena holding everything a
+// query needs, so that replicating the structure to another GPU is a single
+// broadcast of [arena, arena+bytes).
+//
+//   [ArenaHeader | tri64 (9 f64 / face) | tri32 (3 float4 / face) |
+//    fwn nodes (384 B) | closest-point nodes (128 B)]
+//
+// tri64/tri32 are the faces' vertices gathered once at build time (the
+// reference dereferences V through F for every leaf test: AABB.cpp:1413-1432,
+// FastWindingNumberForSoups.h:7260-7269).
+#pragma once
+#include "traverse.h"
+
+static constexpr uint64_t IGLB200_ARENA_MAGIC = 0x32424C47494C4247ull;
+
+struct ArenaHeader {
+  uint64_t magic;
+  uint64_t bytes;
+  int64_t nF, nV, nnodes, nlevels, nexcluded;
+  int32_t order, pad;
+  double bbox_lo[3], bbox_hi[3];  // of the fp64 geometry
+  float absmax, padf;             // max |coordinate| (slack of the fp32 box tests)
+  uint64_t off_tri64, off_tri32, off_fnodes, off_cnodes;
+  uint64_t reserved[8];
+};
+
+struct iglb200_mesh {
+  ArenaHeader h;
+  char *arena = nullptr;  // device
+  bool owns = true;
+  double build_ms = 0.0;
+  int device = 0;
+  const double *tri64() const { return (const double *)(arena + h.off_tri64); }
+  const float4 *tri32() const { return (const float4 *)(arena + h.off_tri32); }
+  const fwn::FwnNode *fnodes() const { return (const fwn::FwnNode *)(arena + h.off_fnodes); }
+  const fwn::CpNode *cnodes() const { return (const fwn::CpNode *)(arena + h.off_cnodes); }
+};
+
+namespace fwn {
+// build.cu (compiled with -fmad=false)
+iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F,
+                          int64_t nF, int64_t f_rs, int64_t f_cs, int order, stream_t s);
+}  // namespace fwn

@@ -1,0 +1,193 @@
+// Device/host plumbing shared by every kernel file.
+//
+// The product is compiled by nvcc for sm_100a only.  The SAME kernel bodies can
+// also be compiled by g++ with -DIGLB200_EMUL: every launch then becomes a plain
+// loop on the host.  That build exists ONLY so that `pytest -m "not gpu"` can
+// check the kernels' logic against the oracle in a container without a GPU; it
+// is produced under tests/_build/ by tests/emul.py and is never loaded by
+// libigl_b200/.  There is no CPU fallback in the product library: without a
+// CUDA device every entry point returns IGLB200_ERR_CUDA.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <stdexcept>
+#include <vector>
+#include <algorithm>
+
+namespace plat {
+// kernels (ours + cub passes) enqueued by the calling thread; reset by the C ABI per call
+inline int &launch_counter() { static thread_local int c = 0; return c; }
+}  // namespace plat
+
+#ifdef IGLB200_EMUL
+// ------------------------------------------------------------------ host loops
+#include <vector_types.h>  // float4/uint4/double3 PODs (host-safe CUDA header)
+#include <vector_functions.h>
+#include <numeric>
+#define HD inline
+#define DEVFN inline
+typedef void *stream_t;
+namespace plat {
+inline float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline uint32_t atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
+inline uint32_t atomic_min(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
+inline uint32_t atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+inline float fsqrt(float x) { return std::sqrt(x); }
+inline float fdiv(float a, float b) { return a / b; }
+inline float fmul(float a, float b) { return a * b; }  // built with -ffp-contract=off
+inline float fadd(float a, float b) { return a + b; }
+inline float ffma(float a, float b, float c) { return a * b + c; }
+inline void *dev_alloc(size_t bytes) { void *p = std::malloc(bytes ? bytes : 1); if (!p) throw std::bad_alloc(); return p; }
+inline void dev_free(void *p) { std::free(p); }
+inline void h2d(void *d, const void *h, size_t n, stream_t) { std::memcpy(d, h, n); }
+inline void d2h(void *h, const void *d, size_t n, stream_t) { std::memcpy(h, d, n); }
+inline void d2d(void *d, const void *s, size_t n, stream_t) { std::memcpy(d, s, n); }
+inline void dev_memset(void *d, int v, size_t n, stream_t) { std::memset(d, v, n); }
+inline void sync(stream_t) {}
+// f(i) for i in [0,n)
+template <class F> void for_n(int64_t n, F f, stream_t) { for (int64_t i = 0; i < n; ++i) f(i); }
+// f(i) for i in [0,*count) with the count living in "device" memory
+template <class F> void for_dyn(const uint32_t *count, F f, stream_t) { for (uint32_t i = 0; i < *count; ++i) f(i); }
+// f.tile(t) for t in [0,*ntiles): block-cooperative on the device, sequential here
+template <class F> void tiles_dyn(const uint32_t *ntiles, F f, stream_t) { for (uint32_t t = 0; t < *ntiles; ++t) f.tile(t); }
+inline void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, stream_t) {
+  uint32_t s = 0;
+  for (int64_t i = 0; i < n; ++i) { uint32_t v = in[i]; out[i] = s; s += v; }
+}
+inline size_t sort_pairs_temp_bytes(int64_t) { return 16; }
+// stable sort of (key,val) by key
+inline void sort_pairs_u32(void *, size_t, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int, stream_t) {
+  std::vector<uint32_t> o(n);
+  std::iota(o.begin(), o.end(), 0u);
+  std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
+  for (int64_t i = 0; i < n; ++i) { kout[i] = kin[o[i]]; vout[i] = vin[o[i]]; }
+}
+}  // namespace plat
+#else
+// ------------------------------------------------------------------ CUDA
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#define HD __host__ __device__ __forceinline__
+#define DEVFN __device__ __forceinline__
+typedef cudaStream_t stream_t;
+namespace plat {
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+inline void check(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define PLAT_CHECK(x) ::plat::check((x), #x)
+HD float u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+HD uint32_t f2u(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+DEVFN uint32_t atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+DEVFN uint32_t atomic_min(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
+DEVFN uint32_t atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+// IEEE round-to-nearest, never contracted into FMA regardless of -fmad
+DEVFN float fsqrt(float x) { return __fsqrt_rn(x); }
+DEVFN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+DEVFN float fmul(float a, float b) { return __fmul_rn(a, b); }
+DEVFN float fadd(float a, float b) { return __fadd_rn(a, b); }
+DEVFN float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+inline void *dev_alloc(size_t bytes) { void *p = nullptr; PLAT_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
+inline void dev_free(void *p) { if (p) cudaFree(p); }
+inline void h2d(void *d, const void *h, size_t n, stream_t s) { if (n) PLAT_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); }
+inline void d2h(void *h, const void *d, size_t n, stream_t s) { if (n) PLAT_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); }
+inline void d2d(void *d, const void *s_, size_t n, stream_t s) { if (n) PLAT_CHECK(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s)); }
+inline void dev_memset(void *d, int v, size_t n, stream_t s) { if (n) PLAT_CHECK(cudaMemsetAsync(d, v, n, s)); }
+inline void sync(stream_t s) { PLAT_CHECK(cudaStreamSynchronize(s)); }
+
+inline int sm_count() {
+  static int n = [] { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+  return n;
+}
+
+template <class F> __global__ void __launch_bounds__(256) k_for_n(int64_t n, F f) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+}
+template <class F> __global__ void __launch_bounds__(256) k_for_dyn(const uint32_t *count, F f) {
+  const uint32_t n = *count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f(i);
+}
+template <class F> __global__ void __launch_bounds__(256) k_tiles_dyn(const uint32_t *ntiles, F f) {
+  const uint32_t n = *ntiles;
+  for (uint32_t t = blockIdx.x; t < n; t += gridDim.x) { f.tile(t); __syncthreads(); }
+}
+template <class F> void for_n(int64_t n, F f, stream_t s) {
+  if (n <= 0) return;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  k_for_n<<<(unsigned)blocks, 256, 0, s>>>(n, f);
+  launch_counter()++;
+  PLAT_CHECK(cudaGetLastError());
+}
+template <class F> void for_dyn(const uint32_t *count, F f, stream_t s) {
+  k_for_dyn<<<sm_count() * 8, 256, 0, s>>>(count, f);
+  launch_counter()++;
+  PLAT_CHECK(cudaGetLastError());
+}
+template <class F> void tiles_dyn(const uint32_t *ntiles, F f, stream_t s) {
+  k_tiles_dyn<<<sm_count() * 8, 256, 0, s>>>(ntiles, f);
+  launch_counter()++;
+  PLAT_CHECK(cudaGetLastError());
+}
+// scratch for cub, grown on demand (one per thread; builds are serialised per handle)
+struct ScanTemp { void *p = nullptr; size_t cap = 0; ~ScanTemp() { dev_free(p); } };
+inline void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, stream_t s) {
+  if (n <= 0) return;
+  static thread_local ScanTemp tmp;
+  size_t need = 0;
+  PLAT_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, s));
+  if (need > tmp.cap) { sync(s); dev_free(tmp.p); tmp.p = dev_alloc(need); tmp.cap = need; }
+  PLAT_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, need, in, out, (int)n, s));
+  launch_counter()++;
+}
+inline size_t sort_pairs_temp_bytes(int64_t n) {
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
+  return need + 256;
+}
+inline void sort_pairs_u32(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, stream_t s) {
+  PLAT_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
+  launch_counter() += 4;
+}
+}  // namespace plat
+#endif
+
+namespace plat {
+// RAII device array
+template <class T> struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) { release(); p = (T *)dev_alloc(count * sizeof(T)); n = count; }
+  void release() { if (p) dev_free(p); p = nullptr; n = 0; }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// order-preserving float <-> uint32 map so box unions can use integer atomics
+HD uint32_t f2ord(float f) { uint32_t u = f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+HD float ord2f(uint32_t u) { return u2f((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+}  // namespace plat

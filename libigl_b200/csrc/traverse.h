@@ -1,0 +1,241 @@
+// Per-query device functions for the two traversals of the hot path.
+//
+//  closest_triangle : branch-and-bound over the 4-wide tree.  fp32 conservative
+//      box tests prune; every triangle that survives is evaluated with
+//      Ericson's routine in fp64 with un-fused arithmetic in the reference's
+//      operation order (/root/reference/include/igl/
+//      point_simplex_squared_distance.cpp:45-110,134), so squared distances are
+//      bit-identical to the CPU restatement and ties can be compared exactly.
+//      Tie rule: lowest face index (the reference keeps the first triangle its
+//      own tree happens to visit, AABB.cpp:787-802 — order dependent).
+//  winding_solid_angle : depth-first Barnes–Hut evaluation
+//      (FastWindingNumberForSoups.h:7148-7284).  The descend test and the exact
+//      triangle term use IEEE un-fused fp32 in the reference's order so that
+//      every branch agrees with it; the far-field polynomial may use FMA.
+#pragma once
+#include "moments.h"
+
+namespace fwn {
+
+#ifdef IGLB200_EMUL
+DEVFN double dmul(double a, double b) { return a * b; }
+DEVFN double dadd(double a, double b) { return a + b; }
+DEVFN double dsub(double a, double b) { return a - b; }
+DEVFN double ddiv(double a, double b) { return a / b; }
+DEVFN float fsub(float a, float b) { return a - b; }
+DEVFN float f_up(double d) { return f_round_up(d); }
+#else
+DEVFN double dmul(double a, double b) { return __dmul_rn(a, b); }
+DEVFN double dadd(double a, double b) { return __dadd_rn(a, b); }
+DEVFN double dsub(double a, double b) { return __dsub_rn(a, b); }
+DEVFN double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+DEVFN float fsub(float a, float b) { return __fsub_rn(a, b); }
+DEVFN float f_up(double d) { return __double2float_ru(d); }
+#endif
+
+struct D3 { double x, y, z; };
+DEVFN D3 d3sub(D3 a, D3 b) { return {dsub(a.x, b.x), dsub(a.y, b.y), dsub(a.z, b.z)}; }
+DEVFN double d3dot(D3 a, D3 b) { return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z)); }
+DEVFN D3 d3madd(D3 a, D3 d, double s) { return {dadd(a.x, dmul(d.x, s)), dadd(a.y, dmul(d.y, s)), dadd(a.z, dmul(d.z, s))}; }
+
+// Ericson, Real-Time Collision Detection ch.5, as used by
+// point_simplex_squared_distance.cpp:45-110
+DEVFN D3 closest_on_triangle(D3 p, D3 a, D3 b, D3 c) {
+  const D3 ab = d3sub(b, a), ac = d3sub(c, a), ap = d3sub(p, a);
+  const double d1 = d3dot(ab, ap), d2 = d3dot(ac, ap);
+  if (d1 <= 0.0 && d2 <= 0.0) return a;
+  const D3 bp = d3sub(p, b);
+  const double d3 = d3dot(ab, bp), d4 = d3dot(ac, bp);
+  if (d3 >= 0.0 && d4 <= d3) return b;
+  const double vc = dsub(dmul(d1, d4), dmul(d3, d2));
+  if (!(a.x == b.x && a.y == b.y && a.z == b.z)) {
+    if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) return d3madd(a, ab, ddiv(d1, dsub(d1, d3)));
+  }
+  const D3 cp = d3sub(p, c);
+  const double d5 = d3dot(ab, cp), d6 = d3dot(ac, cp);
+  if (d6 >= 0.0 && d5 <= d6) return c;
+  const double vb = dsub(dmul(d5, d2), dmul(d1, d6));
+  if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) return d3madd(a, ac, ddiv(d2, dsub(d2, d6)));
+  const double va = dsub(dmul(d3, d6), dmul(d5, d4));
+  const double e43 = dsub(d4, d3), e56 = dsub(d5, d6);
+  if (va <= 0.0 && e43 >= 0.0 && e56 >= 0.0) return d3madd(b, d3sub(c, b), ddiv(e43, dadd(e43, e56)));
+  const double denom = ddiv(1.0, dadd(dadd(va, vb), vc));
+  const double v = dmul(vb, denom), w = dmul(vc, denom);
+  return d3madd(d3madd(a, ab, v), ac, w);
+}
+
+struct CpResult {
+  double sqr_d;
+  int32_t face;
+  D3 c;
+};
+
+static constexpr int CP_STACK = 96;
+
+// squared distance, lower bound, from a point to lane `i` of a node's child boxes
+DEVFN float lane_box_d2(const CpNode &n, int i, float px, float py, float pz, float slack) {
+  const float lx = ((const float *)&n.lox)[i], hx = ((const float *)&n.hix)[i];
+  const float ly = ((const float *)&n.loy)[i], hy = ((const float *)&n.hiy)[i];
+  const float lz = ((const float *)&n.loz)[i], hz = ((const float *)&n.hiz)[i];
+  float dx = fmaxf(fmaxf(lx - px, px - hx) - slack, 0.f);
+  float dy = fmaxf(fmaxf(ly - py, py - hy) - slack, 0.f);
+  float dz = fmaxf(fmaxf(lz - pz, pz - hz) - slack, 0.f);
+  return (dx * dx + dy * dy + dz * dz) * 0.99999952f;  // 1 - 4 ulp: absorbs the rounding of the sum
+}
+
+// Global minimum of |p - tri|^2 over all faces with value < up_sqr_d.
+// `slack` >= the fp32 rounding error of (coordinate - coordinate) for this query.
+DEVFN void closest_triangle(const CpNode *nodes, const double *tri64, D3 p, double up_sqr_d, double low_sqr_d,
+                            float slack, CpResult &res, uint32_t *stack_node, float *stack_d) {
+  res.sqr_d = up_sqr_d;
+  res.face = -1;
+  res.c = {0.0, 0.0, 0.0};
+  const float px = (float)p.x, py = (float)p.y, pz = (float)p.z;
+  float thr = f_up(res.sqr_d);  // prune when lower bound > thr
+  int sp = 0;
+  uint32_t cur = 0;
+  bool have = true;
+  while (true) {
+    if (!have) {
+      if (sp == 0) break;
+      --sp;
+      if (stack_d[sp] > thr) continue;
+      cur = stack_node[sp];
+    }
+    have = false;
+    const CpNode n = nodes[cur];
+    const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
+    float cd[4];
+    uint32_t cn[4];
+    int nint = 0;
+    for (int i = 0; i < 4; ++i) {
+      if (ch[i] == EMPTY) break;
+      const float d2 = lane_box_d2(n, i, px, py, pz, slack);
+      if (d2 > thr) continue;
+      if (ch[i] & INTERNAL_BIT) {
+        // insertion into the (<=4) sorted list of internal children, nearest first
+        int k = nint++;
+        while (k > 0 && cd[k - 1] > d2) { cd[k] = cd[k - 1]; cn[k] = cn[k - 1]; --k; }
+        cd[k] = d2; cn[k] = ch[i] & ~INTERNAL_BIT;
+      } else {
+        const double *t = tri64 + 9 * (size_t)ch[i];
+        const D3 a = {t[0], t[1], t[2]}, b = {t[3], t[4], t[5]}, c = {t[6], t[7], t[8]};
+        const D3 cc = closest_on_triangle(p, a, b, c);
+        const D3 df = d3sub(p, cc);
+        const double dd = d3dot(df, df);
+        if (dd < res.sqr_d || (dd == res.sqr_d && res.face >= 0 && (int32_t)ch[i] < res.face)) {
+          res.sqr_d = dd; res.face = (int32_t)ch[i]; res.c = cc;
+          thr = f_up(dd);
+        }
+      }
+    }
+    if (res.sqr_d < low_sqr_d) break;  // AABB.cpp:1422-1426: nothing below the lower bound is refined
+    // far children first on the stack, nearest continues immediately
+    for (int k = nint - 1; k >= 1; --k) {
+      if (cd[k] > thr) continue;
+      if (sp < CP_STACK) { stack_node[sp] = cn[k]; stack_d[sp] = cd[k]; ++sp; }
+    }
+    if (nint > 0 && cd[0] <= thr) { cur = cn[0]; have = true; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// UTsignedSolidAngleTri (FastWindingNumberForSoups.h:6070-6110), un-fused fp32
+// ---------------------------------------------------------------------------
+DEVFN float f3dot(const float *a, const float *b) {
+  return plat::fadd(plat::fadd(plat::fmul(a[0], b[0]), plat::fmul(a[1], b[1])), plat::fmul(a[2], b[2]));
+}
+DEVFN float tri_solid_angle(const float4 *tri32, uint32_t f, float qx, float qy, float qz) {
+  const float4 A = tri32[3 * (size_t)f], B = tri32[3 * (size_t)f + 1], C = tri32[3 * (size_t)f + 2];
+  float qa[3] = {fsub(A.x, qx), fsub(A.y, qy), fsub(A.z, qz)};
+  float qb[3] = {fsub(B.x, qx), fsub(B.y, qy), fsub(B.z, qz)};
+  float qc[3] = {fsub(C.x, qx), fsub(C.y, qy), fsub(C.z, qz)};
+  const float al = plat::fsqrt(f3dot(qa, qa)), bl = plat::fsqrt(f3dot(qb, qb)), cl = plat::fsqrt(f3dot(qc, qc));
+  if (al == 0.f || bl == 0.f || cl == 0.f) return 0.f;
+  const float ia = plat::fdiv(1.f, al), ib = plat::fdiv(1.f, bl), ic = plat::fdiv(1.f, cl);
+  for (int d = 0; d < 3; ++d) { qa[d] = plat::fmul(qa[d], ia); qb[d] = plat::fmul(qb[d], ib); qc[d] = plat::fmul(qc[d], ic); }
+  const float u[3] = {fsub(qb[0], qa[0]), fsub(qb[1], qa[1]), fsub(qb[2], qa[2])};
+  const float v[3] = {fsub(qc[0], qa[0]), fsub(qc[1], qa[1]), fsub(qc[2], qa[2])};
+  const float cr[3] = {fsub(plat::fmul(u[1], v[2]), plat::fmul(u[2], v[1])),
+                       fsub(plat::fmul(u[2], v[0]), plat::fmul(u[0], v[2])),
+                       fsub(plat::fmul(u[0], v[1]), plat::fmul(u[1], v[0]))};
+  const float num = f3dot(qa, cr);
+  if (num == 0.f) return 0.f;
+  const float den = plat::fadd(plat::fadd(plat::fadd(1.f, f3dot(qa, qb)), f3dot(qa, qc)), f3dot(qb, qc));
+  return 2.f * atan2f(num, den);
+}
+
+static constexpr int FWN_STACK = 96;
+
+// far-field order-<=2 expansion of one child lane (:7200-7241)
+DEVFN float lane_omega(const FwnNode &n, int i, float q0, float q1, float q2, float ql2, int order) {
+#define LN(r) (((const float *)&n.d[r])[i])
+  const float m2 = plat::fdiv(1.0f, ql2);
+  const float m1 = plat::fsqrt(m2);
+  q0 *= m1; q1 *= m1; q2 *= m1;
+  float omega = -m2 * (q0 * LN(R_NX) + q1 * LN(R_NY) + q2 * LN(R_NZ));
+  if (order >= 1) {
+    const float s0 = q0 * q0, s1 = q1 * q1, s2 = q2 * q2;
+    const float m3 = m2 * m1;
+    const float o1 = m3 * (LN(R_NXX) + LN(R_NYY) + LN(R_NZZ) -
+                           3.0f * ((s0 * LN(R_NXX) + s1 * LN(R_NYY) + s2 * LN(R_NZZ)) + q0 * q1 * LN(R_NXY_NYX) +
+                                   q0 * q2 * LN(R_NZX_NXZ) + q1 * q2 * LN(R_NYZ_NZY)));
+    omega += o1;
+    if (order >= 2) {
+      const float c0 = s0 * q0, c1 = s1 * q1, c2 = s2 * q2;
+      const float m4 = m2 * m2;
+      const float t00 = LN(R_2NYYX_NXYY) + LN(R_2NZZX_NXZZ);
+      const float t01 = LN(R_2NZZY_NYZZ) + LN(R_2NXXY_NYXX);
+      const float t02 = LN(R_2NXXZ_NZXX) + LN(R_2NYYZ_NZYY);
+      const float t10 = q1 * LN(R_2NXXY_NYXX) + q2 * LN(R_2NXXZ_NZXX);
+      const float t11 = q2 * LN(R_2NYYZ_NZYY) + q0 * LN(R_2NYYX_NXYY);
+      const float t12 = q0 * LN(R_2NZZX_NXZZ) + q1 * LN(R_2NZZY_NYZZ);
+      const float o2 = m4 * (1.5f * (q0 * (3.f * LN(R_NXXX) + t00) + q1 * (3.f * LN(R_NYYY) + t01) + q2 * (3.f * LN(R_NZZZ) + t02)) -
+                             7.5f * ((c0 * LN(R_NXXX) + c1 * LN(R_NYYY) + c2 * LN(R_NZZZ)) + q0 * q1 * q2 * LN(R_SUMPERM) +
+                                     (s0 * t10 + s1 * t11 + s2 * t12)));
+      omega += o2;
+    }
+  }
+#undef LN
+  return omega;
+}
+
+DEVFN bool finite_f(float x) { return (plat::f2u(x) & 0x7F800000u) != 0x7F800000u; }
+
+// Solid angle (not yet divided by 4 pi) of the whole soup seen from q.
+DEVFN float winding_solid_angle(const FwnNode *nodes, const float4 *tri32, float qx, float qy, float qz, float acc2,
+                                int order, uint32_t *stack, uint32_t *visits /*nullable: [nodes, tris]*/) {
+  float sum = 0.f;
+  int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    const uint32_t ni = stack[--sp];
+    const FwnNode &n = nodes[ni];
+    if (visits) visits[0]++;
+    const float4 R2 = n.d[R_MAXP2], PX = n.d[R_PX], PY = n.d[R_PY], PZ = n.d[R_PZ];
+    const uint4 chv = n.child;
+    const uint32_t ch[4] = {chv.x, chv.y, chv.z, chv.w};
+    uint32_t descend = 0;
+    float node_sum = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const float q0 = fsub(qx, ((const float *)&PX)[i]), q1 = fsub(qy, ((const float *)&PY)[i]), q2 = fsub(qz, ((const float *)&PZ)[i]);
+      const float ql2 = plat::fadd(plat::fadd(plat::fmul(q0, q0), plat::fmul(q1, q1)), plat::fmul(q2, q2));
+      if (ql2 <= plat::fmul(((const float *)&R2)[i], acc2)) { descend |= 1u << i; continue; }
+      const float om = lane_omega(n, i, q0, q1, q2, ql2, order);
+      if (!finite_f(om)) { descend |= 1u << i; continue; }
+      node_sum += om;
+    }
+    sum += node_sum;
+    // children in lane order; push in reverse so that lane 0 pops first
+    for (int i = 3; i >= 0; --i) {
+      if (!((descend >> i) & 1u)) continue;
+      const uint32_t c = ch[i];
+      if (c == EMPTY) continue;
+      if (c & INTERNAL_BIT) { if (sp < FWN_STACK) stack[sp++] = c & ~INTERNAL_BIT; }
+      else { sum += tri_solid_angle(tri32, c, qx, qy, qz); if (visits) visits[1]++; }
+    }
+  }
+  return sum;
+}
+
+}  // namespace fwn
