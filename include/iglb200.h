@@ -128,6 +128,12 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
 /* number of kernels the last *_dev / host call on this thread enqueued */
 int iglb200_last_launch_count(void);
 
+/* Optional per-kernel timing (CUDA events on the launching stream) for the
+ * calling thread.  collect() synchronises, writes "name=ms;name=ms;..." summed
+ * per kernel group since the previous collect, and returns the string length. */
+void iglb200_profile_enable(int on);
+int iglb200_profile_collect(char *out, uint64_t cap);
+
 /* ---- point cloud: fast_winding_number(P,N,A,Q,order,beta,WN)
  *      fast_winding_number.h:44-53,88-131; octree.h; fast_winding_number.cpp:17-344 */
 int iglb200_cloud_create(const void *P, const void *N, const void *A, int is_f64, int64_t nP,

@@ -61,7 +61,7 @@ class Api:
         "iglb200_mesh_arena", "iglb200_mesh_arena_download", "iglb200_mesh_from_arena",
         "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
         "iglb200_query_scratch_bytes", "iglb200_signed_distance_dev", "iglb200_squared_distance_dev",
-        "iglb200_fwn_eval_dev", "iglb200_last_launch_count",
+        "iglb200_fwn_eval_dev", "iglb200_last_launch_count", "iglb200_profile_enable", "iglb200_profile_collect",
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
     ]
@@ -91,6 +91,9 @@ class Api:
         L.iglb200_signed_distance_dev.argtypes = [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _int, _vp]
         L.iglb200_squared_distance_dev.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _vp]
         L.iglb200_fwn_eval_dev.argtypes = [_vp, _vp, _i64, C.c_float, _vp, _vp, _int, _vp]
+        L.iglb200_profile_enable.argtypes = [_int]
+        L.iglb200_profile_enable.restype = None
+        L.iglb200_profile_collect.argtypes = [C.c_char_p, C.c_uint64]
         L.iglb200_cloud_create.argtypes = [_vp, _vp, _vp, _int, _i64, _int, C.POINTER(_vp)]
         L.iglb200_cloud_destroy.argtypes = [_vp]
         L.iglb200_cloud_info.argtypes = [_vp, C.POINTER(_i64)]
@@ -113,6 +116,20 @@ class Api:
 
     def last_launch_count(self):
         return int(self.lib.iglb200_last_launch_count())
+
+    def profile_enable(self, on=True):
+        self.lib.iglb200_profile_enable(int(on))
+
+    def profile_collect(self):
+        """{kernel group: milliseconds} accumulated since the previous collect."""
+        buf = C.create_string_buffer(4096)
+        self.lib.iglb200_profile_collect(buf, 4096)
+        out = {}
+        for kv in buf.value.decode().split(";"):
+            if "=" in kv:
+                k, v = kv.split("=")
+                out[k] = float(v)
+        return out
 
     # -- handles ----------------------------------------------------------
     def Mesh(self, V, F, order=2):

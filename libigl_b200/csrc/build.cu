@@ -2,6 +2,7 @@
 // (fwn_build.h), bottom-up moments and closest-point boxes (moments.h).
 // Compiled with -fmad=false: every fp32 value that feeds a branch in the
 // reference must be reproduced bit for bit.
+#define IGLB200_BUILDER_TU 1
 #include "mesh.h"
 
 namespace fwn {

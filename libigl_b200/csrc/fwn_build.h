@@ -99,6 +99,7 @@ struct ReboxAcc {
   uint32_t lo[2][3], hi[2][3];
 };
 
+#ifdef IGLB200_BUILDER_TU  // only build.cu (compiled with -fmad=false) instantiates the builder
 // ----------------------------------------------------------------------------
 // small-range regimes, one thread per range
 // ----------------------------------------------------------------------------
@@ -888,5 +889,7 @@ inline void build_tree(const float4 *tri32, uint32_t nF, plat::DevBuf<TriBox> &b
   }
   out.nnodes = nnodes;
 }
+
+#endif  // IGLB200_BUILDER_TU
 
 }  // namespace fwn

@@ -6,7 +6,7 @@
 
 using plat::DevBuf;
 
-namespace {
+namespace iglq {
 
 thread_local std::string g_err;
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -157,6 +157,7 @@ const uint32_t *morton_perm(const iglb200_mesh *m, const double *P, int64_t n, v
     mk.lo[d] = c - ext;           // box doubled about its centre
     mk.inv[d] = 1024.0 / (2.0 * ext);
   }
+  plat::Span sp("morton_sort", s);
   plat::for_n(n, mk, s);
   plat::sort_pairs_u32(sc.temp, sc.temp_bytes, sc.kin, sc.kout, sc.vin, sc.perm, n, 30, s);
   return sc.perm;
@@ -189,9 +190,11 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   double low, up;
   bounds_to_sqr(lower, upper, low, up);
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
-  plat::for_n(n, ClosestQuery{m->cnodes(), m->tri64(), P, n, perm, up, low, m->h.absmax, S, I, C}, s);
-  plat::for_n(n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
-                              sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s);
+  { plat::Span sp("closest", s);
+    plat::for_n(n, ClosestQuery{m->cnodes(), m->tri64(), P, n, perm, up, low, m->h.absmax, S, I, C}, s); }
+  { plat::Span sp("winding", s);
+    plat::for_n(n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
+                                sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s); }
 }
 
 void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, double *sqrD, int32_t *I, double *C,
@@ -202,6 +205,7 @@ void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, dou
     return;
   }
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
+  plat::Span sp("closest", s);
   plat::for_n(n, ClosestQuery{m->cnodes(), m->tri64(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C}, s);
 }
 
@@ -210,6 +214,7 @@ void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_s
   if (n == 0) return;
   if (m->h.nnodes == 0) { plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, 0.0, 0, 0.0}, s); return; }
   const uint32_t *perm = morton_perm(m, Q, n, scratch, sort_queries, s);
+  plat::Span sp("winding", s);
   plat::for_n(n, WindingQuery{m->fnodes(), m->tri32(), Q, n, perm, accuracy_scale * accuracy_scale, m->h.order, 0, 0.0, 0.0,
                               (int32_t)m->h.nF, W, nullptr, nullptr, nullptr}, s);
 }
@@ -250,7 +255,8 @@ void download_scalar(const DevBuf<double> &src, int64_t n, void *dst, int is_f64
   plat::sync(s);
 }
 
-}  // namespace
+}  // namespace iglq
+using namespace iglq;
 
 extern "C" {
 
@@ -401,6 +407,8 @@ uint64_t iglb200_query_scratch_bytes(int64_t nP) {
 }
 
 int iglb200_last_launch_count(void) { return plat::launch_counter(); }
+void iglb200_profile_enable(int on) { plat::prof_enable(on != 0); }
+int iglb200_profile_collect(char *out, uint64_t cap) { return plat::prof_collect(out, (size_t)cap); }
 
 int iglb200_signed_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP, int sign_type, double lower, double upper,
                                 double *S, int32_t *I, double *C, double *W, void *scratch, int sort_queries, void *stream) {

@@ -43,6 +43,7 @@ struct Local {  // what a subtree hands to its parent (LocalData :6611-6642)
   Box3 cpbox;  // conservative box of the fp64 geometry
 };
 
+#ifdef IGLB200_BUILDER_TU
 DEVFN float f_round_down(double d) {
 #if defined(__CUDA_ARCH__)
   return __double2float_rd(d);
@@ -297,5 +298,7 @@ struct NodeMoments {
     cnodes[nodei] = cn;
   }
 };
+
+#endif  // IGLB200_BUILDER_TU
 
 }  // namespace fwn

@@ -24,6 +24,7 @@ inline int &launch_counter() { static thread_local int c = 0; return c; }
 }  // namespace plat
 
 #ifdef IGLB200_EMUL
+namespace plat { struct Span { Span(const char *, void *) {} }; inline void prof_enable(bool) {} inline int prof_collect(char *, size_t) { return 0; } }
 // ------------------------------------------------------------------ host loops
 #include <vector_types.h>  // float4/uint4/double3 PODs (host-safe CUDA header)
 #include <vector_functions.h>
@@ -166,6 +167,46 @@ inline size_t sort_pairs_temp_bytes(int64_t n) {
 inline void sort_pairs_u32(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, stream_t s) {
   PLAT_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
   launch_counter() += 4;
+}
+}  // namespace plat
+#endif
+
+#ifndef IGLB200_EMUL
+namespace plat {
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's
+// roofline leg).  Off by default: no events are created or recorded.
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+inline bool &prof_on() { static thread_local bool on = false; return on; }
+inline std::vector<ProfRec> &prof_recs() { static thread_local std::vector<ProfRec> r; return r; }
+inline void prof_enable(bool on) { prof_on() = on; }
+struct Span {
+  bool live; cudaStream_t s; size_t idx;
+  Span(const char *name, cudaStream_t st) : live(prof_on()), s(st), idx(0) {
+    if (!live) return;
+    ProfRec r; r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    idx = prof_recs().size();
+    prof_recs().push_back(r);
+  }
+  ~Span() { if (live) cudaEventRecord(prof_recs()[idx].b, s); }
+};
+// "name=ms;name=ms;..." summed per name over everything recorded since the last collect
+inline int prof_collect(char *out, size_t cap) {
+  std::vector<std::pair<std::string, double>> acc;
+  for (auto &r : prof_recs()) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f; cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    bool found = false;
+    for (auto &p : acc) if (p.first == r.name) { p.second += ms; found = true; }
+    if (!found) acc.push_back({r.name, ms});
+  }
+  prof_recs().clear();
+  std::string sres;
+  for (auto &p : acc) { char b[128]; snprintf(b, sizeof(b), "%s=%.6f;", p.first.c_str(), p.second); sres += b; }
+  if (out && cap) { strncpy(out, sres.c_str(), cap - 1); out[cap - 1] = 0; }
+  return (int)sres.size();
 }
 }  // namespace plat
 #endif

@@ -23,7 +23,7 @@ DEVFN double dadd(double a, double b) { return a + b; }
 DEVFN double dsub(double a, double b) { return a - b; }
 DEVFN double ddiv(double a, double b) { return a / b; }
 DEVFN float fsub(float a, float b) { return a - b; }
-DEVFN float f_up(double d) { return f_round_up(d); }
+DEVFN float f_up(double d) { float f = (float)d; if ((double)f < d) f = std::nextafterf(f, INFINITY); return f; }
 #else
 DEVFN double dmul(double a, double b) { return __dmul_rn(a, b); }
 DEVFN double dadd(double a, double b) { return __dadd_rn(a, b); }

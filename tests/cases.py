@@ -1,0 +1,200 @@
+"""Parity cases run twice: on the host-emulated kernels (CPU, small) and on the
+real CUDA library (`-m gpu`, up to full size)."""
+import numpy as np
+import pytest
+
+import oracle
+import parity
+from libigl_b200 import synth
+from libigl_b200.api import (IglB200Error, SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, SIGNED_DISTANCE_TYPE_PSEUDONORMAL,
+                             SIGNED_DISTANCE_TYPE_UNSIGNED, AABB)
+
+
+def meshes_small():
+    return {
+        "tet": synth.tetrahedron(),
+        "ico1": synth.icosphere(1),
+        "ico3": synth.icosphere(3),
+        "knot": synth.torus_knot(120, 12),
+        "noisy": synth.noisy_sphere(3, 0.02, 7),
+    }
+
+
+def axis_aligned_box_mesh(n=6):
+    """Axis-aligned, highly symmetric grid mesh: many exactly equal box centres (ties,
+    elements equal to the pivot) — the hard case for a topology-exact build."""
+    xs = np.linspace(-1, 1, n + 1)
+    Vs, Fs = [], []
+
+    def face(ax, val, flip):
+        u, v = [a for a in range(3) if a != ax]
+        base = sum(len(x) for x in Vs)
+        g = np.zeros(((n + 1) * (n + 1), 3))
+        U, W = np.meshgrid(xs, xs, indexing="ij")
+        g[:, u] = U.ravel()
+        g[:, v] = W.ravel()
+        g[:, ax] = val
+        Vs.append(g)
+        for i in range(n):
+            for j in range(n):
+                a = base + i * (n + 1) + j
+                b = a + 1
+                c = a + (n + 1)
+                d = c + 1
+                t = [[a, c, d], [a, d, b]]
+                if flip:
+                    t = [[x[0], x[2], x[1]] for x in t]
+                Fs.extend(t)
+
+    for ax in range(3):
+        face(ax, -1.0, ax != 1)
+        face(ax, 1.0, ax == 1)
+    return np.concatenate(Vs), np.array(Fs, np.int32)
+
+
+def case_known_answers(api):
+    # tests/include/igl/signed_distance.cpp:4-43
+    V, F = synth.tetrahedron()
+    S, I, C = api.signed_distance(np.array([[0.5, 0.5, 0.5]]), V, F, SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER)
+    assert abs(S[0] - np.sqrt(1.0 / 12.0)) < 1e-7
+    S, I, C = api.signed_distance(np.array([[0.5, 0.5, 0.5]]), V, F, SIGNED_DISTANCE_TYPE_UNSIGNED)
+    assert abs(S[0] - np.sqrt(1.0 / 12.0)) < 1e-15
+    assert I[0] == 3 and np.allclose(C[0], 1.0 / 3.0, atol=1e-15)
+    # tests/include/igl/AABB.cpp:100-113 on a synthetic soup
+    V, F = synth.soupify(*synth.icosphere(2))
+    BC = (V[F[:, 0]] + V[F[:, 1]] + V[F[:, 2]]) / 3.0
+    tree = AABB(api)
+    tree.init(V, F)
+    D, I, C = tree.squared_distance(V, F, BC)
+    assert np.array_equal(I, np.arange(F.shape[0]))
+    assert np.abs(D).max() < 1e-15
+    D2, I2, C2 = api.point_mesh_squared_distance(BC, V, F)
+    assert np.array_equal(I2, I) and np.array_equal(D2, D)
+
+
+def case_tree_exact(api, meshes):
+    for name, (V, F) in meshes.items():
+        m = api.Mesh(V, F, 2)
+        parity.check_tree_against_reference(m, V, F, what=name)
+        m.close()
+
+
+def case_signed_distance(api, V, F, P, what):
+    m = api.Mesh(V, F, 2)
+    S, I, C, W = m.signed_distance(P, return_W=True)
+    r = parity.check_signed_distance(V, F, P, S, I, C, W, what=what)
+    # S-only overload (signed_distance.h:283-312)
+    assert np.array_equal(m.signed_distance_fast_winding_number(P), S, equal_nan=True)
+    m.close()
+    return r
+
+
+def case_closest_vs_brute(api, V, F, P, what):
+    m = api.Mesh(V, F, 0)
+    D, I, C = m.squared_distance(P)
+    Db, Ib, Cb = oracle.brute_closest(V, F, P)
+    assert np.array_equal(D, Db), what
+    assert np.array_equal(I, Ib), what   # lowest-index tie rule == brute force order
+    assert np.array_equal(C, Cb), what
+    Do, Io, Co = oracle.PortAABB(V, F).squared_distance(P)
+    parity.check_closest(V, F, P, D, I, C, Do, Io, Co, what)
+    m.close()
+
+
+def case_fwn(api, V, F, Q, what):
+    m = api.Mesh(V, F, 2)
+    ref = oracle.RefFwn(V, F)
+    for beta in (2.0, 1.0, 3.5):
+        W = m.fast_winding_number(Q, beta)
+        Wr = ref.winding(Q, beta)
+        d = np.abs(W - Wr)
+        assert (d <= 1e-5 * np.maximum(1.0, np.abs(Wr))).all(), f"{what} beta={beta}: W off by {d.max():.3e}"
+    W1 = api.fast_winding_number(V, F, Q)
+    assert np.array_equal(W1, m.fast_winding_number(Q, 2.0))
+    m.close()
+
+
+def case_bounds_and_sentinels(api):
+    V, F = synth.icosphere(2)
+    P = synth.grid_points(*synth.bbox(V), 12, 2.0)
+    m = api.Mesh(V, F, 2)
+    for lower, upper in ((-0.2, 0.3), (0.1, 0.5), (-0.5, -0.1), (0.0, 0.25)):
+        S, I, C, W = m.signed_distance(P, SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower, upper, True)
+        r = parity.check_signed_distance(V, F, P, S, I, C, W, lower, upper, what=f"bounds {lower},{upper}")
+        assert r["nan"] > 0
+        assert (I[np.isnan(S)] == F.shape[0] + 1).all() and (C[np.isnan(S)] == 0).all()
+    m.close()
+    # #F == 0 (signed_distance.cpp:398-405)
+    S, I, C = api.signed_distance(P[:5], V, np.zeros((0, 3), np.int32))
+    assert np.isnan(S).all() and (I == -1).all() and np.isnan(C).all()
+    # empty query set
+    m = api.Mesh(V, F, 2)
+    S, I, C = m.signed_distance(np.zeros((0, 3)))
+    assert S.shape == (0,) and I.shape == (0,) and C.shape == (0, 3)
+    # other sign types fail loudly (no CPU fallback)
+    with pytest.raises(IglB200Error) as e:
+        m.signed_distance(P[:5], SIGNED_DISTANCE_TYPE_PSEUDONORMAL)
+    assert e.value.code == -4
+    m.close()
+    with pytest.raises(IglB200Error):
+        api.Mesh(V, np.array([[0, 1, 999999]], np.int32))
+
+
+def case_layouts(api):
+    """float32 / float64, row- and column-major, strided views give the same answers."""
+    V, F = synth.icosphere(2)
+    P = synth.random_points(500, -1.5, 1.5, 3)
+    base = api.Mesh(V, F, 2).signed_distance(P, return_W=True)
+    variants = [
+        (np.asfortranarray(V), np.asfortranarray(F), np.asfortranarray(P)),
+        (V, F, np.ascontiguousarray(np.concatenate([P, P], 1))[:, 3:]),
+        (np.ascontiguousarray(np.concatenate([V, V], 1))[:, :3], F, P.astype(np.float32)),
+    ]
+    for Vv, Fv, Pv in variants:
+        out = api.Mesh(Vv, Fv, 2).signed_distance(Pv, return_W=True)
+        for a, b in zip(base, out):
+            assert np.array_equal(a, b, equal_nan=True)
+    # float32 vertices: the mesh IS the float mesh, compare against the oracle on that mesh
+    Vf = V.astype(np.float32)
+    S, I, C, W = api.Mesh(Vf, F, 2).signed_distance(P, return_W=True)
+    parity.check_signed_distance(Vf.astype(np.float64), F, P, S, I, C, W, what="f32 V")
+
+
+def case_degenerate(api):
+    """Degenerate faces [i j j]/[i i i] behave as segments/points (point_mesh_squared_distance.h:23-30);
+    NaN vertices are dropped from the winding tree (FastWindingNumberForSoups.h:4606-4615)."""
+    V, F = synth.icosphere(1)
+    F = F.copy()
+    F[3] = [F[3, 0], F[3, 1], F[3, 1]]
+    F[7] = [F[7, 0], F[7, 0], F[7, 0]]
+    P = synth.random_points(400, -1.5, 1.5, 11)
+    case_closest_vs_brute(api, V, F, P, "degenerate")
+    m = api.Mesh(V, F, 2)
+    parity.check_tree_against_reference(m, V, F, what="degenerate")
+    W = m.fast_winding_number(P)
+    Wr = oracle.RefFwn(V, F).winding(P)
+    assert np.abs(W - Wr).max() <= 1e-5
+    m.close()
+    # duplicated faces / coincident boxes: exercises the "equal to pivot" partition path
+    V2, F2 = axis_aligned_box_mesh(6)
+    F2 = np.concatenate([F2, F2[::3]], 0)
+    m = api.Mesh(V2, F2, 2)
+    parity.check_tree_against_reference(m, V2, F2, what="axis-aligned + duplicates")
+    m.close()
+
+
+def case_arena_roundtrip(api):
+    V, F = synth.icosphere(3)
+    P = synth.random_points(2000, -1.5, 1.5, 5)
+    m = api.Mesh(V, F, 2)
+    ref = m.signed_distance(P, return_W=True)
+    ptr, nbytes = m.arena()
+    from libigl_b200.api import Mesh
+    for copy in (True, False):
+        m2 = Mesh.from_arena(api, ptr, nbytes, copy)
+        out = m2.signed_distance(P, return_W=True)
+        for a, b in zip(ref, out):
+            assert np.array_equal(a, b, equal_nan=True)
+        assert m2.info()["n_nodes"] == m.info()["n_nodes"]
+        m2.close()
+    m.close()

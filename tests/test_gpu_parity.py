@@ -1,0 +1,124 @@
+"""Parity tests proper: the CUDA library (libigl_b200/libiglb200.so, through the
+C ABI) against the oracle, on a real B200.  Same gates as the CPU logic tests
+plus the BASELINE.json configs at full size."""
+import numpy as np
+import pytest
+
+import cases
+import oracle
+import parity
+from libigl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_known_answers(gpu_api):
+    cases.case_known_answers(gpu_api)
+
+
+def test_tree_topology_and_moments_match_reference(gpu_api):
+    ms = cases.meshes_small()
+    ms["axis"] = cases.axis_aligned_box_mesh(8)
+    ms["ico5"] = synth.icosphere(5)
+    ms["knot40k"] = synth.torus_knot(1000, 20)
+    ms["knot1M"] = synth.torus_knot(*synth.knot_dims(1_000_000))
+    cases.case_tree_exact(gpu_api, ms)
+
+
+def test_tiny_meshes_every_size(gpu_api):
+    V, F = synth.icosphere(2)
+    rng = np.random.default_rng(0)
+    ms = {f"n{n}": (V, F[rng.permutation(F.shape[0])[:n]]) for n in list(range(1, 41)) + [64, 65, 100]}
+    cases.case_tree_exact(gpu_api, ms)
+
+
+def test_c1_icosphere_grid64(gpu_api):
+    """BASELINE config c1: 5 120-face icosphere, 64^3 grid over bbox x 1.5."""
+    V, F = synth.icosphere(4)
+    P = synth.grid_points(*synth.bbox(V), 64, 1.5)
+    r = cases.case_signed_distance(gpu_api, V, F, P, "c1")
+    assert r["n"] == 64 ** 3 and r["nan"] == 0
+
+
+def test_signed_distance_knot200k(gpu_api):
+    V, F = synth.torus_knot(2000, 50)
+    P = synth.grid_points(*synth.bbox(V), 48, 1.1)
+    cases.case_signed_distance(gpu_api, V, F, P, "knot200k grid")
+
+
+def test_closest_vs_brute(gpu_api):
+    for name, (V, F) in cases.meshes_small().items():
+        P = synth.random_points(3000, -2.0, 2.0, 1)
+        cases.case_closest_vs_brute(gpu_api, V, F, P, name)
+
+
+def test_fwn(gpu_api):
+    V, F = synth.noisy_sphere(4, 0.02, 7)
+    cases.case_fwn(gpu_api, V, F, synth.random_points(50000, -1.5, 1.5, 2), "noisy")
+
+
+def test_bounds_and_sentinels(gpu_api):
+    cases.case_bounds_and_sentinels(gpu_api)
+
+
+def test_layouts(gpu_api):
+    cases.case_layouts(gpu_api)
+
+
+def test_degenerate(gpu_api):
+    cases.case_degenerate(gpu_api)
+
+
+def test_arena_roundtrip(gpu_api):
+    cases.case_arena_roundtrip(gpu_api)
+
+
+def test_c2_full_size_sample_and_properties(gpu_api):
+    """BASELINE config c2 at full size: 1 M-face torus knot, 256^3 grid.
+    The oracle checks a 200 k-query strided sample; the whole grid is checked
+    through size-independent properties."""
+    V, F = synth.torus_knot(*synth.knot_dims(1_000_000))
+    assert F.shape[0] == 1_000_000
+    m = gpu_api.Mesh(V, F, 2)
+    P = synth.grid_points(*synth.bbox(V), 256, 1.1)
+    S, I, C, W = m.signed_distance(P, return_W=True)
+    assert not np.isnan(S).any()
+    # properties on all 16.7 M rows
+    assert (I >= 0).all() and (I < F.shape[0]).all()
+    d = np.linalg.norm(P - C, axis=1)
+    assert np.abs(np.abs(S) - d * np.abs(1 - 2 * np.abs(W))).max() < 1e-12      # S = (1-2|w|) sqrt(d2)
+    inside = W > 0.5
+    assert (S[inside] <= 0).all() and (S[~inside] >= 0).all()
+    assert 0.001 < inside.mean() < 0.2                                           # the tube is thin
+    # closest point lies on the reported face: re-evaluating that face gives the same distance
+    k = np.arange(0, P.shape[0], 83)
+    assert np.array_equal(oracle.face_distance(V, F, P[k], I[k]), (d[k] ** 2)) or \
+        np.abs(oracle.face_distance(V, F, P[k], I[k]) - d[k] ** 2).max() < 1e-12
+    # oracle on a strided sample
+    ref = oracle.RefFwn(V, F)
+    tree = oracle.PortAABB(V, F)
+    r = parity.check_signed_distance(V, F, P[k], S[k], I[k], C[k], W[k], what="c2 sample", fwn=ref, tree=tree)
+    assert r["n"] == len(k)
+    # barycenters of a face sample: I == face, d2 == 0 (tests/include/igl/AABB.cpp:111-112 at 1 M faces)
+    fs = np.arange(0, F.shape[0], 97)
+    BC = (V[F[fs, 0]] + V[F[fs, 1]] + V[F[fs, 2]]) / 3.0
+    D, Ib, Cb = m.squared_distance(BC)
+    assert np.abs(D).max() < 1e-24
+    same = Ib == fs
+    assert same.mean() > 0.99   # a barycentre rounded onto a neighbouring face's plane may tie at d2==0
+    assert (oracle.face_distance(V, F, BC[~same], Ib[~same]) <= D[~same] + 1e-30).all()
+    m.close()
+
+
+def test_c3_noisy_sphere_random_queries(gpu_api):
+    """BASELINE config c3 (reduced to 1.3 M faces / 2 M queries for the oracle's sake):
+    squared_distance only, bit-exact distances against the restated AABB."""
+    V, F = synth.noisy_sphere(8, 0.01, 0)
+    P = synth.random_points(2_000_000, -1.5, 1.5, 1)
+    m = gpu_api.Mesh(V, F, 0)
+    D, I, C = m.squared_distance(P)
+    k = np.arange(0, P.shape[0], 10)
+    Do, Io, Co = oracle.PortAABB(V, F).squared_distance(P[k])
+    parity.check_closest(V, F, P[k], D[k], I[k], C[k], Do, Io, Co, "c3 sample")
+    assert np.abs(np.linalg.norm(P - C, axis=1) ** 2 - D).max() < 1e-12
+    m.close()
