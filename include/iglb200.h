@@ -128,6 +128,11 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
 /* number of kernels the last *_dev / host call on this thread enqueued */
 int iglb200_last_launch_count(void);
 
+/* Mean work per query of both traversals on this mesh, for the algorithmic-flop
+ * figure: out = {closest: nodes, triangles; winding: nodes, triangles}.
+ * P is a HOST pointer, column-major doubles; keep n below ~1e6. */
+int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colmajor, int64_t n, double out[4]);
+
 /* Optional per-kernel timing (CUDA events on the launching stream) for the
  * calling thread.  collect() synchronises, writes "name=ms;name=ms;..." summed
  * per kernel group since the previous collect, and returns the string length. */

@@ -62,6 +62,7 @@ class Api:
         "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
         "iglb200_query_scratch_bytes", "iglb200_signed_distance_dev", "iglb200_squared_distance_dev",
         "iglb200_fwn_eval_dev", "iglb200_last_launch_count", "iglb200_profile_enable", "iglb200_profile_collect",
+        "iglb200_debug_visit_counts",
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
     ]
@@ -91,6 +92,7 @@ class Api:
         L.iglb200_signed_distance_dev.argtypes = [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _int, _vp]
         L.iglb200_squared_distance_dev.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _vp]
         L.iglb200_fwn_eval_dev.argtypes = [_vp, _vp, _i64, C.c_float, _vp, _vp, _int, _vp]
+        L.iglb200_debug_visit_counts.argtypes = [_vp, _vp, _i64, C.POINTER(_dbl)]
         L.iglb200_profile_enable.argtypes = [_int]
         L.iglb200_profile_enable.restype = None
         L.iglb200_profile_collect.argtypes = [C.c_char_p, C.c_uint64]
@@ -235,6 +237,13 @@ class Mesh:
         h = _vp()
         api.check(api.lib.iglb200_mesh_from_arena(_vp(device_ptr), nbytes, int(copy), C.byref(h)))
         return Mesh(api, None, None, _handle=h)
+
+    def visit_counts(self, P):
+        """Mean nodes / triangles touched per query by the closest-point and winding traversals."""
+        P = np.asfortranarray(np.asarray(P, np.float64))
+        out = (_dbl * 4)()
+        self.api.check(self.api.lib.iglb200_debug_visit_counts(self.h, P.ctypes.data_as(_vp), P.shape[0], out))
+        return dict(cp_nodes=out[0], cp_tris=out[1], fwn_nodes=out[2], fwn_tris=out[3])
 
     # igl::signed_distance with prebuilt structures
     def signed_distance(self, P, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower_bound=None,

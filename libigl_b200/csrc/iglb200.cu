@@ -129,6 +129,24 @@ struct WindingQuery {
   }
 };
 
+// work counters of both traversals (bench.py's algorithmic-flop figure, tests)
+struct CountVisits {
+  const fwn::CpNode *cnodes; const double *tri64; const fwn::FwnNode *fnodes; const float4 *tri32;
+  const double *P; int64_t n; float absmax; int order;
+  uint32_t *acc;  // [4] cp nodes, cp tris, fwn nodes, fwn tris (sums; n must keep them < 2^32)
+  DEVFN void operator()(int64_t i) const {
+    const fwn::D3 p = {P[i], P[n + i], P[2 * n + i]};
+    uint32_t sn[fwn::CP_STACK]; float sd[fwn::CP_STACK];
+    uint32_t v[2] = {0, 0}, w[2] = {0, 0};
+    fwn::CpResult r;
+    const float M = fmaxf(fmaxf(fabsf((float)p.x), fabsf((float)p.y)), fmaxf(fabsf((float)p.z), absmax));
+    fwn::closest_triangle(cnodes, tri64, p, INFINITY, 0.0, M * 2.3841858e-7f, r, sn, sd, v);
+    fwn::winding_solid_angle(fnodes, tri32, (float)p.x, (float)p.y, (float)p.z, 4.0f, order, sn, w);
+    plat::atomic_add(&acc[0], v[0]); plat::atomic_add(&acc[1], v[1]);
+    plat::atomic_add(&acc[2], w[0]); plat::atomic_add(&acc[3], w[1]);
+  }
+};
+
 struct FillConst { double *S; int32_t *I; double *C; double *W; int64_t n; double sv; int32_t iv; double cv;
   DEVFN void operator()(int64_t i) const { if (S) S[i] = sv; if (I) I[i] = iv; if (C) { C[i] = cv; C[n + i] = cv; C[2 * n + i] = cv; } if (W) W[i] = sv; } };
 
@@ -407,6 +425,24 @@ uint64_t iglb200_query_scratch_bytes(int64_t nP) {
 }
 
 int iglb200_last_launch_count(void) { return plat::launch_counter(); }
+
+int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colmajor, int64_t n, double out[4]) {
+  API_BEGIN
+  check_mesh(m);
+  if (n <= 0 || !P_host_colmajor || !out || m->h.nnodes == 0) throw std::invalid_argument("bad arguments");
+  require_device();
+  DevBuf<double> dP((size_t)3 * n);
+  DevBuf<uint32_t> acc(4);
+  plat::h2d(dP.p, P_host_colmajor, (size_t)24 * n, nullptr);
+  plat::dev_memset(acc.p, 0, 16, nullptr);
+  plat::for_n(n, CountVisits{m->cnodes(), m->tri64(), m->fnodes(), m->tri32(), dP.p, n, m->h.absmax, m->h.order, acc.p}, nullptr);
+  uint32_t h[4];
+  plat::d2h(h, acc.p, 16, nullptr);
+  plat::sync(nullptr);
+  for (int k = 0; k < 4; ++k) out[k] = (double)h[k] / (double)n;
+  return IGLB200_OK;
+  API_END
+}
 void iglb200_profile_enable(int on) { plat::prof_enable(on != 0); }
 int iglb200_profile_collect(char *out, uint64_t cap) { return plat::prof_collect(out, (size_t)cap); }
 

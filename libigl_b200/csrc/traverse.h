@@ -86,7 +86,8 @@ DEVFN float lane_box_d2(const CpNode &n, int i, float px, float py, float pz, fl
 // Global minimum of |p - tri|^2 over all faces with value < up_sqr_d.
 // `slack` >= the fp32 rounding error of (coordinate - coordinate) for this query.
 DEVFN void closest_triangle(const CpNode *nodes, const double *tri64, D3 p, double up_sqr_d, double low_sqr_d,
-                            float slack, CpResult &res, uint32_t *stack_node, float *stack_d) {
+                            float slack, CpResult &res, uint32_t *stack_node, float *stack_d,
+                            uint32_t *visits = nullptr /* [nodes, tris] */) {
   res.sqr_d = up_sqr_d;
   res.face = -1;
   res.c = {0.0, 0.0, 0.0};
@@ -104,6 +105,7 @@ DEVFN void closest_triangle(const CpNode *nodes, const double *tri64, D3 p, doub
     }
     have = false;
     const CpNode n = nodes[cur];
+    if (visits) visits[0]++;
     const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
     float cd[4];
     uint32_t cn[4];
@@ -118,6 +120,7 @@ DEVFN void closest_triangle(const CpNode *nodes, const double *tri64, D3 p, doub
         while (k > 0 && cd[k - 1] > d2) { cd[k] = cd[k - 1]; cn[k] = cn[k - 1]; --k; }
         cd[k] = d2; cn[k] = ch[i] & ~INTERNAL_BIT;
       } else {
+        if (visits) visits[1]++;
         const double *t = tri64 + 9 * (size_t)ch[i];
         const D3 a = {t[0], t[1], t[2]}, b = {t[3], t[4], t[5]}, c = {t[6], t[7], t[8]};
         const D3 cc = closest_on_triangle(p, a, b, c);
