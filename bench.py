@@ -263,6 +263,7 @@ def ours(args):
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    api.check(api.lib.iglb200_poll_device_error())
     prof = api.profile_collect()
     api.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None

@@ -125,11 +125,16 @@ int iglb200_squared_distance_dev(const iglb200_mesh *m, const double *P, int64_t
                                  void *scratch, int sort_queries, void *stream);
 int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, float accuracy_scale,
                          double *W, void *scratch, int sort_queries, void *stream);
+/* After synchronising a stream that ran *_dev calls: 0, or an error if a device-side
+ * condition (traversal stack overflow) invalidated their results.  The host-pointer
+ * entry points check this themselves. */
+int iglb200_poll_device_error(void);
 /* number of kernels the last *_dev / host call on this thread enqueued */
 int iglb200_last_launch_count(void);
 
 /* Mean work per query of both traversals on this mesh, for the algorithmic-flop
- * figure: out = {closest: nodes, triangles; winding: nodes, triangles}.
+ * figure: out = {closest: nodes, faces PER WARP of 32 Morton-adjacent queries (they
+ * share one walk); winding: nodes, faces per query}.
  * P is a HOST pointer, column-major doubles; keep n below ~1e6. */
 int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colmajor, int64_t n, double out[4]);
 

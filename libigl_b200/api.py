@@ -62,7 +62,7 @@ class Api:
         "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
         "iglb200_query_scratch_bytes", "iglb200_signed_distance_dev", "iglb200_squared_distance_dev",
         "iglb200_fwn_eval_dev", "iglb200_last_launch_count", "iglb200_profile_enable", "iglb200_profile_collect",
-        "iglb200_debug_visit_counts",
+        "iglb200_debug_visit_counts", "iglb200_poll_device_error",
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
     ]
@@ -239,11 +239,11 @@ class Mesh:
         return Mesh(api, None, None, _handle=h)
 
     def visit_counts(self, P):
-        """Mean nodes / triangles touched per query by the closest-point and winding traversals."""
+        """Mean nodes / faces touched: closest-point walk per warp of 32 queries, winding per query."""
         P = np.asfortranarray(np.asarray(P, np.float64))
         out = (_dbl * 4)()
         self.api.check(self.api.lib.iglb200_debug_visit_counts(self.h, P.ctypes.data_as(_vp), P.shape[0], out))
-        return dict(cp_nodes=out[0], cp_tris=out[1], fwn_nodes=out[2], fwn_tris=out[3])
+        return dict(cp_nodes_per_warp=out[0], cp_tris_per_warp=out[1], fwn_nodes=out[2], fwn_tris=out[3])
 
     # igl::signed_distance with prebuilt structures
     def signed_distance(self, P, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower_bound=None,
@@ -347,7 +347,7 @@ def parse_arena(buf: np.ndarray):
     h = buf[:hdr.itemsize].view(hdr)[0]
     nF, nn = int(h["nF"]), int(h["nnodes"])
     tri64 = buf[int(h["off_tri64"]):int(h["off_tri64"]) + 72 * nF].view(np.float64).reshape(nF, 3, 3)
-    tri32 = buf[int(h["off_tri32"]):int(h["off_tri32"]) + 48 * nF].view(np.float32).reshape(nF, 3, 4)
+    tri32 = buf[int(h["off_tri32"]):int(h["off_tri32"]) + 64 * nF].view(np.float32).reshape(nF, 4, 4)
     fn = buf[int(h["off_fnodes"]):int(h["off_fnodes"]) + 384 * nn]
     fchild = fn.view(np.uint32).reshape(nn, 96)[:, :4].copy()
     fdata = fn.view(np.float32).reshape(nn, 96)[:, 4:].reshape(nn, 23, 4).copy()

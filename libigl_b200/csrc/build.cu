@@ -21,13 +21,15 @@ template <class VT> struct GatherFaces {
   uint32_t *bbacc;    // [6] order-encoded fp32 hull (rounded outward) of the geometry
   DEVFN void operator()(int64_t f) const {
     float amax = 0.f;
+    double vtx[3][3];
     for (int k = 0; k < 3; ++k) {
       int64_t vi = F[f * f_rs + k * f_cs];
       if (vi < 0 || vi >= nV) { plat::atomic_max(err, 1u); vi = 0; }
       double x[3];
       for (int d = 0; d < 3; ++d) x[d] = (double)V[vi * v_rs + d * v_cs];
       for (int d = 0; d < 3; ++d) tri64[9 * f + 3 * k + d] = x[d];
-      tri32[3 * f + k] = make_float4((float)x[0], (float)x[1], (float)x[2], 0.f);
+      tri32[TRI32_STRIDE * f + k] = make_float4((float)x[0], (float)x[1], (float)x[2], 0.f);
+      for (int d = 0; d < 3; ++d) vtx[k][d] = x[d];
       for (int d = 0; d < 3; ++d) {
         const float up = f_round_up(fabs(x[d]));
         if (up == up) amax = fmaxf(amax, up);
@@ -36,6 +38,32 @@ template <class VT> struct GatherFaces {
       }
     }
     plat::atomic_max(absacc, plat::f2ord(amax));
+    // fp32-stage data of the closest-triangle search (see traverse.h: tri_dist_f32)
+    double e[3][3], l2[3];
+    for (int d = 0; d < 3; ++d) { e[0][d] = vtx[1][d] - vtx[0][d]; e[1][d] = vtx[2][d] - vtx[1][d]; e[2][d] = vtx[0][d] - vtx[2][d]; }
+    for (int k = 0; k < 3; ++k) l2[k] = e[k][0] * e[k][0] + e[k][1] * e[k][1] + e[k][2] * e[k][2];
+    const double nx = e[0][1] * (-e[2][2]) - e[0][2] * (-e[2][1]);   // ab x ac, ac = -e_ca
+    const double ny = e[0][2] * (-e[2][0]) - e[0][0] * (-e[2][2]);
+    const double nz = e[0][0] * (-e[2][1]) - e[0][1] * (-e[2][0]);
+    const double a2 = sqrt(nx * nx + ny * ny + nz * nz);            // twice the area
+    const double L2 = fmax(l2[0], fmax(l2[1], l2[2])), L = sqrt(L2);
+    const double height = (L > 0.0) ? a2 / L : 0.0;
+    const double U = 5.9604644775390625e-08 * (double)amax;         // 2^-24 * max |coordinate| of this face
+    float fnx, fny, fnz, kappa;
+    const bool finite = (a2 == a2) && (L2 < 1e300);
+    if (finite && height > 0.0 && 8.0 * U <= height * 0.000244140625) {
+      // plane test usable: the fp32 vertices tilt the plane by <= ~8U/height <= 2^-12 rad
+      fnx = (float)(nx / a2); fny = (float)(ny / a2); fnz = (float)(nz / a2);
+      kappa = (float)(CP_KAPPA0 + 16.0 * (L / height));
+    } else {
+      // sliver / degenerate: distance to the boundary only; off by at most height/2 (stored negated)
+      fnx = fny = fnz = NAN;
+      kappa = finite ? -(float)(0.51 * height + 1e-30) : -INFINITY;
+    }
+    float4 *t = tri32 + TRI32_STRIDE * f;
+    t[0].w = fnx; t[1].w = fny; t[2].w = fnz;
+    t[3] = make_float4(l2[0] > 0.0 ? (float)(1.0 / l2[0]) : 0.f, l2[1] > 0.0 ? (float)(1.0 / l2[1]) : 0.f,
+                       l2[2] > 0.0 ? (float)(1.0 / l2[2]) : 0.f, kappa);
   }
 };
 
@@ -58,7 +86,7 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
     plat::h2d(dV.p, V, v_span * vsz, s);
     plat::h2d(dF.p, F, f_span * 4, s);
     DevBuf<double> tri64((size_t)9 * nF);
-    DevBuf<float4> tri32((size_t)3 * nF);
+    DevBuf<float4> tri32((size_t)TRI32_STRIDE * nF);
     DevBuf<uint32_t> acc(8);
     {
       const uint32_t init[8] = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
@@ -91,13 +119,13 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
     auto align = [](uint64_t x) { return (x + 255) & ~uint64_t(255); };
     uint64_t off = align(sizeof(ArenaHeader));
     m->h.off_tri64 = off; off = align(off + (uint64_t)72 * nF);
-    m->h.off_tri32 = off; off = align(off + (uint64_t)48 * nF);
+    m->h.off_tri32 = off; off = align(off + (uint64_t)16 * TRI32_STRIDE * nF);
     m->h.off_fnodes = off; off = align(off + (uint64_t)sizeof(FwnNode) * nn);
     m->h.off_cnodes = off; off = align(off + (uint64_t)sizeof(CpNode) * nn);
     m->h.bytes = off;
     m->arena = (char *)plat::dev_alloc(off);
     plat::d2d(m->arena + m->h.off_tri64, tri64.p, (size_t)72 * nF, s);
-    plat::d2d(m->arena + m->h.off_tri32, tri32.p, (size_t)48 * nF, s);
+    plat::d2d(m->arena + m->h.off_tri32, tri32.p, (size_t)16 * TRI32_STRIDE * nF, s);
     if (nn) {
       DevBuf<Local> locals((size_t)nn);
       for (int l = tree_levels(tree) - 1; l >= 0; --l) {

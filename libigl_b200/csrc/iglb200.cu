@@ -81,23 +81,189 @@ struct MortonKeys {  // 30-bit Morton code of each query inside the doubled scen
   }
 };
 
-struct ClosestQuery {  // one thread per query (AABB.cpp:1135-1218 semantics)
-  const fwn::CpNode *nodes; const double *tri64;
+struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
+  const fwn::CpNode *nodes; const double *tri64; const float4 *tri32;
   const double *P; int64_t n; const uint32_t *perm;
   double up, low; float absmax;
   double *sqrD; int32_t *I; double *C;
-  DEVFN void operator()(int64_t t) const {
-    const int64_t i = perm ? (int64_t)perm[t] : t;
-    const fwn::D3 p = {P[i], P[n + i], P[2 * n + i]};
-    uint32_t sn[fwn::CP_STACK]; float sd[fwn::CP_STACK];
-    fwn::CpResult r;
-    const float M = fmaxf(fmaxf(fabsf((float)p.x), fabsf((float)p.y)), fmaxf(fabsf((float)p.z), absmax));
-    if (low > up) { r.sqr_d = low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
-    else fwn::closest_triangle(nodes, tri64, p, up, low, M * 2.3841858e-7f, r, sn, sd);
-    sqrD[i] = r.sqr_d; I[i] = r.face;
-    C[i] = r.c.x; C[n + i] = r.c.y; C[2 * n + i] = r.c.z;
-  }
+  uint32_t *counters;  // nullable: [0] node visits, [1] face tests (summed over warps)
 };
+
+DEVFN void closest_store(const ClosestArgs &a, int64_t i, const fwn::CpResult &r) {
+  a.sqrD[i] = r.sqr_d; a.I[i] = r.face;
+  a.C[i] = r.c.x; a.C[a.n + i] = r.c.y; a.C[2 * a.n + i] = r.c.z;
+}
+
+#ifdef IGLB200_EMUL
+// Host emulation of one warp: identical control flow, lanes looped.
+void closest_packet_emul(const ClosestArgs &a, int64_t base) {
+  using namespace fwn;
+  static thread_local CpStackEntry stack[CP_STACK];
+  CpLane L[32]; D3 p[32]; bool valid[32]; int64_t qi[32];
+  for (int l = 0; l < 32; ++l) {
+    const int64_t t = base + l;
+    valid[l] = t < a.n;
+    qi[l] = valid[l] ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
+    p[l] = valid[l] ? D3{a.P[qi[l]], a.P[a.n + qi[l]], a.P[2 * a.n + qi[l]]} : D3{0.0, 0.0, 0.0};
+    lane_init(L[l], p[l], a.up, a.absmax);
+    if (!valid[l] || a.low > a.up) { L[l].best_ub = -INFINITY; L[l].thr2 = -1.f; }
+  }
+  int sp = 0; uint32_t cur = 0; bool have = true; uint32_t nvis = 0, ntri = 0;
+  while (true) {
+    if (!have) {
+      if (sp == 0) break;
+      --sp;
+      const CpStackEntry &e = stack[sp];
+      bool any = false;
+      for (int l = 0; l < 32; ++l) any |= box6_d2(e.box, L[l].px, L[l].py, L[l].pz, L[l].slack) <= L[l].thr2;
+      if (!any) continue;
+      cur = e.node;
+    }
+    have = false; ++nvis;
+    const CpNode n = a.nodes[cur];
+    const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
+    float d2[32][4];
+    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i)
+      d2[l][i] = (ch[i] == EMPTY) ? INFINITY : lane_box_d2(n, i, L[l].px, L[l].py, L[l].pz, L[l].slack);
+    for (int i = 0; i < 4; ++i) {
+      if (ch[i] == EMPTY || (ch[i] & INTERNAL_BIT)) continue;
+      bool any = false;
+      for (int l = 0; l < 32; ++l) any |= d2[l][i] <= L[l].thr2;
+      if (!any) continue;
+      ++ntri;
+      for (int l = 0; l < 32; ++l) {
+        float err; const float d32 = tri_dist_f32(a.tri32, ch[i], L[l].px, L[l].py, L[l].pz, L[l].u, err);
+        lane_offer(L[l], a.tri64, p[l], ch[i], d32, err);
+      }
+    }
+    uint32_t key[4]; uint32_t id[4]; int lane_of[4]; int nint = 0;
+    for (int i = 0; i < 4; ++i) {
+      if (ch[i] == EMPTY || !(ch[i] & INTERNAL_BIT)) continue;
+      uint32_t m = 0x7F800000u;
+      for (int l = 0; l < 32; ++l) if (d2[l][i] <= L[l].thr2) m = std::min(m, plat::f2u(d2[l][i]));
+      if (m == 0x7F800000u) continue;
+      int k = nint++;
+      while (k > 0 && key[k - 1] > m) { key[k] = key[k - 1]; id[k] = id[k - 1]; lane_of[k] = lane_of[k - 1]; --k; }
+      key[k] = m; id[k] = ch[i] & ~INTERNAL_BIT; lane_of[k] = i;
+    }
+    for (int k = nint - 1; k >= 1; --k) {
+      if (sp >= CP_STACK) throw std::runtime_error("closest-point stack overflow");
+      CpStackEntry &e = stack[sp++];
+      const int i = lane_of[k];
+      e.node = id[k]; e.dmin = plat::u2f(key[k]);
+      e.box[0] = ((const float *)&n.lox)[i]; e.box[1] = ((const float *)&n.loy)[i]; e.box[2] = ((const float *)&n.loz)[i];
+      e.box[3] = ((const float *)&n.hix)[i]; e.box[4] = ((const float *)&n.hiy)[i]; e.box[5] = ((const float *)&n.hiz)[i];
+    }
+    if (nint > 0) { cur = id[0]; have = true; }
+  }
+  for (int l = 0; l < 32; ++l) {
+    if (!valid[l]) continue;
+    CpResult r;
+    if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
+    else lane_finish(L[l], a.tri64, p[l], a.up, r);
+    closest_store(a, qi[l], r);
+  }
+  if (a.counters) { a.counters[0] += nvis; a.counters[1] += ntri; }
+}
+void launch_closest(const ClosestArgs &a, stream_t) {
+  for (int64_t base = 0; base < a.n; base += 32) closest_packet_emul(a, base);
+}
+void throw_if_overflow(stream_t) {}
+#else
+__global__ void __launch_bounds__(128) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
+  using namespace fwn;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  __shared__ CpStackEntry stacks[4][CP_STACK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CpStackEntry *stack = stacks[warp];
+  for (int64_t base = ((int64_t)blockIdx.x * 4 + warp) * 32; base < a.n; base += (int64_t)gridDim.x * 128) {
+    const int64_t t = base + lane;
+    const bool valid = t < a.n;
+    const int64_t qi = valid ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
+    const D3 p = valid ? D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]} : D3{0.0, 0.0, 0.0};
+    CpLane L;
+    lane_init(L, p, a.up, a.absmax);
+    if (!valid || a.low > a.up) { L.best_ub = -INFINITY; L.thr2 = -1.f; }
+    int sp = 0; uint32_t cur = 0; bool have = true; uint32_t nvis = 0, ntri = 0;
+    while (true) {
+      if (!have) {
+        if (sp == 0) break;
+        --sp;
+        const CpStackEntry &e = stack[sp];
+        const bool w = box6_d2(e.box, L.px, L.py, L.pz, L.slack) <= L.thr2;
+        if (!__any_sync(FULL, w)) continue;
+        cur = e.node;
+      }
+      have = false; ++nvis;
+      const CpNode n = a.nodes[cur];
+      const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
+      float d2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d2[i] = (ch[i] == EMPTY) ? INFINITY : lane_box_d2(n, i, L.px, L.py, L.pz, L.slack);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ch[i] == EMPTY || (ch[i] & INTERNAL_BIT)) continue;     // warp-uniform
+        if (!__any_sync(FULL, d2[i] <= L.thr2)) continue;
+        ++ntri;
+        float err; const float d32 = tri_dist_f32(a.tri32, ch[i], L.px, L.py, L.pz, L.u, err);
+        lane_offer(L, a.tri64, p, ch[i], d32, err);
+      }
+      uint32_t key[4], id[4]; int lane_of[4]; int nint = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ch[i] == EMPTY || !(ch[i] & INTERNAL_BIT)) continue;    // warp-uniform
+        const uint32_t m = __reduce_min_sync(FULL, (d2[i] <= L.thr2) ? __float_as_uint(d2[i]) : 0x7F800000u);
+        if (m == 0x7F800000u) continue;
+        int k = nint++;
+        while (k > 0 && key[k - 1] > m) { key[k] = key[k - 1]; id[k] = id[k - 1]; lane_of[k] = lane_of[k - 1]; --k; }
+        key[k] = m; id[k] = ch[i] & ~INTERNAL_BIT; lane_of[k] = i;
+      }
+      for (int k = nint - 1; k >= 1; --k) {
+        if (sp >= CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); continue; }
+        if (lane == 0) {
+          CpStackEntry &e = stack[sp];
+          const int i = lane_of[k];
+          e.node = id[k]; e.dmin = __uint_as_float(key[k]);
+          e.box[0] = ((const float *)&n.lox)[i]; e.box[1] = ((const float *)&n.loy)[i]; e.box[2] = ((const float *)&n.loz)[i];
+          e.box[3] = ((const float *)&n.hix)[i]; e.box[4] = ((const float *)&n.hiy)[i]; e.box[5] = ((const float *)&n.hiz)[i];
+        }
+        ++sp;
+      }
+      __syncwarp();
+      if (nint > 0) { cur = id[0]; have = true; }
+    }
+    if (valid) {
+      CpResult r;
+      if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
+      else lane_finish(L, a.tri64, p, a.up, r);
+      closest_store(a, qi, r);
+    }
+    if (a.counters && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
+    __syncwarp();
+  }
+}
+struct OverflowFlag { uint32_t *d = nullptr; ~OverflowFlag() { plat::dev_free(d); } };
+uint32_t *overflow_flag() {
+  static thread_local OverflowFlag f;
+  if (!f.d) { f.d = (uint32_t *)plat::dev_alloc(4); cudaMemset(f.d, 0, 4); }
+  return f.d;
+}
+// stack overflow in a walk (tree deeper than the per-warp stack can follow) must never pass silently
+void throw_if_overflow(stream_t s) {
+  uint32_t h = 0;
+  plat::d2h(&h, overflow_flag(), 4, s);
+  plat::sync(s);
+  if (h) { cudaMemset(overflow_flag(), 0, 4); throw std::runtime_error("closest-point traversal stack overflow (tree too deep)"); }
+}
+void launch_closest(const ClosestArgs &a, stream_t s) {
+  if (a.n <= 0) return;
+  const int64_t warps = (a.n + 31) / 32;
+  const int64_t blocks = std::min<int64_t>((warps + 3) / 4, (int64_t)plat::sm_count() * 64);
+  closest_packet_kernel<<<(unsigned)blocks, 128, 0, s>>>(a, overflow_flag());
+  plat::launch_counter()++;
+  PLAT_CHECK(cudaGetLastError());
+}
+#endif
 
 // winding number and, optionally, the fused epilogue of signed_distance.cpp:99-135
 struct WindingQuery {
@@ -129,21 +295,16 @@ struct WindingQuery {
   }
 };
 
-// work counters of both traversals (bench.py's algorithmic-flop figure, tests)
-struct CountVisits {
-  const fwn::CpNode *cnodes; const double *tri64; const fwn::FwnNode *fnodes; const float4 *tri32;
-  const double *P; int64_t n; float absmax; int order;
-  uint32_t *acc;  // [4] cp nodes, cp tris, fwn nodes, fwn tris (sums; n must keep them < 2^32)
+// work counters of the winding traversal (the closest-triangle walk counts per warp, see ClosestArgs)
+struct CountWinding {
+  const fwn::FwnNode *fnodes; const float4 *tri32;
+  const double *P; int64_t n; int order;
+  uint32_t *acc;  // [2] fwn nodes, fwn tris (sums; n must keep them < 2^32)
   DEVFN void operator()(int64_t i) const {
-    const fwn::D3 p = {P[i], P[n + i], P[2 * n + i]};
-    uint32_t sn[fwn::CP_STACK]; float sd[fwn::CP_STACK];
-    uint32_t v[2] = {0, 0}, w[2] = {0, 0};
-    fwn::CpResult r;
-    const float M = fmaxf(fmaxf(fabsf((float)p.x), fabsf((float)p.y)), fmaxf(fabsf((float)p.z), absmax));
-    fwn::closest_triangle(cnodes, tri64, p, INFINITY, 0.0, M * 2.3841858e-7f, r, sn, sd, v);
-    fwn::winding_solid_angle(fnodes, tri32, (float)p.x, (float)p.y, (float)p.z, 4.0f, order, sn, w);
-    plat::atomic_add(&acc[0], v[0]); plat::atomic_add(&acc[1], v[1]);
-    plat::atomic_add(&acc[2], w[0]); plat::atomic_add(&acc[3], w[1]);
+    uint32_t sn[fwn::FWN_STACK];
+    uint32_t w[2] = {0, 0};
+    fwn::winding_solid_angle(fnodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], 4.0f, order, sn, w);
+    plat::atomic_add(&acc[0], w[0]); plat::atomic_add(&acc[1], w[1]);
   }
 };
 
@@ -155,20 +316,12 @@ struct FillConst { double *S; int32_t *I; double *C; double *W; int64_t n; doubl
 #ifdef IGLB200_EMUL
 template <class F> void launch_query(const char *, int64_t n, F f, stream_t s) { plat::for_n(n, f, s); }
 #else
-__global__ void __launch_bounds__(128) closest_triangle_kernel(int64_t n, ClosestQuery f) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
-}
 __global__ void __launch_bounds__(128) winding_number_kernel(int64_t n, WindingQuery f) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
 }
 inline unsigned query_grid(int64_t n, int threads) {
   const int64_t blocks = (n + threads - 1) / threads;
   return (unsigned)std::min<int64_t>(blocks, 0x7FFFFFFF);
-}
-void launch_query(const char *, int64_t n, ClosestQuery f, stream_t s) {
-  closest_triangle_kernel<<<query_grid(n, 128), 128, 0, s>>>(n, f);
-  plat::launch_counter()++;
-  PLAT_CHECK(cudaGetLastError());
 }
 void launch_query(const char *, int64_t n, WindingQuery f, stream_t s) {
   winding_number_kernel<<<query_grid(n, 128), 128, 0, s>>>(n, f);
@@ -236,7 +389,7 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   bounds_to_sqr(lower, upper, low, up);
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   { plat::Span sp("closest", s);
-    launch_query("closest", n, ClosestQuery{m->cnodes(), m->tri64(), P, n, perm, up, low, m->h.absmax, S, I, C}, s); }
+    launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->tri32(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr}, s); }
   { plat::Span sp("winding", s);
     launch_query("winding", n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
                                             sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s); }
@@ -251,7 +404,7 @@ void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, dou
   }
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   plat::Span sp("closest", s);
-  launch_query("closest", n, ClosestQuery{m->cnodes(), m->tri64(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C}, s);
+  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->tri32(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr}, s);
 }
 
 void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_scale, double *W, void *scratch,
@@ -452,21 +605,34 @@ uint64_t iglb200_query_scratch_bytes(int64_t nP) {
 }
 
 int iglb200_last_launch_count(void) { return plat::launch_counter(); }
+int iglb200_poll_device_error(void) {
+  API_BEGIN
+  require_device();
+  throw_if_overflow(nullptr);
+  return IGLB200_OK;
+  API_END
+}
 
 int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colmajor, int64_t n, double out[4]) {
   API_BEGIN
   check_mesh(m);
   if (n <= 0 || !P_host_colmajor || !out || m->h.nnodes == 0) throw std::invalid_argument("bad arguments");
   require_device();
-  DevBuf<double> dP((size_t)3 * n);
+  DevBuf<double> dP((size_t)3 * n), dD((size_t)n), dC((size_t)3 * n);
+  DevBuf<int32_t> dI((size_t)n);
   DevBuf<uint32_t> acc(4);
+  DevBuf<char> scratch(iglb200_query_scratch_bytes(n));
   plat::h2d(dP.p, P_host_colmajor, (size_t)24 * n, nullptr);
   plat::dev_memset(acc.p, 0, 16, nullptr);
-  plat::for_n(n, CountVisits{m->cnodes(), m->tri64(), m->fnodes(), m->tri32(), dP.p, n, m->h.absmax, m->h.order, acc.p}, nullptr);
+  const uint32_t *perm = morton_perm(m, dP.p, n, scratch.p, 1, nullptr);
+  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->tri32(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p}, nullptr);
+  plat::for_n(n, CountWinding{m->fnodes(), m->tri32(), dP.p, n, m->h.order, acc.p + 2}, nullptr);
   uint32_t h[4];
   plat::d2h(h, acc.p, 16, nullptr);
   plat::sync(nullptr);
-  for (int k = 0; k < 4; ++k) out[k] = (double)h[k] / (double)n;
+  // closest: per WARP (32 queries share a walk); winding: per query
+  out[0] = (double)h[0] / (double)((n + 31) / 32); out[1] = (double)h[1] / (double)((n + 31) / 32);
+  out[2] = (double)h[2] / (double)n; out[3] = (double)h[3] / (double)n;
   return IGLB200_OK;
   API_END
 }
@@ -526,7 +692,7 @@ int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, 
   plat::d2h(I, dI.p, (size_t)4 * nP, s);
   download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);
   if (W) download_scalar(dW, nP, W, w_is_f64, s);
-  plat::sync(s);
+  throw_if_overflow(s);
   return IGLB200_OK;
   API_END
 }
@@ -548,7 +714,7 @@ int iglb200_squared_distance(const iglb200_mesh *m, const void *P, int p_is_f64,
   download_scalar(dS, nP, sqrD, d_is_f64, s);
   plat::d2h(I, dI.p, (size_t)4 * nP, s);
   download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);
-  plat::sync(s);
+  throw_if_overflow(s);
   return IGLB200_OK;
   API_END
 }

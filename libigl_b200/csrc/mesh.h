@@ -2,7 +2,7 @@
 // query needs, so that replicating the structure to another GPU is a single
 // broadcast of [arena, arena+bytes).
 //
-//   [ArenaHeader | tri64 (9 f64 / face) | tri32 (3 float4 / face) |
+//   [ArenaHeader | tri64 (9 f64 / face) | tri32 (4 float4 / face) |
 //    fwn nodes (384 B) | closest-point nodes (128 B)]
 //
 // tri64/tri32 are the faces' vertices gathered once at build time (the

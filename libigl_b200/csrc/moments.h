@@ -35,6 +35,14 @@ struct alignas(128) CpNode {  // 128 B = one L2 line: child boxes SoA over the 4
   uint4 pad;
 };
 
+// fp32 face record, 4 float4 = 64 B:
+//   [a.xyz | n.x] [b.xyz | n.y] [c.xyz | n.z] [1/|ab|^2, 1/|bc|^2, 1/|ca|^2, kappa]
+// a,b,c = (float)vertex as the reference's V.cast<float>() (signed_distance.cpp:66): the winding
+// number and the moments read exactly these.  n (unit normal from the fp64 vertices; NaN when
+// the face is too thin for a plane test), the inverse squared edge lengths and the error
+// weight kappa serve the fp32 stage of the closest-triangle search (traverse.h).
+static constexpr int TRI32_STRIDE = 4;
+
 struct Local {  // what a subtree hands to its parent (LocalData :6611-6642)
   Box3 box;
   float P[3], areaP[3], N[3], area;
@@ -118,7 +126,7 @@ DEVFN void sort_axis(const F3 *values, int axis, int *o) {  // (:6733-6757)
 // item functor (:6668-6890)
 DEVFN void tri_local(const float4 *tri32, const double *tri64, const TriBox *boxes, uint32_t f, int order, Local &L) {
   F3 values[3];
-  for (int k = 0; k < 3; ++k) { const float4 p = tri32[3 * (size_t)f + k]; values[k].v[0] = p.x; values[k].v[1] = p.y; values[k].v[2] = p.z; }
+  for (int k = 0; k < 3; ++k) { const float4 p = tri32[TRI32_STRIDE * (size_t)f + k]; values[k].v[0] = p.x; values[k].v[1] = p.y; values[k].v[2] = p.z; }
   const F3 &a = values[0], &b = values[1], &c = values[2];
   float ab[3], ac[3];
   for (int d = 0; d < 3; ++d) { ab[d] = b.v[d] - a.v[d]; ac[d] = c.v[d] - a.v[d]; }

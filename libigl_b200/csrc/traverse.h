@@ -70,7 +70,146 @@ struct CpResult {
   D3 c;
 };
 
-static constexpr int CP_STACK = 96;
+// ---------------------------------------------------------------------------
+// Closest triangle, two stages.
+//
+// Stage 1 (fp32, inside the tree walk): a robust point-triangle distance with a
+// two-sided error bound.  It is NOT Ericson's routine: the barycentric formula
+// loses all accuracy on thin triangles in fp32, and a one-sided error would
+// make pruning unsafe.  Instead
+//     inside the prism over the face ?  |plane distance|
+//                                    :  min over the three edges of the
+//                                       point-segment distance,
+// every term of which is a difference/dot of quantities of magnitude <= |p-v|,
+// so |d32 - d| <= kappa * 2^-24 * max(|p|,|v|)  (kappa stored per face; faces too
+// thin for a plane test use the boundary only and carry their height as extra
+// error).  A face is a CANDIDATE while d32 - err <= (smallest d32 + err seen).
+// Stage 2 (fp64, after the walk): the few surviving candidates — the winner and
+// whatever ties with it inside the fp32 error band, e.g. the faces around a
+// shared vertex — are evaluated with Ericson's routine in the reference's
+// un-fused operation order; minimum squared distance wins, lowest face index
+// on exact ties.  The result is therefore exactly what an all-fp64 search
+// returns.
+// ---------------------------------------------------------------------------
+#ifndef CP_KAPPA0
+#define CP_KAPPA0 48.0
+#endif
+static constexpr int CP_NCAND = 8;
+
+DEVFN float tri_dist_f32(const float4 *tri32, uint32_t f, float px, float py, float pz, float u, float &err) {
+  const float4 *t = tri32 + TRI32_STRIDE * (size_t)f;
+  const float4 A = t[0], B = t[1], C = t[2], E = t[3];
+  const float wax = px - A.x, way = py - A.y, waz = pz - A.z;
+  const float wbx = px - B.x, wby = py - B.y, wbz = pz - B.z;
+  const float wcx = px - C.x, wcy = py - C.y, wcz = pz - C.z;
+  const float abx = B.x - A.x, aby = B.y - A.y, abz = B.z - A.z;
+  const float bcx = C.x - B.x, bcy = C.y - B.y, bcz = C.z - B.z;
+  const float cax = A.x - C.x, cay = A.y - C.y, caz = A.z - C.z;
+  // point-segment distances (t clamped; a zero-length edge has inverse length 0 -> its start point)
+  float tt = fminf(fmaxf((wax * abx + way * aby + waz * abz) * E.x, 0.f), 1.f);
+  float qx = wax - tt * abx, qy = way - tt * aby, qz = waz - tt * abz;
+  float d2 = qx * qx + qy * qy + qz * qz;
+  tt = fminf(fmaxf((wbx * bcx + wby * bcy + wbz * bcz) * E.y, 0.f), 1.f);
+  qx = wbx - tt * bcx; qy = wby - tt * bcy; qz = wbz - tt * bcz;
+  d2 = fminf(d2, qx * qx + qy * qy + qz * qz);
+  tt = fminf(fmaxf((wcx * cax + wcy * cay + wcz * caz) * E.z, 0.f), 1.f);
+  qx = wcx - tt * cax; qy = wcy - tt * cay; qz = wcz - tt * caz;
+  d2 = fminf(d2, qx * qx + qy * qy + qz * qz);
+  // inside the prism over the face: (edge x w) . n >= 0 for all three edges (false for NaN normals)
+  const float nx = A.w, ny = B.w, nz = C.w;
+  const float s0 = (aby * waz - abz * way) * nx + (abz * wax - abx * waz) * ny + (abx * way - aby * wax) * nz;
+  const float s1 = (bcy * wbz - bcz * wby) * nx + (bcz * wbx - bcx * wbz) * ny + (bcx * wby - bcy * wbx) * nz;
+  const float s2 = (cay * wcz - caz * wcy) * nx + (caz * wcx - cax * wcz) * ny + (cax * wcy - cay * wcx) * nz;
+  if (s0 >= 0.f && s1 >= 0.f && s2 >= 0.f) {
+    const float pd = wax * nx + way * ny + waz * nz;
+    d2 = pd * pd;
+  }
+  err = (E.w >= 0.f) ? E.w * u : ((float)CP_KAPPA0 * u - E.w);
+#ifdef CP_ERR_SCALE   // test hook: shrink the band to probe how much margin the bound has
+  err *= (float)CP_ERR_SCALE;
+#endif
+  return sqrtf(d2);
+}
+
+// running state of one query during the walk
+struct CpLane {
+  float px, py, pz;
+  float slack;    // rounding allowance of the fp32 box tests
+  float u;        // 2^-24 * max(|p|, |mesh|)
+  float best_ub;  // fp32 upper bound of the distance to the nearest face seen so far
+  float thr2;     // prune a box when its squared lower bound exceeds this
+  int ncand;
+  uint32_t cand_face[CP_NCAND];
+  float cand_lb[CP_NCAND];
+  // exact best among the candidates already evaluated in fp64
+  double ex_d2;
+  int32_t ex_face;
+  D3 ex_c;
+};
+
+DEVFN void lane_set_ub(CpLane &L, float ub) {
+  L.best_ub = ub;
+  L.thr2 = ub * ub * 1.0000005f;  // rounded up
+}
+
+DEVFN void lane_init(CpLane &L, D3 p, double up_sqr_d, float absmax) {
+  L.px = (float)p.x; L.py = (float)p.y; L.pz = (float)p.z;
+  const float M = fmaxf(fmaxf(fabsf(L.px), fabsf(L.py)), fmaxf(fabsf(L.pz), absmax));
+  L.slack = M * 2.3841858e-7f;
+  L.u = M * 5.9604645e-8f * 1.0000002f;
+  L.ncand = 0;
+  L.ex_d2 = up_sqr_d; L.ex_face = -1; L.ex_c = {0.0, 0.0, 0.0};
+  const float ub = (up_sqr_d < 3.0e38) ? f_up(sqrt(up_sqr_d)) * 1.0000002f : INFINITY;
+  L.best_ub = ub;
+  L.thr2 = (up_sqr_d < 3.0e38) ? f_up(up_sqr_d) * 1.0000005f : INFINITY;
+}
+
+// fp64 evaluation of one face; strict improvement or exact tie with a lower index replaces the best
+DEVFN void lane_exact(CpLane &L, const double *tri64, D3 p, uint32_t f) {
+  const double *t = tri64 + 9 * (size_t)f;
+  const D3 a = {t[0], t[1], t[2]}, b = {t[3], t[4], t[5]}, c = {t[6], t[7], t[8]};
+  const D3 cc = closest_on_triangle(p, a, b, c);
+  const D3 df = d3sub(p, cc);
+  const double dd = d3dot(df, df);
+  if (dd < L.ex_d2 || (dd == L.ex_d2 && L.ex_face >= 0 && (int32_t)f < L.ex_face)) {
+    L.ex_d2 = dd; L.ex_face = (int32_t)f; L.ex_c = cc;
+  }
+}
+
+// evaluate every live candidate in fp64 and empty the list
+DEVFN void lane_flush(CpLane &L, const double *tri64, D3 p) {
+  for (int k = 0; k < L.ncand; ++k)
+    if (L.cand_lb[k] <= L.best_ub) lane_exact(L, tri64, p, L.cand_face[k]);
+  L.ncand = 0;
+  if (L.ex_face >= 0) {
+    const float ub = f_up(sqrt(L.ex_d2)) * 1.0000002f;
+    if (ub < L.best_ub) lane_set_ub(L, ub);
+  }
+}
+
+// stage-1 result for face f
+DEVFN void lane_offer(CpLane &L, const double *tri64, D3 p, uint32_t f, float d32, float err) {
+  const float lb = d32 - err;
+  if (!(lb <= L.best_ub)) return;
+  if (L.ncand == CP_NCAND) {
+    // drop candidates that fell out of the band; if the list is still full, settle it in fp64
+    int m = 0;
+    for (int k = 0; k < CP_NCAND; ++k)
+      if (L.cand_lb[k] <= L.best_ub) { L.cand_lb[m] = L.cand_lb[k]; L.cand_face[m] = L.cand_face[k]; ++m; }
+    L.ncand = m;
+    if (m == CP_NCAND) lane_flush(L, tri64, p);
+    if (!(lb <= L.best_ub)) return;
+  }
+  L.cand_face[L.ncand] = f; L.cand_lb[L.ncand] = lb; ++L.ncand;
+  const float ub = d32 + err;
+  if (ub < L.best_ub) lane_set_ub(L, ub);
+}
+
+DEVFN void lane_finish(CpLane &L, const double *tri64, D3 p, double up_sqr_d, CpResult &res) {
+  lane_flush(L, tri64, p);
+  res.sqr_d = L.ex_d2; res.face = L.ex_face; res.c = L.ex_c;
+  if (!(res.sqr_d < up_sqr_d)) { res.sqr_d = up_sqr_d; res.face = -1; res.c = {0.0, 0.0, 0.0}; }
+}
 
 // squared distance, lower bound, from a point to lane `i` of a node's child boxes
 DEVFN float lane_box_d2(const CpNode &n, int i, float px, float py, float pz, float slack) {
@@ -82,65 +221,19 @@ DEVFN float lane_box_d2(const CpNode &n, int i, float px, float py, float pz, fl
   float dz = fmaxf(fmaxf(lz - pz, pz - hz) - slack, 0.f);
   return (dx * dx + dy * dy + dz * dz) * 0.99999952f;  // 1 - 4 ulp: absorbs the rounding of the sum
 }
-
-// Global minimum of |p - tri|^2 over all faces with value < up_sqr_d.
-// `slack` >= the fp32 rounding error of (coordinate - coordinate) for this query.
-DEVFN void closest_triangle(const CpNode *nodes, const double *tri64, D3 p, double up_sqr_d, double low_sqr_d,
-                            float slack, CpResult &res, uint32_t *stack_node, float *stack_d,
-                            uint32_t *visits = nullptr /* [nodes, tris] */) {
-  res.sqr_d = up_sqr_d;
-  res.face = -1;
-  res.c = {0.0, 0.0, 0.0};
-  const float px = (float)p.x, py = (float)p.y, pz = (float)p.z;
-  float thr = f_up(res.sqr_d);  // prune when lower bound > thr
-  int sp = 0;
-  uint32_t cur = 0;
-  bool have = true;
-  while (true) {
-    if (!have) {
-      if (sp == 0) break;
-      --sp;
-      if (stack_d[sp] > thr) continue;
-      cur = stack_node[sp];
-    }
-    have = false;
-    const CpNode n = nodes[cur];
-    if (visits) visits[0]++;
-    const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
-    float cd[4];
-    uint32_t cn[4];
-    int nint = 0;
-    for (int i = 0; i < 4; ++i) {
-      if (ch[i] == EMPTY) break;
-      const float d2 = lane_box_d2(n, i, px, py, pz, slack);
-      if (d2 > thr) continue;
-      if (ch[i] & INTERNAL_BIT) {
-        // insertion into the (<=4) sorted list of internal children, nearest first
-        int k = nint++;
-        while (k > 0 && cd[k - 1] > d2) { cd[k] = cd[k - 1]; cn[k] = cn[k - 1]; --k; }
-        cd[k] = d2; cn[k] = ch[i] & ~INTERNAL_BIT;
-      } else {
-        if (visits) visits[1]++;
-        const double *t = tri64 + 9 * (size_t)ch[i];
-        const D3 a = {t[0], t[1], t[2]}, b = {t[3], t[4], t[5]}, c = {t[6], t[7], t[8]};
-        const D3 cc = closest_on_triangle(p, a, b, c);
-        const D3 df = d3sub(p, cc);
-        const double dd = d3dot(df, df);
-        if (dd < res.sqr_d || (dd == res.sqr_d && res.face >= 0 && (int32_t)ch[i] < res.face)) {
-          res.sqr_d = dd; res.face = (int32_t)ch[i]; res.c = cc;
-          thr = f_up(dd);
-        }
-      }
-    }
-    if (res.sqr_d < low_sqr_d) break;  // AABB.cpp:1422-1426: nothing below the lower bound is refined
-    // far children first on the stack, nearest continues immediately
-    for (int k = nint - 1; k >= 1; --k) {
-      if (cd[k] > thr) continue;
-      if (sp < CP_STACK) { stack_node[sp] = cn[k]; stack_d[sp] = cd[k]; ++sp; }
-    }
-    if (nint > 0 && cd[0] <= thr) { cur = cn[0]; have = true; }
-  }
+DEVFN float box6_d2(const float *b, float px, float py, float pz, float slack) {  // b = lo xyz, hi xyz
+  float dx = fmaxf(fmaxf(b[0] - px, px - b[3]) - slack, 0.f);
+  float dy = fmaxf(fmaxf(b[1] - py, py - b[4]) - slack, 0.f);
+  float dz = fmaxf(fmaxf(b[2] - pz, pz - b[5]) - slack, 0.f);
+  return (dx * dx + dy * dy + dz * dz) * 0.99999952f;
 }
+
+// The walk itself is a PACKET traversal: the 32 queries of a warp (neighbours in
+// Morton order) share one stack and visit a node when ANY of them still needs it,
+// so every box and face test runs on all 32 lanes at once (iglb200.cu:
+// closest_packet_kernel; host emulation: closest_packet_emul).
+static constexpr int CP_STACK = 128;   // entries per warp: node id + the node's own box
+struct CpStackEntry { uint32_t node; float box[6]; float dmin; };
 
 // ---------------------------------------------------------------------------
 // UTsignedSolidAngleTri (FastWindingNumberForSoups.h:6070-6110), un-fused fp32
@@ -149,7 +242,7 @@ DEVFN float f3dot(const float *a, const float *b) {
   return plat::fadd(plat::fadd(plat::fmul(a[0], b[0]), plat::fmul(a[1], b[1])), plat::fmul(a[2], b[2]));
 }
 DEVFN float tri_solid_angle(const float4 *tri32, uint32_t f, float qx, float qy, float qz) {
-  const float4 A = tri32[3 * (size_t)f], B = tri32[3 * (size_t)f + 1], C = tri32[3 * (size_t)f + 2];
+  const float4 A = tri32[TRI32_STRIDE * (size_t)f], B = tri32[TRI32_STRIDE * (size_t)f + 1], C = tri32[TRI32_STRIDE * (size_t)f + 2];
   float qa[3] = {fsub(A.x, qx), fsub(A.y, qy), fsub(A.z, qz)};
   float qb[3] = {fsub(B.x, qx), fsub(B.y, qy), fsub(B.z, qz)};
   float qc[3] = {fsub(C.x, qx), fsub(C.y, qy), fsub(C.z, qz)};

@@ -198,3 +198,51 @@ def case_arena_roundtrip(api):
         assert m2.info()["n_nodes"] == m.info()["n_nodes"]
         m2.close()
     m.close()
+
+
+def adversarial_soup(rng, n, kind):
+    c = rng.uniform(-1, 1, (n, 3))
+    if kind == "normal":
+        a, b, d = (c + rng.normal(0, 0.05, (n, 3)) for _ in range(3))
+    elif kind == "sliver":
+        e = rng.normal(0, 0.1, (n, 3))
+        t = rng.uniform(0.2, 0.8, (n, 1))
+        a, b, d = c, c + e, c + t * e + rng.normal(0, 1, (n, 3)) * (10.0 ** rng.uniform(-9, -2, (n, 1)))
+    elif kind == "needle":
+        a, b, d = c, c + rng.normal(0, 0.3, (n, 3)), c + rng.normal(0, 1, (n, 3)) * (10.0 ** rng.uniform(-8, -3, (n, 1)))
+    elif kind == "tiny":
+        s = 10.0 ** rng.uniform(-7, -3, (n, 1))
+        a, b, d = (c + rng.normal(0, 1, (n, 3)) * s for _ in range(3))
+    elif kind == "offset":
+        off = np.array([1000.0, -2000.0, 500.0])
+        a = c * 0.1 + off + rng.normal(0, 0.01, (n, 3))
+        b, d = a + rng.normal(0, 0.01, (n, 3)), a + rng.normal(0, 0.01, (n, 3))
+    else:  # degenerate: segments and points
+        a, b = c, c + rng.normal(0, 0.1, (n, 3))
+        d = b.copy()
+        d[::2] = a[::2]
+    V = np.concatenate([a, b, d])
+    F = np.stack([np.arange(n), np.arange(n) + n, np.arange(n) + 2 * n], 1).astype(np.int32)
+    return V, F
+
+
+def case_adversarial_triangles(api, n_tri=300, reps=2):
+    """The fp32 stage of the closest-triangle search must never lose the fp64 winner:
+    slivers, needles, tiny faces, large coordinate offsets, degenerate faces; queries on,
+    near and far from the surface.  Result must equal the fp64 brute force bit for bit."""
+    rng = np.random.default_rng(123)
+    for kind in ("normal", "sliver", "needle", "tiny", "offset", "degenerate"):
+        for _ in range(reps):
+            V, F = adversarial_soup(rng, n_tri, kind)
+            lo, hi = V.min(0), V.max(0)
+            ext = (hi - lo).max()
+            near = V[rng.integers(0, len(V), 1200)] + rng.normal(0, 1, (1200, 3)) * (10.0 ** rng.uniform(-9, -1, (1200, 1))) * ext
+            P = np.concatenate([rng.uniform(lo - 0.5 * ext, hi + 0.5 * ext, (1200, 3)), near, V[:200],
+                                (lo + hi) / 2 + rng.normal(0, 10 * ext, (150, 3))])
+            m = api.Mesh(V, F, 0)
+            D, I, C = m.squared_distance(P)
+            Db, Ib, Cb = oracle.brute_closest(V, F, P)
+            assert np.array_equal(D, Db), kind
+            assert np.array_equal(I, Ib), kind
+            assert np.array_equal(C, Cb), kind
+            m.close()

@@ -64,3 +64,7 @@ def test_degenerate(emul_api):
 
 def test_arena_roundtrip(emul_api):
     cases.case_arena_roundtrip(emul_api)
+
+
+def test_adversarial_triangles(emul_api):
+    cases.case_adversarial_triangles(emul_api)

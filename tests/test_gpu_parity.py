@@ -122,3 +122,7 @@ def test_c3_noisy_sphere_random_queries(gpu_api):
     parity.check_closest(V, F, P[k], D[k], I[k], C[k], Do, Io, Co, "c3 sample")
     assert np.abs(np.linalg.norm(P - C, axis=1) ** 2 - D).max() < 1e-12
     m.close()
+
+
+def test_adversarial_triangles(gpu_api):
+    cases.case_adversarial_triangles(gpu_api)
