@@ -25,7 +25,8 @@ from .api import (  # noqa: F401
     Mesh,
 )
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libiglb200.so")
+# IGLB200_LIBRARY lets a tuning run point at another build of the SAME CUDA library
+LIB_PATH = os.environ.get("IGLB200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libiglb200.so")
 _api = None
 
 

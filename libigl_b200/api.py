@@ -343,11 +343,11 @@ def parse_arena(buf: np.ndarray):
                     ("nlevels", "<i8"), ("nexcluded", "<i8"), ("order", "<i4"), ("pad", "<i4"),
                     ("bbox_lo", "<f8", 3), ("bbox_hi", "<f8", 3), ("absmax", "<f4"), ("padf", "<f4"),
                     ("off_tri64", "<u8"), ("off_tri32", "<u8"), ("off_fnodes", "<u8"), ("off_cnodes", "<u8"),
-                    ("reserved", "<u8", 8)])
+                    ("off_triq", "<u8"), ("reserved", "<u8", 7)])
     h = buf[:hdr.itemsize].view(hdr)[0]
     nF, nn = int(h["nF"]), int(h["nnodes"])
     tri64 = buf[int(h["off_tri64"]):int(h["off_tri64"]) + 72 * nF].view(np.float64).reshape(nF, 3, 3)
-    tri32 = buf[int(h["off_tri32"]):int(h["off_tri32"]) + 64 * nF].view(np.float32).reshape(nF, 4, 4)
+    tri32 = buf[int(h["off_tri32"]):int(h["off_tri32"]) + 48 * nF].view(np.float32).reshape(nF, 3, 4)
     fn = buf[int(h["off_fnodes"]):int(h["off_fnodes"]) + 384 * nn]
     fchild = fn.view(np.uint32).reshape(nn, 96)[:, :4].copy()
     fdata = fn.view(np.float32).reshape(nn, 96)[:, 4:].reshape(nn, 23, 4).copy()

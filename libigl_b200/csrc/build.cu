@@ -16,6 +16,7 @@ template <class VT> struct GatherFaces {
   int64_t f_rs, f_cs;
   double *tri64;
   float4 *tri32;
+  float4 *triq;
   uint32_t *err;      // [0] = out-of-range index seen
   uint32_t *absacc;   // order-encoded max |coordinate|
   uint32_t *bbacc;    // [6] order-encoded fp32 hull (rounded outward) of the geometry
@@ -38,32 +39,52 @@ template <class VT> struct GatherFaces {
       }
     }
     plat::atomic_max(absacc, plat::f2ord(amax));
-    // fp32-stage data of the closest-triangle search (see traverse.h: tri_dist_f32)
-    double e[3][3], l2[3];
-    for (int d = 0; d < 3; ++d) { e[0][d] = vtx[1][d] - vtx[0][d]; e[1][d] = vtx[2][d] - vtx[1][d]; e[2][d] = vtx[0][d] - vtx[2][d]; }
-    for (int k = 0; k < 3; ++k) l2[k] = e[k][0] * e[k][0] + e[k][1] * e[k][1] + e[k][2] * e[k][2];
-    const double nx = e[0][1] * (-e[2][2]) - e[0][2] * (-e[2][1]);   // ab x ac, ac = -e_ca
-    const double ny = e[0][2] * (-e[2][0]) - e[0][0] * (-e[2][2]);
-    const double nz = e[0][0] * (-e[2][1]) - e[0][1] * (-e[2][0]);
-    const double a2 = sqrt(nx * nx + ny * ny + nz * nz);            // twice the area
-    const double L2 = fmax(l2[0], fmax(l2[1], l2[2])), L = sqrt(L2);
-    const double height = (L > 0.0) ? a2 / L : 0.0;
-    const double U = 5.9604644775390625e-08 * (double)amax;         // 2^-24 * max |coordinate| of this face
-    float fnx, fny, fnz, kappa;
-    const bool finite = (a2 == a2) && (L2 < 1e300);
-    if (finite && height > 0.0 && 8.0 * U <= height * 0.000244140625) {
-      // plane test usable: the fp32 vertices tilt the plane by <= ~8U/height <= 2^-12 rad
-      fnx = (float)(nx / a2); fny = (float)(ny / a2); fnz = (float)(nz / a2);
-      kappa = (float)(CP_KAPPA0 + 16.0 * (L / height));
-    } else {
-      // sliver / degenerate: distance to the boundary only; off by at most height/2 (stored negated)
-      fnx = fny = fnz = NAN;
-      kappa = finite ? -(float)(0.51 * height + 1e-30) : -INFINITY;
+    // fp32-stage record of the closest-triangle search (traverse.h: tri_dist_f32): local frame in fp64
+    int k0 = 0;
+    double best = -1.0;
+    for (int k = 0; k < 3; ++k) {
+      double l2 = 0.0;
+      for (int d = 0; d < 3; ++d) { const double e = vtx[(k + 1) % 3][d] - vtx[k][d]; l2 += e * e; }
+      if (l2 > best) { best = l2; k0 = k; }
     }
-    float4 *t = tri32 + TRI32_STRIDE * f;
-    t[0].w = fnx; t[1].w = fny; t[2].w = fnz;
-    t[3] = make_float4(l2[0] > 0.0 ? (float)(1.0 / l2[0]) : 0.f, l2[1] > 0.0 ? (float)(1.0 / l2[1]) : 0.f,
-                       l2[2] > 0.0 ? (float)(1.0 / l2[2]) : 0.f, kappa);
+    const double *A = vtx[k0], *B = vtx[(k0 + 1) % 3], *Cc = vtx[(k0 + 2) % 3];
+    double u[3], ac[3], n[3], v[3];
+    const double Ln = sqrt(best > 0.0 ? best : 0.0);
+    for (int d = 0; d < 3; ++d) { u[d] = (Ln > 0.0) ? (B[d] - A[d]) / Ln : (d == 0 ? 1.0 : 0.0); ac[d] = Cc[d] - A[d]; }
+    n[0] = u[1] * ac[2] - u[2] * ac[1]; n[1] = u[2] * ac[0] - u[0] * ac[2]; n[2] = u[0] * ac[1] - u[1] * ac[0];
+    double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    const double acl = sqrt(ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2]);
+    bool flat = !(nl > 1e-14 * acl) || !(nl == nl) || !(Ln > 0.0);
+    if (!flat) {
+      // the cross product of a thin face is mostly rounding noise: force n orthogonal to u.
+      // A wrong rotation of n about u by theta moves the apex by height*theta ~ the noise itself.
+      for (int d = 0; d < 3; ++d) n[d] /= nl;
+      const double nu = n[0] * u[0] + n[1] * u[1] + n[2] * u[2];
+      for (int d = 0; d < 3; ++d) n[d] -= nu * u[d];
+      nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      flat = !(nl > 0.5);
+    }
+    if (flat) {
+      // segment or point: any unit normal orthogonal to u will do
+      const int m = (fabs(u[0]) <= fabs(u[1]) && fabs(u[0]) <= fabs(u[2])) ? 0 : (fabs(u[1]) <= fabs(u[2]) ? 1 : 2);
+      double e[3] = {0.0, 0.0, 0.0};
+      e[m] = 1.0;
+      n[0] = u[1] * e[2] - u[2] * e[1]; n[1] = u[2] * e[0] - u[0] * e[2]; n[2] = u[0] * e[1] - u[1] * e[0];
+      nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    }
+    for (int d = 0; d < 3; ++d) n[d] /= nl;
+    v[0] = n[1] * u[2] - n[2] * u[1]; v[1] = n[2] * u[0] - n[0] * u[2]; v[2] = n[0] * u[1] - n[1] * u[0];
+    double cx = u[0] * ac[0] + u[1] * ac[1] + u[2] * ac[2];
+    double cy = flat ? 0.0 : (v[0] * ac[0] + v[1] * ac[1] + v[2] * ac[2]);
+    if (flat) {
+      // the apex lies on the line of the longest edge (within rounding): clamp it onto the edge
+      cx = cx < 0.0 ? 0.0 : (cx > Ln ? Ln : cx);
+    } else if (cy < 0.0) { cy = 0.0; }
+    float4 *q = triq + TRIQ_STRIDE * f;
+    q[0] = make_float4((float)A[0], (float)A[1], (float)A[2], (float)Ln);
+    q[1] = make_float4((float)u[0], (float)u[1], (float)u[2], (float)cx);
+    q[2] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)cy);
+    q[3] = make_float4((float)n[0], (float)n[1], (float)n[2], 0.f);
   }
 };
 
@@ -86,16 +107,16 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
     plat::h2d(dV.p, V, v_span * vsz, s);
     plat::h2d(dF.p, F, f_span * 4, s);
     DevBuf<double> tri64((size_t)9 * nF);
-    DevBuf<float4> tri32((size_t)TRI32_STRIDE * nF);
+    DevBuf<float4> tri32((size_t)TRI32_STRIDE * nF), triq((size_t)TRIQ_STRIDE * nF);
     DevBuf<uint32_t> acc(8);
     {
       const uint32_t init[8] = {0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
       plat::h2d(acc.p, init, sizeof(init), s);
     }
     if (v_is_f64)
-      plat::for_n(nF, GatherFaces<double>{(const double *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, acc.p, acc.p + 1, acc.p + 2}, s);
+      plat::for_n(nF, GatherFaces<double>{(const double *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, triq.p, acc.p, acc.p + 1, acc.p + 2}, s);
     else
-      plat::for_n(nF, GatherFaces<float>{(const float *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, acc.p, acc.p + 1, acc.p + 2}, s);
+      plat::for_n(nF, GatherFaces<float>{(const float *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, triq.p, acc.p, acc.p + 1, acc.p + 2}, s);
     uint32_t hacc[8];
     plat::d2h(hacc, acc.p, sizeof(hacc), s);
     plat::sync(s);
@@ -120,12 +141,14 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
     uint64_t off = align(sizeof(ArenaHeader));
     m->h.off_tri64 = off; off = align(off + (uint64_t)72 * nF);
     m->h.off_tri32 = off; off = align(off + (uint64_t)16 * TRI32_STRIDE * nF);
+    m->h.off_triq = off; off = align(off + (uint64_t)16 * TRIQ_STRIDE * nF);
     m->h.off_fnodes = off; off = align(off + (uint64_t)sizeof(FwnNode) * nn);
     m->h.off_cnodes = off; off = align(off + (uint64_t)sizeof(CpNode) * nn);
     m->h.bytes = off;
     m->arena = (char *)plat::dev_alloc(off);
     plat::d2d(m->arena + m->h.off_tri64, tri64.p, (size_t)72 * nF, s);
     plat::d2d(m->arena + m->h.off_tri32, tri32.p, (size_t)16 * TRI32_STRIDE * nF, s);
+    plat::d2d(m->arena + m->h.off_triq, triq.p, (size_t)16 * TRIQ_STRIDE * nF, s);
     if (nn) {
       DevBuf<Local> locals((size_t)nn);
       for (int l = tree_levels(tree) - 1; l >= 0; --l) {

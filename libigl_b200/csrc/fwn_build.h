@@ -262,11 +262,11 @@ DEVFN void nth_element_seq(const TriBox *boxes, uint32_t *a, uint32_t n, uint32_
 // kernels (functors; see platform.h for the launchers)
 // ----------------------------------------------------------------------------
 struct TriBoxes {  // per-triangle fp32 boxes (:6566-6590); also flags NaN/Inf boxes (:4488-4500)
-  const float4 *tri;  // 4 float4 per face, the first three hold a,b,c in .xyz (moments.h: TRI32_STRIDE)
+  const float4 *tri;  // 3 float4 per face: a,b,c (fp32 vertices, .w unused)
   TriBox *boxes;
   uint32_t *bad;
   DEVFN void operator()(int64_t f) const {
-    const float4 a = tri[4 * f], b = tri[4 * f + 1], c = tri[4 * f + 2];
+    const float4 a = tri[3 * f], b = tri[3 * f + 1], c = tri[3 * f + 2];
     // SYSmin/SYSmax keep the FIRST argument unless the second is strictly
     // smaller/larger (:253-258), so a NaN in vertex a sticks and one in b or c is dropped
     #define IGLB_MN(x, y) (((x) > (y)) ? (y) : (x))

@@ -82,7 +82,7 @@ struct MortonKeys {  // 30-bit Morton code of each query inside the doubled scen
 };
 
 struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
-  const fwn::CpNode *nodes; const double *tri64; const float4 *tri32;
+  const fwn::CpNode *nodes; const double *tri64; const float4 *triq;
   const double *P; int64_t n; const uint32_t *perm;
   double up, low; float absmax;
   double *sqrD; int32_t *I; double *C;
@@ -108,7 +108,8 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     lane_init(L[l], p[l], a.up, a.absmax);
     if (!valid[l] || a.low > a.up) { L[l].best_ub = -INFINITY; L[l].thr2 = -1.f; }
   }
-  int sp = 0; uint32_t cur = 0; bool have = true; uint32_t nvis = 0, ntri = 0;
+  uint32_t nvis = 0, ntri = 0;
+  int sp = 0; uint32_t cur = 0; bool have = true;
   while (true) {
     if (!have) {
       if (sp == 0) break;
@@ -132,7 +133,8 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
       if (!any) continue;
       ++ntri;
       for (int l = 0; l < 32; ++l) {
-        float err; const float d32 = tri_dist_f32(a.tri32, ch[i], L[l].px, L[l].py, L[l].pz, L[l].u, err);
+        const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
+        float err; const float d32 = tri_dist_f32(tq[0], tq[1], tq[2], tq[3], L[l].px, L[l].py, L[l].pz, L[l].u, err);
         lane_offer(L[l], a.tri64, p[l], ch[i], d32, err);
       }
     }
@@ -170,7 +172,12 @@ void launch_closest(const ClosestArgs &a, stream_t) {
 }
 void throw_if_overflow(stream_t) {}
 #else
-__global__ void __launch_bounds__(128) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
+DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+#ifndef CP_MIN_BLOCKS
+#define CP_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
   using namespace fwn;
   constexpr unsigned FULL = 0xFFFFFFFFu;
   __shared__ CpStackEntry stacks[4][CP_STACK];
@@ -180,11 +187,14 @@ __global__ void __launch_bounds__(128) closest_packet_kernel(ClosestArgs a, uint
     const int64_t t = base + lane;
     const bool valid = t < a.n;
     const int64_t qi = valid ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
-    const D3 p = valid ? D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]} : D3{0.0, 0.0, 0.0};
     CpLane L;
-    lane_init(L, p, a.up, a.absmax);
+    {
+      const D3 p = valid ? D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]} : D3{0.0, 0.0, 0.0};
+      lane_init(L, p, a.up, a.absmax);
+    }
     if (!valid || a.low > a.up) { L.best_ub = -INFINITY; L.thr2 = -1.f; }
-    int sp = 0; uint32_t cur = 0; bool have = true; uint32_t nvis = 0, ntri = 0;
+    uint32_t nvis = 0, ntri = 0;
+    int sp = 0; uint32_t cur = 0; bool have = true;
     while (true) {
       if (!have) {
         if (sp == 0) break;
@@ -197,6 +207,13 @@ __global__ void __launch_bounds__(128) closest_packet_kernel(ClosestArgs a, uint
       have = false; ++nvis;
       const CpNode n = a.nodes[cur];
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
+      // the children will be needed within a few hundred cycles: start pulling them into L1 now
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ch[i] == EMPTY) continue;
+        if (ch[i] & INTERNAL_BIT) prefetch_l1(a.nodes + (ch[i] & ~INTERNAL_BIT));
+        else prefetch_l1(a.triq + TRIQ_STRIDE * (size_t)ch[i]);
+      }
       float d2[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) d2[i] = (ch[i] == EMPTY) ? INFINITY : lane_box_d2(n, i, L.px, L.py, L.pz, L.slack);
@@ -205,37 +222,63 @@ __global__ void __launch_bounds__(128) closest_packet_kernel(ClosestArgs a, uint
         if (ch[i] == EMPTY || (ch[i] & INTERNAL_BIT)) continue;     // warp-uniform
         if (!__any_sync(FULL, d2[i] <= L.thr2)) continue;
         ++ntri;
-        float err; const float d32 = tri_dist_f32(a.tri32, ch[i], L.px, L.py, L.pz, L.u, err);
-        lane_offer(L, a.tri64, p, ch[i], d32, err);
+        const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
+        const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3];
+        float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
+        const float lb = d32 - err;
+        if (lb <= L.best_ub) {   // few lanes; the list handling stays off the common path
+          const D3 p = D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]};
+          lane_offer(L, a.tri64, p, ch[i], d32, err);
+        }
       }
-      uint32_t key[4], id[4]; int lane_of[4]; int nint = 0;
+      // wanted internal children, ranked by the smallest lower bound any lane has for them.
+      // Everything below is warp-uniform and statically indexed (no local memory).
+      uint32_t key[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        key[i] = 0x7F800000u;
         if (ch[i] == EMPTY || !(ch[i] & INTERNAL_BIT)) continue;    // warp-uniform
-        const uint32_t m = __reduce_min_sync(FULL, (d2[i] <= L.thr2) ? __float_as_uint(d2[i]) : 0x7F800000u);
-        if (m == 0x7F800000u) continue;
-        int k = nint++;
-        while (k > 0 && key[k - 1] > m) { key[k] = key[k - 1]; id[k] = id[k - 1]; lane_of[k] = lane_of[k - 1]; --k; }
-        key[k] = m; id[k] = ch[i] & ~INTERNAL_BIT; lane_of[k] = i;
+        key[i] = __reduce_min_sync(FULL, (d2[i] <= L.thr2) ? __float_as_uint(d2[i]) : 0x7F800000u);
       }
-      for (int k = nint - 1; k >= 1; --k) {
-        if (sp >= CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); continue; }
-        if (lane == 0) {
-          CpStackEntry &e = stack[sp];
-          const int i = lane_of[k];
-          e.node = id[k]; e.dmin = __uint_as_float(key[k]);
-          e.box[0] = ((const float *)&n.lox)[i]; e.box[1] = ((const float *)&n.loy)[i]; e.box[2] = ((const float *)&n.loz)[i];
-          e.box[3] = ((const float *)&n.hix)[i]; e.box[4] = ((const float *)&n.hiy)[i]; e.box[5] = ((const float *)&n.hiz)[i];
+      int rank[4], nint = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        nint += (key[i] != 0x7F800000u);
+        int r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j != i) r += (key[j] < key[i]) || (key[j] == key[i] && j < i);
+        rank[i] = r;
+      }
+      // lanes 0..3 each own one child: the nearest becomes `cur`, the others go on the stack, farthest first
+      if (sp + nint > CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); nint = 0; }
+      {
+        const int j = lane & 3;
+        const uint32_t myc = j == 0 ? ch[0] : j == 1 ? ch[1] : j == 2 ? ch[2] : ch[3];
+        const uint32_t myk = j == 0 ? key[0] : j == 1 ? key[1] : j == 2 ? key[2] : key[3];
+        const int myr = j == 0 ? rank[0] : j == 1 ? rank[1] : j == 2 ? rank[2] : rank[3];
+        if (lane < 4 && myk != 0x7F800000u && myr >= 1 && nint > 0) {
+          CpStackEntry &e = stack[sp + (nint - 1 - myr)];
+          e.node = myc & ~INTERNAL_BIT; e.dmin = __uint_as_float(myk);
+          // the node's registers are long dead: re-read this child's box (an L1 hit)
+          const float *nb = (const float *)(a.nodes + cur);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) e.box[k] = nb[4 * k + j];
         }
-        ++sp;
       }
+      uint32_t next = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (key[i] != 0x7F800000u && rank[i] == 0) next = ch[i] & ~INTERNAL_BIT;
+      if (nint > 0) sp += nint - 1;
       __syncwarp();
-      if (nint > 0) { cur = id[0]; have = true; }
+      if (nint > 0) { cur = next; have = true; }
     }
     if (valid) {
       CpResult r;
       if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
-      else lane_finish(L, a.tri64, p, a.up, r);
+      else {
+        const D3 p = D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]};
+        lane_finish(L, a.tri64, p, a.up, r);
+      }
       closest_store(a, qi, r);
     }
     if (a.counters && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
@@ -389,7 +432,7 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   bounds_to_sqr(lower, upper, low, up);
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   { plat::Span sp("closest", s);
-    launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->tri32(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr}, s); }
+    launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr}, s); }
   { plat::Span sp("winding", s);
     launch_query("winding", n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
                                             sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s); }
@@ -404,7 +447,7 @@ void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, dou
   }
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   plat::Span sp("closest", s);
-  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->tri32(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr}, s);
+  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr}, s);
 }
 
 void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_scale, double *W, void *scratch,
@@ -625,7 +668,7 @@ int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colma
   plat::h2d(dP.p, P_host_colmajor, (size_t)24 * n, nullptr);
   plat::dev_memset(acc.p, 0, 16, nullptr);
   const uint32_t *perm = morton_perm(m, dP.p, n, scratch.p, 1, nullptr);
-  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->tri32(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p}, nullptr);
+  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p}, nullptr);
   plat::for_n(n, CountWinding{m->fnodes(), m->tri32(), dP.p, n, m->h.order, acc.p + 2}, nullptr);
   uint32_t h[4];
   plat::d2h(h, acc.p, 16, nullptr);

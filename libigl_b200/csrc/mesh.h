@@ -2,7 +2,7 @@
 // query needs, so that replicating the structure to another GPU is a single
 // broadcast of [arena, arena+bytes).
 //
-//   [ArenaHeader | tri64 (9 f64 / face) | tri32 (4 float4 / face) |
+//   [ArenaHeader | tri64 (9 f64 / face) | tri32 (3 float4 / face) | triq (4 float4 / face) |
 //    fwn nodes (384 B) | closest-point nodes (128 B)]
 //
 // tri64/tri32 are the faces' vertices gathered once at build time (the
@@ -20,8 +20,8 @@ struct ArenaHeader {
   int32_t order, pad;
   double bbox_lo[3], bbox_hi[3];  // of the fp64 geometry
   float absmax, padf;             // max |coordinate| (slack of the fp32 box tests)
-  uint64_t off_tri64, off_tri32, off_fnodes, off_cnodes;
-  uint64_t reserved[8];
+  uint64_t off_tri64, off_tri32, off_fnodes, off_cnodes, off_triq;
+  uint64_t reserved[7];
 };
 
 struct iglb200_mesh {
@@ -32,6 +32,7 @@ struct iglb200_mesh {
   int device = 0;
   const double *tri64() const { return (const double *)(arena + h.off_tri64); }
   const float4 *tri32() const { return (const float4 *)(arena + h.off_tri32); }
+  const float4 *triq() const { return (const float4 *)(arena + h.off_triq); }
   const fwn::FwnNode *fnodes() const { return (const fwn::FwnNode *)(arena + h.off_fnodes); }
   const fwn::CpNode *cnodes() const { return (const fwn::CpNode *)(arena + h.off_cnodes); }
 };

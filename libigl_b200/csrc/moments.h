@@ -35,13 +35,15 @@ struct alignas(128) CpNode {  // 128 B = one L2 line: child boxes SoA over the 4
   uint4 pad;
 };
 
-// fp32 face record, 4 float4 = 64 B:
-//   [a.xyz | n.x] [b.xyz | n.y] [c.xyz | n.z] [1/|ab|^2, 1/|bc|^2, 1/|ca|^2, kappa]
-// a,b,c = (float)vertex as the reference's V.cast<float>() (signed_distance.cpp:66): the winding
-// number and the moments read exactly these.  n (unit normal from the fp64 vertices; NaN when
-// the face is too thin for a plane test), the inverse squared edge lengths and the error
-// weight kappa serve the fp32 stage of the closest-triangle search (traverse.h).
-static constexpr int TRI32_STRIDE = 4;
+// tri32: 3 float4 per face, a,b,c = (float)vertex in .xyz — the reference's V.cast<float>()
+// (signed_distance.cpp:66); the winding number and the moments read exactly these.
+static constexpr int TRI32_STRIDE = 3;
+// triq: 4 float4 per face for the fp32 stage of the closest-triangle search (traverse.h):
+// the face in its own orthonormal frame, derived from the fp64 vertices:
+//   [o.xyz | L] [u.xyz | cx] [v.xyz | cy] [n.xyz | unused]
+// o = start of the longest edge (as float), u along that edge, n the unit normal, v = n x u;
+// in that frame the vertices are (0,0), (L,0), (cx,cy) with cy >= 0 (cy == 0: segment / point).
+static constexpr int TRIQ_STRIDE = 4;
 
 struct Local {  // what a subtree hands to its parent (LocalData :6611-6642)
   Box3 box;

@@ -24,6 +24,7 @@ DEVFN double dsub(double a, double b) { return a - b; }
 DEVFN double ddiv(double a, double b) { return a / b; }
 DEVFN float fsub(float a, float b) { return a - b; }
 DEVFN float f_up(double d) { float f = (float)d; if ((double)f < d) f = std::nextafterf(f, INFINITY); return f; }
+DEVFN float __frcp_rn(float x) { return 1.0f / x; }
 #else
 DEVFN double dmul(double a, double b) { return __dmul_rn(a, b); }
 DEVFN double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -94,57 +95,53 @@ struct CpResult {
 #ifndef CP_KAPPA0
 #define CP_KAPPA0 48.0
 #endif
-static constexpr int CP_NCAND = 8;
+static constexpr int CP_NCAND = 4;
 
-DEVFN float tri_dist_f32(const float4 *tri32, uint32_t f, float px, float py, float pz, float u, float &err) {
-  const float4 *t = tri32 + TRI32_STRIDE * (size_t)f;
-  const float4 A = t[0], B = t[1], C = t[2], E = t[3];
-  const float wax = px - A.x, way = py - A.y, waz = pz - A.z;
-  const float wbx = px - B.x, wby = py - B.y, wbz = pz - B.z;
-  const float wcx = px - C.x, wcy = py - C.y, wcz = pz - C.z;
-  const float abx = B.x - A.x, aby = B.y - A.y, abz = B.z - A.z;
-  const float bcx = C.x - B.x, bcy = C.y - B.y, bcz = C.z - B.z;
-  const float cax = A.x - C.x, cay = A.y - C.y, caz = A.z - C.z;
-  // point-segment distances (t clamped; a zero-length edge has inverse length 0 -> its start point)
-  float tt = fminf(fmaxf((wax * abx + way * aby + waz * abz) * E.x, 0.f), 1.f);
-  float qx = wax - tt * abx, qy = way - tt * aby, qz = waz - tt * abz;
-  float d2 = qx * qx + qy * qy + qz * qz;
-  tt = fminf(fmaxf((wbx * bcx + wby * bcy + wbz * bcz) * E.y, 0.f), 1.f);
-  qx = wbx - tt * bcx; qy = wby - tt * bcy; qz = wbz - tt * bcz;
-  d2 = fminf(d2, qx * qx + qy * qy + qz * qz);
-  tt = fminf(fmaxf((wcx * cax + wcy * cay + wcz * caz) * E.z, 0.f), 1.f);
-  qx = wcx - tt * cax; qy = wcy - tt * cay; qz = wcz - tt * caz;
-  d2 = fminf(d2, qx * qx + qy * qy + qz * qz);
-  // inside the prism over the face: (edge x w) . n >= 0 for all three edges (false for NaN normals)
-  const float nx = A.w, ny = B.w, nz = C.w;
-  const float s0 = (aby * waz - abz * way) * nx + (abz * wax - abx * waz) * ny + (abx * way - aby * wax) * nz;
-  const float s1 = (bcy * wbz - bcz * wby) * nx + (bcz * wbx - bcx * wbz) * ny + (bcx * wby - bcy * wbx) * nz;
-  const float s2 = (cay * wcz - caz * wcy) * nx + (caz * wcx - cax * wcz) * ny + (cax * wcy - cay * wcx) * nz;
-  if (s0 >= 0.f && s1 >= 0.f && s2 >= 0.f) {
-    const float pd = wax * nx + way * ny + waz * nz;
-    d2 = pd * pd;
-  }
-  err = (E.w >= 0.f) ? E.w * u : ((float)CP_KAPPA0 * u - E.w);
+// |d32 - d| <= CP_KAPPA0 * u,  u = 2^-24 * max(|p|, |mesh|): the frame is exact to fp32 rounding
+// whatever the face's shape (no aspect-ratio amplification), the origin is off by < 1 ulp.
+DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, const float4 Q3, float px, float py, float pz,
+                         float u, float &err) {
+  const float wx = px - Q0.x, wy = py - Q0.y, wz = pz - Q0.z;
+  const float x = wx * Q1.x + wy * Q1.y + wz * Q1.z;
+  const float y = wx * Q2.x + wy * Q2.y + wz * Q2.z;
+  const float z = wx * Q3.x + wy * Q3.y + wz * Q3.z;
+  const float L = Q0.w, cx = Q1.w, cy = Q2.w;
+  // edge (0,0)-(L,0)
+  const float dx0 = x - fminf(fmaxf(x, 0.f), L);
+  float d2 = dx0 * dx0 + y * y;
+  // edge (0,0)-(cx,cy)
+  float t = fminf(fmaxf((x * cx + y * cy) * __frcp_rn(cx * cx + cy * cy), 0.f), 1.f);
+  float qx = x - t * cx, qy = y - t * cy;
+  d2 = fminf(d2, qx * qx + qy * qy);
+  // edge (L,0)-(cx,cy)
+  const float ex = cx - L, xl = x - L;
+  t = fminf(fmaxf((xl * ex + y * cy) * __frcp_rn(ex * ex + cy * cy), 0.f), 1.f);
+  qx = xl - t * ex; qy = y - t * cy;
+  d2 = fminf(d2, qx * qx + qy * qy);
+  // inside the face (proper triangles only)
+  const bool inside = (cy > 0.f) && (y >= 0.f) && (cy * x - cx * y >= 0.f) && (ex * y - cy * xl >= 0.f);
+  d2 = inside ? 0.f : d2;
+  err = (float)CP_KAPPA0 * u;
 #ifdef CP_ERR_SCALE   // test hook: shrink the band to probe how much margin the bound has
   err *= (float)CP_ERR_SCALE;
 #endif
-  return sqrtf(d2);
+  return sqrtf(d2 + z * z);
 }
 
-// running state of one query during the walk
+// running state of one query during the walk (kept in registers: no dynamic indexing)
 struct CpLane {
   float px, py, pz;
   float slack;    // rounding allowance of the fp32 box tests
   float u;        // 2^-24 * max(|p|, |mesh|)
   float best_ub;  // fp32 upper bound of the distance to the nearest face seen so far
   float thr2;     // prune a box when its squared lower bound exceeds this
+  float min_lb;   // smallest lower bound among the listed candidates
   int ncand;
-  uint32_t cand_face[CP_NCAND];
-  float cand_lb[CP_NCAND];
+  uint32_t cf0, cf1, cf2, cf3;  // candidate faces
+  float cl0, cl1, cl2, cl3;     // their lower bounds
   // exact best among the candidates already evaluated in fp64
   double ex_d2;
   int32_t ex_face;
-  D3 ex_c;
 };
 
 DEVFN void lane_set_ub(CpLane &L, float ub) {
@@ -157,30 +154,43 @@ DEVFN void lane_init(CpLane &L, D3 p, double up_sqr_d, float absmax) {
   const float M = fmaxf(fmaxf(fabsf(L.px), fabsf(L.py)), fmaxf(fabsf(L.pz), absmax));
   L.slack = M * 2.3841858e-7f;
   L.u = M * 5.9604645e-8f * 1.0000002f;
-  L.ncand = 0;
-  L.ex_d2 = up_sqr_d; L.ex_face = -1; L.ex_c = {0.0, 0.0, 0.0};
+  L.ncand = 0; L.min_lb = INFINITY;
+  L.cf0 = L.cf1 = L.cf2 = L.cf3 = 0u;
+  L.cl0 = L.cl1 = L.cl2 = L.cl3 = INFINITY;
+  L.ex_d2 = up_sqr_d; L.ex_face = -1;
   const float ub = (up_sqr_d < 3.0e38) ? f_up(sqrt(up_sqr_d)) * 1.0000002f : INFINITY;
   L.best_ub = ub;
   L.thr2 = (up_sqr_d < 3.0e38) ? f_up(up_sqr_d) * 1.0000005f : INFINITY;
 }
 
-// fp64 evaluation of one face; strict improvement or exact tie with a lower index replaces the best
-DEVFN void lane_exact(CpLane &L, const double *tri64, D3 p, uint32_t f) {
+DEVFN double face_sqr_distance(const double *tri64, D3 p, uint32_t f, D3 &cc) {
   const double *t = tri64 + 9 * (size_t)f;
   const D3 a = {t[0], t[1], t[2]}, b = {t[3], t[4], t[5]}, c = {t[6], t[7], t[8]};
-  const D3 cc = closest_on_triangle(p, a, b, c);
+  cc = closest_on_triangle(p, a, b, c);
   const D3 df = d3sub(p, cc);
-  const double dd = d3dot(df, df);
-  if (dd < L.ex_d2 || (dd == L.ex_d2 && L.ex_face >= 0 && (int32_t)f < L.ex_face)) {
-    L.ex_d2 = dd; L.ex_face = (int32_t)f; L.ex_c = cc;
-  }
+  return d3dot(df, df);
 }
 
-// evaluate every live candidate in fp64 and empty the list
-DEVFN void lane_flush(CpLane &L, const double *tri64, D3 p) {
-  for (int k = 0; k < L.ncand; ++k)
-    if (L.cand_lb[k] <= L.best_ub) lane_exact(L, tri64, p, L.cand_face[k]);
-  L.ncand = 0;
+// fp64 evaluation of one face; strict improvement or exact tie with a lower index replaces the best
+DEVFN void lane_exact(CpLane &L, const double *tri64, D3 p, uint32_t f) {
+  D3 cc;
+  const double dd = face_sqr_distance(tri64, p, f, cc);
+  if (dd < L.ex_d2 || (dd == L.ex_d2 && L.ex_face >= 0 && (int32_t)f < L.ex_face)) { L.ex_d2 = dd; L.ex_face = (int32_t)f; }
+}
+
+// evaluate every live candidate in fp64 and empty the list (rare: kept out of line so the
+// fp64 code does not sit in the walk's instruction footprint)
+#ifdef IGLB200_EMUL
+inline
+#else
+static __device__ __noinline__
+#endif
+void lane_flush(CpLane &L, const double *tri64, D3 p) {
+  if (L.ncand > 0 && L.cl0 <= L.best_ub) lane_exact(L, tri64, p, L.cf0);
+  if (L.ncand > 1 && L.cl1 <= L.best_ub) lane_exact(L, tri64, p, L.cf1);
+  if (L.ncand > 2 && L.cl2 <= L.best_ub) lane_exact(L, tri64, p, L.cf2);
+  if (L.ncand > 3 && L.cl3 <= L.best_ub) lane_exact(L, tri64, p, L.cf3);
+  L.ncand = 0; L.min_lb = INFINITY;
   if (L.ex_face >= 0) {
     const float ub = f_up(sqrt(L.ex_d2)) * 1.0000002f;
     if (ub < L.best_ub) lane_set_ub(L, ub);
@@ -191,24 +201,26 @@ DEVFN void lane_flush(CpLane &L, const double *tri64, D3 p) {
 DEVFN void lane_offer(CpLane &L, const double *tri64, D3 p, uint32_t f, float d32, float err) {
   const float lb = d32 - err;
   if (!(lb <= L.best_ub)) return;
+  const float ub = d32 + err;
+  if (ub < L.min_lb) { L.ncand = 0; L.min_lb = INFINITY; }   // every listed candidate is now out of the band
   if (L.ncand == CP_NCAND) {
-    // drop candidates that fell out of the band; if the list is still full, settle it in fp64
-    int m = 0;
-    for (int k = 0; k < CP_NCAND; ++k)
-      if (L.cand_lb[k] <= L.best_ub) { L.cand_lb[m] = L.cand_lb[k]; L.cand_face[m] = L.cand_face[k]; ++m; }
-    L.ncand = m;
-    if (m == CP_NCAND) lane_flush(L, tri64, p);
+    lane_flush(L, tri64, p);
     if (!(lb <= L.best_ub)) return;
   }
-  L.cand_face[L.ncand] = f; L.cand_lb[L.ncand] = lb; ++L.ncand;
-  const float ub = d32 + err;
+  if (L.ncand == 0) { L.cf0 = f; L.cl0 = lb; }
+  else if (L.ncand == 1) { L.cf1 = f; L.cl1 = lb; }
+  else if (L.ncand == 2) { L.cf2 = f; L.cl2 = lb; }
+  else { L.cf3 = f; L.cl3 = lb; }
+  ++L.ncand;
+  L.min_lb = fminf(L.min_lb, lb);
   if (ub < L.best_ub) lane_set_ub(L, ub);
 }
 
 DEVFN void lane_finish(CpLane &L, const double *tri64, D3 p, double up_sqr_d, CpResult &res) {
   lane_flush(L, tri64, p);
-  res.sqr_d = L.ex_d2; res.face = L.ex_face; res.c = L.ex_c;
-  if (!(res.sqr_d < up_sqr_d)) { res.sqr_d = up_sqr_d; res.face = -1; res.c = {0.0, 0.0, 0.0}; }
+  res.sqr_d = L.ex_d2; res.face = L.ex_face; res.c = {0.0, 0.0, 0.0};
+  if (!(res.sqr_d < up_sqr_d) || res.face < 0) { res.sqr_d = up_sqr_d; res.face = -1; return; }
+  face_sqr_distance(tri64, p, (uint32_t)res.face, res.c);   // closest point of the winner
 }
 
 // squared distance, lower bound, from a point to lane `i` of a node's child boxes
