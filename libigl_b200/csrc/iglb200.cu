@@ -116,47 +116,52 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
       --sp;
       const CpStackEntry &e = stack[sp];
       bool any = false;
-      for (int l = 0; l < 32; ++l) any |= box6_d2(e.box, L[l].px, L[l].py, L[l].pz, L[l].slack) <= L[l].thr2;
+      for (int l = 0; l < 32; ++l) any |= box6_d2(e.box, L[l]) <= L[l].thr2;
       if (!any) continue;
       cur = e.node;
     }
     have = false; ++nvis;
     const CpNode n = a.nodes[cur];
     const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
+    const uint32_t imask = n.pad.x, tmask = n.pad.y;
     float d2[32][4];
-    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i)
-      d2[l][i] = (ch[i] == EMPTY) ? INFINITY : lane_box_d2(n, i, L[l].px, L[l].py, L[l].pz, L[l].slack);
+    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) d2[l][i] = lane_box_d2(n, i, L[l]);
+    // faces first: they tighten the bounds the internal children are judged by
+    uint32_t wt = 0;
+    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) if (d2[l][i] <= L[l].thr2) wt |= 1u << i;
+    wt &= tmask;
     for (int i = 0; i < 4; ++i) {
-      if (ch[i] == EMPTY || (ch[i] & INTERNAL_BIT)) continue;
-      bool any = false;
-      for (int l = 0; l < 32; ++l) any |= d2[l][i] <= L[l].thr2;
-      if (!any) continue;
+      if (!((wt >> i) & 1u)) continue;
       ++ntri;
+      const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
       for (int l = 0; l < 32; ++l) {
-        const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
         float err; const float d32 = tri_dist_f32(tq[0], tq[1], tq[2], tq[3], L[l].px, L[l].py, L[l].pz, L[l].u, err);
         lane_offer(L[l], a.tri64, p[l], ch[i], d32, err);
       }
     }
-    uint32_t key[4]; uint32_t id[4]; int lane_of[4]; int nint = 0;
-    for (int i = 0; i < 4; ++i) {
-      if (ch[i] == EMPTY || !(ch[i] & INTERNAL_BIT)) continue;
-      uint32_t m = 0x7F800000u;
-      for (int l = 0; l < 32; ++l) if (d2[l][i] <= L[l].thr2) m = std::min(m, plat::f2u(d2[l][i]));
-      if (m == 0x7F800000u) continue;
-      int k = nint++;
-      while (k > 0 && key[k - 1] > m) { key[k] = key[k - 1]; id[k] = id[k - 1]; lane_of[k] = lane_of[k - 1]; --k; }
-      key[k] = m; id[k] = ch[i] & ~INTERNAL_BIT; lane_of[k] = i;
+    // internal children some lane still needs; the one with the smallest lower bound is walked next,
+    // the others are stacked in lane order
+    uint32_t wi = 0, best = 0xFFFFFFFFu;
+    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) {
+      if (!((imask >> i) & 1u) || !(d2[l][i] <= L[l].thr2)) continue;
+      wi |= 1u << i;
+      best = std::min(best, (plat::f2u(d2[l][i]) & ~3u) | (uint32_t)i);
     }
-    for (int k = nint - 1; k >= 1; --k) {
-      if (sp >= CP_STACK) throw std::runtime_error("closest-point stack overflow");
-      CpStackEntry &e = stack[sp++];
-      const int i = lane_of[k];
-      e.node = id[k]; e.dmin = plat::u2f(key[k]);
-      e.box[0] = ((const float *)&n.lox)[i]; e.box[1] = ((const float *)&n.loy)[i]; e.box[2] = ((const float *)&n.loz)[i];
-      e.box[3] = ((const float *)&n.hix)[i]; e.box[4] = ((const float *)&n.hiy)[i]; e.box[5] = ((const float *)&n.hiz)[i];
+    if (wi) {
+      const int nb = (int)(best & 3u);
+      const uint32_t push = wi & ~(1u << nb);
+      const int npush = __builtin_popcount(push);
+      if (sp + npush > CP_STACK) throw std::runtime_error("closest-point stack overflow");
+      for (int j = 0; j < 4; ++j) {
+        if (!((push >> j) & 1u)) continue;
+        CpStackEntry &e = stack[sp + __builtin_popcount(push & ((1u << j) - 1u))];
+        const float *nbx = (const float *)&n;
+        for (int k = 0; k < 6; ++k) e.box[k] = nbx[4 * k + j];
+        e.node = ch[j] & ~INTERNAL_BIT;
+      }
+      sp += npush;
+      cur = ch[nb] & ~INTERNAL_BIT; have = true;
     }
-    if (nint > 0) { cur = id[0]; have = true; }
   }
   for (int l = 0; l < 32; ++l) {
     if (!valid[l]) continue;
@@ -177,6 +182,9 @@ DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" 
 #ifndef CP_MIN_BLOCKS
 #define CP_MIN_BLOCKS 5
 #endif
+// One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
+// Per node: 4 box tests per lane, two warp reductions (which children does anybody still
+// need; which of them is nearest), faces tested by all lanes at once.
 __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
   using namespace fwn;
   constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -200,77 +208,80 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
         if (sp == 0) break;
         --sp;
         const CpStackEntry &e = stack[sp];
-        const bool w = box6_d2(e.box, L.px, L.py, L.pz, L.slack) <= L.thr2;
+        const bool w = box6_d2(e.box, L) <= L.thr2;
         if (!__any_sync(FULL, w)) continue;
         cur = e.node;
       }
       have = false; ++nvis;
-      const CpNode n = a.nodes[cur];
+      const CpNode *np = a.nodes + cur;
+      const CpNode n = *np;
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
-      // the children will be needed within a few hundred cycles: start pulling them into L1 now
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (ch[i] == EMPTY) continue;
-        if (ch[i] & INTERNAL_BIT) prefetch_l1(a.nodes + (ch[i] & ~INTERNAL_BIT));
-        else prefetch_l1(a.triq + TRIQ_STRIDE * (size_t)ch[i]);
+      const uint32_t imask = n.pad.x, tmask = n.pad.y;
+      // lanes 0..3 start pulling "their" child (node or face record) into L1
+      if (lane < 4 && ((imask | tmask) >> lane) & 1u) {
+        const uint32_t c = lane == 0 ? ch[0] : lane == 1 ? ch[1] : lane == 2 ? ch[2] : ch[3];
+        prefetch_l1((c & INTERNAL_BIT) ? (const void *)(a.nodes + (c & ~INTERNAL_BIT)) : (const void *)(a.triq + TRIQ_STRIDE * (size_t)c));
       }
       float d2[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) d2[i] = (ch[i] == EMPTY) ? INFINITY : lane_box_d2(n, i, L.px, L.py, L.pz, L.slack);
+      for (int i = 0; i < 4; ++i) d2[i] = lane_box_d2(n, i, L);
+      // faces first: they tighten the bounds the internal children are judged by
+      uint32_t wt = 0;
+      if (tmask) {   // warp-uniform
+        uint32_t mine = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mine |= (d2[i] <= L.thr2) ? (1u << i) : 0u;
+        wt = __reduce_or_sync(FULL, mine) & tmask;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (ch[i] == EMPTY || (ch[i] & INTERNAL_BIT)) continue;     // warp-uniform
-        if (!__any_sync(FULL, d2[i] <= L.thr2)) continue;
+        if (!((wt >> i) & 1u)) continue;     // warp-uniform
         ++ntri;
         const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
         const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3];
         float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
-        const float lb = d32 - err;
-        if (lb <= L.best_ub) {   // few lanes; the list handling stays off the common path
+        if (d32 - err <= L.best_ub) {   // few lanes; the list handling stays off the common path
           const D3 p = D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]};
           lane_offer(L, a.tri64, p, ch[i], d32, err);
         }
       }
-      // wanted internal children, ranked by the smallest lower bound any lane has for them.
-      // Everything below is warp-uniform and statically indexed (no local memory).
-      uint32_t key[4];
+      if (imask) {   // warp-uniform
+        uint32_t mine = 0, mykey = 0xFFFFFFFFu;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        key[i] = 0x7F800000u;
-        if (ch[i] == EMPTY || !(ch[i] & INTERNAL_BIT)) continue;    // warp-uniform
-        key[i] = __reduce_min_sync(FULL, (d2[i] <= L.thr2) ? __float_as_uint(d2[i]) : 0x7F800000u);
-      }
-      int rank[4], nint = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        nint += (key[i] != 0x7F800000u);
-        int r = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (j != i) r += (key[j] < key[i]) || (key[j] == key[i] && j < i);
-        rank[i] = r;
-      }
-      // lanes 0..3 each own one child: the nearest becomes `cur`, the others go on the stack, farthest first
-      if (sp + nint > CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); nint = 0; }
-      {
-        const int j = lane & 3;
-        const uint32_t myc = j == 0 ? ch[0] : j == 1 ? ch[1] : j == 2 ? ch[2] : ch[3];
-        const uint32_t myk = j == 0 ? key[0] : j == 1 ? key[1] : j == 2 ? key[2] : key[3];
-        const int myr = j == 0 ? rank[0] : j == 1 ? rank[1] : j == 2 ? rank[2] : rank[3];
-        if (lane < 4 && myk != 0x7F800000u && myr >= 1 && nint > 0) {
-          CpStackEntry &e = stack[sp + (nint - 1 - myr)];
-          e.node = myc & ~INTERNAL_BIT; e.dmin = __uint_as_float(myk);
-          // the node's registers are long dead: re-read this child's box (an L1 hit)
-          const float *nb = (const float *)(a.nodes + cur);
-#pragma unroll
-          for (int k = 0; k < 6; ++k) e.box[k] = nb[4 * k + j];
+        for (int i = 0; i < 4; ++i) {
+          const bool w = ((imask >> i) & 1u) && (d2[i] <= L.thr2);
+          mine |= w ? (1u << i) : 0u;
+          mykey = w ? min(mykey, (__float_as_uint(d2[i]) & ~3u) | (uint32_t)i) : mykey;
+        }
+        const uint32_t wi = __reduce_or_sync(FULL, mine);
+        if (wi) {
+          const uint32_t best = __reduce_min_sync(FULL, mykey);
+          const int nb = (int)(best & 3u);
+          const uint32_t push = wi & ~(1u << nb);
+          const int npush = __popc(push);
+          if (sp + npush > CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); }
+          else if (push) {
+            // 24 lanes copy the 6x4 box floats of this node; lane t holds float t = 4*k + j (plane k, child j)
+            if (lane < 24) {
+              const int j = lane & 3, k = lane >> 2;
+              if ((push >> j) & 1u) {
+                const float v = ((const float *)np)[lane];
+                stack[sp + __popc(push & ((1u << j) - 1u))].box[k] = v;
+              }
+            } else if (lane < 28) {
+              const int j = lane & 3;
+              if ((push >> j) & 1u) {
+                const uint32_t c = j == 0 ? ch[0] : j == 1 ? ch[1] : j == 2 ? ch[2] : ch[3];
+                stack[sp + __popc(push & ((1u << j) - 1u))].node = c & ~INTERNAL_BIT;
+              }
+            }
+            sp += npush;
+          }
+          cur = (nb == 0 ? ch[0] : nb == 1 ? ch[1] : nb == 2 ? ch[2] : ch[3]) & ~INTERNAL_BIT;
+          have = true;
         }
       }
-      uint32_t next = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) if (key[i] != 0x7F800000u && rank[i] == 0) next = ch[i] & ~INTERNAL_BIT;
-      if (nint > 0) sp += nint - 1;
       __syncwarp();
-      if (nint > 0) { cur = next; have = true; }
     }
     if (valid) {
       CpResult r;

@@ -32,7 +32,7 @@ struct alignas(16) FwnNode {  // 384 B
 struct alignas(128) CpNode {  // 128 B = one L2 line: child boxes SoA over the 4 lanes
   float4 lox, loy, loz, hix, hiy, hiz;
   uint4 child;
-  uint4 pad;
+  uint4 pad;  // .x = bitmask of lanes that are internal nodes, .y = lanes that are faces
 };
 
 // tri32: 3 float4 per face, a,b,c = (float)vertex in .xyz — the reference's V.cast<float>()
@@ -207,7 +207,14 @@ struct NodeMoments {
     CpNode cn;
     fn.child = make_uint4(child[0], child[1], child[2], child[3]);
     cn.child = fn.child;
-    cn.pad = make_uint4(0, 0, 0, 0);
+    {
+      uint32_t imask = 0, tmask = 0;  // lanes holding internal nodes / faces
+      for (int i = 0; i < 4; ++i) {
+        if (child[i] == EMPTY) continue;
+        if (child[i] & INTERNAL_BIT) imask |= 1u << i; else tmask |= 1u << i;
+      }
+      cn.pad = make_uint4(imask, tmask, 0, 0);
+    }
     for (int r = 0; r < R_COUNT; ++r) fn.d[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     Local out;
     float N[3] = {cd[0].N[0], cd[0].N[1], cd[0].N[2]};

@@ -24,8 +24,12 @@ DEVFN double dsub(double a, double b) { return a - b; }
 DEVFN double ddiv(double a, double b) { return a / b; }
 DEVFN float fsub(float a, float b) { return a - b; }
 DEVFN float f_up(double d) { float f = (float)d; if ((double)f < d) f = std::nextafterf(f, INFINITY); return f; }
-DEVFN float __frcp_rn(float x) { return 1.0f / x; }
+DEVFN float rcp_fast(float x) { return 1.0f / x; }
+DEVFN float sqrt_fast(float x) { return std::sqrt(x); }
 #else
+// 1-2 ulp approximations (single MUFU op); their error is covered by CP_KAPPA0
+DEVFN float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DEVFN float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 DEVFN double dmul(double a, double b) { return __dmul_rn(a, b); }
 DEVFN double dadd(double a, double b) { return __dadd_rn(a, b); }
 DEVFN double dsub(double a, double b) { return __dsub_rn(a, b); }
@@ -110,12 +114,12 @@ DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, cons
   const float dx0 = x - fminf(fmaxf(x, 0.f), L);
   float d2 = dx0 * dx0 + y * y;
   // edge (0,0)-(cx,cy)
-  float t = fminf(fmaxf((x * cx + y * cy) * __frcp_rn(cx * cx + cy * cy), 0.f), 1.f);
+  float t = fminf(fmaxf((x * cx + y * cy) * rcp_fast(cx * cx + cy * cy), 0.f), 1.f);
   float qx = x - t * cx, qy = y - t * cy;
   d2 = fminf(d2, qx * qx + qy * qy);
   // edge (L,0)-(cx,cy)
   const float ex = cx - L, xl = x - L;
-  t = fminf(fmaxf((xl * ex + y * cy) * __frcp_rn(ex * ex + cy * cy), 0.f), 1.f);
+  t = fminf(fmaxf((xl * ex + y * cy) * rcp_fast(ex * ex + cy * cy), 0.f), 1.f);
   qx = xl - t * ex; qy = y - t * cy;
   d2 = fminf(d2, qx * qx + qy * qy);
   // inside the face (proper triangles only)
@@ -125,12 +129,13 @@ DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, cons
 #ifdef CP_ERR_SCALE   // test hook: shrink the band to probe how much margin the bound has
   err *= (float)CP_ERR_SCALE;
 #endif
-  return sqrtf(d2 + z * z);
+  return sqrt_fast(d2 + z * z);
 }
 
 // running state of one query during the walk (kept in registers: no dynamic indexing)
 struct CpLane {
   float px, py, pz;
+  float xm, ym, zm, xp, yp, zp;  // p -/+ slack: the box tests absorb their own rounding this way
   float slack;    // rounding allowance of the fp32 box tests
   float u;        // 2^-24 * max(|p|, |mesh|)
   float best_ub;  // fp32 upper bound of the distance to the nearest face seen so far
@@ -146,13 +151,15 @@ struct CpLane {
 
 DEVFN void lane_set_ub(CpLane &L, float ub) {
   L.best_ub = ub;
-  L.thr2 = ub * ub * 1.0000005f;  // rounded up
+  L.thr2 = ub * ub * 1.000001f;  // rounded up, and absorbs the rounding of a box test's sum of squares
 }
 
 DEVFN void lane_init(CpLane &L, D3 p, double up_sqr_d, float absmax) {
   L.px = (float)p.x; L.py = (float)p.y; L.pz = (float)p.z;
   const float M = fmaxf(fmaxf(fabsf(L.px), fabsf(L.py)), fmaxf(fabsf(L.pz), absmax));
   L.slack = M * 2.3841858e-7f;
+  L.xm = L.px - L.slack; L.ym = L.py - L.slack; L.zm = L.pz - L.slack;
+  L.xp = L.px + L.slack; L.yp = L.py + L.slack; L.zp = L.pz + L.slack;
   L.u = M * 5.9604645e-8f * 1.0000002f;
   L.ncand = 0; L.min_lb = INFINITY;
   L.cf0 = L.cf1 = L.cf2 = L.cf3 = 0u;
@@ -160,7 +167,7 @@ DEVFN void lane_init(CpLane &L, D3 p, double up_sqr_d, float absmax) {
   L.ex_d2 = up_sqr_d; L.ex_face = -1;
   const float ub = (up_sqr_d < 3.0e38) ? f_up(sqrt(up_sqr_d)) * 1.0000002f : INFINITY;
   L.best_ub = ub;
-  L.thr2 = (up_sqr_d < 3.0e38) ? f_up(up_sqr_d) * 1.0000005f : INFINITY;
+  L.thr2 = (up_sqr_d < 3.0e38) ? f_up(up_sqr_d) * 1.000001f : INFINITY;
 }
 
 DEVFN double face_sqr_distance(const double *tri64, D3 p, uint32_t f, D3 &cc) {
@@ -223,21 +230,21 @@ DEVFN void lane_finish(CpLane &L, const double *tri64, D3 p, double up_sqr_d, Cp
   face_sqr_distance(tri64, p, (uint32_t)res.face, res.c);   // closest point of the winner
 }
 
-// squared distance, lower bound, from a point to lane `i` of a node's child boxes
-DEVFN float lane_box_d2(const CpNode &n, int i, float px, float py, float pz, float slack) {
-  const float lx = ((const float *)&n.lox)[i], hx = ((const float *)&n.hix)[i];
-  const float ly = ((const float *)&n.loy)[i], hy = ((const float *)&n.hiy)[i];
-  const float lz = ((const float *)&n.loz)[i], hz = ((const float *)&n.hiz)[i];
-  float dx = fmaxf(fmaxf(lx - px, px - hx) - slack, 0.f);
-  float dy = fmaxf(fmaxf(ly - py, py - hy) - slack, 0.f);
-  float dz = fmaxf(fmaxf(lz - pz, pz - hz) - slack, 0.f);
-  return (dx * dx + dy * dy + dz * dz) * 0.99999952f;  // 1 - 4 ulp: absorbs the rounding of the sum
+// Lower bound of the squared distance from the query to a box: the query is widened by
+// `slack` (xm..xp) so that fp32 rounding can only make the result smaller; the rounding of the
+// sum itself is absorbed by thr2 (lane_set_ub).
+DEVFN float box_lb2(float lx, float ly, float lz, float hx, float hy, float hz, const CpLane &L) {
+  const float dx = fmaxf(fmaxf(lx - L.xp, L.xm - hx), 0.f);
+  const float dy = fmaxf(fmaxf(ly - L.yp, L.ym - hy), 0.f);
+  const float dz = fmaxf(fmaxf(lz - L.zp, L.zm - hz), 0.f);
+  return dx * dx + dy * dy + dz * dz;
 }
-DEVFN float box6_d2(const float *b, float px, float py, float pz, float slack) {  // b = lo xyz, hi xyz
-  float dx = fmaxf(fmaxf(b[0] - px, px - b[3]) - slack, 0.f);
-  float dy = fmaxf(fmaxf(b[1] - py, py - b[4]) - slack, 0.f);
-  float dz = fmaxf(fmaxf(b[2] - pz, pz - b[5]) - slack, 0.f);
-  return (dx * dx + dy * dy + dz * dz) * 0.99999952f;
+DEVFN float lane_box_d2(const CpNode &n, int i, const CpLane &L) {
+  return box_lb2(((const float *)&n.lox)[i], ((const float *)&n.loy)[i], ((const float *)&n.loz)[i],
+                 ((const float *)&n.hix)[i], ((const float *)&n.hiy)[i], ((const float *)&n.hiz)[i], L);
+}
+DEVFN float box6_d2(const float *b, const CpLane &L) {  // b = lo xyz, hi xyz
+  return box_lb2(b[0], b[1], b[2], b[3], b[4], b[5], L);
 }
 
 // The walk itself is a PACKET traversal: the 32 queries of a warp (neighbours in
@@ -245,7 +252,7 @@ DEVFN float box6_d2(const float *b, float px, float py, float pz, float slack) {
 // so every box and face test runs on all 32 lanes at once (iglb200.cu:
 // closest_packet_kernel; host emulation: closest_packet_emul).
 static constexpr int CP_STACK = 128;   // entries per warp: node id + the node's own box
-struct CpStackEntry { uint32_t node; float box[6]; float dmin; };
+struct CpStackEntry { float box[6]; uint32_t node; uint32_t pad; };
 
 // ---------------------------------------------------------------------------
 // UTsignedSolidAngleTri (FastWindingNumberForSoups.h:6070-6110), un-fused fp32
