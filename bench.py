@@ -170,7 +170,6 @@ def ours(args):
     import torch.distributed as dist
 
     import libigl_b200
-    from libigl_b200.api import Mesh
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,39 +189,18 @@ def ours(args):
     keep = None
     if world == 1:
         mesh = api.Mesh(V, F, 2)
-        info = mesh.info()
     else:
-        if rank == 0:
-            mesh0 = api.Mesh(V, F, 2)
-            info = mesh0.info()
-            ptr, nbytes = mesh0.arena()
-        else:
-            nbytes = 0
-        nb = torch.tensor([nbytes], dtype=torch.int64, device=dev)
-        dist.broadcast(nb, 0)
-        nbytes = int(nb.item())
-        if rank == 0:
-            class _Raw:
-                pass
-            raw = _Raw()
-            raw.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-            buf = torch.as_tensor(raw, device=dev)
-        else:
-            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        from libigl_b200.dist import broadcast_mesh
+        mesh = api.Mesh(V, F, 2) if rank == 0 else None
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
-        dist.broadcast(buf, 0)
+        mesh, keep = broadcast_mesh(api, mesh, src=0, device=dev)
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
-        if rank == 0:
-            mesh = mesh0
-        else:
-            mesh = Mesh.from_arena(api, buf.data_ptr(), nbytes, copy=False)
-            keep = buf
-            info = mesh.info()
+    info = mesh.info()
 
     # --- device-resident buffers (canonical layout: column-major doubles)
     Pcm = np.ascontiguousarray(P.T)                      # [3, n] == column-major n x 3

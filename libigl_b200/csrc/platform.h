@@ -38,6 +38,8 @@ inline uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline uint32_t atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 inline uint32_t atomic_min(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 inline uint32_t atomic_max(uint32_t *p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+inline void atomic_min64(unsigned long long *p, unsigned long long v) { if (v < *p) *p = v; }
+inline void atomic_max64(unsigned long long *p, unsigned long long v) { if (v > *p) *p = v; }
 inline float fsqrt(float x) { return std::sqrt(x); }
 inline float fdiv(float a, float b) { return a / b; }
 inline float fmul(float a, float b) { return a * b; }  // built with -ffp-contract=off
@@ -63,6 +65,13 @@ inline void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, str
 inline size_t sort_pairs_temp_bytes(int64_t) { return 16; }
 // stable sort of (key,val) by key
 inline void sort_pairs_u32(void *, size_t, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int, stream_t) {
+  std::vector<uint32_t> o(n);
+  std::iota(o.begin(), o.end(), 0u);
+  std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
+  for (int64_t i = 0; i < n; ++i) { kout[i] = kin[o[i]]; vout[i] = vin[o[i]]; }
+}
+inline size_t sort_pairs64_temp_bytes(int64_t) { return 16; }
+inline void sort_pairs_u64(void *, size_t, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, stream_t) {
   std::vector<uint32_t> o(n);
   std::iota(o.begin(), o.end(), 0u);
   std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
@@ -99,6 +108,8 @@ HD uint32_t f2u(float f) {
 DEVFN uint32_t atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 DEVFN uint32_t atomic_min(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
 DEVFN uint32_t atomic_max(uint32_t *p, uint32_t v) { return atomicMax(p, v); }
+DEVFN void atomic_min64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+DEVFN void atomic_max64(unsigned long long *p, unsigned long long v) { atomicMax(p, v); }
 // IEEE round-to-nearest, never contracted into FMA regardless of -fmad
 DEVFN float fsqrt(float x) { return __fsqrt_rn(x); }
 DEVFN float fdiv(float a, float b) { return __fdiv_rn(a, b); }
@@ -163,6 +174,15 @@ inline size_t sort_pairs_temp_bytes(int64_t n) {
   size_t need = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 32);
   return need + 256;
+}
+inline size_t sort_pairs64_temp_bytes(int64_t n) {
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64);
+  return need + 256;
+}
+inline void sort_pairs_u64(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, stream_t s) {
+  PLAT_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
+  launch_counter() += 9;
 }
 inline void sort_pairs_u32(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, stream_t s) {
   PLAT_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
@@ -231,4 +251,12 @@ template <class T> struct DevBuf {
 // order-preserving float <-> uint32 map so box unions can use integer atomics
 HD uint32_t f2ord(float f) { uint32_t u = f2u(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 HD float ord2f(uint32_t u) { return u2f((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+HD unsigned long long d2ord(double d) {
+  unsigned long long u; memcpy(&u, &d, 8);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+HD double ord2d(unsigned long long u) {
+  u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+  double d; memcpy(&d, &u, 8); return d;
+}
 }  // namespace plat

@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing for the query path: one process per GPU (torchrun), torch.distributed
+for the collectives (NCCL over NVLink on GPUs; gloo in the CPU tests).
+
+The path shards by queries only — the trees are read-only:
+  1. rank `src` builds the mesh handle on its GPU;
+  2. the handle's flat arena (one contiguous device allocation, position independent) is
+     replicated with ONE broadcast (ncclBroadcast under the hood);
+  3. every rank answers its contiguous slice of the queries; no communication during traversal;
+  4. results are gathered to rank 0 (or stay sharded).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from .api import Api, Mesh
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of n queries for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _arena_tensor(api: Api, ptr: int, nbytes: int, device):
+    """Zero-copy torch view of [ptr, ptr+nbytes)."""
+    import torch
+    if "EMULATION" in api.version():  # host-emulated kernels (tests): "device" memory is host memory
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        return torch.from_numpy(np.ctypeslib.as_array(buf))
+
+    class _Raw:
+        pass
+
+    raw = _Raw()
+    raw.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(raw, device=device)
+
+
+def broadcast_mesh(api: Api, mesh, src: int = 0, device=None, group=None):
+    """Replicate `mesh` (valid on rank `src`, None elsewhere) to every rank.
+    Returns (mesh, keepalive): non-source ranks get a handle that borrows `keepalive`."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    emul = "EMULATION" in api.version()
+    dev = torch.device("cpu") if emul else (device or torch.device("cuda", torch.cuda.current_device()))
+    nb = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == src:
+        ptr, nbytes = mesh.arena()
+        nb[0] = nbytes
+    dist.broadcast(nb, src, group=group)
+    nbytes = int(nb.item())
+    if rank == src:
+        buf = _arena_tensor(api, ptr, nbytes, dev)
+    else:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dist.broadcast(buf, src, group=group)
+    if rank == src:
+        return mesh, None
+    return Mesh.from_arena(api, buf.data_ptr(), nbytes, copy=False), buf
+
+
+def gather_rows(local: np.ndarray, n_total: int, dst: int = 0, group=None):
+    """Concatenate per-rank row blocks (in rank order) on rank `dst`; None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    parts = [None] * world if rank == dst else None
+    dist.gather_object(np.ascontiguousarray(local), parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = np.concatenate(parts, axis=0)
+    assert out.shape[0] == n_total
+    return out

@@ -246,3 +246,88 @@ def case_adversarial_triangles(api, n_tri=300, reps=2):
             assert np.array_equal(I, Ib), kind
             assert np.array_equal(C, Cb), kind
             m.close()
+
+
+def case_cloud_golden(api):
+    """tests/include/igl/fast_winding_number.cpp:17-53 (1e-15)."""
+    P = np.array([[0.1, 0.2, 0.3]])
+    N = np.array([[4.0, 5.0, 6.0]])
+    N /= np.linalg.norm(N)
+    A = np.array([0.7])
+    Q = np.array([[0, 0, 0], [4, -3, 2], [-1, 1, 3], [0, 5, -2.0]])
+    gold = np.array([0.38779369004261133, -0.00041235296362485, -0.00362978253577090, -0.00041235296362485])
+    W = api.fast_winding_number(P, N, A, Q, 2, 2.0)
+    assert np.abs(W - gold).max() < 1e-15
+    assert np.abs(api.fast_winding_number(P, N, A, Q) - gold).max() < 1e-15   # default order 2, beta 2
+
+
+def case_cloud(api, n_points, n_queries, orders=(0, 1, 2), betas=(2.0, 1.0, 0.0)):
+    """Point-cloud FWN against the restated octree + expansion oracle: same cells, W to 1e-5
+    (observed ~1e-14: both sides are double precision and differ only in summation order)."""
+    V, F = synth.icosphere(4)
+    P, N, A = synth.oriented_cloud(V, F, n_points, 2)
+    Q = synth.random_points(n_queries, -1.5, 1.5, 4)
+    for order in orders:
+        c = api.Cloud(P, N, A, order)
+        o = oracle.PortCloud(P, N, A, order)
+        assert c.info()["n_cells"] == o.num_cells()
+        for beta in betas:
+            W = c.eval(Q, beta)
+            Wo = o.eval(Q, beta)
+            d = np.abs(W - Wo)
+            assert (d <= 1e-5 * np.maximum(1.0, np.abs(Wo))).all(), f"order {order} beta {beta}: {d.max():.3e}"
+            assert d.max() < 1e-10
+        c.close()
+    # the expansion is an approximation of the exact dipole sum: agree to ~1e-2 inside/outside
+    c = api.Cloud(P, N, A, 2)
+    W = c.eval(Q, 2.0)
+    Wb = c.eval(Q[:300], 0.0)
+    assert np.abs(W[:300] - Wb).max() < 2e-2
+    r = np.linalg.norm(Q, axis=1)
+    assert (W[r < 0.8] > 0.9).all() and (np.abs(W[r > 1.3]) < 0.1).all()
+    # float32 inputs and empty query set
+    assert c.eval(np.zeros((0, 3))).shape == (0,)
+    assert np.abs(c.eval(Q.astype(np.float32)) - W).max() < 1e-12
+    c.close()
+    # duplicate points: the depth cap (42 levels) keeps the build finite
+    P2 = np.concatenate([P[:50], P[:50]])
+    c2 = api.Cloud(P2, np.concatenate([N[:50], N[:50]]), np.concatenate([A[:50], A[:50]]), 2)
+    W2 = c2.eval(Q[:100], 2.0)
+    assert np.isfinite(W2).all()
+    c2.close()
+
+
+def case_golden_fixtures(api):
+    """Committed outputs of the genuine reference code (tests/golden/make_golden.py)."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in ("ico2", "knot"):
+        g = np.load(os.path.join(gold, f"soup_{name}.npz"))
+        V, F, P = g["V"], g["F"], g["P"]
+        m = api.Mesh(V, F, 2)
+        a = m.download()
+        pr = parity.match_nodes(a["fwn_child"], g["nodes"])
+        assert pr is not None and len(pr) == g["nodes"].shape[0], "topology differs from the golden reference tree"
+        da, db = a["fwn_data"][pr[:, 0]], g["boxdata"][pr[:, 1]]
+        assert np.array_equal(da[:, :4].view(np.uint32), db[:, :4].view(np.uint32))
+        fin = np.isfinite(db)
+        assert np.abs(da[fin] - db[fin]).max() <= 1e-6 * np.abs(db[fin]).max()
+        for beta, key in ((2.0, "W_beta2"), (1.0, "W_beta1")):
+            assert np.abs(m.fast_winding_number(P, beta) - g[key]).max() <= 1e-5
+        S, I, C, W = m.signed_distance(P, return_W=True)
+        assert np.abs(S - g["S"]).max() <= 1e-5 * np.abs(g["S"]).max()
+        assert np.abs(W - g["W_sd"]).max() <= 1e-5
+        D, Ib, Cb = m.squared_distance(P)
+        assert np.array_equal(D, g["sqrD_brute"]) and np.array_equal(Ib, g["I_brute"])
+        m.close()
+    g = np.load(os.path.join(gold, "soup_bounds.npz"))
+    S, I, C = api.Mesh(g["V"], g["F"], 2).signed_distance(g["P"], SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, float(g["lower"]), float(g["upper"]))
+    assert np.array_equal(np.isnan(S), np.isnan(g["S"]))
+    ok = ~np.isnan(S)
+    assert np.abs(S[ok] - g["S"][ok]).max() <= 1e-5 and np.array_equal(I[~ok], g["I"][~ok]) and np.array_equal(C[~ok], g["C"][~ok])
+    g = np.load(os.path.join(gold, "cloud.npz"))
+    for order in (0, 1, 2):
+        c = api.Cloud(g["P"], g["N"], g["A"], order)
+        assert c.info()["n_cells"] == int(g[f"ncells_order{order}"])
+        assert np.abs(c.eval(g["Q"], 2.0) - g[f"WN_order{order}"]).max() < 1e-12
+        c.close()

@@ -1,0 +1,105 @@
+// The reference's own known-answer tests for the hot path, re-created against include/iglb200/*.h
+// (Catch2 and the libigl test data are not available here):
+//   tests/include/igl/signed_distance.cpp:4-43      single_tet
+//   tests/include/igl/fast_winding_number.cpp:17-53 one_point_cloud
+//   tests/include/igl/AABB.cpp:100-113              barycentres of a soup
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "mini_eigen.h"
+#include "iglb200/signed_distance.h"
+#include "iglb200/point_mesh_squared_distance.h"
+
+using namespace mini;
+#define REQUIRE(x) do { if (!(x)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #x); std::exit(1); } } while (0)
+
+static void tet(MatrixXd &V, MatrixXi &F) {
+  V.resize(4, 3); F.resize(4, 3);
+  const double v[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  const int f[4][3] = {{0, 1, 3}, {0, 2, 1}, {0, 3, 2}, {1, 2, 3}};
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 3; ++j) { V(i, j) = v[i][j]; F(i, j) = f[i][j]; }
+}
+
+int main() {
+  MatrixXd V; MatrixXi F;
+  tet(V, F);
+  MatrixXd P(1, 3);
+  P(0, 0) = P(0, 1) = P(0, 2) = 0.5;
+  // signed_distance: single_tet
+  for (auto type : {iglb200::SIGNED_DISTANCE_TYPE_UNSIGNED, iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER}) {
+    VectorXd S; VectorXi I; MatrixXd C, N;
+    iglb200::signed_distance(P, V, F, type, S, I, C, N);
+    REQUIRE(S.rows() == 1 && I.rows() == 1 && C.rows() == 1 && C.cols() == 3);
+    const double tol = type == iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER ? 1e-7 : 1e-15;
+    REQUIRE(std::fabs(S(0) - std::sqrt(1. / 12.)) <= tol);
+    REQUIRE(I(0) == 3);
+    REQUIRE(N.rows() == 0);   // untouched, as in the reference
+  }
+  // other sign types must fail loudly
+  {
+    VectorXd S; VectorXi I; MatrixXd C, N;
+    bool threw = false;
+    try { iglb200::signed_distance(P, V, F, iglb200::SIGNED_DISTANCE_TYPE_PSEUDONORMAL, S, I, C, N); }
+    catch (const iglb200::Error &e) { threw = (e.code == IGLB200_ERR_UNSUPPORTED); }
+    REQUIRE(threw);
+  }
+  // row-major and float inputs give the same answer
+  {
+    RowMatrixXd Vr, Pr; RowMatrixXi Fr; MatrixXf Pf;
+    Vr.assign_from(V); Fr.assign_from(F); Pr.assign_from(P); Pf.assign_from(P);
+    VectorXd S, S2, W; VectorXi I; MatrixXd C, N; RowMatrixXd Cr;
+    iglb200::signed_distance(Pr, Vr, Fr, iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, S, I, Cr, N);
+    iglb200::signed_distance_with_winding_number(Pf, V, F, S2, I, C, W);
+    REQUIRE(S(0) == S2(0));
+    REQUIRE(std::fabs(W(0)) < 1e-6);
+    for (int d = 0; d < 3; ++d) REQUIRE(Cr(0, d) == C(0, d));
+  }
+  // empty F (signed_distance.cpp:398-405)
+  {
+    MatrixXi F0(0, 3);
+    VectorXd S; VectorXi I; MatrixXd C, N;
+    iglb200::signed_distance(P, V, F0, iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, S, I, C, N);
+    REQUIRE(std::isnan(S(0)) && I(0) == -1 && std::isnan(C(0, 0)));
+  }
+  // AABB: barycentres of a soup -> I == face, d == 0; plus the prebuilt-structure overloads
+  {
+    MatrixXd BC(4, 3), C;
+    for (int f = 0; f < 4; ++f) for (int d = 0; d < 3; ++d) BC(f, d) = (V(F(f, 0), d) + V(F(f, 1), d) + V(F(f, 2), d)) / 3.0;
+    iglb200::AABB<MatrixXd, 3> tree;
+    tree.init(V, F);
+    VectorXd sqrD; VectorXi I;
+    tree.squared_distance(V, F, BC, sqrD, I, C);
+    for (int f = 0; f < 4; ++f) { REQUIRE(I(f) == f); REQUIRE(sqrD(f) <= 1e-30); }
+    VectorXd sqrD2; VectorXi I2; MatrixXd C2;
+    iglb200::point_mesh_squared_distance(BC, V, F, sqrD2, I2, C2);
+    for (int f = 0; f < 4; ++f) REQUIRE(I2(f) == I(f) && sqrD2(f) == sqrD(f));
+    iglb200::FastWindingNumberBVH bvh;
+    iglb200::fast_winding_number(V, F, 2, bvh);
+    VectorXd S;
+    iglb200::signed_distance_fast_winding_number(P, V, F, tree, bvh, S);
+    REQUIRE(std::fabs(S(0) - std::sqrt(1. / 12.)) <= 1e-7);
+    MatrixXd Q(2, 3);
+    Q(0, 0) = Q(0, 1) = Q(0, 2) = 0.1; Q(1, 0) = Q(1, 1) = Q(1, 2) = 2.0;
+    VectorXd W, W2;
+    iglb200::fast_winding_number(bvh, 2.0f, Q, W);
+    iglb200::fast_winding_number(V, F, Q, W2);
+    REQUIRE(std::fabs(W(0) - 1.0) < 1e-5 && std::fabs(W(1)) < 1e-3 && W(0) == W2(0) && W(1) == W2(1));
+  }
+  // fast_winding_number: one_point_cloud
+  {
+    MatrixXd Pc(1, 3), Nc(1, 3), Q(4, 3); VectorXd A(1, 1), WN, WN2;
+    Pc(0, 0) = 0.1; Pc(0, 1) = 0.2; Pc(0, 2) = 0.3;
+    const double nrm = std::sqrt(16. + 25. + 36.);
+    Nc(0, 0) = 4 / nrm; Nc(0, 1) = 5 / nrm; Nc(0, 2) = 6 / nrm;
+    A(0) = 0.7;
+    const double q[4][3] = {{0, 0, 0}, {4, -3, 2}, {-1, 1, 3}, {0, 5, -2}};
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 3; ++j) Q(i, j) = q[i][j];
+    iglb200::fast_winding_number(Pc, Nc, A, Q, 2, 2.0, WN);
+    iglb200::fast_winding_number(Pc, Nc, A, Q, WN2);
+    const double gold[4] = {0.38779369004261133, -0.00041235296362485, -0.00362978253577090, -0.00041235296362485};
+    for (int i = 0; i < 4; ++i) { REQUIRE(std::fabs(WN(i) - gold[i]) < 1e-15); REQUIRE(WN2(i) == WN(i)); }
+  }
+  std::printf("OK\n");
+  return 0;
+}

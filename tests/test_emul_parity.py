@@ -68,3 +68,15 @@ def test_arena_roundtrip(emul_api):
 
 def test_adversarial_triangles(emul_api):
     cases.case_adversarial_triangles(emul_api)
+
+
+def test_cloud_golden(emul_api):
+    cases.case_cloud_golden(emul_api)
+
+
+def test_cloud_vs_oracle(emul_api):
+    cases.case_cloud(emul_api, 3000, 2000)
+
+
+def test_golden_fixtures(emul_api):
+    cases.case_golden_fixtures(emul_api)

@@ -126,3 +126,20 @@ def test_c3_noisy_sphere_random_queries(gpu_api):
 
 def test_adversarial_triangles(gpu_api):
     cases.case_adversarial_triangles(gpu_api)
+
+
+def test_cloud_golden(gpu_api):
+    cases.case_cloud_golden(gpu_api)
+
+
+def test_cloud_vs_oracle(gpu_api):
+    cases.case_cloud(gpu_api, 3000, 2000)
+
+
+def test_c4_cloud_reduced(gpu_api):
+    """BASELINE config c4 reduced to what the CPU oracle finishes quickly: 200 k points, 100 k queries."""
+    cases.case_cloud(gpu_api, 200000, 100000, orders=(2,), betas=(2.0,))
+
+
+def test_golden_fixtures(gpu_api):
+    cases.case_golden_fixtures(gpu_api)

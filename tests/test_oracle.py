@@ -1,0 +1,92 @@
+"""Pins the oracle: the reference's own known-answer tests, the committed golden fixtures
+(generated from the genuine reference code, tests/golden/make_golden.py) and brute force."""
+import os
+
+import numpy as np
+
+import oracle
+from libigl_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_single_tet_all_queries():
+    # tests/include/igl/signed_distance.cpp:4-43 (FWN tolerance 1e-7)
+    V, F = synth.tetrahedron()
+    S, I, C, W = oracle.signed_distance_fwn(np.array([[0.5, 0.5, 0.5]]), V, F)
+    assert abs(S[0] - np.sqrt(1 / 12)) < 1e-7 and I[0] == 3
+    assert abs(W[0] - 1.897e-8) < 1e-10          # SURVEY [probe] of the genuine core
+    S, _, _, W = oracle.signed_distance_fwn(np.array([[0.1, 0.1, 0.1]]), V, F)
+    assert abs(W[0] - 1.0000001) < 1e-6 and S[0] < 0
+
+
+def test_one_point_cloud_golden():
+    # tests/include/igl/fast_winding_number.cpp:17-53 (1e-15)
+    P = np.array([[0.1, 0.2, 0.3]])
+    N = np.array([[4.0, 5.0, 6.0]])
+    N /= np.linalg.norm(N)
+    Q = np.array([[0, 0, 0], [4, -3, 2], [-1, 1, 3], [0, 5, -2.0]])
+    gold = np.array([0.38779369004261133, -0.00041235296362485, -0.00362978253577090, -0.00041235296362485])
+    assert np.abs(oracle.PortCloud(P, N, np.array([0.7]), 2).eval(Q, 2) - gold).max() < 1e-15
+
+
+def test_soup_barycentres():
+    # tests/include/igl/AABB.cpp:100-113 on a synthetic soup
+    V, F = synth.soupify(*synth.icosphere(3))
+    BC = (V[F[:, 0]] + V[F[:, 1]] + V[F[:, 2]]) / 3
+    t = oracle.PortAABB(V, F)
+    D, I, C = t.squared_distance(BC)
+    assert np.array_equal(I, np.arange(len(F))) and np.abs(D).max() < 1e-15
+    assert t.num_nodes() == 2 * len(F) - 1
+
+
+def exact_winding(V, F, Q):
+    a, b, c = (V[F[:, k]][None] - Q[:, None] for k in range(3))
+    la, lb, lc = (np.linalg.norm(x, axis=2) for x in (a, b, c))
+    num = np.einsum("qfi,qfi->qf", a, np.cross(b, c))
+    den = la * lb * lc + np.einsum("qfi,qfi->qf", a, b) * lc + np.einsum("qfi,qfi->qf", b, c) * la + np.einsum("qfi,qfi->qf", c, a) * lb
+    return (2 * np.arctan2(num, den)).sum(1) / (4 * np.pi)
+
+
+def test_fwn_against_exact_winding_number():
+    # tests/include/igl/fast_winding_number.cpp:55-107 re-created on synthetic closed meshes (tol 1e-2)
+    for V, F in (synth.icosphere(3), synth.torus_knot(150, 12)):
+        Q = np.concatenate([V.mean(0, keepdims=True), synth.random_points(200, V.min(), V.max(), 9)])
+        Wx = exact_winding(V, F, Q)
+        assert np.abs(oracle.RefFwn(V, F).winding(Q) - Wx).max() < 1e-2
+        # the cloud of the reference test: face barycentres, unit face normals, face areas
+        a, b, c = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+        n = np.cross(b - a, c - a)
+        dbl = np.linalg.norm(n, axis=1)
+        Wc = oracle.PortCloud((a + b + c) / 3, n / dbl[:, None], dbl / 2, 2).eval(Q[:1], 2.0)
+        assert abs(Wc[0] - Wx[0]) < 1e-2
+
+
+def test_restated_aabb_equals_brute_force():
+    for V, F in (synth.icosphere(2), synth.torus_knot(60, 8), synth.noisy_sphere(2, 0.05, 1)):
+        P = synth.random_points(800, -3, 3, 2)
+        D, I, C = oracle.PortAABB(V, F).squared_distance(P)
+        Db, Ib, Cb = oracle.brute_closest(V, F, P)
+        assert np.array_equal(D, Db)
+        mism = I != Ib
+        assert np.array_equal(oracle.face_distance(V, F, P[mism], I[mism]), Db[mism])   # ties only
+
+
+def test_oracle_reproduces_golden_fixtures():
+    for name in ("ico2", "knot"):
+        g = np.load(os.path.join(GOLD, f"soup_{name}.npz"))
+        ref = oracle.RefFwn(g["V"], g["F"], 2)
+        assert np.array_equal(ref.nodes(), g["nodes"])
+        assert np.array_equal(ref.boxdata().view(np.uint32), g["boxdata"].view(np.uint32))
+        assert np.array_equal(ref.winding(g["P"]), g["W_beta2"])
+        assert np.array_equal(ref.winding(g["P"], 1.0), g["W_beta1"])
+        S, I, C, W = oracle.signed_distance_fwn(g["P"], g["V"], g["F"], fwn=ref)
+        assert np.array_equal(S, g["S"]) and np.array_equal(I, g["I"]) and np.array_equal(C, g["C"])
+    g = np.load(os.path.join(GOLD, "soup_bounds.npz"))
+    S, I, C, W = oracle.signed_distance_fwn(g["P"], g["V"], g["F"], float(g["lower"]), float(g["upper"]))
+    assert np.array_equal(S, g["S"], equal_nan=True) and np.array_equal(I, g["I"]) and np.isnan(S).sum() > 0
+    g = np.load(os.path.join(GOLD, "cloud.npz"))
+    for order in (0, 1, 2):
+        o = oracle.PortCloud(g["P"], g["N"], g["A"], order)
+        assert o.num_cells() == int(g[f"ncells_order{order}"])
+        assert np.abs(o.eval(g["Q"], 2.0) - g[f"WN_order{order}"]).max() < 1e-15
