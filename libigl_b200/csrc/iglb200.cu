@@ -507,6 +507,60 @@ void download_scalar(const DevBuf<double> &src, int64_t n, void *dst, int is_f64
   plat::sync(s);
 }
 
+
+#ifndef IGLB200_EMUL
+// Host-pointer calls in the canonical layout (column-major doubles — Eigen's default) are
+// streamed: the batch is cut into chunks, and chunk k+1's upload, chunk k's kernels and chunk
+// k-1's download run concurrently on two streams with a grow-only per-thread device workspace
+// (no cudaMalloc/cudaFree on the call path).
+struct Pipeline {
+  static constexpr int64_t CHUNK = int64_t(1) << 21;
+  cudaStream_t st[2] = {nullptr, nullptr};
+  char *buf[2] = {nullptr, nullptr};
+  size_t cap = 0;
+  ~Pipeline() { for (int k = 0; k < 2; ++k) { if (buf[k]) cudaFree(buf[k]); if (st[k]) cudaStreamDestroy(st[k]); } }
+  void ensure(size_t bytes) {
+    for (int k = 0; k < 2; ++k) if (!st[k]) PLAT_CHECK(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+    if (bytes <= cap) return;
+    for (int k = 0; k < 2; ++k) { if (buf[k]) { PLAT_CHECK(cudaFree(buf[k])); buf[k] = nullptr; } }
+    for (int k = 0; k < 2; ++k) buf[k] = (char *)plat::dev_alloc(bytes);
+    cap = bytes;
+  }
+};
+Pipeline &pipeline() { static thread_local Pipeline p; return p; }
+
+// mode 0: signed distance (S,I,C,W), 1: squared distance (S=sqrD,I,C), 2: winding number only (W)
+void run_streamed(const iglb200_mesh *m, int mode, const double *P, int64_t n, int sign_type, double lower, double upper,
+                  float accuracy_scale, double *S, int32_t *I, double *C, double *W) {
+  Pipeline &pl = pipeline();
+  const int64_t chunk = std::min<int64_t>(Pipeline::CHUNK, n);
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t oP = 0, oS = oP + al(24 * chunk), oC = oS + al(8 * chunk), oW = oC + al(24 * chunk), oI = oW + al(8 * chunk),
+               oX = oI + al(4 * chunk), total = oX + al(iglb200_query_scratch_bytes(chunk));
+  pl.ensure(total);
+  for (int64_t b = 0, k = 0; b < n; b += chunk, ++k) {
+    const int64_t mcount = std::min(chunk, n - b);
+    cudaStream_t s = pl.st[k & 1];
+    char *base = pl.buf[k & 1];
+    double *dP = (double *)(base + oP), *dS = (double *)(base + oS), *dC = (double *)(base + oC), *dW = (double *)(base + oW);
+    int32_t *dI = (int32_t *)(base + oI);
+    for (int d = 0; d < 3; ++d) plat::h2d(dP + d * mcount, P + d * n + b, (size_t)8 * mcount, s);
+    if (mode == 0) run_signed_distance(m, dP, mcount, sign_type, lower, upper, dS, dI, dC, W ? dW : nullptr, base + oX, 1, s);
+    else if (mode == 1) run_squared_distance(m, dP, mcount, dS, dI, dC, base + oX, 1, s);
+    else run_fwn(m, dP, mcount, accuracy_scale, dW, base + oX, 1, s);
+    if (mode != 2) {
+      plat::d2h(S + b, dS, (size_t)8 * mcount, s);
+      plat::d2h(I + b, dI, (size_t)4 * mcount, s);
+      for (int d = 0; d < 3; ++d) plat::d2h(C + d * n + b, dC + d * mcount, (size_t)8 * mcount, s);
+    }
+    if (W && mode != 1) plat::d2h(W + b, dW, (size_t)8 * mcount, s);
+  }
+  plat::sync(pl.st[0]);
+  plat::sync(pl.st[1]);
+  throw_if_overflow(nullptr);
+}
+#endif
+
 }  // namespace iglq
 using namespace iglq;
 
@@ -736,6 +790,12 @@ int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, 
   if (nP > 0 && (c_rs <= 0 || c_cs <= 0)) throw std::invalid_argument("strides must be positive");
   require_device();
   plat::launch_counter() = 0;
+#ifndef IGLB200_EMUL
+  if (nP > 0 && p_is_f64 && p_rs == 1 && p_cs == nP && s_is_f64 && c_is_f64 && c_rs == 1 && c_cs == nP && (!W || w_is_f64)) {
+    run_streamed(m, 0, (const double *)P, nP, sign_type, lower, upper, 2.0f, (double *)S, I, (double *)C, (double *)W);
+    return IGLB200_OK;
+  }
+#endif
   stream_t s = nullptr;
   DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP), dW(W ? (size_t)nP : 0);
   DevBuf<int32_t> dI((size_t)nP);
@@ -759,6 +819,12 @@ int iglb200_squared_distance(const iglb200_mesh *m, const void *P, int p_is_f64,
   if (nP > 0 && (c_rs <= 0 || c_cs <= 0)) throw std::invalid_argument("strides must be positive");
   require_device();
   plat::launch_counter() = 0;
+#ifndef IGLB200_EMUL
+  if (nP > 0 && p_is_f64 && p_rs == 1 && p_cs == nP && d_is_f64 && c_is_f64 && c_rs == 1 && c_cs == nP) {
+    run_streamed(m, 1, (const double *)P, nP, 0, 0.0, 0.0, 2.0f, (double *)sqrD, I, (double *)C, nullptr);
+    return IGLB200_OK;
+  }
+#endif
   stream_t s = nullptr;
   DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP);
   DevBuf<int32_t> dI((size_t)nP);
@@ -780,6 +846,12 @@ int iglb200_fwn_eval(const iglb200_mesh *m, const void *Q, int q_is_f64, int64_t
   if (nQ < 0 || (nQ > 0 && (!Q || !W))) throw std::invalid_argument("null pointer");
   require_device();
   plat::launch_counter() = 0;
+#ifndef IGLB200_EMUL
+  if (nQ > 0 && q_is_f64 && q_rs == 1 && q_cs == nQ && w_is_f64) {
+    run_streamed(m, 2, (const double *)Q, nQ, 0, 0.0, 0.0, accuracy_scale, nullptr, nullptr, nullptr, (double *)W);
+    return IGLB200_OK;
+  }
+#endif
   stream_t s = nullptr;
   DevBuf<double> dQ, dW((size_t)nQ);
   DevBuf<char> scratch(iglb200_query_scratch_bytes(nQ));

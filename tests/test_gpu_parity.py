@@ -81,8 +81,13 @@ def test_c2_full_size_sample_and_properties(gpu_api):
     assert F.shape[0] == 1_000_000
     m = gpu_api.Mesh(V, F, 2)
     P = synth.grid_points(*synth.bbox(V), 256, 1.1)
-    S, I, C, W = m.signed_distance(P, return_W=True)
+    # column-major doubles (Eigen's default layout) take the streamed path: 8 chunks on two streams
+    S, I, C, W = m.signed_distance(np.asfortranarray(P), return_W=True)
     assert not np.isnan(S).any()
+    # the row-major call (whole-batch path) must give the same bits
+    kk = slice(5_000_000, 5_300_000)
+    S2, I2, C2, W2 = m.signed_distance(P[kk], return_W=True)
+    assert np.array_equal(S2, S[kk]) and np.array_equal(I2, I[kk]) and np.array_equal(C2, C[kk]) and np.array_equal(W2, W[kk])
     # properties on all 16.7 M rows
     assert (I >= 0).all() and (I < F.shape[0]).all()
     d = np.linalg.norm(P - C, axis=1)
