@@ -99,13 +99,13 @@ DEVFN void closest_store(const ClosestArgs &a, int64_t i, const fwn::CpResult &r
 void closest_packet_emul(const ClosestArgs &a, int64_t base) {
   using namespace fwn;
   static thread_local CpStackEntry stack[CP_STACK];
-  CpLane L[32]; D3 p[32]; bool valid[32]; int64_t qi[32];
+  CpLane L[32]; CpExact X[32]; CpQueryRef qr[32]; bool valid[32]; int64_t qi[32];
   for (int l = 0; l < 32; ++l) {
     const int64_t t = base + l;
     valid[l] = t < a.n;
     qi[l] = valid[l] ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
-    p[l] = valid[l] ? D3{a.P[qi[l]], a.P[a.n + qi[l]], a.P[2 * a.n + qi[l]]} : D3{0.0, 0.0, 0.0};
-    lane_init(L[l], p[l], a.up, a.absmax);
+    qr[l] = CpQueryRef{a.P, a.n, qi[l]};
+    lane_init(L[l], X[l], valid[l] ? load_query(qr[l]) : D3{0.0, 0.0, 0.0}, a.up, a.absmax);
     if (!valid[l] || a.low > a.up) { L[l].best_ub = -INFINITY; L[l].thr2 = -1.f; }
   }
   uint32_t nvis = 0, ntri = 0;
@@ -136,7 +136,7 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
       const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
       for (int l = 0; l < 32; ++l) {
         float err; const float d32 = tri_dist_f32(tq[0], tq[1], tq[2], tq[3], L[l].px, L[l].py, L[l].pz, L[l].u, err);
-        lane_offer(L[l], a.tri64, p[l], ch[i], d32, err);
+        lane_offer(L[l], X[l], a.tri64, qr[l], ch[i], d32, err);
       }
     }
     // internal children some lane still needs; the one with the smallest lower bound is walked next,
@@ -167,7 +167,7 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     if (!valid[l]) continue;
     CpResult r;
     if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
-    else lane_finish(L[l], a.tri64, p[l], a.up, r);
+    else lane_finish(L[l], X[l], a.tri64, qr[l], a.up, r);
     closest_store(a, qi[l], r);
   }
   if (a.counters) { a.counters[0] += nvis; a.counters[1] += ntri; }
@@ -185,10 +185,13 @@ DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" 
 // One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
+template <bool COUNT>
 __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
   using namespace fwn;
   constexpr unsigned FULL = 0xFFFFFFFFu;
   __shared__ CpStackEntry stacks[4][CP_STACK];
+  __shared__ CpExact exact[128];
+  CpExact &X = exact[threadIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CpStackEntry *stack = stacks[warp];
   for (int64_t base = ((int64_t)blockIdx.x * 4 + warp) * 32; base < a.n; base += (int64_t)gridDim.x * 128) {
@@ -196,10 +199,8 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
     const bool valid = t < a.n;
     const int64_t qi = valid ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
     CpLane L;
-    {
-      const D3 p = valid ? D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]} : D3{0.0, 0.0, 0.0};
-      lane_init(L, p, a.up, a.absmax);
-    }
+    const CpQueryRef qr{a.P, a.n, qi};
+    lane_init(L, X, valid ? load_query(qr) : D3{0.0, 0.0, 0.0}, a.up, a.absmax);
     if (!valid || a.low > a.up) { L.best_ub = -INFINITY; L.thr2 = -1.f; }
     uint32_t nvis = 0, ntri = 0;
     int sp = 0; uint32_t cur = 0; bool have = true;
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
         if (!__any_sync(FULL, w)) continue;
         cur = e.node;
       }
-      have = false; ++nvis;
+      have = false;
+      if (COUNT) ++nvis;
       const CpNode *np = a.nodes + cur;
       const CpNode n = *np;
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
@@ -233,17 +235,17 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
         for (int i = 0; i < 4; ++i) mine |= (d2[i] <= L.thr2) ? (1u << i) : 0u;
         wt = __reduce_or_sync(FULL, mine) & tmask;
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (!((wt >> i) & 1u)) continue;     // warp-uniform
-        ++ntri;
-        const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
+      // one face at a time (not unrolled: four faces in flight would double the register count)
+#pragma unroll 1
+      while (wt) {     // warp-uniform
+        const int i = __ffs(wt) - 1;
+        wt &= wt - 1;
+        const uint32_t f = i == 0 ? ch[0] : i == 1 ? ch[1] : i == 2 ? ch[2] : ch[3];
+        if (COUNT) ++ntri;
+        const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)f;
         const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3];
         float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
-        if (d32 - err <= L.best_ub) {   // few lanes; the list handling stays off the common path
-          const D3 p = D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]};
-          lane_offer(L, a.tri64, p, ch[i], d32, err);
-        }
+        if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, f, d32, err);   // few lanes
       }
       if (imask) {   // warp-uniform
         uint32_t mine = 0, mykey = 0xFFFFFFFFu;
@@ -286,13 +288,10 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
     if (valid) {
       CpResult r;
       if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
-      else {
-        const D3 p = D3{a.P[qi], a.P[a.n + qi], a.P[2 * a.n + qi]};
-        lane_finish(L, a.tri64, p, a.up, r);
-      }
+      else lane_finish(L, X, a.tri64, qr, a.up, r);
       closest_store(a, qi, r);
     }
-    if (a.counters && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
+    if (COUNT && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
     __syncwarp();
   }
 }
@@ -313,7 +312,8 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   if (a.n <= 0) return;
   const int64_t warps = (a.n + 31) / 32;
   const int64_t blocks = std::min<int64_t>((warps + 3) / 4, (int64_t)plat::sm_count() * 64);
-  closest_packet_kernel<<<(unsigned)blocks, 128, 0, s>>>(a, overflow_flag());
+  if (a.counters) closest_packet_kernel<true><<<(unsigned)blocks, 128, 0, s>>>(a, overflow_flag());
+  else closest_packet_kernel<false><<<(unsigned)blocks, 128, 0, s>>>(a, overflow_flag());
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }
@@ -370,7 +370,10 @@ struct FillConst { double *S; int32_t *I; double *C; double *W; int64_t n; doubl
 #ifdef IGLB200_EMUL
 template <class F> void launch_query(const char *, int64_t n, F f, stream_t s) { plat::for_n(n, f, s); }
 #else
-__global__ void __launch_bounds__(128) winding_number_kernel(int64_t n, WindingQuery f) {
+#ifndef WN_MIN_BLOCKS
+#define WN_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, WN_MIN_BLOCKS) winding_number_kernel(int64_t n, WindingQuery f) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
 }
 inline unsigned query_grid(int64_t n, int threads) {

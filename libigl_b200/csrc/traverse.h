@@ -99,7 +99,7 @@ struct CpResult {
 #ifndef CP_KAPPA0
 #define CP_KAPPA0 48.0
 #endif
-static constexpr int CP_NCAND = 4;
+static constexpr int CP_NCAND = 3;
 
 // |d32 - d| <= CP_KAPPA0 * u,  u = 2^-24 * max(|p|, |mesh|): the frame is exact to fp32 rounding
 // whatever the face's shape (no aspect-ratio amplification), the origin is off by < 1 ulp.
@@ -136,35 +136,41 @@ DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, cons
 struct CpLane {
   float px, py, pz;
   float xm, ym, zm, xp, yp, zp;  // p -/+ slack: the box tests absorb their own rounding this way
-  float slack;    // rounding allowance of the fp32 box tests
   float u;        // 2^-24 * max(|p|, |mesh|)
   float best_ub;  // fp32 upper bound of the distance to the nearest face seen so far
   float thr2;     // prune a box when its squared lower bound exceeds this
   float min_lb;   // smallest lower bound among the listed candidates
   int ncand;
-  uint32_t cf0, cf1, cf2, cf3;  // candidate faces
-  float cl0, cl1, cl2, cl3;     // their lower bounds
-  // exact best among the candidates already evaluated in fp64
-  double ex_d2;
-  int32_t ex_face;
+  uint32_t cf0, cf1, cf2;  // candidate faces
+  float cl0, cl1, cl2;     // their lower bounds
 };
+// exact best among the candidates already evaluated in fp64 (touched only by the rare fp64
+// stage: lives in shared memory on the device so it does not cost registers in the walk)
+struct CpExact {
+  double d2;
+  int32_t face;
+  int32_t pad;
+};
+// where the query itself can be re-read by the fp64 stage
+struct CpQueryRef { const double *P; int64_t n, qi; };
+DEVFN D3 load_query(const CpQueryRef &q) { return D3{q.P[q.qi], q.P[q.n + q.qi], q.P[2 * q.n + q.qi]}; }
 
 DEVFN void lane_set_ub(CpLane &L, float ub) {
   L.best_ub = ub;
   L.thr2 = ub * ub * 1.000001f;  // rounded up, and absorbs the rounding of a box test's sum of squares
 }
 
-DEVFN void lane_init(CpLane &L, D3 p, double up_sqr_d, float absmax) {
+DEVFN void lane_init(CpLane &L, CpExact &X, D3 p, double up_sqr_d, float absmax) {
   L.px = (float)p.x; L.py = (float)p.y; L.pz = (float)p.z;
   const float M = fmaxf(fmaxf(fabsf(L.px), fabsf(L.py)), fmaxf(fabsf(L.pz), absmax));
-  L.slack = M * 2.3841858e-7f;
-  L.xm = L.px - L.slack; L.ym = L.py - L.slack; L.zm = L.pz - L.slack;
-  L.xp = L.px + L.slack; L.yp = L.py + L.slack; L.zp = L.pz + L.slack;
+  const float slack = M * 2.3841858e-7f;   // rounding allowance of the fp32 box tests
+  L.xm = L.px - slack; L.ym = L.py - slack; L.zm = L.pz - slack;
+  L.xp = L.px + slack; L.yp = L.py + slack; L.zp = L.pz + slack;
   L.u = M * 5.9604645e-8f * 1.0000002f;
   L.ncand = 0; L.min_lb = INFINITY;
-  L.cf0 = L.cf1 = L.cf2 = L.cf3 = 0u;
-  L.cl0 = L.cl1 = L.cl2 = L.cl3 = INFINITY;
-  L.ex_d2 = up_sqr_d; L.ex_face = -1;
+  L.cf0 = L.cf1 = L.cf2 = 0u;
+  L.cl0 = L.cl1 = L.cl2 = INFINITY;
+  X.d2 = up_sqr_d; X.face = -1; X.pad = 0;
   const float ub = (up_sqr_d < 3.0e38) ? f_up(sqrt(up_sqr_d)) * 1.0000002f : INFINITY;
   L.best_ub = ub;
   L.thr2 = (up_sqr_d < 3.0e38) ? f_up(up_sqr_d) * 1.000001f : INFINITY;
@@ -179,10 +185,10 @@ DEVFN double face_sqr_distance(const double *tri64, D3 p, uint32_t f, D3 &cc) {
 }
 
 // fp64 evaluation of one face; strict improvement or exact tie with a lower index replaces the best
-DEVFN void lane_exact(CpLane &L, const double *tri64, D3 p, uint32_t f) {
+DEVFN void lane_exact(CpExact &X, const double *tri64, D3 p, uint32_t f) {
   D3 cc;
   const double dd = face_sqr_distance(tri64, p, f, cc);
-  if (dd < L.ex_d2 || (dd == L.ex_d2 && L.ex_face >= 0 && (int32_t)f < L.ex_face)) { L.ex_d2 = dd; L.ex_face = (int32_t)f; }
+  if (dd < X.d2 || (dd == X.d2 && X.face >= 0 && (int32_t)f < X.face)) { X.d2 = dd; X.face = (int32_t)f; }
 }
 
 // evaluate every live candidate in fp64 and empty the list (rare: kept out of line so the
@@ -192,42 +198,41 @@ inline
 #else
 static __device__ __noinline__
 #endif
-void lane_flush(CpLane &L, const double *tri64, D3 p) {
-  if (L.ncand > 0 && L.cl0 <= L.best_ub) lane_exact(L, tri64, p, L.cf0);
-  if (L.ncand > 1 && L.cl1 <= L.best_ub) lane_exact(L, tri64, p, L.cf1);
-  if (L.ncand > 2 && L.cl2 <= L.best_ub) lane_exact(L, tri64, p, L.cf2);
-  if (L.ncand > 3 && L.cl3 <= L.best_ub) lane_exact(L, tri64, p, L.cf3);
+void lane_flush(CpLane &L, CpExact &X, const double *tri64, CpQueryRef q) {
+  const D3 p = load_query(q);
+  if (L.ncand > 0 && L.cl0 <= L.best_ub) lane_exact(X, tri64, p, L.cf0);
+  if (L.ncand > 1 && L.cl1 <= L.best_ub) lane_exact(X, tri64, p, L.cf1);
+  if (L.ncand > 2 && L.cl2 <= L.best_ub) lane_exact(X, tri64, p, L.cf2);
   L.ncand = 0; L.min_lb = INFINITY;
-  if (L.ex_face >= 0) {
-    const float ub = f_up(sqrt(L.ex_d2)) * 1.0000002f;
+  if (X.face >= 0) {
+    const float ub = f_up(sqrt(X.d2)) * 1.0000002f;
     if (ub < L.best_ub) lane_set_ub(L, ub);
   }
 }
 
-// stage-1 result for face f
-DEVFN void lane_offer(CpLane &L, const double *tri64, D3 p, uint32_t f, float d32, float err) {
+// stage-1 result for face f (caller has already checked d32 - err <= best_ub)
+DEVFN void lane_offer(CpLane &L, CpExact &X, const double *tri64, const CpQueryRef &q, uint32_t f, float d32, float err) {
   const float lb = d32 - err;
   if (!(lb <= L.best_ub)) return;
   const float ub = d32 + err;
   if (ub < L.min_lb) { L.ncand = 0; L.min_lb = INFINITY; }   // every listed candidate is now out of the band
   if (L.ncand == CP_NCAND) {
-    lane_flush(L, tri64, p);
+    lane_flush(L, X, tri64, q);
     if (!(lb <= L.best_ub)) return;
   }
   if (L.ncand == 0) { L.cf0 = f; L.cl0 = lb; }
   else if (L.ncand == 1) { L.cf1 = f; L.cl1 = lb; }
-  else if (L.ncand == 2) { L.cf2 = f; L.cl2 = lb; }
-  else { L.cf3 = f; L.cl3 = lb; }
+  else { L.cf2 = f; L.cl2 = lb; }
   ++L.ncand;
   L.min_lb = fminf(L.min_lb, lb);
   if (ub < L.best_ub) lane_set_ub(L, ub);
 }
 
-DEVFN void lane_finish(CpLane &L, const double *tri64, D3 p, double up_sqr_d, CpResult &res) {
-  lane_flush(L, tri64, p);
-  res.sqr_d = L.ex_d2; res.face = L.ex_face; res.c = {0.0, 0.0, 0.0};
+DEVFN void lane_finish(CpLane &L, CpExact &X, const double *tri64, const CpQueryRef &q, double up_sqr_d, CpResult &res) {
+  lane_flush(L, X, tri64, q);
+  res.sqr_d = X.d2; res.face = X.face; res.c = {0.0, 0.0, 0.0};
   if (!(res.sqr_d < up_sqr_d) || res.face < 0) { res.sqr_d = up_sqr_d; res.face = -1; return; }
-  face_sqr_distance(tri64, p, (uint32_t)res.face, res.c);   // closest point of the winner
+  face_sqr_distance(tri64, load_query(q), (uint32_t)res.face, res.c);   // closest point of the winner
 }
 
 // Lower bound of the squared distance from the query to a box: the query is widened by
@@ -282,37 +287,59 @@ DEVFN float tri_solid_angle(const float4 *tri32, uint32_t f, float qx, float qy,
 
 static constexpr int FWN_STACK = 96;
 
-// far-field order-<=2 expansion of one child lane (:7200-7241)
-DEVFN float lane_omega(const FwnNode &n, int i, float q0, float q1, float q2, float ql2, int order) {
-#define LN(r) (((const float *)&n.d[r])[i])
-  const float m2 = plat::fdiv(1.0f, ql2);
-  const float m1 = plat::fsqrt(m2);
-  q0 *= m1; q1 *= m1; q2 *= m1;
-  float omega = -m2 * (q0 * LN(R_NX) + q1 * LN(R_NY) + q2 * LN(R_NZ));
-  if (order >= 1) {
-    const float s0 = q0 * q0, s1 = q1 * q1, s2 = q2 * q2;
-    const float m3 = m2 * m1;
-    const float o1 = m3 * (LN(R_NXX) + LN(R_NYY) + LN(R_NZZ) -
-                           3.0f * ((s0 * LN(R_NXX) + s1 * LN(R_NYY) + s2 * LN(R_NZZ)) + q0 * q1 * LN(R_NXY_NYX) +
-                                   q0 * q2 * LN(R_NZX_NXZ) + q1 * q2 * LN(R_NYZ_NZY)));
-    omega += o1;
-    if (order >= 2) {
-      const float c0 = s0 * q0, c1 = s1 * q1, c2 = s2 * q2;
-      const float m4 = m2 * m2;
-      const float t00 = LN(R_2NYYX_NXYY) + LN(R_2NZZX_NXZZ);
-      const float t01 = LN(R_2NZZY_NYZZ) + LN(R_2NXXY_NYXX);
-      const float t02 = LN(R_2NXXZ_NZXX) + LN(R_2NYYZ_NZYY);
-      const float t10 = q1 * LN(R_2NXXY_NYXX) + q2 * LN(R_2NXXZ_NZXX);
-      const float t11 = q2 * LN(R_2NYYZ_NZYY) + q0 * LN(R_2NYYX_NXYY);
-      const float t12 = q0 * LN(R_2NZZX_NXZZ) + q1 * LN(R_2NZZY_NYZZ);
-      const float o2 = m4 * (1.5f * (q0 * (3.f * LN(R_NXXX) + t00) + q1 * (3.f * LN(R_NYYY) + t01) + q2 * (3.f * LN(R_NZZZ) + t02)) -
-                             7.5f * ((c0 * LN(R_NXXX) + c1 * LN(R_NYYY) + c2 * LN(R_NZZZ)) + q0 * q1 * q2 * LN(R_SUMPERM) +
-                                     (s0 * t10 + s1 * t11 + s2 * t12)));
-      omega += o2;
+// Far-field order-<=2 expansion (:7200-7241) of all four child lanes of a node at once, the way
+// the reference's SSE code does it: every coefficient row is one 16-byte load whose four
+// components belong to the four children.  q (already relative to each child's centre) and
+// ql2 = |q|^2 come from the caller's descend test.
+struct Lanes4 { float v[4]; };
+DEVFN Lanes4 row4(const float4 *p) { const float4 t = *p; return Lanes4{{t.x, t.y, t.z, t.w}}; }
+
+DEVFN void node_omega4(const FwnNode &n, Lanes4 q0, Lanes4 q1, Lanes4 q2, const Lanes4 &ql2, int order, Lanes4 &omega) {
+  Lanes4 m1, m2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m2.v[i] = plat::fdiv(1.0f, ql2.v[i]);
+    m1.v[i] = plat::fsqrt(m2.v[i]);
+    q0.v[i] *= m1.v[i]; q1.v[i] *= m1.v[i]; q2.v[i] *= m1.v[i];
+  }
+  {
+    const Lanes4 NX = row4(&n.d[R_NX]), NY = row4(&n.d[R_NY]), NZ = row4(&n.d[R_NZ]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) omega.v[i] = -m2.v[i] * (q0.v[i] * NX.v[i] + q1.v[i] * NY.v[i] + q2.v[i] * NZ.v[i]);
+  }
+  if (order < 1) return;
+  {
+    const Lanes4 NXX = row4(&n.d[R_NXX]), NYY = row4(&n.d[R_NYY]), NZZ = row4(&n.d[R_NZZ]);
+    const Lanes4 NXY = row4(&n.d[R_NXY_NYX]), NYZ = row4(&n.d[R_NYZ_NZY]), NZX = row4(&n.d[R_NZX_NXZ]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a0 = q0.v[i], a1 = q1.v[i], a2 = q2.v[i];
+      const float o1 = (m2.v[i] * m1.v[i]) * (NXX.v[i] + NYY.v[i] + NZZ.v[i] -
+                                             3.0f * ((a0 * a0 * NXX.v[i] + a1 * a1 * NYY.v[i] + a2 * a2 * NZZ.v[i]) +
+                                                     a0 * a1 * NXY.v[i] + a0 * a2 * NZX.v[i] + a1 * a2 * NYZ.v[i]));
+      omega.v[i] += o1;
     }
   }
-#undef LN
-  return omega;
+  if (order < 2) return;
+  {
+    const Lanes4 NXXX = row4(&n.d[R_NXXX]), NYYY = row4(&n.d[R_NYYY]), NZZZ = row4(&n.d[R_NZZZ]), SP = row4(&n.d[R_SUMPERM]);
+    const Lanes4 XXY = row4(&n.d[R_2NXXY_NYXX]), XXZ = row4(&n.d[R_2NXXZ_NZXX]), YYZ = row4(&n.d[R_2NYYZ_NZYY]);
+    const Lanes4 YYX = row4(&n.d[R_2NYYX_NXYY]), ZZX = row4(&n.d[R_2NZZX_NXZZ]), ZZY = row4(&n.d[R_2NZZY_NYZZ]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a0 = q0.v[i], a1 = q1.v[i], a2 = q2.v[i];
+      const float s0 = a0 * a0, s1 = a1 * a1, s2 = a2 * a2;
+      const float t00 = YYX.v[i] + ZZX.v[i], t01 = ZZY.v[i] + XXY.v[i], t02 = XXZ.v[i] + YYZ.v[i];
+      const float t10 = a1 * XXY.v[i] + a2 * XXZ.v[i];
+      const float t11 = a2 * YYZ.v[i] + a0 * YYX.v[i];
+      const float t12 = a0 * ZZX.v[i] + a1 * ZZY.v[i];
+      const float o2 = (m2.v[i] * m2.v[i]) *
+                       (1.5f * (a0 * (3.f * NXXX.v[i] + t00) + a1 * (3.f * NYYY.v[i] + t01) + a2 * (3.f * NZZZ.v[i] + t02)) -
+                        7.5f * ((s0 * a0 * NXXX.v[i] + s1 * a1 * NYYY.v[i] + s2 * a2 * NZZZ.v[i]) + a0 * a1 * a2 * SP.v[i] +
+                                (s0 * t10 + s1 * t11 + s2 * t12)));
+      omega.v[i] += o2;
+    }
+  }
 }
 
 DEVFN bool finite_f(float x) { return (plat::f2u(x) & 0x7F800000u) != 0x7F800000u; }
@@ -327,18 +354,27 @@ DEVFN float winding_solid_angle(const FwnNode *nodes, const float4 *tri32, float
     const uint32_t ni = stack[--sp];
     const FwnNode &n = nodes[ni];
     if (visits) visits[0]++;
-    const float4 R2 = n.d[R_MAXP2], PX = n.d[R_PX], PY = n.d[R_PY], PZ = n.d[R_PZ];
+    const Lanes4 R2 = row4(&n.d[R_MAXP2]), PX = row4(&n.d[R_PX]), PY = row4(&n.d[R_PY]), PZ = row4(&n.d[R_PZ]);
     const uint4 chv = n.child;
     const uint32_t ch[4] = {chv.x, chv.y, chv.z, chv.w};
     uint32_t descend = 0;
     float node_sum = 0.f;
+    Lanes4 q0, q1, q2, ql2;
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float q0 = fsub(qx, ((const float *)&PX)[i]), q1 = fsub(qy, ((const float *)&PY)[i]), q2 = fsub(qz, ((const float *)&PZ)[i]);
-      const float ql2 = plat::fadd(plat::fadd(plat::fmul(q0, q0), plat::fmul(q1, q1)), plat::fmul(q2, q2));
-      if (ql2 <= plat::fmul(((const float *)&R2)[i], acc2)) { descend |= 1u << i; continue; }
-      const float om = lane_omega(n, i, q0, q1, q2, ql2, order);
-      if (!finite_f(om)) { descend |= 1u << i; continue; }
-      node_sum += om;
+      q0.v[i] = fsub(qx, PX.v[i]); q1.v[i] = fsub(qy, PY.v[i]); q2.v[i] = fsub(qz, PZ.v[i]);
+      ql2.v[i] = plat::fadd(plat::fadd(plat::fmul(q0.v[i], q0.v[i]), plat::fmul(q1.v[i], q1.v[i])), plat::fmul(q2.v[i], q2.v[i]));
+      if (ql2.v[i] <= plat::fmul(R2.v[i], acc2)) descend |= 1u << i;   // absent lanes have R2 = +inf
+    }
+    if (descend != 0xFu) {   // :7194-7198: nothing to approximate when all four descend
+      Lanes4 om;
+      node_omega4(n, q0, q1, q2, ql2, order, om);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if ((descend >> i) & 1u) continue;
+        if (!finite_f(om.v[i])) descend |= 1u << i;   // :7249-7251
+        else node_sum += om.v[i];
+      }
     }
     sum += node_sum;
     // children in lane order; push in reverse so that lane 0 pops first
