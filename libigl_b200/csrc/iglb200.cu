@@ -219,11 +219,25 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
       const CpNode n = *np;
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
       const uint32_t imask = n.pad.x, tmask = n.pad.y;
+#ifndef CP_PREFETCH
+#define CP_PREFETCH 0   // measured: the extra instructions cost more than the L1 misses they save
+#endif
+#if CP_PREFETCH == 1
       // lanes 0..3 start pulling "their" child (node or face record) into L1
       if (lane < 4 && ((imask | tmask) >> lane) & 1u) {
         const uint32_t c = lane == 0 ? ch[0] : lane == 1 ? ch[1] : lane == 2 ? ch[2] : ch[3];
         prefetch_l1((c & INTERNAL_BIT) ? (const void *)(a.nodes + (c & ~INTERNAL_BIT)) : (const void *)(a.triq + TRIQ_STRIDE * (size_t)c));
       }
+#elif CP_PREFETCH == 2
+      if (lane < 16) {   // lane = 4*sector + child
+        const int j = lane & 3, sec = lane >> 2;
+        if (((imask | tmask) >> j) & 1u) {
+          const uint32_t c = j == 0 ? ch[0] : j == 1 ? ch[1] : j == 2 ? ch[2] : ch[3];
+          if (c & INTERNAL_BIT) prefetch_l1((const char *)(a.nodes + (c & ~INTERNAL_BIT)) + 32 * sec);
+          else if (sec < 2) prefetch_l1((const char *)(a.triq + TRIQ_STRIDE * (size_t)c) + 32 * sec);
+        }
+      }
+#endif
       float d2[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) d2[i] = lane_box_d2(n, i, L);
