@@ -98,7 +98,7 @@ DEVFN void closest_store(const ClosestArgs &a, int64_t i, const fwn::CpResult &r
 // Host emulation of one warp: identical control flow, lanes looped.
 void closest_packet_emul(const ClosestArgs &a, int64_t base) {
   using namespace fwn;
-  static thread_local CpStackEntry stack[CP_STACK];
+  static thread_local uint32_t stack[CP_STACK];
   CpLane L[32]; CpExact X[32]; CpQueryRef qr[32]; bool valid[32]; int64_t qi[32];
   for (int l = 0; l < 32; ++l) {
     const int64_t t = base + l;
@@ -114,11 +114,7 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     if (!have) {
       if (sp == 0) break;
       --sp;
-      const CpStackEntry &e = stack[sp];
-      bool any = false;
-      for (int l = 0; l < 32; ++l) any |= box6_d2(e.box, L[l]) <= L[l].thr2;
-      if (!any) continue;
-      cur = e.node;
+      cur = stack[sp];
     }
     have = false; ++nvis;
     const CpNode n = a.nodes[cur];
@@ -154,10 +150,7 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
       if (sp + npush > CP_STACK) throw std::runtime_error("closest-point stack overflow");
       for (int j = 0; j < 4; ++j) {
         if (!((push >> j) & 1u)) continue;
-        CpStackEntry &e = stack[sp + __builtin_popcount(push & ((1u << j) - 1u))];
-        const float *nbx = (const float *)&n;
-        for (int k = 0; k < 6; ++k) e.box[k] = nbx[4 * k + j];
-        e.node = ch[j] & ~INTERNAL_BIT;
+        stack[sp + __builtin_popcount(push & ((1u << j) - 1u))] = ch[j] & ~INTERNAL_BIT;
       }
       sp += npush;
       cur = ch[nb] & ~INTERNAL_BIT; have = true;
@@ -185,16 +178,19 @@ DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" 
 // One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
+#ifndef CP_WARPS
+#define CP_WARPS 4
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
+__global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
   using namespace fwn;
   constexpr unsigned FULL = 0xFFFFFFFFu;
-  __shared__ CpStackEntry stacks[4][CP_STACK];
-  __shared__ CpExact exact[128];
+  __shared__ uint32_t stacks[CP_WARPS][CP_STACK];
+  __shared__ CpExact exact[32 * CP_WARPS];
   CpExact &X = exact[threadIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  CpStackEntry *stack = stacks[warp];
-  for (int64_t base = ((int64_t)blockIdx.x * 4 + warp) * 32; base < a.n; base += (int64_t)gridDim.x * 128) {
+  uint32_t *stack = stacks[warp];
+  for (int64_t base = ((int64_t)blockIdx.x * CP_WARPS + warp) * 32; base < a.n; base += (int64_t)gridDim.x * (32 * CP_WARPS)) {
     const int64_t t = base + lane;
     const bool valid = t < a.n;
     const int64_t qi = valid ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
@@ -208,10 +204,9 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
       if (!have) {
         if (sp == 0) break;
         --sp;
-        const CpStackEntry &e = stack[sp];
-        const bool w = box6_d2(e.box, L) <= L.thr2;
-        if (!__any_sync(FULL, w)) continue;
-        cur = e.node;
+        // no re-test against the tightened bounds here: measured slower than simply visiting the
+        // node (its four box tests reject it just as well)
+        cur = stack[sp];
       }
       have = false;
       if (COUNT) ++nvis;
@@ -277,19 +272,9 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) closest_packet_kernel(Clos
           const int npush = __popc(push);
           if (sp + npush > CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); }
           else if (push) {
-            // 24 lanes copy the 6x4 box floats of this node; lane t holds float t = 4*k + j (plane k, child j)
-            if (lane < 24) {
-              const int j = lane & 3, k = lane >> 2;
-              if ((push >> j) & 1u) {
-                const float v = ((const float *)np)[lane];
-                stack[sp + __popc(push & ((1u << j) - 1u))].box[k] = v;
-              }
-            } else if (lane < 28) {
-              const int j = lane & 3;
-              if ((push >> j) & 1u) {
-                const uint32_t c = j == 0 ? ch[0] : j == 1 ? ch[1] : j == 2 ? ch[2] : ch[3];
-                stack[sp + __popc(push & ((1u << j) - 1u))].node = c & ~INTERNAL_BIT;
-              }
+            if (lane < 4 && ((push >> lane) & 1u)) {
+              const uint32_t c = lane == 0 ? ch[0] : lane == 1 ? ch[1] : lane == 2 ? ch[2] : ch[3];
+              stack[sp + __popc(push & ((1u << lane) - 1u))] = c & ~INTERNAL_BIT;
             }
             sp += npush;
           }
@@ -325,9 +310,9 @@ void throw_if_overflow(stream_t s) {
 void launch_closest(const ClosestArgs &a, stream_t s) {
   if (a.n <= 0) return;
   const int64_t warps = (a.n + 31) / 32;
-  const int64_t blocks = std::min<int64_t>((warps + 3) / 4, (int64_t)plat::sm_count() * 64);
-  if (a.counters) closest_packet_kernel<true><<<(unsigned)blocks, 128, 0, s>>>(a, overflow_flag());
-  else closest_packet_kernel<false><<<(unsigned)blocks, 128, 0, s>>>(a, overflow_flag());
+  const int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)plat::sm_count() * 64);
+  if (a.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
+  else closest_packet_kernel<false><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }

@@ -99,7 +99,10 @@ struct CpResult {
 #ifndef CP_KAPPA0
 #define CP_KAPPA0 48.0
 #endif
-static constexpr int CP_NCAND = 3;
+#ifndef CP_NCAND_N
+#define CP_NCAND_N 3
+#endif
+static constexpr int CP_NCAND = CP_NCAND_N;
 
 // |d32 - d| <= CP_KAPPA0 * u,  u = 2^-24 * max(|p|, |mesh|): the frame is exact to fp32 rounding
 // whatever the face's shape (no aspect-ratio amplification), the origin is off by < 1 ulp.
@@ -248,16 +251,12 @@ DEVFN float lane_box_d2(const CpNode &n, int i, const CpLane &L) {
   return box_lb2(((const float *)&n.lox)[i], ((const float *)&n.loy)[i], ((const float *)&n.loz)[i],
                  ((const float *)&n.hix)[i], ((const float *)&n.hiy)[i], ((const float *)&n.hiz)[i], L);
 }
-DEVFN float box6_d2(const float *b, const CpLane &L) {  // b = lo xyz, hi xyz
-  return box_lb2(b[0], b[1], b[2], b[3], b[4], b[5], L);
-}
 
 // The walk itself is a PACKET traversal: the 32 queries of a warp (neighbours in
 // Morton order) share one stack and visit a node when ANY of them still needs it,
 // so every box and face test runs on all 32 lanes at once (iglb200.cu:
 // closest_packet_kernel; host emulation: closest_packet_emul).
-static constexpr int CP_STACK = 128;   // entries per warp: node id + the node's own box
-struct CpStackEntry { float box[6]; uint32_t node; uint32_t pad; };
+static constexpr int CP_STACK = 192;   // node ids per warp (3 per level at most)
 
 // ---------------------------------------------------------------------------
 // UTsignedSolidAngleTri (FastWindingNumberForSoups.h:6070-6110), un-fused fp32
