@@ -27,7 +27,7 @@ DEVFN float f_up(double d) { float f = (float)d; if ((double)f < d) f = std::nex
 DEVFN float rcp_fast(float x) { return 1.0f / x; }
 DEVFN float sqrt_fast(float x) { return std::sqrt(x); }
 #else
-// 1-2 ulp approximations (single MUFU op); their error is covered by CP_KAPPA0
+// 1-2 ulp approximations (single MUFU op); their error is covered by CP_KAPPA_W
 DEVFN float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 DEVFN float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 DEVFN double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -96,16 +96,23 @@ struct CpResult {
 // on exact ties.  The result is therefore exactly what an all-fp64 search
 // returns.
 // ---------------------------------------------------------------------------
-#ifndef CP_KAPPA0
-#define CP_KAPPA0 48.0
+#ifndef CP_KAPPA_W
+#define CP_KAPPA_W 24.0
+#endif
+#ifndef CP_KAPPA_IN
+#define CP_KAPPA_IN 4.0
 #endif
 #ifndef CP_NCAND_N
 #define CP_NCAND_N 3
 #endif
 static constexpr int CP_NCAND = CP_NCAND_N;
 
-// |d32 - d| <= CP_KAPPA0 * u,  u = 2^-24 * max(|p|, |mesh|): the frame is exact to fp32 rounding
-// whatever the face's shape (no aspect-ratio amplification), the origin is off by < 1 ulp.
+// Error bound |d32 - d| <= err, shape independent (no aspect-ratio amplification):
+//   input rounding   (float)p and (float)origin move the configuration by <= 2*sqrt(3)*u, u = 2^-24*max(|p|,|mesh|)
+//   everything else  is relative to w = p - origin: rounding of w (1.7), of the frame vectors (1.7), of the
+//                    three dot products (5.2), of the 2-D edge distances (~6), approximate rcp/sqrt (~4)
+//                    => < 19 * 2^-24 * |w|
+// err = CP_KAPPA_W * 2^-24 * (|x|+|y|+|z|) + CP_KAPPA_IN * u   with (|x|+|y|+|z|) >= |w|.
 DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, const float4 Q3, float px, float py, float pz,
                          float u, float &err) {
   const float wx = px - Q0.x, wy = py - Q0.y, wz = pz - Q0.z;
@@ -128,7 +135,7 @@ DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, cons
   // inside the face (proper triangles only)
   const bool inside = (cy > 0.f) && (y >= 0.f) && (cy * x - cx * y >= 0.f) && (ex * y - cy * xl >= 0.f);
   d2 = inside ? 0.f : d2;
-  err = (float)CP_KAPPA0 * u;
+  err = (float)(CP_KAPPA_W * 5.9604644775390625e-08) * (fabsf(x) + fabsf(y) + fabsf(z)) + (float)CP_KAPPA_IN * u;
 #ifdef CP_ERR_SCALE   // test hook: shrink the band to probe how much margin the bound has
   err *= (float)CP_ERR_SCALE;
 #endif
