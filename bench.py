@@ -293,8 +293,14 @@ def ours(args):
         t_dom = kernel_ms[dom] * 1e-3
         alg_bytes = BYTES_PER_QUERY * nq + info["device_bytes"]   # per launch: query I/O + one read of the tree
         ach = alg_bytes / t_dom / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if dom == "closest" and os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("queries") == nq and tj.get("faces") == int(F.shape[0]):
+                traffic = tj["dram_bytes_per_launch"]   # ncu --set full capture of this kernel on this workload
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": int(alg_bytes),
                 "launch_ms": kernel_ms[dom],
                 "note": "not HBM bound: arithmetic intensity ~1e3 flop/B; see fp32 below and DESIGN.md"}
 
