@@ -331,3 +331,41 @@ def case_golden_fixtures(api):
         assert c.info()["n_cells"] == int(g[f"ncells_order{order}"])
         assert np.abs(c.eval(g["Q"], 2.0) - g[f"WN_order{order}"]).max() < 1e-12
         c.close()
+
+
+def _soup_at(rng, centers, size):
+    n = len(centers)
+    a, b, c = (centers + rng.normal(0, size, (n, 3)) for _ in range(3))
+    return np.concatenate([a, b, c]), np.stack([np.arange(n), np.arange(n) + n, np.arange(n) + 2 * n], 1).astype(np.int32)
+
+
+def case_builder_corner_paths(api):
+    """Builder paths natural meshes rarely reach, each against the genuine reference tree:
+    no admissible plane (a cluster plus far outliers: all boxes in one of the 16 spans) -> the
+    quick-select fallback (FastWindingNumberForSoups.h:5708-5754); centre-sorted and reverse-sorted
+    inputs (long chains in the closed-form partition); NaN/Inf vertices (boxes excluded, :4606-4615)."""
+    rng = np.random.default_rng(3)
+    for ncl, nout in ((500, 1), (2000, 3), (300, 40)):
+        cen = np.concatenate([rng.normal(0, 0.01, (ncl, 3)), rng.uniform(-100, 100, (nout, 3))])
+        V, F = _soup_at(rng, cen[rng.permutation(len(cen))], 0.002)
+        m = api.Mesh(V, F, 2)
+        parity.check_tree_against_reference(m, V, F, what=f"cluster {ncl} + {nout} outliers")
+        m.close()
+    for order in (1, -1):
+        x = np.linspace(0, 1, 3000)[::order]
+        V, F = _soup_at(rng, np.stack([x, 0.01 * np.sin(40 * x), 0 * x], 1), 0.0005)
+        m = api.Mesh(V, F, 2)
+        parity.check_tree_against_reference(m, V, F, what="sorted centres")
+        m.close()
+    V, F = synth.icosphere(2)
+    Vn = np.concatenate([V, [[np.nan, 0, 0], [np.inf, 1, 1], [0, 0, 0.5]]])
+    Fn = np.concatenate([F, [[len(V), 0, 1], [len(V) + 1, 2, 3], [4, len(V) + 2, 5]]]).astype(np.int32)
+    m = api.Mesh(Vn, Fn, 2)
+    assert m.info()["n_excluded"] == 2
+    ref = oracle.RefFwn(Vn, Fn)
+    a = m.download()
+    pr = parity.match_nodes(a["fwn_child"], ref.nodes())
+    assert pr is not None and len(pr) == len(ref.nodes())
+    Q = synth.random_points(500, -1.5, 1.5, 1)
+    assert np.abs(m.fast_winding_number(Q) - ref.winding(Q)).max() < 1e-5
+    m.close()

@@ -80,3 +80,7 @@ def test_cloud_vs_oracle(emul_api):
 
 def test_golden_fixtures(emul_api):
     cases.case_golden_fixtures(emul_api)
+
+
+def test_builder_corner_paths(emul_api):
+    cases.case_builder_corner_paths(emul_api)

@@ -148,3 +148,7 @@ def test_c4_cloud_reduced(gpu_api):
 
 def test_golden_fixtures(gpu_api):
     cases.case_golden_fixtures(gpu_api)
+
+
+def test_builder_corner_paths(gpu_api):
+    cases.case_builder_corner_paths(gpu_api)
