@@ -26,10 +26,12 @@ DEVFN float fsub(float a, float b) { return a - b; }
 DEVFN float f_up(double d) { float f = (float)d; if ((double)f < d) f = std::nextafterf(f, INFINITY); return f; }
 DEVFN float rcp_fast(float x) { return 1.0f / x; }
 DEVFN float sqrt_fast(float x) { return std::sqrt(x); }
+DEVFN float rsqrt_fast(float x) { return 1.0f / std::sqrt(x); }
 #else
 // 1-2 ulp approximations (single MUFU op); their error is covered by CP_KAPPA_W
 DEVFN float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 DEVFN float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DEVFN float rsqrt_fast(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 DEVFN double dmul(double a, double b) { return __dmul_rn(a, b); }
 DEVFN double dadd(double a, double b) { return __dadd_rn(a, b); }
 DEVFN double dsub(double a, double b) { return __dsub_rn(a, b); }
@@ -302,10 +304,12 @@ DEVFN Lanes4 row4(const float4 *p) { const float4 t = *p; return Lanes4{{t.x, t.
 
 DEVFN void node_omega4(const FwnNode &n, Lanes4 q0, Lanes4 q1, Lanes4 q2, const Lanes4 &ql2, int order, Lanes4 &omega) {
   Lanes4 m1, m2;
+  // 1/|q| by one MUFU op (<= 2 ulp): the polynomial below is an approximation with ~1e-3 truncation
+  // error anyway, and no branch depends on these values except the is-finite test
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    m2.v[i] = plat::fdiv(1.0f, ql2.v[i]);
-    m1.v[i] = plat::fsqrt(m2.v[i]);
+    m1.v[i] = rsqrt_fast(ql2.v[i]);
+    m2.v[i] = m1.v[i] * m1.v[i];
     q0.v[i] *= m1.v[i]; q1.v[i] *= m1.v[i]; q2.v[i] *= m1.v[i];
   }
   {

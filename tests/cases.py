@@ -101,7 +101,21 @@ def case_closest_vs_brute(api, V, F, P, what):
     m.close()
 
 
+def case_fwn_orders(api, V, F, Q):
+    """Taylor orders 0 and 1 (fast_winding_number(V,F,order,bvh), order < 2) against the genuine core."""
+    for order in (0, 1):
+        m = api.Mesh(V, F, order)
+        ref = oracle.RefFwn(V, F, order)
+        a = m.download()
+        pr = parity.match_nodes(a["fwn_child"], ref.nodes())
+        assert pr is not None
+        W, Wr = m.fast_winding_number(Q, 2.0), ref.winding(Q, 2.0)
+        assert np.abs(W - Wr).max() <= 1e-5, f"order {order}: {np.abs(W - Wr).max():.3e}"
+        m.close()
+
+
 def case_fwn(api, V, F, Q, what):
+    case_fwn_orders(api, V, F, Q[:2000])
     m = api.Mesh(V, F, 2)
     ref = oracle.RefFwn(V, F)
     for beta in (2.0, 1.0, 3.5):
