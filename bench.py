@@ -216,7 +216,7 @@ def ours(args):
 
     def step():
         api.check(api.lib.iglb200_signed_distance_dev(mesh.h, dP.data_ptr(), nq, 4, lower, upper, dS.data_ptr(),
-                                                      dI.data_ptr(), dC.data_ptr(), dW.data_ptr(), scratch.data_ptr(),
+                                                      dI.data_ptr(), dC.data_ptr(), dW.data_ptr(), None, scratch.data_ptr(),
                                                       int(args.sort), stream.cuda_stream))
 
     torch.cuda.synchronize()
@@ -260,7 +260,7 @@ def ours(args):
     def e2e_step():
         api.check(api.lib.iglb200_signed_distance(mesh.h, hP.data_ptr(), 1, nq, 1, nq, 4, lower, upper,
                                                   hS.data_ptr(), 1, hI.data_ptr(), hC.data_ptr(), 1, 1, nq,
-                                                  hW.data_ptr(), 1))
+                                                  hW.data_ptr(), 1, None, 1, 1, nq))
 
     e2e_step()
     torch.cuda.synchronize()

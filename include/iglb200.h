@@ -38,9 +38,9 @@ extern "C" {
 #define IGLB200_ERR_UNSUPPORTED (-4)
 #define IGLB200_ERR_INTERNAL (-5)
 
-/* igl::SignedDistanceType, signed_distance.h:20-34.  Only UNSIGNED and
- * FAST_WINDING_NUMBER are implemented; the others return
- * IGLB200_ERR_UNSUPPORTED (no silent fallback). */
+/* igl::SignedDistanceType, signed_distance.h:20-34.  UNSIGNED, FAST_WINDING_NUMBER and
+ * PSEUDONORMAL (mesh created with IGLB200_MESH_PSEUDONORMALS) are implemented;
+ * WINDING_NUMBER / DEFAULT return IGLB200_ERR_UNSUPPORTED (no silent fallback). */
 #define IGLB200_SIGN_PSEUDONORMAL 0
 #define IGLB200_SIGN_WINDING_NUMBER 1
 #define IGLB200_SIGN_DEFAULT 2
@@ -65,6 +65,12 @@ int iglb200_host_free(void *p);
 int iglb200_mesh_create(const void *V, int v_is_f64, int64_t nV, int64_t v_row_stride, int64_t v_col_stride,
                         const int32_t *F, int64_t nF, int64_t f_row_stride, int64_t f_col_stride,
                         int fwn_order, iglb200_mesh **out);
+/* flags: IGLB200_MESH_PSEUDONORMALS also precomputes face / angle-weighted vertex / uniform edge
+ * normals (signed_distance.cpp:68-76: per_face_normals, per_vertex_normals, per_edge_normals). */
+#define IGLB200_MESH_PSEUDONORMALS 1
+int iglb200_mesh_create_ex(const void *V, int v_is_f64, int64_t nV, int64_t v_row_stride, int64_t v_col_stride,
+                           const int32_t *F, int64_t nF, int64_t f_row_stride, int64_t f_col_stride,
+                           int fwn_order, int flags, iglb200_mesh **out);
 int iglb200_mesh_destroy(iglb200_mesh *m);
 /* info[0]=#faces, [1]=#tree nodes, [2]=#levels, [3]=device bytes, [4]=#faces excluded (NaN/Inf boxes) */
 int iglb200_mesh_info(const iglb200_mesh *m, int64_t info[8]);
@@ -85,16 +91,18 @@ int iglb200_mesh_from_arena(const void *device_ptr, uint64_t bytes, int copy, ig
 
 /* ---- igl::signed_distance(P,V,F,sign_type,lower,upper,S,I,C,N)
  *      signed_distance.h:61-89, signed_distance.cpp:28-139, 372-416.
- *      N is not written for these sign types (as in the reference).
+ *      N (optional, may be NULL) is written only for PSEUDONORMAL, as in the reference
+ *      (the normal the sign was taken from, signed_distance.cpp:125-131).
  *      W (optional, may be NULL) receives the winding number the sign was made
- *      from — an extension.  Out-of-bounds rows: S=NaN, I=#F+1, C=0, W=NaN
- *      (signed_distance.cpp:99-105).  #F==0: S=NaN, I=-1, C=NaN (:398-405). */
+ *      from — an extension (NaN for the other sign types).  Out-of-bounds rows: S=NaN, I=#F+1,
+ *      C=0, W=NaN, N=0 (signed_distance.cpp:99-105).  #F==0: S=NaN, I=-1, C=NaN, N=NaN (:398-405). */
 int iglb200_signed_distance(const iglb200_mesh *m,
                             const void *P, int p_is_f64, int64_t nP, int64_t p_row_stride, int64_t p_col_stride,
                             int sign_type, double lower_bound, double upper_bound,
                             void *S, int s_is_f64, int32_t *I,
                             void *C, int c_is_f64, int64_t c_row_stride, int64_t c_col_stride,
-                            void *W, int w_is_f64);
+                            void *W, int w_is_f64,
+                            void *N, int n_is_f64, int64_t n_row_stride, int64_t n_col_stride);
 
 /* ---- AABB::squared_distance(V,Ele,P,sqrD,I,C) batch, AABB.h:722-728,
  *      AABB.cpp:1241-1265; also point_mesh_squared_distance.h:54-60. */
@@ -118,7 +126,7 @@ int iglb200_fwn_eval(const iglb200_mesh *m,
 uint64_t iglb200_query_scratch_bytes(int64_t nP);
 int iglb200_signed_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP,
                                 int sign_type, double lower_bound, double upper_bound,
-                                double *S, int32_t *I, double *C, double *W,
+                                double *S, int32_t *I, double *C, double *W, double *N,
                                 void *scratch, int sort_queries, void *stream);
 int iglb200_squared_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP,
                                  double *sqrD, int32_t *I, double *C,

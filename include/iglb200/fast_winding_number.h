@@ -19,14 +19,14 @@ struct FastWindingNumberBVH {
 
 namespace detail {
 template <class DerivedV, class DerivedF>
-inline iglb200_mesh *make_mesh(const DerivedV &V, const DerivedF &F, int order) {
+inline iglb200_mesh *make_mesh(const DerivedV &V, const DerivedF &F, int order, int flags = 0) {
   static_assert(std::is_same<typename DerivedF::Scalar, int>::value || std::is_same<typename DerivedF::Scalar, int32_t>::value,
                 "iglb200: F must hold 32-bit ints");
   if (V.cols() != 3 || (F.rows() && F.cols() != 3)) throw Error(IGLB200_ERR_ARG, "iglb200: V must be #Vx3 and F #Fx3");
   auto v = view(V);
   iglb200_mesh *m = nullptr;
-  check(iglb200_mesh_create(v.ptr, v.is_f64, v.rows, v.rs, v.cs, (const int32_t *)F.data(), (int64_t)F.rows(),
-                            F.rows() ? row_stride(F) : 3, F.rows() ? col_stride(F) : 1, order, &m));
+  check(iglb200_mesh_create_ex(v.ptr, v.is_f64, v.rows, v.rs, v.cs, (const int32_t *)F.data(), (int64_t)F.rows(),
+                               F.rows() ? row_stride(F) : 3, F.rows() ? col_stride(F) : 1, order, flags, &m));
   return m;
 }
 }  // namespace detail

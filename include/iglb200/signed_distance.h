@@ -1,8 +1,8 @@
 // igl::signed_distance with the reference's Eigen signatures, computed on the GPU.
 //   /root/reference/include/igl/signed_distance.h:20-34 (enum), :61-89 and :91-110 (signed_distance),
 //   :283-312 (signed_distance_fast_winding_number); semantics signed_distance.cpp:28-139, 372-440.
-// Only SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER and _UNSIGNED run on the device; the other sign
-// types throw iglb200::Error(IGLB200_ERR_UNSUPPORTED) — there is no CPU fallback.
+// SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, _UNSIGNED and _PSEUDONORMAL run on the device;
+// _WINDING_NUMBER / _DEFAULT throw iglb200::Error(IGLB200_ERR_UNSUPPORTED) — there is no CPU fallback.
 #pragma once
 #include "AABB.h"
 
@@ -39,29 +39,32 @@ struct ScratchC {
   int64_t innerStride() const { return 1; }
   int64_t outerStride() const { return n; }
 };
-template <class DerivedP, class DerivedS, class DerivedI, class DerivedC, class DerivedW>
+template <class DerivedP, class DerivedS, class DerivedI, class DerivedC, class DerivedW, class DerivedN = ScratchC>
 inline void sd_query(const iglb200_mesh *mesh, const DerivedP &P, int sign_type, double lower, double upper, DerivedS &S, DerivedI &I,
-                     DerivedC &C, DerivedW *W) {
+                     DerivedC &C, DerivedW *W, DerivedN *N = nullptr) {
   static_assert(sizeof(typename DerivedI::Scalar) == 4, "iglb200: I must hold 32-bit ints");
   S.resize(P.rows(), 1);
   I.resize(P.rows(), 1);
   C.resize(P.rows(), 3);
   if (W) W->resize(P.rows(), 1);
+  if (N) N->resize(P.rows(), 3);
   auto p = view(P);
   auto c = view(C);
+  int64_t nrs = 1, ncs = 1; int nf64 = 1; void *nptr = nullptr;
+  if (N) { auto nv = view(*N); nrs = nv.rs; ncs = nv.cs; nf64 = nv.is_f64; nptr = (void *)N->data(); }
   check(iglb200_signed_distance(mesh, p.ptr, p.is_f64, p.rows, p.rs, p.cs, sign_type, lower, upper, (void *)S.data(),
                                 std::is_same<typename DerivedS::Scalar, double>::value ? 1 : 0, (int32_t *)I.data(), (void *)C.data(),
                                 c.is_f64, c.rs, c.cs, W ? (void *)W->data() : nullptr,
-                                W ? (std::is_same<typename DerivedW::Scalar, double>::value ? 1 : 0) : 1));
+                                W ? (std::is_same<typename DerivedW::Scalar, double>::value ? 1 : 0) : 1, nptr, nf64, nrs, ncs));
 }
 }  // namespace detail
 
-// signed_distance(P,V,F,sign_type,lower_bound,upper_bound,S,I,C,N).  N is left untouched for the
-// supported sign types, exactly as the reference does (only PSEUDONORMAL writes it, signed_distance.cpp:75).
+// signed_distance(P,V,F,sign_type,lower_bound,upper_bound,S,I,C,N).  N is written only for
+// PSEUDONORMAL and left untouched otherwise, exactly as the reference does (signed_distance.cpp:75).
 template <class DerivedP, class DerivedV, class DerivedF, class DerivedS, class DerivedI, class DerivedC, class DerivedN>
 inline void signed_distance(const DerivedP &P, const DerivedV &V, const DerivedF &F, const SignedDistanceType sign_type,
                             const typename DerivedV::Scalar lower_bound, const typename DerivedV::Scalar upper_bound, DerivedS &S,
-                            DerivedI &I, DerivedC &C, DerivedN & /*N*/) {
+                            DerivedI &I, DerivedC &C, DerivedN &N) {
   if (F.rows() == 0) {  // signed_distance.cpp:398-405
     S.resize(P.rows(), 1); I.resize(P.rows(), 1); C.resize(P.rows(), 3);
     for (int64_t i = 0; i < (int64_t)P.rows(); ++i) {
@@ -71,10 +74,11 @@ inline void signed_distance(const DerivedP &P, const DerivedV &V, const DerivedF
     }
     return;
   }
-  iglb200_mesh *m = detail::make_mesh(V, F, 2);
+  const bool pseudo = sign_type == SIGNED_DISTANCE_TYPE_PSEUDONORMAL;
+  iglb200_mesh *m = detail::make_mesh(V, F, 2, pseudo ? IGLB200_MESH_PSEUDONORMALS : 0);
   try {
-    detail::sd_query<DerivedP, DerivedS, DerivedI, DerivedC, DerivedS>(m, P, (int)sign_type, (double)lower_bound, (double)upper_bound, S, I,
-                                                                     C, nullptr);
+    detail::sd_query<DerivedP, DerivedS, DerivedI, DerivedC, DerivedS, DerivedN>(m, P, (int)sign_type, (double)lower_bound,
+                                                                               (double)upper_bound, S, I, C, nullptr, pseudo ? &N : nullptr);
   } catch (...) { iglb200_mesh_destroy(m); throw; }
   iglb200_mesh_destroy(m);
 }

@@ -57,7 +57,7 @@ class Api:
     SYMBOLS = [
         "iglb200_last_error", "iglb200_version", "iglb200_device_count", "iglb200_set_device",
         "iglb200_host_alloc", "iglb200_host_free",
-        "iglb200_mesh_create", "iglb200_mesh_destroy", "iglb200_mesh_info", "iglb200_mesh_build_ms",
+        "iglb200_mesh_create", "iglb200_mesh_create_ex", "iglb200_mesh_destroy", "iglb200_mesh_info", "iglb200_mesh_build_ms",
         "iglb200_mesh_arena", "iglb200_mesh_arena_download", "iglb200_mesh_from_arena",
         "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
         "iglb200_query_scratch_bytes", "iglb200_signed_distance_dev", "iglb200_squared_distance_dev",
@@ -76,6 +76,7 @@ class Api:
         L.iglb200_host_alloc.argtypes = [C.POINTER(_vp), C.c_uint64]
         L.iglb200_host_free.argtypes = [_vp]
         L.iglb200_mesh_create.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, C.POINTER(_vp)]
+        L.iglb200_mesh_create_ex.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, C.POINTER(_vp)]
         L.iglb200_mesh_destroy.argtypes = [_vp]
         L.iglb200_mesh_info.argtypes = [_vp, C.POINTER(_i64)]
         L.iglb200_mesh_build_ms.argtypes = [_vp]
@@ -84,12 +85,12 @@ class Api:
         L.iglb200_mesh_arena_download.argtypes = [_vp, _vp, C.c_uint64]
         L.iglb200_mesh_from_arena.argtypes = [_vp, C.c_uint64, _int, C.POINTER(_vp)]
         L.iglb200_signed_distance.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _int, _dbl, _dbl,
-                                              _vp, _int, _vp, _vp, _int, _i64, _i64, _vp, _int]
+                                              _vp, _int, _vp, _vp, _int, _i64, _i64, _vp, _int, _vp, _int, _i64, _i64]
         L.iglb200_squared_distance.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _int, _i64, _i64]
         L.iglb200_fwn_eval.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, C.c_float, _vp, _int]
         L.iglb200_query_scratch_bytes.argtypes = [_i64]
         L.iglb200_query_scratch_bytes.restype = C.c_uint64
-        L.iglb200_signed_distance_dev.argtypes = [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _int, _vp]
+        L.iglb200_signed_distance_dev.argtypes = [_vp, _vp, _i64, _int, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]
         L.iglb200_squared_distance_dev.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _vp]
         L.iglb200_fwn_eval_dev.argtypes = [_vp, _vp, _i64, C.c_float, _vp, _vp, _int, _vp]
         L.iglb200_debug_visit_counts.argtypes = [_vp, _vp, _i64, C.POINTER(_dbl)]
@@ -134,8 +135,8 @@ class Api:
         return out
 
     # -- handles ----------------------------------------------------------
-    def Mesh(self, V, F, order=2):
-        return Mesh(self, V, F, order)
+    def Mesh(self, V, F, order=2, pseudonormals=False):
+        return Mesh(self, V, F, order, pseudonormals=pseudonormals)
 
     def Cloud(self, P, N, A, order=2):
         return Cloud(self, P, N, A, order)
@@ -143,14 +144,17 @@ class Api:
     # -- reference-named free functions -------------------------------------
     def signed_distance(self, P, V, F, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER,
                         lower_bound=None, upper_bound=None, return_W=False):
-        """igl::signed_distance: returns S, I, C (and W if asked).  N is not produced for
-        the supported sign types, exactly as in the reference."""
+        """igl::signed_distance: returns S, I, C (+ N for PSEUDONORMAL, the only sign type that
+        writes it in the reference; + W if asked)."""
         F = np.asarray(F)
+        pseudo = int(sign_type) == SIGNED_DISTANCE_TYPE_PSEUDONORMAL
         if F.shape[0] == 0:  # signed_distance.cpp:398-405
             n = np.asarray(P).shape[0]
             out = (np.full(n, np.nan), np.full(n, -1, np.int32), np.full((n, 3), np.nan))
+            if pseudo:
+                out = out + (np.full((n, 3), np.nan),)
             return out + (np.full(n, np.nan),) if return_W else out
-        m = Mesh(self, V, F, 2)
+        m = Mesh(self, V, F, 2, pseudonormals=pseudo)
         try:
             return m.signed_distance(P, sign_type, lower_bound, upper_bound, return_W)
         finally:
@@ -188,7 +192,7 @@ class Api:
 class Mesh:
     """AABB<MatrixXd,3> + FastWindingNumberBVH built on the device (one handle)."""
 
-    def __init__(self, api: Api, V, F, order=2, _handle=None):
+    def __init__(self, api: Api, V, F, order=2, _handle=None, pseudonormals=False):
         self.api = api
         self.h = _vp()
         if _handle is not None:
@@ -202,9 +206,9 @@ class Mesh:
             F = F.astype(np.int32)
         if F.shape[0] and (F.strides[0] <= 0 or F.strides[1] <= 0):
             F = np.ascontiguousarray(F)
-        api.check(api.lib.iglb200_mesh_create(vp, vf64, nV, vrs, vcs, F.ctypes.data_as(_vp), F.shape[0],
-                                              F.strides[0] // 4 if F.shape[0] else 3, F.strides[1] // 4 if F.shape[0] else 1,
-                                              int(order), C.byref(self.h)))
+        api.check(api.lib.iglb200_mesh_create_ex(vp, vf64, nV, vrs, vcs, F.ctypes.data_as(_vp), F.shape[0],
+                                                 F.strides[0] // 4 if F.shape[0] else 3, F.strides[1] // 4 if F.shape[0] else 1,
+                                                 int(order), 1 if pseudonormals else 0, C.byref(self.h)))
 
     def close(self):
         if self.h:
@@ -217,6 +221,7 @@ class Mesh:
         a = (_i64 * 8)()
         self.api.check(self.api.lib.iglb200_mesh_info(self.h, a))
         return dict(n_faces=a[0], n_nodes=a[1], n_levels=a[2], device_bytes=a[3], n_excluded=a[4], order=a[5],
+                    pseudonormals=bool(a[6]),
                     build_ms=float(self.api.lib.iglb200_mesh_build_ms(self.h)))
 
     def arena(self):
@@ -257,11 +262,15 @@ class Mesh:
         I = np.empty(n, np.int32)
         Cc = np.empty((n, 3), np.float64, order="F")
         W = np.empty(n, np.float64) if return_W else None
+        pseudo = int(sign_type) == SIGNED_DISTANCE_TYPE_PSEUDONORMAL
+        N = np.empty((n, 3), np.float64, order="F") if pseudo else None
         self.api.check(self.api.lib.iglb200_signed_distance(
             self.h, pp, pf64, n, prs, pcs, int(sign_type), float(lower_bound), float(upper_bound),
             S.ctypes.data_as(_vp), 1, I.ctypes.data_as(_vp), Cc.ctypes.data_as(_vp), 1, 1, max(n, 1),
-            W.ctypes.data_as(_vp) if return_W else None, 1))
-        return (S, I, Cc, W) if return_W else (S, I, Cc)
+            W.ctypes.data_as(_vp) if return_W else None, 1,
+            N.ctypes.data_as(_vp) if pseudo else None, 1, 1, max(n, 1)))
+        out = (S, I, Cc, N) if pseudo else (S, I, Cc)
+        return out + (W,) if return_W else out
 
     # igl::signed_distance_fast_winding_number(P,V,F,tree,fwn_bvh,S): S only
     def signed_distance_fast_winding_number(self, P):
@@ -343,7 +352,7 @@ def parse_arena(buf: np.ndarray):
                     ("nlevels", "<i8"), ("nexcluded", "<i8"), ("order", "<i4"), ("pad", "<i4"),
                     ("bbox_lo", "<f8", 3), ("bbox_hi", "<f8", 3), ("absmax", "<f4"), ("padf", "<f4"),
                     ("off_tri64", "<u8"), ("off_tri32", "<u8"), ("off_fnodes", "<u8"), ("off_cnodes", "<u8"),
-                    ("off_triq", "<u8"), ("reserved", "<u8", 7)])
+                    ("off_triq", "<u8"), ("off_pn", "<u8"), ("reserved", "<u8", 6)])
     h = buf[:hdr.itemsize].view(hdr)[0]
     nF, nn = int(h["nF"]), int(h["nnodes"])
     tri64 = buf[int(h["off_tri64"]):int(h["off_tri64"]) + 72 * nF].view(np.float64).reshape(nF, 3, 3)
@@ -354,4 +363,8 @@ def parse_arena(buf: np.ndarray):
     cn = buf[int(h["off_cnodes"]):int(h["off_cnodes"]) + 128 * nn]
     cbox = cn.view(np.float32).reshape(nn, 32)[:, :24].reshape(nn, 6, 4).copy()
     cchild = cn.view(np.uint32).reshape(nn, 32)[:, 24:28].copy()
-    return dict(header=h, tri64=tri64, tri32=tri32, fwn_child=fchild, fwn_data=fdata, cp_box=cbox, cp_child=cchild)
+    pn = None
+    if int(h["off_pn"]):
+        pn = buf[int(h["off_pn"]):int(h["off_pn"]) + 168 * nF].view(np.float64).reshape(nF, 7, 3).copy()
+    return dict(header=h, tri64=tri64, tri32=tri32, fwn_child=fchild, fwn_data=fdata, cp_box=cbox, cp_child=cchild,
+                pseudonormals=pn)

@@ -88,10 +88,103 @@ template <class VT> struct GatherFaces {
   }
 };
 
+// ---- pseudonormals (SIGNED_DISTANCE_TYPE_PSEUDONORMAL): per_face_normals.cpp:14-37,
+// internal_angles.cpp:13-43, per_vertex_normals.cpp:40-104 (ANGLE), per_edge_normals.cpp:24-76 (UNIFORM).
+// Sums run in the reference's order (faces by index) so the normals come out bit-identical:
+// corners / half-edges are stably radix-sorted by vertex / undirected-edge key and each group is
+// summed sequentially by the thread that finds its head.
+static constexpr int PN_STRIDE = 21;
+
+struct FaceNormalAngles {
+  const double *tri64; double *pn; double *ang;  // ang: 3 per face
+  DEVFN void operator()(int64_t f) const {
+    const double *t = tri64 + 9 * f;
+    const double v1[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, v2[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
+    const double n[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+    const double r = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int d = 0; d < 3; ++d) pn[PN_STRIDE * f + d] = (r == 0) ? 0.0 : n[d] / r;
+    for (int j = 0; j < 3; ++j) {
+      const double *x = t + 3 * ((j + 2) % 3), *y = t + 3 * j, *z = t + 3 * ((j + 1) % 3);
+      double a1[3], a2[3];
+      for (int d = 0; d < 3; ++d) { a1[d] = x[d] - y[d]; a2[d] = z[d] - y[d]; }
+      const double n1 = sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), n2 = sqrt(a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2]);
+      double u[3], w[3];
+      for (int d = 0; d < 3; ++d) { u[d] = a1[d] / n1 - a2[d] / n2; w[d] = a1[d] / n1 + a2[d] / n2; }
+      ang[3 * f + j] = 2.0 * atan(sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) / sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
+    }
+  }
+};
+struct CornerKeys {  // corner c = 3f+j: vertex key (32 bit) and undirected-edge key (64 bit, the edge opposite corner j)
+  const int32_t *F; int64_t f_rs, f_cs;
+  uint32_t *vkey, *val; uint64_t *ekey;
+  DEVFN void operator()(int64_t c) const {
+    const int64_t f = c / 3; const int j = (int)(c % 3);
+    vkey[c] = (uint32_t)F[f * f_rs + j * f_cs];
+    const uint64_t a = (uint32_t)F[f * f_rs + ((j + 1) % 3) * f_cs], b = (uint32_t)F[f * f_rs + ((j + 2) % 3) * f_cs];
+    ekey[c] = ((a < b ? a : b) << 32) | (a < b ? b : a);
+    val[c] = (uint32_t)c;
+  }
+};
+DEVFN void pn_normalize(double *v) {
+  const double z = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  if (z > 0) { const double r = sqrt(z); v[0] /= r; v[1] /= r; v[2] /= r; }
+}
+struct VertexNormals {  // one thread per sorted corner; group heads do the (ordered) sum
+  const uint32_t *key, *val; int64_t n; const double *ang; double *pn;
+  DEVFN void operator()(int64_t i) const {
+    if (i > 0 && key[i - 1] == key[i]) return;
+    double acc[3] = {0, 0, 0};
+    int64_t j = i;
+    for (; j < n && key[j] == key[i]; ++j) {
+      const uint32_t c = val[j];
+      const double w = ang[c];
+      for (int d = 0; d < 3; ++d) acc[d] += w * pn[PN_STRIDE * (int64_t)(c / 3) + d];
+    }
+    pn_normalize(acc);
+    for (int64_t k = i; k < j; ++k) { const uint32_t c = val[k]; for (int d = 0; d < 3; ++d) pn[PN_STRIDE * (int64_t)(c / 3) + 3 + 3 * (c % 3) + d] = acc[d]; }
+  }
+};
+struct EdgeNormals {
+  const uint64_t *key; const uint32_t *val; int64_t n; double *pn;
+  DEVFN void operator()(int64_t i) const {
+    if (i > 0 && key[i - 1] == key[i]) return;
+    double acc[3] = {0, 0, 0};
+    int64_t j = i;
+    for (; j < n && key[j] == key[i]; ++j) { const uint32_t c = val[j]; for (int d = 0; d < 3; ++d) acc[d] += pn[PN_STRIDE * (int64_t)(c / 3) + d]; }
+    pn_normalize(acc);
+    for (int64_t k = i; k < j; ++k) { const uint32_t c = val[k]; for (int d = 0; d < 3; ++d) pn[PN_STRIDE * (int64_t)(c / 3) + 12 + 3 * (c % 3) + d] = acc[d]; }
+  }
+};
+
+static void build_pseudonormals(const double *tri64, const int32_t *dF, int64_t f_rs, int64_t f_cs, int64_t nF, double *pn, stream_t s) {
+  using plat::DevBuf;
+  if (nF == 0) return;
+  const int64_t nc = 3 * nF;
+  DevBuf<double> ang((size_t)nc);
+  DevBuf<uint32_t> vkey((size_t)nc), vkey2((size_t)nc), val((size_t)nc), val2((size_t)nc);
+  DevBuf<uint64_t> ekey((size_t)nc), ekey2((size_t)nc);
+  plat::for_n(nF, FaceNormalAngles{tri64, pn, ang.p}, s);
+  plat::for_n(nc, CornerKeys{dF, f_rs, f_cs, vkey.p, val.p, ekey.p}, s);
+  {
+    const size_t tb = plat::sort_pairs_temp_bytes(nc);
+    DevBuf<char> tmp(tb);
+    plat::sort_pairs_u32(tmp.p, tb, vkey.p, vkey2.p, val.p, val2.p, nc, 32, s);
+    plat::for_n(nc, VertexNormals{vkey2.p, val2.p, nc, ang.p, pn}, s);
+    plat::sync(s);
+  }
+  {
+    const size_t tb = plat::sort_pairs64_temp_bytes(nc);
+    DevBuf<char> tmp(tb);
+    plat::sort_pairs_u64(tmp.p, tb, ekey.p, ekey2.p, val.p, val2.p, nc, s);
+    plat::for_n(nc, EdgeNormals{ekey2.p, val2.p, nc, pn}, s);
+    plat::sync(s);
+  }
+}
+
 static int tree_levels(const Tree &t) { return (int)t.level_start.size() - 1; }
 
 iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F,
-                          int64_t nF, int64_t f_rs, int64_t f_cs, int order, stream_t s) {
+                          int64_t nF, int64_t f_rs, int64_t f_cs, int order, int flags, stream_t s) {
   using plat::DevBuf;
   iglb200_mesh *m = new iglb200_mesh;
   std::memset(&m->h, 0, sizeof(m->h));
@@ -127,7 +220,6 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
       m->h.bbox_hi[d] = nF ? (double)plat::ord2f(hacc[5 + d]) : 0.0;
     }
     dV.release();
-    dF.release();
 
     DevBuf<TriBox> boxes;
     Tree tree;
@@ -144,6 +236,8 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
     m->h.off_triq = off; off = align(off + (uint64_t)16 * TRIQ_STRIDE * nF);
     m->h.off_fnodes = off; off = align(off + (uint64_t)sizeof(FwnNode) * nn);
     m->h.off_cnodes = off; off = align(off + (uint64_t)sizeof(CpNode) * nn);
+    m->h.off_pn = 0;
+    if (flags & 1) { m->h.off_pn = off; off = align(off + (uint64_t)8 * PN_STRIDE * nF); }
     m->h.bytes = off;
     m->arena = (char *)plat::dev_alloc(off);
     plat::d2d(m->arena + m->h.off_tri64, tri64.p, (size_t)72 * nF, s);
@@ -159,6 +253,8 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
       // faces dropped by the NaN/Inf filter = faces not referenced by any node
       plat::sync(s);
     }
+    if (flags & 1) build_pseudonormals((const double *)(m->arena + m->h.off_tri64), dF.p, f_rs, f_cs, nF, (double *)(m->arena + m->h.off_pn), s);
+    dF.release();
     plat::h2d(m->arena, &m->h, sizeof(ArenaHeader), s);
     plat::sync(s);
   } catch (...) {

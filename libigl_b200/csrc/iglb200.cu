@@ -361,6 +361,73 @@ struct CountWinding {
   }
 };
 
+// SIGNED_DISTANCE_TYPE_PSEUDONORMAL epilogue: igl::pseudonormal_test (pseudonormal_test.cpp:24-150) on the
+// winning face, S = s*sqrt(d2), N = the normal used (signed_distance.cpp:125-135); out-of-bounds rows as :99-105
+struct PseudonormalQuery {
+  const double *tri64, *pn;
+  const double *P; int64_t n;
+  double up, low; int32_t nF;
+  double *S; int32_t *I; double *C; double *N;  // S holds sqrD on entry
+  DEVFN static double dist3(const double *p, const double *q) {
+    const double x = p[0] - q[0], y = p[1] - q[1], z = p[2] - q[2];
+    return sqrt(x * x + y * y + z * z);
+  }
+  DEVFN void operator()(int64_t i) const {
+    const double sqrd = S[i];
+    if (sqrd >= up || sqrd < low) {
+      S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
+      if (N) { N[i] = 0.0; N[n + i] = 0.0; N[2 * n + i] = 0.0; }
+      return;
+    }
+    const int32_t f = I[i];
+    const double q[3] = {P[i], P[n + i], P[2 * n + i]}, c[3] = {C[i], C[n + i], C[2 * n + i]};
+    const double *t = tri64 + 9 * (size_t)f, *A = t, *B = t + 3, *Cv = t + 6;
+    const double *np = pn + 21 * (size_t)f;   // face normal
+    // doublearea(A,B,C): Kahan's Heron on the sorted edge lengths (doublearea.cpp:103-112,166-177)
+    double l0 = dist3(B, Cv), l1 = dist3(Cv, A), l2 = dist3(A, B), tmp;
+    if (l0 < l1) { tmp = l0; l0 = l1; l1 = tmp; }
+    if (l1 < l2) { tmp = l1; l1 = l2; l2 = tmp; }
+    if (l0 < l1) { tmp = l0; l0 = l1; l1 = tmp; }
+    const double area = 2.0 * 0.25 * sqrt((l0 + (l1 + l2)) * (l2 - (l0 - l1)) * (l2 + (l0 - l1)) * (l0 + (l1 - l2)));
+    const double MIN_DOUBLE_AREA = 1e-4, epsilon = 1e-12;
+    if (area > MIN_DOUBLE_AREA) {
+      double v0[3], v1[3], v2[3];
+      for (int d = 0; d < 3; ++d) { v0[d] = B[d] - A[d]; v1[d] = Cv[d] - A[d]; v2[d] = c[d] - A[d]; }
+      const double d00 = v0[0] * v0[0] + v0[1] * v0[1] + v0[2] * v0[2], d01 = v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2];
+      const double d11 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2], d20 = v2[0] * v0[0] + v2[1] * v0[1] + v2[2] * v0[2];
+      const double d21 = v2[0] * v1[0] + v2[1] * v1[1] + v2[2] * v1[2];
+      const double denom = d00 * d11 - d01 * d01;
+      double b[3];
+      b[1] = (d11 * d20 - d01 * d21) / denom;
+      b[2] = (d00 * d21 - d01 * d20) / denom;
+      b[0] = 1.0f - (b[1] + b[2]);
+      const int type = (b[0] <= epsilon) + (b[1] <= epsilon) + (b[2] <= epsilon);
+      if (type == 2) { for (int x = 0; x < 3; ++x) if (b[x] > epsilon) { np = pn + 21 * (size_t)f + 3 + 3 * x; break; } }
+      else if (type == 1) { for (int x = 0; x < 3; ++x) if (b[x] <= epsilon) { np = pn + 21 * (size_t)f + 12 + 3 * x; break; } }
+    } else {
+      bool found = false;
+      for (int v = 0; v < 3 && !found; ++v)
+        if (dist3(c, t + 3 * v) < epsilon) { found = true; np = pn + 21 * (size_t)f + 3 + 3 * v; }
+      for (int e = 0; e < 3 && !found; ++e) {
+        const double *Sv = t + 3 * ((e + 1) % 3), *D = t + 3 * ((e + 2) % 3);
+        double dms[3], smp[3];
+        for (int d = 0; d < 3; ++d) { dms[d] = D[d] - Sv[d]; smp[d] = Sv[d] - c[d]; }
+        const double vs = dms[0] * dms[0] + dms[1] * dms[1] + dms[2] * dms[2];
+        const double tt = -(dms[0] * smp[0] + dms[1] * smp[1] + dms[2] * smp[2]) / vs;
+        double sq;
+        if (tt < 0) sq = smp[0] * smp[0] + smp[1] * smp[1] + smp[2] * smp[2];
+        else if (tt > 1) { const double dd = dist3(c, D); sq = dd * dd; }
+        else { double pr[3]; for (int d = 0; d < 3; ++d) pr[d] = (1 - tt) * Sv[d] + tt * D[d]; const double dd = dist3(c, pr); sq = dd * dd; }
+        if (sqrt(sq) < epsilon) { found = true; np = pn + 21 * (size_t)f + 12 + 3 * e; }
+      }
+    }
+    const double nx = np[0], ny = np[1], nz = np[2];
+    const double dotp = (q[0] - c[0]) * nx + (q[1] - c[1]) * ny + (q[2] - c[2]) * nz;
+    S[i] = (dotp >= 0 ? 1. : -1.) * sqrt(sqrd);
+    if (N) { N[i] = nx; N[n + i] = ny; N[2 * n + i] = nz; }
+  }
+};
+
 struct FillConst { double *S; int32_t *I; double *C; double *W; int64_t n; double sv; int32_t iv; double cv;
   DEVFN void operator()(int64_t i) const { if (S) S[i] = sv; if (I) I[i] = iv; if (C) { C[i] = cv; C[n + i] = cv; C[2 * n + i] = cv; } if (W) W[i] = sv; } };
 
@@ -428,17 +495,21 @@ void bounds_to_sqr(double lower, double upper, double &low, double &up) {  // si
 }
 
 void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int sign_type, double lower, double upper,
-                         double *S, int32_t *I, double *C, double *W, void *scratch, int sort_queries, stream_t s) {
-  if (sign_type != IGLB200_SIGN_FAST_WINDING_NUMBER && sign_type != IGLB200_SIGN_UNSIGNED) {
-    throw std::domain_error("sign type not implemented on the device (only UNSIGNED and FAST_WINDING_NUMBER); no CPU fallback");
+                         double *S, int32_t *I, double *C, double *W, double *N, void *scratch, int sort_queries, stream_t s) {
+  if (sign_type != IGLB200_SIGN_FAST_WINDING_NUMBER && sign_type != IGLB200_SIGN_UNSIGNED && sign_type != IGLB200_SIGN_PSEUDONORMAL) {
+    throw std::domain_error("sign type not implemented on the device (only UNSIGNED, FAST_WINDING_NUMBER and PSEUDONORMAL); no CPU fallback");
   }
+  if (sign_type == IGLB200_SIGN_PSEUDONORMAL && m->h.nF > 0 && !m->pn())
+    throw std::invalid_argument("mesh was created without IGLB200_MESH_PSEUDONORMALS");
   if (n == 0) return;
   if (m->h.nF == 0) {  // signed_distance.cpp:398-405
     plat::for_n(n, FillConst{S, I, C, W, n, NAN, -1, NAN}, s);
+    if (N) plat::for_n(n, FillConst{nullptr, nullptr, N, nullptr, n, NAN, -1, NAN}, s);
     return;
   }
   if (m->h.nnodes == 0) {  // every face excluded: nothing to be close to
     plat::for_n(n, FillConst{S, I, C, W, n, NAN, (int32_t)m->h.nF + 1, 0.0}, s);
+    if (N) plat::for_n(n, FillConst{nullptr, nullptr, N, nullptr, n, NAN, -1, 0.0}, s);
     return;
   }
   double low, up;
@@ -446,6 +517,12 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   { plat::Span sp("closest", s);
     launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr}, s); }
+  if (sign_type == IGLB200_SIGN_PSEUDONORMAL) {
+    plat::Span sp("pseudonormal", s);
+    plat::for_n(n, PseudonormalQuery{m->tri64(), m->pn(), P, n, up, low, (int32_t)m->h.nF, S, I, C, N}, s);
+    if (W) plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, NAN, 0, 0.0}, s);
+    return;
+  }
   { plat::Span sp("winding", s);
     launch_query("winding", n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
                                             sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s); }
@@ -533,12 +610,12 @@ Pipeline &pipeline() { static thread_local Pipeline p; return p; }
 
 // mode 0: signed distance (S,I,C,W), 1: squared distance (S=sqrD,I,C), 2: winding number only (W)
 void run_streamed(const iglb200_mesh *m, int mode, const double *P, int64_t n, int sign_type, double lower, double upper,
-                  float accuracy_scale, double *S, int32_t *I, double *C, double *W) {
+                  float accuracy_scale, double *S, int32_t *I, double *C, double *W, double *N = nullptr) {
   Pipeline &pl = pipeline();
   const int64_t chunk = std::min<int64_t>(Pipeline::CHUNK, n);
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   const size_t oP = 0, oS = oP + al(24 * chunk), oC = oS + al(8 * chunk), oW = oC + al(24 * chunk), oI = oW + al(8 * chunk),
-               oX = oI + al(4 * chunk), total = oX + al(iglb200_query_scratch_bytes(chunk));
+               oN = oI + al(4 * chunk), oX = oN + al(N ? 24 * chunk : 0), total = oX + al(iglb200_query_scratch_bytes(chunk));
   pl.ensure(total);
   for (int64_t b = 0, k = 0; b < n; b += chunk, ++k) {
     const int64_t mcount = std::min(chunk, n - b);
@@ -547,7 +624,8 @@ void run_streamed(const iglb200_mesh *m, int mode, const double *P, int64_t n, i
     double *dP = (double *)(base + oP), *dS = (double *)(base + oS), *dC = (double *)(base + oC), *dW = (double *)(base + oW);
     int32_t *dI = (int32_t *)(base + oI);
     for (int d = 0; d < 3; ++d) plat::h2d(dP + d * mcount, P + d * n + b, (size_t)8 * mcount, s);
-    if (mode == 0) run_signed_distance(m, dP, mcount, sign_type, lower, upper, dS, dI, dC, W ? dW : nullptr, base + oX, 1, s);
+    double *dN = N ? (double *)(base + oN) : nullptr;
+    if (mode == 0) run_signed_distance(m, dP, mcount, sign_type, lower, upper, dS, dI, dC, W ? dW : nullptr, dN, base + oX, 1, s);
     else if (mode == 1) run_squared_distance(m, dP, mcount, dS, dI, dC, base + oX, 1, s);
     else run_fwn(m, dP, mcount, accuracy_scale, dW, base + oX, 1, s);
     if (mode != 2) {
@@ -556,6 +634,7 @@ void run_streamed(const iglb200_mesh *m, int mode, const double *P, int64_t n, i
       for (int d = 0; d < 3; ++d) plat::d2h(C + d * n + b, dC + d * mcount, (size_t)8 * mcount, s);
     }
     if (W && mode != 1) plat::d2h(W + b, dW, (size_t)8 * mcount, s);
+    if (N && mode == 0) for (int d = 0; d < 3; ++d) plat::d2h(N + d * n + b, dN + d * mcount, (size_t)8 * mcount, s);
   }
   plat::sync(pl.st[0]);
   plat::sync(pl.st[1]);
@@ -624,6 +703,11 @@ int iglb200_host_free(void *p) {
 
 int iglb200_mesh_create(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F, int64_t nF,
                         int64_t f_rs, int64_t f_cs, int fwn_order, iglb200_mesh **out) {
+  return iglb200_mesh_create_ex(V, v_is_f64, nV, v_rs, v_cs, F, nF, f_rs, f_cs, fwn_order, 0, out);
+}
+
+int iglb200_mesh_create_ex(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F, int64_t nF,
+                           int64_t f_rs, int64_t f_cs, int fwn_order, int flags, iglb200_mesh **out) {
   API_BEGIN
   if (!out) throw std::invalid_argument("null out");
   *out = nullptr;
@@ -636,7 +720,7 @@ int iglb200_mesh_create(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, i
   plat::launch_counter() = 0;
   Timer t;
   t.start(nullptr);
-  iglb200_mesh *m = fwn::create_mesh(V, v_is_f64, nV, v_rs, v_cs, F, nF, f_rs, f_cs, fwn_order, nullptr);
+  iglb200_mesh *m = fwn::create_mesh(V, v_is_f64, nV, v_rs, v_cs, F, nF, f_rs, f_cs, fwn_order, flags, nullptr);
   m->build_ms = t.stop(nullptr);
 #ifndef IGLB200_EMUL
   cudaGetDevice(&m->device);
@@ -661,7 +745,7 @@ int iglb200_mesh_info(const iglb200_mesh *m, int64_t info[8]) {
   API_BEGIN
   check_mesh(m);
   info[0] = m->h.nF; info[1] = m->h.nnodes; info[2] = m->h.nlevels; info[3] = (int64_t)m->h.bytes; info[4] = m->h.nexcluded;
-  info[5] = m->h.order; info[6] = 0; info[7] = 0;
+  info[5] = m->h.order; info[6] = m->h.off_pn ? 1 : 0; info[7] = 0;
   return IGLB200_OK;
   API_END
 }
@@ -750,13 +834,13 @@ void iglb200_profile_enable(int on) { plat::prof_enable(on != 0); }
 int iglb200_profile_collect(char *out, uint64_t cap) { return plat::prof_collect(out, (size_t)cap); }
 
 int iglb200_signed_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP, int sign_type, double lower, double upper,
-                                double *S, int32_t *I, double *C, double *W, void *scratch, int sort_queries, void *stream) {
+                                double *S, int32_t *I, double *C, double *W, double *N, void *scratch, int sort_queries, void *stream) {
   API_BEGIN
   check_mesh(m);
   if (nP < 0 || (nP > 0 && (!P || !S || !I || !C))) throw std::invalid_argument("null pointer");
   require_device();
   plat::launch_counter() = 0;
-  run_signed_distance(m, P, nP, sign_type, lower, upper, S, I, C, W, scratch, sort_queries, (stream_t)stream);
+  run_signed_distance(m, P, nP, sign_type, lower, upper, S, I, C, W, N, scratch, sort_queries, (stream_t)stream);
   return IGLB200_OK;
   API_END
 }
@@ -785,7 +869,7 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
 
 int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
                             int sign_type, double lower, double upper, void *S, int s_is_f64, int32_t *I, void *C, int c_is_f64,
-                            int64_t c_rs, int64_t c_cs, void *W, int w_is_f64) {
+                            int64_t c_rs, int64_t c_cs, void *W, int w_is_f64, void *N, int n_is_f64, int64_t n_rs, int64_t n_cs) {
   API_BEGIN
   check_mesh(m);
   if (nP < 0 || (nP > 0 && (!P || !S || !I || !C))) throw std::invalid_argument("null pointer");
@@ -793,17 +877,20 @@ int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, 
   require_device();
   plat::launch_counter() = 0;
 #ifndef IGLB200_EMUL
-  if (nP > 0 && p_is_f64 && p_rs == 1 && p_cs == nP && s_is_f64 && c_is_f64 && c_rs == 1 && c_cs == nP && (!W || w_is_f64)) {
-    run_streamed(m, 0, (const double *)P, nP, sign_type, lower, upper, 2.0f, (double *)S, I, (double *)C, (double *)W);
+  if (N && nP > 0 && (n_rs <= 0 || n_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  if (nP > 0 && p_is_f64 && p_rs == 1 && p_cs == nP && s_is_f64 && c_is_f64 && c_rs == 1 && c_cs == nP && (!W || w_is_f64) &&
+      (!N || (n_is_f64 && n_rs == 1 && n_cs == nP))) {
+    run_streamed(m, 0, (const double *)P, nP, sign_type, lower, upper, 2.0f, (double *)S, I, (double *)C, (double *)W, (double *)N);
     return IGLB200_OK;
   }
 #endif
   stream_t s = nullptr;
-  DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP), dW(W ? (size_t)nP : 0);
+  DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP), dW(W ? (size_t)nP : 0), dN(N ? (size_t)3 * nP : 0);
   DevBuf<int32_t> dI((size_t)nP);
   DevBuf<char> scratch(iglb200_query_scratch_bytes(nP));
   upload_points(P, p_is_f64, nP, p_rs, p_cs, dP, s);
-  run_signed_distance(m, dP.p, nP, sign_type, lower, upper, dS.p, dI.p, dC.p, W ? dW.p : nullptr, scratch.p, 1, s);
+  run_signed_distance(m, dP.p, nP, sign_type, lower, upper, dS.p, dI.p, dC.p, W ? dW.p : nullptr, N ? dN.p : nullptr, scratch.p, 1, s);
+  if (N) download_points(dN, nP, N, n_is_f64, n_rs, n_cs, s);
   download_scalar(dS, nP, S, s_is_f64, s);
   plat::d2h(I, dI.p, (size_t)4 * nP, s);
   download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);

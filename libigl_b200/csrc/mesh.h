@@ -3,7 +3,7 @@
 // broadcast of [arena, arena+bytes).
 //
 //   [ArenaHeader | tri64 (9 f64 / face) | tri32 (3 float4 / face) | triq (4 float4 / face) |
-//    fwn nodes (384 B) | closest-point nodes (128 B)]
+//    fwn nodes (384 B) | closest-point nodes (128 B) | optional pseudonormals (21 f64 / face)]
 //
 // tri64/tri32 are the faces' vertices gathered once at build time (the
 // reference dereferences V through F for every leaf test: AABB.cpp:1413-1432,
@@ -21,7 +21,8 @@ struct ArenaHeader {
   double bbox_lo[3], bbox_hi[3];  // of the fp64 geometry
   float absmax, padf;             // max |coordinate| (slack of the fp32 box tests)
   uint64_t off_tri64, off_tri32, off_fnodes, off_cnodes, off_triq;
-  uint64_t reserved[7];
+  uint64_t off_pn;  // 21 f64 / face: face normal, 3 corner (vertex) normals, 3 edge normals; 0 = absent
+  uint64_t reserved[6];
 };
 
 struct iglb200_mesh {
@@ -35,10 +36,11 @@ struct iglb200_mesh {
   const float4 *triq() const { return (const float4 *)(arena + h.off_triq); }
   const fwn::FwnNode *fnodes() const { return (const fwn::FwnNode *)(arena + h.off_fnodes); }
   const fwn::CpNode *cnodes() const { return (const fwn::CpNode *)(arena + h.off_cnodes); }
+  const double *pn() const { return h.off_pn ? (const double *)(arena + h.off_pn) : nullptr; }
 };
 
 namespace fwn {
 // build.cu (compiled with -fmad=false)
 iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F,
-                          int64_t nF, int64_t f_rs, int64_t f_cs, int order, stream_t s);
+                          int64_t nF, int64_t f_rs, int64_t f_cs, int order, int flags, stream_t s);
 }  // namespace fwn

@@ -69,6 +69,11 @@ def port():
                                     _c_dp, _c_ip, _c_dp, _c_lp]
         L.port_cp_brute.argtypes = [_c_dp, _c_ip, C.c_int64, _c_dp, C.c_int64, _c_dp, _c_ip, _c_dp]
         L.port_cp_face_distance.argtypes = [_c_dp, _c_ip, _c_dp, _c_ip, C.c_int64, _c_dp, _c_dp]
+        L.port_pseudo_create.restype = C.c_void_p
+        L.port_pseudo_create.argtypes = [_c_dp, C.c_int64, _c_ip, C.c_int64]
+        L.port_pseudo_destroy.argtypes = [C.c_void_p]
+        L.port_pseudo_normals.argtypes = [C.c_void_p, _c_dp, _c_dp, _c_dp]
+        L.port_pseudo_test.argtypes = [C.c_void_p, _c_dp, _c_ip, _c_dp, C.c_int64, _c_dp, _c_dp]
         L.port_cloud_create.restype = C.c_void_p
         L.port_cloud_create.argtypes = [_c_dp, _c_dp, _c_dp, C.c_int64, C.c_int]
         L.port_cloud_destroy.argtypes = [C.c_void_p]
@@ -244,6 +249,55 @@ def signed_distance_fwn(P, V, F, lower=None, upper=None, tree=None, fwn=None):
     Cc[oob] = 0.0
     w[oob] = np.nan
     return S, I, Cc, w
+
+
+class PortPseudonormal:
+    """Restated normals + igl::pseudonormal_test (SIGNED_DISTANCE_TYPE_PSEUDONORMAL)."""
+
+    def __init__(self, V, F):
+        self.V = np.ascontiguousarray(V, dtype=np.float64)
+        self.F = np.ascontiguousarray(F, dtype=np.int32)
+        self.h = port().port_pseudo_create(_dp(self.V), self.V.shape[0], _ip(self.F), self.F.shape[0])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            port().port_pseudo_destroy(self.h)
+            self.h = None
+
+    def normals(self):
+        FN = np.empty((self.F.shape[0], 3)); VN = np.empty((self.V.shape[0], 3)); EN = np.empty((self.F.shape[0], 3, 3))
+        port().port_pseudo_normals(self.h, _dp(FN), _dp(VN), _dp(EN))
+        return FN, VN, EN
+
+    def test(self, Q, I, Cc):
+        Q = np.ascontiguousarray(Q, dtype=np.float64); I = np.ascontiguousarray(I, dtype=np.int32)
+        Cc = np.ascontiguousarray(Cc, dtype=np.float64)
+        S = np.empty(Q.shape[0]); N = np.empty((Q.shape[0], 3))
+        port().port_pseudo_test(self.h, _dp(Q), _ip(I), _dp(Cc), Q.shape[0], _dp(S), _dp(N))
+        return S, N
+
+
+def signed_distance_pseudonormal(P, V, F, lower=None, upper=None, tree=None, pseudo=None):
+    """igl::signed_distance(..., SIGNED_DISTANCE_TYPE_PSEUDONORMAL, ...): S, I, C, N (signed_distance.cpp:28-139)."""
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    F = np.ascontiguousarray(F, dtype=np.int32)
+    if lower is None:
+        lower = np.finfo(np.float64).tiny
+    if upper is None:
+        upper = np.finfo(np.float64).max
+    low, up = signed_distance_bounds(lower, upper)
+    tree = tree or PortAABB(V, F)
+    pseudo = pseudo or PortPseudonormal(V, F)
+    sqrD, I, Cc = tree.squared_distance(P, low, up)
+    oob = (sqrD >= up) | (sqrD < low)
+    s, N = pseudo.test(P, np.where(oob, -1, I), Cc)
+    S = s * np.sqrt(sqrD)
+    S[oob] = np.nan
+    I = I.copy()
+    I[oob] = F.shape[0] + 1
+    Cc[oob] = 0.0
+    N[oob] = 0.0   # the reference leaves these rows of N untouched (N.resize at :75)
+    return S, I, Cc, N
 
 
 class PortCloud:

@@ -452,6 +452,99 @@ double cloud_eval_rec(const Cloud &c, const double q[3], const std::vector<int> 
   return wn;
 }
 
+
+// ---------------------------------------------------------------------------
+// SIGNED_DISTANCE_TYPE_PSEUDONORMAL (signed_distance.cpp:68-76, 125-131):
+// per_face_normals.cpp:14-37, internal_angles.cpp:13-43 (corner lambda),
+// per_vertex_normals.cpp:40-104 (ANGLE weighting, faces accumulated in index order),
+// per_edge_normals.cpp:24-76 (UNIFORM weighting; EMAP(f+c*m) = undirected edge opposite corner c),
+// pseudonormal_test.cpp:24-150, barycentric_coordinates.cpp (3-corner overload),
+// doublearea.cpp:103-112 + 166-177 (Kahan's Heron), project_to_line_segment.cpp / project_to_line.cpp:38-53.
+// ---------------------------------------------------------------------------
+struct Pseudo {
+  const double *V; const int *F; int64_t nV, nF;
+  std::vector<double> FN, VN, EN;  // nF x 3, nV x 3, (3 nF) x 3 (per face corner: the edge opposite it)
+};
+
+inline void normalize3(double *v) {  // Eigen's normalize(): divide by the norm when it is positive
+  const double z = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  if (z > 0) { const double r = std::sqrt(z); v[0] /= r; v[1] /= r; v[2] /= r; }
+}
+
+double corner_angle(const double *x, const double *y, const double *z) {
+  double v1[3], v2[3];
+  for (int d = 0; d < 3; ++d) { v1[d] = x[d] - y[d]; v2[d] = z[d] - y[d]; }
+  const double n1 = std::sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+  const double n2 = std::sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+  double a[3], b[3];
+  for (int d = 0; d < 3; ++d) { a[d] = v1[d] / n1 - v2[d] / n2; b[d] = v1[d] / n1 + v2[d] / n2; }
+  return 2.0 * std::atan(std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]) / std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]));
+}
+
+double doublearea3(const double *A, const double *B, const double *C) {
+  auto dist = [](const double *p, const double *q) {
+    const double x = p[0] - q[0], y = p[1] - q[1], z = p[2] - q[2];
+    return std::sqrt(x * x + y * y + z * z);
+  };
+  double l[3] = {dist(B, C), dist(C, A), dist(A, B)};
+  std::sort(l, l + 3, [](double a, double b) { return a > b; });  // descending
+  const double arg = (l[0] + (l[1] + l[2])) * (l[2] - (l[0] - l[1])) * (l[2] + (l[0] - l[1])) * (l[0] + (l[1] - l[2]));
+  return 2.0 * 0.25 * std::sqrt(arg);
+}
+
+void pseudonormal_test(const Pseudo &ps, const double *q, int f, const double *c, double &s, double *n) {
+  const double *A = ps.V + 3 * (int64_t)ps.F[3 * (int64_t)f], *B = ps.V + 3 * (int64_t)ps.F[3 * (int64_t)f + 1],
+               *C = ps.V + 3 * (int64_t)ps.F[3 * (int64_t)f + 2];
+  const double area = doublearea3(A, B, C);
+  const double MIN_DOUBLE_AREA = 1e-4, epsilon = 1e-12;
+  const double *pick = ps.FN.data() + 3 * (int64_t)f;
+  if (area > MIN_DOUBLE_AREA) {
+    double v0[3], v1[3], v2[3];
+    for (int d = 0; d < 3; ++d) { v0[d] = B[d] - A[d]; v1[d] = C[d] - A[d]; v2[d] = c[d] - A[d]; }
+    const double d00 = v0[0] * v0[0] + v0[1] * v0[1] + v0[2] * v0[2], d01 = v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2];
+    const double d11 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2], d20 = v2[0] * v0[0] + v2[1] * v0[1] + v2[2] * v0[2];
+    const double d21 = v2[0] * v1[0] + v2[1] * v1[1] + v2[2] * v1[2];
+    const double denom = d00 * d11 - d01 * d01;
+    double b[3];
+    b[1] = (d11 * d20 - d01 * d21) / denom;
+    b[2] = (d00 * d21 - d01 * d20) / denom;
+    b[0] = 1.0f - (b[1] + b[2]);
+    const int type = (b[0] <= epsilon) + (b[1] <= epsilon) + (b[2] <= epsilon);
+    if (type == 2) {
+      for (int x = 0; x < 3; ++x) if (b[x] > epsilon) { pick = ps.VN.data() + 3 * (int64_t)ps.F[3 * (int64_t)f + x]; break; }
+    } else if (type == 1) {
+      for (int x = 0; x < 3; ++x) if (b[x] <= epsilon) { pick = ps.EN.data() + 3 * (3 * (int64_t)f + x); break; }
+    }
+  } else {
+    bool found = false;
+    for (int v = 0; v < 3 && !found; ++v) {
+      const double *P = ps.V + 3 * (int64_t)ps.F[3 * (int64_t)f + v];
+      const double x = c[0] - P[0], y = c[1] - P[1], z = c[2] - P[2];
+      if (std::sqrt(x * x + y * y + z * z) < epsilon) { found = true; pick = ps.VN.data() + 3 * (int64_t)ps.F[3 * (int64_t)f + v]; }
+    }
+    for (int e = 0; e < 3 && !found; ++e) {
+      const double *S = ps.V + 3 * (int64_t)ps.F[3 * (int64_t)f + (e + 1) % 3], *D = ps.V + 3 * (int64_t)ps.F[3 * (int64_t)f + (e + 2) % 3];
+      double dms[3], smp[3];
+      for (int d = 0; d < 3; ++d) { dms[d] = D[d] - S[d]; smp[d] = S[d] - c[d]; }
+      const double vs = dms[0] * dms[0] + dms[1] * dms[1] + dms[2] * dms[2];
+      double t = -(dms[0] * smp[0] + dms[1] * smp[1] + dms[2] * smp[2]) / vs;
+      double sq;
+      if (t < 0) { sq = smp[0] * smp[0] + smp[1] * smp[1] + smp[2] * smp[2]; }
+      else if (t > 1) { const double x = c[0] - D[0], y = c[1] - D[1], z = c[2] - D[2]; sq = x * x + y * y + z * z; }
+      else {
+        double pr[3];
+        for (int d = 0; d < 3; ++d) pr[d] = (1 - t) * S[d] + t * D[d];
+        const double x = c[0] - pr[0], y = c[1] - pr[1], z = c[2] - pr[2];
+        sq = x * x + y * y + z * z;
+      }
+      if (std::sqrt(sq) < epsilon) { found = true; pick = ps.EN.data() + 3 * (3 * (int64_t)f + e); }
+    }
+  }
+  for (int d = 0; d < 3; ++d) n[d] = pick[d];
+  const double dotp = (q[0] - c[0]) * n[0] + (q[1] - c[1]) * n[1] + (q[2] - c[2]) * n[2];
+  s = (dotp >= 0 ? 1. : -1.);
+}
+
 }  // namespace
 
 extern "C" {
@@ -652,6 +745,61 @@ void port_cloud_eval(void *p, const double *Q, int64_t m, double beta, double *W
         },
         1000);
   }
+}
+
+
+// ---- pseudonormal sign ---------------------------------------------------
+void *port_pseudo_create(const double *V, int64_t nV, const int *F, int64_t nF) {
+  Pseudo *ps = new Pseudo;
+  ps->V = V; ps->F = F; ps->nV = nV; ps->nF = nF;
+  ps->FN.assign(3 * nF, 0.0); ps->VN.assign(3 * nV, 0.0); ps->EN.assign(9 * nF, 0.0);
+  for (int64_t f = 0; f < nF; ++f) {
+    const double *a = V + 3 * (int64_t)F[3 * f], *b = V + 3 * (int64_t)F[3 * f + 1], *c = V + 3 * (int64_t)F[3 * f + 2];
+    const double v1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, v2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    double n[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+    const double r = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int d = 0; d < 3; ++d) ps->FN[3 * f + d] = (r == 0) ? 0.0 : n[d] / r;
+  }
+  // angle-weighted vertex normals, faces in index order
+  for (int64_t f = 0; f < nF; ++f)
+    for (int j = 0; j < 3; ++j) {
+      const double w = corner_angle(V + 3 * (int64_t)F[3 * f + (j + 2) % 3], V + 3 * (int64_t)F[3 * f + j], V + 3 * (int64_t)F[3 * f + (j + 1) % 3]);
+      for (int d = 0; d < 3; ++d) ps->VN[3 * (int64_t)F[3 * f + j] + d] += w * ps->FN[3 * f + d];
+    }
+  for (int64_t v = 0; v < nV; ++v) normalize3(&ps->VN[3 * v]);
+  // uniform edge normals: sum of the face normals of every face using the undirected edge, in (f, c) order
+  std::vector<std::pair<uint64_t, int64_t>> he(3 * nF);
+  for (int64_t f = 0; f < nF; ++f)
+    for (int c = 0; c < 3; ++c) {
+      const uint64_t a = (uint64_t)F[3 * f + (c + 1) % 3], b = (uint64_t)F[3 * f + (c + 2) % 3];
+      he[3 * f + c] = {(std::min(a, b) << 32) | std::max(a, b), 3 * f + c};
+    }
+  std::stable_sort(he.begin(), he.end(), [](const std::pair<uint64_t, int64_t> &x, const std::pair<uint64_t, int64_t> &y) { return x.first < y.first; });
+  for (size_t i = 0; i < he.size();) {
+    size_t j = i;
+    double acc[3] = {0, 0, 0};
+    for (; j < he.size() && he[j].first == he[i].first; ++j)
+      for (int d = 0; d < 3; ++d) acc[d] += ps->FN[3 * (he[j].second / 3) + d];
+    normalize3(acc);
+    for (size_t k = i; k < j; ++k) for (int d = 0; d < 3; ++d) ps->EN[3 * he[k].second + d] = acc[d];
+    i = j;
+  }
+  return ps;
+}
+void port_pseudo_destroy(void *p) { delete (Pseudo *)p; }
+void port_pseudo_normals(void *p, double *FN, double *VN, double *EN) {
+  const Pseudo &ps = *(Pseudo *)p;
+  if (FN) std::memcpy(FN, ps.FN.data(), ps.FN.size() * 8);
+  if (VN) std::memcpy(VN, ps.VN.data(), ps.VN.size() * 8);
+  if (EN) std::memcpy(EN, ps.EN.data(), ps.EN.size() * 8);
+}
+// sign and normal for each (query, closest face, closest point)
+void port_pseudo_test(void *p, const double *Q, const int *I, const double *C, int64_t n, double *S, double *N) {
+  const Pseudo &ps = *(Pseudo *)p;
+  port_parallel_for(n, [&](int64_t k) {
+    if (I[k] < 0 || I[k] >= ps.nF) { S[k] = 1.0; N[3 * k] = N[3 * k + 1] = N[3 * k + 2] = 0.0; return; }
+    pseudonormal_test(ps, Q + 3 * k, I[k], C + 3 * k, S[k], N + 3 * k);
+  }, 10000);
 }
 
 }  // extern "C"

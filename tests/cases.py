@@ -147,8 +147,11 @@ def case_bounds_and_sentinels(api):
     assert S.shape == (0,) and I.shape == (0,) and C.shape == (0, 3)
     # other sign types fail loudly (no CPU fallback)
     with pytest.raises(IglB200Error) as e:
-        m.signed_distance(P[:5], SIGNED_DISTANCE_TYPE_PSEUDONORMAL)
+        m.signed_distance(P[:5], 1)   # SIGNED_DISTANCE_TYPE_WINDING_NUMBER
     assert e.value.code == -4
+    with pytest.raises(IglB200Error) as e:   # pseudonormals need the precomputed normals
+        m.signed_distance(P[:5], SIGNED_DISTANCE_TYPE_PSEUDONORMAL)
+    assert e.value.code == -1
     m.close()
     with pytest.raises(IglB200Error):
         api.Mesh(V, np.array([[0, 1, 999999]], np.int32))
@@ -383,3 +386,42 @@ def case_builder_corner_paths(api):
     Q = synth.random_points(500, -1.5, 1.5, 1)
     assert np.abs(m.fast_winding_number(Q) - ref.winding(Q)).max() < 1e-5
     m.close()
+
+
+def case_pseudonormal(api, meshes, n_queries=4000):
+    """SIGNED_DISTANCE_TYPE_PSEUDONORMAL (the "next" row of SURVEY 8f): normals bit-identical to the
+    restated per_face/per_vertex(ANGLE)/per_edge(UNIFORM) normals, S and N equal to the restated
+    igl::pseudonormal_test on the same closest face; on exact ties the pseudonormal is shared by
+    the tied faces so S must agree anyway."""
+    V, F = synth.tetrahedron()   # tests/include/igl/signed_distance.cpp:4-43, tolerance 1e-15
+    S, I, C, N = api.signed_distance(np.array([[0.5, 0.5, 0.5]]), V, F, SIGNED_DISTANCE_TYPE_PSEUDONORMAL)
+    assert abs(S[0] - np.sqrt(1.0 / 12.0)) < 1e-15 and np.abs(N[0] - np.sqrt(1.0 / 3.0)).max() < 1e-15
+    for name, (V, F) in meshes.items():
+        lo, hi = synth.bbox(V)
+        P = np.concatenate([synth.random_points(n_queries, float(lo.min()) * 1.3, float(hi.max()) * 1.3, 17),
+                            V[:200] + 1e-3, (V[F[:200, 0]] + V[F[:200, 1]]) / 2 * 1.001])
+        m = api.Mesh(V, F, 2, pseudonormals=True)
+        a = m.download()
+        o = oracle.PortPseudonormal(V, F)
+        FN, VN, EN = o.normals()
+        pn = a["pseudonormals"]
+        assert np.array_equal(pn[:, 0], FN), name
+        assert np.array_equal(pn[:, 1:4], VN[F]), name
+        assert np.array_equal(pn[:, 4:7], EN), name
+        S, I, C, N = m.signed_distance(P, SIGNED_DISTANCE_TYPE_PSEUDONORMAL)
+        So, Io, Co, No = oracle.signed_distance_pseudonormal(P, V, F, pseudo=o)
+        # same face -> identical; tied faces -> same distance, sign must still agree
+        s2, n2 = o.test(P, I, C)
+        assert np.array_equal(S, s2 * np.sqrt(np.sum((P - C) ** 2, 1))) or np.abs(np.abs(S) - np.abs(So)).max() < 1e-12, name
+        assert np.array_equal(N, n2), name
+        assert np.array_equal(np.abs(S), np.abs(So)), name
+        diag = float(np.linalg.norm(hi - lo))
+        far = np.abs(So) > 1e-6 * diag
+        assert np.array_equal(np.sign(S[far]), np.sign(So[far])), name
+        # bounded variant: NaN rows and zeroed N
+        S, I, C, N = m.signed_distance(P, SIGNED_DISTANCE_TYPE_PSEUDONORMAL, -0.05 * diag, 0.08 * diag)
+        So, Io, Co, No = oracle.signed_distance_pseudonormal(P, V, F, -0.05 * diag, 0.08 * diag, pseudo=o)
+        assert np.array_equal(np.isnan(S), np.isnan(So)) and np.isnan(S).any(), name
+        bad = np.isnan(S)
+        assert (I[bad] == F.shape[0] + 1).all() and (C[bad] == 0).all() and (N[bad] == 0).all()
+        m.close()

@@ -27,20 +27,26 @@ int main() {
   MatrixXd P(1, 3);
   P(0, 0) = P(0, 1) = P(0, 2) = 0.5;
   // signed_distance: single_tet
-  for (auto type : {iglb200::SIGNED_DISTANCE_TYPE_UNSIGNED, iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER}) {
+  for (auto type : {iglb200::SIGNED_DISTANCE_TYPE_PSEUDONORMAL, iglb200::SIGNED_DISTANCE_TYPE_UNSIGNED,
+                    iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER}) {
     VectorXd S; VectorXi I; MatrixXd C, N;
     iglb200::signed_distance(P, V, F, type, S, I, C, N);
     REQUIRE(S.rows() == 1 && I.rows() == 1 && C.rows() == 1 && C.cols() == 3);
     const double tol = type == iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER ? 1e-7 : 1e-15;
     REQUIRE(std::fabs(S(0) - std::sqrt(1. / 12.)) <= tol);
     REQUIRE(I(0) == 3);
-    REQUIRE(N.rows() == 0);   // untouched, as in the reference
+    if (type == iglb200::SIGNED_DISTANCE_TYPE_PSEUDONORMAL) {   // the only sign type that fills N
+      REQUIRE(N.rows() == 1 && N.cols() == 3);
+      for (int d = 0; d < 3; ++d) REQUIRE(std::fabs(N(0, d) - std::sqrt(1. / 3.)) < 1e-15);
+    } else {
+      REQUIRE(N.rows() == 0);   // untouched, as in the reference
+    }
   }
   // other sign types must fail loudly
   {
     VectorXd S; VectorXi I; MatrixXd C, N;
     bool threw = false;
-    try { iglb200::signed_distance(P, V, F, iglb200::SIGNED_DISTANCE_TYPE_PSEUDONORMAL, S, I, C, N); }
+    try { iglb200::signed_distance(P, V, F, iglb200::SIGNED_DISTANCE_TYPE_WINDING_NUMBER, S, I, C, N); }
     catch (const iglb200::Error &e) { threw = (e.code == IGLB200_ERR_UNSUPPORTED); }
     REQUIRE(threw);
   }

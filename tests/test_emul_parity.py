@@ -84,3 +84,7 @@ def test_golden_fixtures(emul_api):
 
 def test_builder_corner_paths(emul_api):
     cases.case_builder_corner_paths(emul_api)
+
+
+def test_pseudonormal_sign(emul_api):
+    cases.case_pseudonormal(emul_api, cases.meshes_small())

@@ -152,3 +152,7 @@ def test_golden_fixtures(gpu_api):
 
 def test_builder_corner_paths(gpu_api):
     cases.case_builder_corner_paths(gpu_api)
+
+
+def test_pseudonormal_sign(gpu_api):
+    cases.case_pseudonormal(gpu_api, dict(cases.meshes_small(), knot200k=synth.torus_knot(2000, 50)))

@@ -52,7 +52,7 @@ def run_sd(api, name, V, F, P, sample_stride, check=True):
 
     def step():
         api.check(api.lib.iglb200_signed_distance_dev(m.h, dP.data_ptr(), n, 4, lo, up, dS.data_ptr(), dI.data_ptr(),
-                                                      dC.data_ptr(), dW.data_ptr(), scr.data_ptr(), 1, None))
+                                                      dC.data_ptr(), dW.data_ptr(), None, scr.data_ptr(), 1, None))
     ms = timed(step)
     api.check(api.lib.iglb200_poll_device_error())
     out = dict(config=name, faces=int(F.shape[0]), queries=int(n), ms=ms, qps=n / ms * 1e3, build_ms=info["build_ms"],
