@@ -406,14 +406,15 @@ def case_pseudonormal(api, meshes, n_queries=4000):
         FN, VN, EN = o.normals()
         pn = a["pseudonormals"]
         assert np.array_equal(pn[:, 0], FN), name
-        assert np.array_equal(pn[:, 1:4], VN[F]), name
+        # vertex normals are weighted by 2*atan(..) corner angles: CUDA's atan and glibc's differ by an ulp
+        assert np.abs(pn[:, 1:4] - VN[F]).max() < 1e-14, name
         assert np.array_equal(pn[:, 4:7], EN), name
         S, I, C, N = m.signed_distance(P, SIGNED_DISTANCE_TYPE_PSEUDONORMAL)
         So, Io, Co, No = oracle.signed_distance_pseudonormal(P, V, F, pseudo=o)
         # same face -> identical; tied faces -> same distance, sign must still agree
         s2, n2 = o.test(P, I, C)
-        assert np.array_equal(S, s2 * np.sqrt(np.sum((P - C) ** 2, 1))) or np.abs(np.abs(S) - np.abs(So)).max() < 1e-12, name
-        assert np.array_equal(N, n2), name
+        assert np.abs(N - n2).max() < 1e-14, name
+        assert np.array_equal(np.sign(S), s2) or np.array_equal(np.sign(S[np.abs(So) > 0]), s2[np.abs(So) > 0]), name
         assert np.array_equal(np.abs(S), np.abs(So)), name
         diag = float(np.linalg.norm(hi - lo))
         far = np.abs(So) > 1e-6 * diag
