@@ -330,13 +330,18 @@ def ours(args):
             tree = oracle.PortAABB(V, F)
             _, _, _, cnt = tree.squared_distance(samp, count=True)
             n_cp_node, n_cp_tri = cnt[0] / samp.shape[0], cnt[1] / samp.shape[0]
-            flops_q = FLOP_NODE_FWN * 20.2 + FLOP_TRI_FWN * 1.0 + FLOP_NODE_CP * n_cp_node + FLOP_TRI_CP * n_cp_tri
-            fp32_peak = 2 * 128 * 148 * sm_max * 1e6
+            vc = mesh.visit_counts(samp[:65536])   # the winding walk is the reference's own: same nodes, same faces
+            n_fwn_node, n_fwn_tri = vc["fwn_nodes"], vc["fwn_tris"]
+            flops_q = FLOP_NODE_FWN * n_fwn_node + FLOP_TRI_FWN * n_fwn_tri + FLOP_NODE_CP * n_cp_node + FLOP_TRI_CP * n_cp_tri
+            measured = float(api.lib.iglb200_debug_fp32_peak_tflops())
+            fp32_peak = measured * 1e12 if measured > 0 else 2 * 128 * 148 * sm_max * 1e6
             line["fp32"] = {"flops_per_query": flops_q, "achieved_tflops": flops_q * value / 1e12,
                             "peak_tflops": fp32_peak / 1e12, "frac": flops_q * value / fp32_peak,
                             "counts": {"cp_nodes_per_query_reference_tree": n_cp_node, "cp_tris_per_query": n_cp_tri,
-                                       "fwn_nodes_per_query": 20.2},
-                            "note": "work of the reference algorithm (binary AABB, 1 tri/leaf) per SURVEY §8(d); peak = 2*128*148*sm_max"}
+                                       "fwn_nodes_per_query": n_fwn_node, "fwn_tris_per_query": n_fwn_tri,
+                                       "ours_cp_nodes_per_warp": vc["cp_nodes_per_warp"], "ours_cp_faces_per_warp": vc["cp_tris_per_warp"]},
+                            "peak_source": "FMA micro-benchmark on this GPU" if measured > 0 else "2*128*148*sm_max",
+                            "note": "work of the reference algorithm (binary AABB, 1 tri/leaf) per SURVEY §8(d)"}
         except Exception as ex:  # the flop estimate is informative only
             line["fp32"] = {"error": str(ex)}
     print(json.dumps(line), flush=True)

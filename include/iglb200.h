@@ -146,6 +146,10 @@ int iglb200_last_launch_count(void);
  * P is a HOST pointer, column-major doubles; keep n below ~1e6. */
 int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colmajor, int64_t n, double out[4]);
 
+/* Measured FP32 FMA peak of the current device in TFLOP/s (a dependent-chain FMA micro-benchmark);
+ * the denominator of bench.py's fp32 roofline fraction.  <0 on error. */
+double iglb200_debug_fp32_peak_tflops(void);
+
 /* Optional per-kernel timing (CUDA events on the launching stream) for the
  * calling thread.  collect() synchronises, writes "name=ms;name=ms;..." summed
  * per kernel group since the previous collect, and returns the string length. */

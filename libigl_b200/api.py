@@ -62,7 +62,7 @@ class Api:
         "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
         "iglb200_query_scratch_bytes", "iglb200_signed_distance_dev", "iglb200_squared_distance_dev",
         "iglb200_fwn_eval_dev", "iglb200_last_launch_count", "iglb200_profile_enable", "iglb200_profile_collect",
-        "iglb200_debug_visit_counts", "iglb200_poll_device_error",
+        "iglb200_debug_visit_counts", "iglb200_poll_device_error", "iglb200_debug_fp32_peak_tflops",
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
     ]
@@ -94,6 +94,7 @@ class Api:
         L.iglb200_squared_distance_dev.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _int, _vp]
         L.iglb200_fwn_eval_dev.argtypes = [_vp, _vp, _i64, C.c_float, _vp, _vp, _int, _vp]
         L.iglb200_debug_visit_counts.argtypes = [_vp, _vp, _i64, C.POINTER(_dbl)]
+        L.iglb200_debug_fp32_peak_tflops.restype = _dbl
         L.iglb200_profile_enable.argtypes = [_int]
         L.iglb200_profile_enable.restype = None
         L.iglb200_profile_collect.argtypes = [C.c_char_p, C.c_uint64]

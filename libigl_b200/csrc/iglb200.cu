@@ -799,6 +799,45 @@ uint64_t iglb200_query_scratch_bytes(int64_t nP) {
 }
 
 int iglb200_last_launch_count(void) { return plat::launch_counter(); }
+#ifndef IGLB200_EMUL
+// FP32 FMA micro-benchmark: 8 independent chains per thread, 4096 FMAs each
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, float a, float b) {
+  float x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = threadIdx.x * 1e-3f + k;
+  for (int it = 0; it < 4096; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = fmaf(x[k], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  if (s == 123.456f) out[0] = s;   // never true; keeps the loop alive
+}
+#endif
+double iglb200_debug_fp32_peak_tflops(void) {
+#ifdef IGLB200_EMUL
+  return 0.0;
+#else
+  try {
+    require_device();
+    float *d = (float *)plat::dev_alloc(4);
+    const int blocks = plat::sm_count() * 16;
+    fp32_peak_kernel<<<blocks, 256>>>(d, 1.0000001f, 1e-7f);
+    cudaDeviceSynchronize();
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    for (int r = 0; r < 10; ++r) fp32_peak_kernel<<<blocks, 256>>>(d, 1.0000001f, 1e-7f);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    plat::dev_free(d);
+    const double flops = 10.0 * (double)blocks * 256.0 * 8.0 * 4096.0 * 2.0;
+    return flops / (ms * 1e-3) / 1e12;
+  } catch (...) { return -1.0; }
+#endif
+}
 int iglb200_poll_device_error(void) {
   API_BEGIN
   require_device();
