@@ -22,9 +22,19 @@ template <class DerivedV, class DerivedF>
 inline iglb200_mesh *make_mesh(const DerivedV &V, const DerivedF &F, int order, int flags = 0) {
   static_assert(std::is_same<typename DerivedF::Scalar, int>::value || std::is_same<typename DerivedF::Scalar, int32_t>::value,
                 "iglb200: F must hold 32-bit ints");
-  if (V.cols() != 3 || (F.rows() && F.cols() != 3)) throw Error(IGLB200_ERR_ARG, "iglb200: V must be #Vx3 and F #Fx3");
+  if (V.cols() != 3 || (F.rows() && (F.cols() < 1 || F.cols() > 3))) throw Error(IGLB200_ERR_ARG, "iglb200: V must be #Vx3 and F #Fx3 (or #Fx2/#Fx1)");
   auto v = view(V);
   iglb200_mesh *m = nullptr;
+  if (F.rows() && F.cols() != 3) {
+    // segments / points: corner k is Ele(i, k % cols) (point_simplex_squared_distance.cpp:126-130)
+    const int64_t n = (int64_t)F.rows(), nc = (int64_t)F.cols();
+    int32_t *t = new int32_t[(size_t)3 * n];
+    for (int64_t i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) t[3 * i + k] = (int32_t)F(i, k % nc);
+    const int rc = iglb200_mesh_create_ex(v.ptr, v.is_f64, v.rows, v.rs, v.cs, t, n, 3, 1, order, flags, &m);
+    delete[] t;
+    check(rc);
+    return m;
+  }
   check(iglb200_mesh_create_ex(v.ptr, v.is_f64, v.rows, v.rs, v.cs, (const int32_t *)F.data(), (int64_t)F.rows(),
                                F.rows() ? row_stride(F) : 3, F.rows() ? col_stride(F) : 1, order, flags, &m));
   return m;

@@ -50,6 +50,10 @@ def point_mesh_squared_distance(P, V, Ele):
     return lib().point_mesh_squared_distance(P, V, Ele)
 
 
+def hausdorff(VA, FA, VB, FB):
+    return lib().hausdorff(VA, FA, VB, FB)
+
+
 def fast_winding_number(*args, **kw):
     return lib().fast_winding_number(*args, **kw)
 

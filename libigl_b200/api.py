@@ -168,6 +168,12 @@ class Api:
         finally:
             m.close()
 
+    def hausdorff(self, VA, FA, VB, FB):
+        """igl::hausdorff (hausdorff.cpp:20-39): vertex-to-surface distances both ways, on the device."""
+        dBA = self.point_mesh_squared_distance(VA, VB, FB)[0]
+        dAB = self.point_mesh_squared_distance(VB, VA, FA)[0]
+        return float(np.sqrt(max(dBA.max(), dAB.max())))
+
     def fast_winding_number(self, *args, **kw):
         """Overloads of igl::fast_winding_number:
         (V, F, Q) -> W                         soup one-shot (fast_winding_number.cpp:367-378)
@@ -201,8 +207,12 @@ class Mesh:
             return
         Vk, vp, vf64, nV, vrs, vcs = _mat(V, "V")
         F = np.asarray(F)
+        if F.ndim == 2 and F.shape[1] in (1, 2):
+            # segments / points: the reference reads corner k as Ele(i, k % cols)
+            # (point_simplex_squared_distance.cpp:126-130), i.e. a degenerate triangle
+            F = F[:, [0, 1 % F.shape[1], 2 % F.shape[1]]]
         if F.ndim != 2 or F.shape[1] != 3:
-            raise ValueError(f"F must be #Fx3, got {F.shape}")
+            raise ValueError(f"F must be #Fx3 (or #Fx2 / #Fx1 element lists), got {F.shape}")
         if F.dtype != np.int32:
             F = F.astype(np.int32)
         if F.shape[0] and (F.strides[0] <= 0 or F.strides[1] <= 0):

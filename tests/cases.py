@@ -426,3 +426,25 @@ def case_pseudonormal(api, meshes, n_queries=4000):
         bad = np.isnan(S)
         assert (I[bad] == F.shape[0] + 1).all() and (C[bad] == 0).all() and (N[bad] == 0).all()
         m.close()
+
+
+def case_segments_points_hausdorff(api):
+    """Ele with 2 / 1 columns (point_mesh_squared_distance.h:23-30) and igl::hausdorff (hausdorff.cpp:20-39)."""
+    rng = np.random.default_rng(4)
+    V = rng.uniform(-1, 1, (300, 3))
+    P = rng.uniform(-1.5, 1.5, (2000, 3))
+    E = rng.integers(0, 300, (400, 2)).astype(np.int32)
+    D, I, C = api.point_mesh_squared_distance(P, V, E)
+    Db, Ib, Cb = oracle.brute_closest(V, E[:, [0, 1, 0]], P)
+    assert np.array_equal(D, Db) and np.array_equal(I, Ib) and np.array_equal(C, Cb)
+    Pt = np.arange(300, dtype=np.int32)[:, None]
+    D, I, C = api.point_mesh_squared_distance(P, V, Pt)
+    d2 = ((P[:, None, :] - V[None]) ** 2).sum(2)
+    assert np.array_equal(I, d2.argmin(1)) and np.allclose(D, d2.min(1), rtol=1e-14, atol=0)
+    VA, FA = synth.icosphere(2)
+    VB, FB = synth.icosphere(3)
+    VB = VB * 1.1 + 0.05
+    h = api.hausdorff(VA, FA, VB, FB)
+    dBA = oracle.brute_closest(VB, FB, VA)[0].max()
+    dAB = oracle.brute_closest(VA, FA, VB)[0].max()
+    assert h == np.sqrt(max(dBA, dAB))

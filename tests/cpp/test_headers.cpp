@@ -10,6 +10,7 @@
 #include "mini_eigen.h"
 #include "iglb200/signed_distance.h"
 #include "iglb200/point_mesh_squared_distance.h"
+#include "iglb200/hausdorff.h"
 
 using namespace mini;
 #define REQUIRE(x) do { if (!(x)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #x); std::exit(1); } } while (0)
@@ -91,6 +92,19 @@ int main() {
     iglb200::fast_winding_number(bvh, 2.0f, Q, W);
     iglb200::fast_winding_number(V, F, Q, W2);
     REQUIRE(std::fabs(W(0) - 1.0) < 1e-5 && std::fabs(W(1)) < 1e-3 && W(0) == W2(0) && W(1) == W2(1));
+  }
+  // segments (Ele with two columns) and hausdorff
+  {
+    MatrixXi E(1, 2); E(0, 0) = 0; E(0, 1) = 1;       // the edge (0,0,0)-(1,0,0)
+    MatrixXd Q(1, 3), C; Q(0, 0) = 0.5; Q(0, 1) = 2.0; Q(0, 2) = 0.0;
+    VectorXd sqrD; VectorXi I;
+    iglb200::point_mesh_squared_distance(Q, V, E, sqrD, I, C);
+    REQUIRE(sqrD(0) == 4.0 && I(0) == 0 && C(0, 0) == 0.5 && C(0, 1) == 0.0);
+    MatrixXd V2; V2.assign_from(V);
+    for (int i = 0; i < 4; ++i) V2(i, 0) += 0.25;
+    double d = -1;
+    iglb200::hausdorff(V, F, V2, F, d);
+    REQUIRE(std::fabs(d - 0.25) < 1e-15);
   }
   // fast_winding_number: one_point_cloud
   {

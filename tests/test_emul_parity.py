@@ -88,3 +88,7 @@ def test_builder_corner_paths(emul_api):
 
 def test_pseudonormal_sign(emul_api):
     cases.case_pseudonormal(emul_api, cases.meshes_small())
+
+
+def test_segments_points_hausdorff(emul_api):
+    cases.case_segments_points_hausdorff(emul_api)

@@ -156,3 +156,7 @@ def test_builder_corner_paths(gpu_api):
 
 def test_pseudonormal_sign(gpu_api):
     cases.case_pseudonormal(gpu_api, dict(cases.meshes_small(), knot200k=synth.torus_knot(2000, 50)))
+
+
+def test_segments_points_hausdorff(gpu_api):
+    cases.case_segments_points_hausdorff(gpu_api)
