@@ -310,7 +310,9 @@ void throw_if_overflow(stream_t s) {
 void launch_closest(const ClosestArgs &a, stream_t s) {
   if (a.n <= 0) return;
   const int64_t warps = (a.n + 31) / 32;
-  const int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)plat::sm_count() * 64);
+  // one packet per warp, blocks in Morton order: the packets in flight form one sliding window of the
+  // query set, so the tree region they touch stays L2-resident (a grid-stride loop spreads it over ~14 regions)
+  const int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)0x7FFFFFFF);
   if (a.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
   else closest_packet_kernel<false><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
   plat::launch_counter()++;
