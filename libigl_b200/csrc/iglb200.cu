@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         const int i = __ffs(wt) - 1;
         wt &= wt - 1;
         const uint32_t f = i == 0 ? ch[0] : i == 1 ? ch[1] : i == 2 ? ch[2] : ch[3];
+#ifdef CP_COUNT_LANES
+        if (COUNT) ntri += __popc(__ballot_sync(FULL, d2[i] <= L.thr2));
+#else
         if (COUNT) ++ntri;
+#endif
         const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)f;
         const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3];
         float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
