@@ -90,6 +90,8 @@ class ClockSampler:
 
 def workload(n_faces, grid, rank=0):
     V, F = synth.torus_knot(*synth.knot_dims(n_faces))
+    if os.environ.get("IGLB200_BENCH_SHUFFLE_FACES"):   # tuning aid: same mesh, rows of F in random order
+        F = np.ascontiguousarray(F[np.random.default_rng(0).permutation(F.shape[0])])
     lo, hi = synth.bbox(V)
     # every rank answers a different grid of the same size (weak scaling): scale 1.1, 1.11, ...
     P = synth.grid_points(lo, hi, grid, 1.1 + 0.01 * rank)
