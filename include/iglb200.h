@@ -168,6 +168,47 @@ int iglb200_cloud_eval(const iglb200_cloud *c,
 int iglb200_cloud_eval_dev(const iglb200_cloud *c, const double *Q, int64_t nQ, double beta, double *WN,
                            void *stream);
 
+/* ---- voxel grids around the path, device resident
+ *      voxel_grid.h:30-37 (voxel_grid.cpp:14-88), flood_fill.h (flood_fill.cpp:11-98),
+ *      marching_cubes.h:39-66 (marching_cubes.cpp:19-112, march_cube.cpp:24-142),
+ *      offset_surface.h (offset_surface.cpp:18-48: the host wrappers compose it from these calls).
+ * A grid owns its vertex positions GV (n x 3) and one scalar S per vertex, both in device memory;
+ * n = side[0]*side[1]*side[2] <= 2^31-1, x fastest (grid.cpp:22-44). */
+typedef struct iglb200_grid iglb200_grid;
+typedef struct iglb200_surface iglb200_surface;
+
+/* igl::voxel_grid(box, s, pad_count, GV, side).  The (V, offset, ...) overload is the box
+ * [min(V) - offset, max(V) + offset] (voxel_grid.cpp:80-86). */
+int iglb200_grid_create(const double box_min[3], const double box_max[3], int s, int pad_count, iglb200_grid **out);
+/* wraps caller-supplied vertex positions (host, strided n x 3 doubles) of an nx*ny*nz grid */
+int iglb200_grid_create_from(const double *GV, int64_t gv_row_stride, int64_t gv_col_stride, int nx, int ny, int nz,
+                             iglb200_grid **out);
+int iglb200_grid_destroy(iglb200_grid *g);
+/* side, vertex count, and the first and last vertex (corners[0..2], corners[3..5]); any may be NULL */
+int iglb200_grid_info(const iglb200_grid *g, int side[3], int64_t *n, double corners[6]);
+/* device pointers: GV column-major (x[n], y[n], z[n]) and S[n]; valid until destroy */
+int iglb200_grid_device(iglb200_grid *g, const double **GV_colmajor, double **S);
+int iglb200_grid_get_GV(const iglb200_grid *g, double *GV, int64_t gv_row_stride, int64_t gv_col_stride);
+int iglb200_grid_set_S(iglb200_grid *g, const double *S);
+int iglb200_grid_get_S(const iglb200_grid *g, double *S);
+/* S = igl::signed_distance(GV, mesh, sign_type, lower, upper) (signed_distance.cpp:28-139); I, C, N are not kept */
+int iglb200_grid_signed_distance(iglb200_grid *g, const iglb200_mesh *m, int sign_type, double lower, double upper);
+/* igl::flood_fill(side, S) */
+int iglb200_grid_flood_fill(iglb200_grid *g);
+/* igl::marching_cubes(S - shift, GV, side..., isovalue, V, F, E2V); offset_surface.cpp:46-47 is
+ * shift = isolevel, isovalue = 0 */
+int iglb200_grid_marching_cubes(const iglb200_grid *g, double shift, double isovalue, iglb200_surface **out);
+int iglb200_surface_info(const iglb200_surface *s, int64_t *nV, int64_t *nF);
+/* V: nV x 3 row-major doubles; F: nF x 3 row-major; E: nV x 2 = the grid edge (i < j) under each vertex,
+ * i.e. the E2V map of marching_cubes.h:58-66 listed by vertex.  Any may be NULL. */
+int iglb200_surface_get(const iglb200_surface *s, double *V, int32_t *F, int32_t *E);
+int iglb200_surface_device(const iglb200_surface *s, const double **V, const int32_t **F, const int32_t **E);
+int iglb200_surface_destroy(iglb200_surface *s);
+/* host-pointer one-shots: igl::flood_fill(res, S) in place; igl::marching_cubes(S, GV, nx, ny, nz, isovalue, ...) */
+int iglb200_flood_fill(const int res[3], double *S);
+int iglb200_marching_cubes(const double *S, const double *GV, int64_t gv_row_stride, int64_t gv_col_stride,
+                           int nx, int ny, int nz, double isovalue, iglb200_surface **out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,5 +66,21 @@ def cloud(P, N, A, order=2) -> Cloud:
     return lib().Cloud(P, N, A, order)
 
 
+def voxel_grid(*args):
+    return lib().voxel_grid(*args)
+
+
+def flood_fill(res, S):
+    return lib().flood_fill(res, S)
+
+
+def marching_cubes(S, GV, nx, ny, nz, isovalue=0.0, return_E2V=False):
+    return lib().marching_cubes(S, GV, nx, ny, nz, isovalue, return_E2V)
+
+
+def offset_surface(V, F, isolevel, s, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER):
+    return lib().offset_surface(V, F, isolevel, s, sign_type)
+
+
 def AABB():
     return _AABB(lib())

@@ -65,6 +65,10 @@ class Api:
         "iglb200_debug_visit_counts", "iglb200_poll_device_error", "iglb200_debug_fp32_peak_tflops",
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
+        "iglb200_grid_create", "iglb200_grid_create_from", "iglb200_grid_destroy", "iglb200_grid_info", "iglb200_grid_device",
+        "iglb200_grid_get_GV", "iglb200_grid_set_S", "iglb200_grid_get_S", "iglb200_grid_signed_distance",
+        "iglb200_grid_flood_fill", "iglb200_grid_marching_cubes", "iglb200_surface_info", "iglb200_surface_get",
+        "iglb200_surface_device", "iglb200_surface_destroy", "iglb200_flood_fill", "iglb200_marching_cubes",
     ]
 
     def __init__(self, lib: C.CDLL):
@@ -103,6 +107,23 @@ class Api:
         L.iglb200_cloud_info.argtypes = [_vp, C.POINTER(_i64)]
         L.iglb200_cloud_eval.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _dbl, _vp, _int]
         L.iglb200_cloud_eval_dev.argtypes = [_vp, _vp, _i64, _dbl, _vp, _vp]
+        L.iglb200_grid_create.argtypes = [_vp, _vp, _int, _int, C.POINTER(_vp)]
+        L.iglb200_grid_create_from.argtypes = [_vp, _i64, _i64, _int, _int, _int, C.POINTER(_vp)]
+        L.iglb200_grid_destroy.argtypes = [_vp]
+        L.iglb200_grid_info.argtypes = [_vp, _vp, C.POINTER(_i64), _vp]
+        L.iglb200_grid_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
+        L.iglb200_grid_get_GV.argtypes = [_vp, _vp, _i64, _i64]
+        L.iglb200_grid_set_S.argtypes = [_vp, _vp]
+        L.iglb200_grid_get_S.argtypes = [_vp, _vp]
+        L.iglb200_grid_signed_distance.argtypes = [_vp, _vp, _int, _dbl, _dbl]
+        L.iglb200_grid_flood_fill.argtypes = [_vp]
+        L.iglb200_grid_marching_cubes.argtypes = [_vp, _dbl, _dbl, C.POINTER(_vp)]
+        L.iglb200_surface_info.argtypes = [_vp, C.POINTER(_i64), C.POINTER(_i64)]
+        L.iglb200_surface_get.argtypes = [_vp, _vp, _vp, _vp]
+        L.iglb200_surface_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
+        L.iglb200_surface_destroy.argtypes = [_vp]
+        L.iglb200_flood_fill.argtypes = [_vp, _vp]
+        L.iglb200_marching_cubes.argtypes = [_vp, _vp, _i64, _i64, _int, _int, _int, _dbl, C.POINTER(_vp)]
 
     # -- plumbing ---------------------------------------------------------
     def check(self, rc):
@@ -142,7 +163,68 @@ class Api:
     def Cloud(self, P, N, A, order=2):
         return Cloud(self, P, N, A, order)
 
+    def Grid(self, box_min=None, box_max=None, s=None, pad_count=0, GV=None, side=None):
+        return Grid(self, box_min, box_max, s, pad_count, GV=GV, side=side)
+
     # -- reference-named free functions -------------------------------------
+    def voxel_grid(self, V_or_box, offset_or_s, s_or_pad, pad_count=None):
+        """igl::voxel_grid: (V, offset, s, pad_count) or ((box_min, box_max), s, pad_count) -> GV, side
+        (voxel_grid.cpp:68-88 / :14-66)."""
+        if pad_count is None:
+            (bmin, bmax), s, pad = V_or_box, offset_or_s, s_or_pad
+        else:
+            V = np.asarray(V_or_box, np.float64)
+            bmin, bmax, s, pad = V.min(0) - offset_or_s, V.max(0) + offset_or_s, s_or_pad, pad_count
+        g = Grid(self, bmin, bmax, s, pad)
+        try:
+            return g.GV(), g.side
+        finally:
+            g.close()
+
+    def flood_fill(self, res, S):
+        """igl::flood_fill(res, S): returns the filled copy (flood_fill.cpp:11-98)."""
+        res = np.ascontiguousarray(res, dtype=np.int32)
+        S = np.array(S, dtype=np.float64, copy=True).reshape(-1)
+        if S.size != int(np.prod(res.astype(np.int64))):
+            raise ValueError("S must hold prod(res) values")
+        self.check(self.lib.iglb200_flood_fill(res.ctypes.data_as(_vp), S.ctypes.data_as(_vp)))
+        return S
+
+    def marching_cubes(self, S, GV, nx, ny, nz, isovalue=0.0, return_E2V=False):
+        """igl::marching_cubes(S, GV, nx, ny, nz, isovalue, V, F[, E2V]) (marching_cubes.cpp:19-112)."""
+        S = np.ascontiguousarray(S, dtype=np.float64).reshape(-1)
+        GV = np.asarray(GV, np.float64)
+        if GV.ndim != 2 or GV.shape[1] != 3 or GV.shape[0] != S.size or S.size != int(nx) * int(ny) * int(nz):
+            raise ValueError("GV must be (nx*ny*nz) x 3 and S nx*ny*nz")
+        if not (GV.flags.c_contiguous or GV.flags.f_contiguous):
+            GV = np.ascontiguousarray(GV)
+        h = _vp()
+        self.check(self.lib.iglb200_marching_cubes(S.ctypes.data_as(_vp), GV.ctypes.data_as(_vp), GV.strides[0] // 8,
+                                                   GV.strides[1] // 8, int(nx), int(ny), int(nz), float(isovalue), C.byref(h)))
+        sf = Surface(self, h)
+        try:
+            return sf.get(return_E2V)
+        finally:
+            sf.close()
+
+    def offset_surface(self, V, F, isolevel, s, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER):
+        """igl::offset_surface(V, F, isolevel, s, signed_distance_type, SV, SF, GV, side, S)
+        (offset_surface.cpp:18-48); the grid never leaves the device between the stages."""
+        V = np.asarray(V, np.float64)
+        pseudo = int(sign_type) == SIGNED_DISTANCE_TYPE_PSEUDONORMAL
+        g = Grid(self, V.min(0) - isolevel, V.max(0) + isolevel, s, 1)     # voxel_grid(V, isolevel, s, 1, GV, side)
+        m = Mesh(self, V, F, 2, pseudonormals=pseudo)
+        try:
+            c = g.corners()
+            h = (c[3] - c[0]) / float(g.side[0] - 1)                        # :31-32
+            g.signed_distance(m, sign_type, isolevel - np.sqrt(3.0) * h, isolevel + np.sqrt(3.0) * h)
+            g.flood_fill()
+            SV, SF = g.marching_cubes(0.0, shift=isolevel)
+            return SV, SF, g.GV(), g.side, g.S()
+        finally:
+            m.close()
+            g.close()
+
     def signed_distance(self, P, V, F, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER,
                         lower_bound=None, upper_bound=None, return_W=False):
         """igl::signed_distance: returns S, I, C (+ N for PSEUDONORMAL, the only sign type that
@@ -355,6 +437,115 @@ class Cloud:
         self.api.check(self.api.lib.iglb200_cloud_eval(self.h, qp, qf64, n, qrs, qcs, float(beta),
                                                        W.ctypes.data_as(_vp), 1))
         return W
+
+
+class Surface:
+    """Result of marching cubes, resident on the device until fetched."""
+
+    def __init__(self, api: Api, handle):
+        self.api = api
+        self.h = handle
+
+    def close(self):
+        if self.h:
+            self.api.lib.iglb200_surface_destroy(self.h)
+            self.h = _vp()
+
+    __del__ = close
+
+    def sizes(self):
+        nv, nf = _i64(), _i64()
+        self.api.check(self.api.lib.iglb200_surface_info(self.h, C.byref(nv), C.byref(nf)))
+        return int(nv.value), int(nf.value)
+
+    def get(self, with_E2V=False):
+        nv, nf = self.sizes()
+        V = np.empty((nv, 3), np.float64)
+        F = np.empty((nf, 3), np.int32)
+        E = np.empty((nv, 2), np.int32) if with_E2V else None
+        self.api.check(self.api.lib.iglb200_surface_get(self.h, V.ctypes.data_as(_vp), F.ctypes.data_as(_vp),
+                                                        E.ctypes.data_as(_vp) if with_E2V else None))
+        return (V, F, E) if with_E2V else (V, F)
+
+
+class Grid:
+    """A voxel grid (positions GV + one value S per vertex) kept on the device:
+    voxel_grid -> signed_distance -> flood_fill -> marching_cubes without a host round trip."""
+
+    def __init__(self, api: Api, box_min=None, box_max=None, s=None, pad_count=0, GV=None, side=None):
+        self.api = api
+        self.h = _vp()
+        if GV is not None:
+            GV = np.asarray(GV, np.float64)
+            if not (GV.flags.c_contiguous or GV.flags.f_contiguous):
+                GV = np.ascontiguousarray(GV)
+            api.check(api.lib.iglb200_grid_create_from(GV.ctypes.data_as(_vp), GV.strides[0] // 8, GV.strides[1] // 8,
+                                                       int(side[0]), int(side[1]), int(side[2]), C.byref(self.h)))
+        else:
+            bmin = np.ascontiguousarray(box_min, dtype=np.float64)
+            bmax = np.ascontiguousarray(box_max, dtype=np.float64)
+            api.check(api.lib.iglb200_grid_create(bmin.ctypes.data_as(_vp), bmax.ctypes.data_as(_vp), int(s), int(pad_count),
+                                                  C.byref(self.h)))
+        sd = (C.c_int * 3)()
+        n = _i64()
+        api.check(api.lib.iglb200_grid_info(self.h, sd, C.byref(n), None))
+        self.side = np.array(list(sd), np.int32)
+        self.n = int(n.value)
+
+    def close(self):
+        if self.h:
+            self.api.lib.iglb200_grid_destroy(self.h)
+            self.h = _vp()
+
+    __del__ = close
+
+    def corners(self):
+        c = (_dbl * 6)()
+        self.api.check(self.api.lib.iglb200_grid_info(self.h, None, None, c))
+        return np.array(list(c))
+
+    def device_ptrs(self):
+        gv, s = _vp(), _vp()
+        self.api.check(self.api.lib.iglb200_grid_device(self.h, C.byref(gv), C.byref(s)))
+        return gv.value, s.value
+
+    def GV(self):
+        out = np.empty((self.n, 3), np.float64)
+        self.api.check(self.api.lib.iglb200_grid_get_GV(self.h, out.ctypes.data_as(_vp), 3, 1))
+        return out
+
+    def S(self):
+        out = np.empty(self.n, np.float64)
+        self.api.check(self.api.lib.iglb200_grid_get_S(self.h, out.ctypes.data_as(_vp)))
+        return out
+
+    def set_S(self, S):
+        S = np.ascontiguousarray(S, dtype=np.float64).reshape(-1)
+        if S.size != self.n:
+            raise ValueError("S must hold one value per grid vertex")
+        self.api.check(self.api.lib.iglb200_grid_set_S(self.h, S.ctypes.data_as(_vp)))
+
+    def signed_distance(self, mesh, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower_bound=None, upper_bound=None):
+        if lower_bound is None:
+            lower_bound = np.finfo(np.float64).tiny
+        if upper_bound is None:
+            upper_bound = np.finfo(np.float64).max
+        self.api.check(self.api.lib.iglb200_grid_signed_distance(self.h, mesh.h, int(sign_type), float(lower_bound),
+                                                                 float(upper_bound)))
+
+    def flood_fill(self):
+        self.api.check(self.api.lib.iglb200_grid_flood_fill(self.h))
+
+    def marching_cubes(self, isovalue=0.0, shift=0.0, return_E2V=False, keep=False):
+        h = _vp()
+        self.api.check(self.api.lib.iglb200_grid_marching_cubes(self.h, float(shift), float(isovalue), C.byref(h)))
+        sf = Surface(self.api, h)
+        if keep:
+            return sf
+        try:
+            return sf.get(return_E2V)
+        finally:
+            sf.close()
 
 
 def parse_arena(buf: np.ndarray):

@@ -2,7 +2,9 @@
 #include "../../include/iglb200.h"
 #include "mesh.h"
 #include "cloud.h"
+#include "grid.h"
 #include <chrono>
+#include <memory>
 
 using plat::DevBuf;
 
@@ -1015,6 +1017,201 @@ int iglb200_fwn_eval(const iglb200_mesh *m, const void *Q, int q_is_f64, int64_t
 }
 
 // ---- point cloud ----------------------------------------------------------
+// ---------------------------------------------------------------- voxel grids (grid.h)
+namespace {
+void check_grid(const iglb200_grid *g) { if (!g) throw std::invalid_argument("null grid handle"); }
+void check_surface(const iglb200_surface *s) { if (!s) throw std::invalid_argument("null surface handle"); }
+struct ColsToStrided { const double *src; int64_t n; double *dst; int64_t rs, cs; DEVFN void operator()(int64_t i) const { for (int j = 0; j < 3; ++j) dst[i * rs + j * cs] = src[j * n + i]; } };
+}  // namespace
+
+int iglb200_grid_create(const double box_min[3], const double box_max[3], int s, int pad_count, iglb200_grid **out) {
+  API_BEGIN
+  if (!box_min || !box_max || !out) throw std::invalid_argument("null pointer");
+  require_device();
+  *out = grid::create(box_min, box_max, s, pad_count, nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_create_from(const double *GV, int64_t gv_rs, int64_t gv_cs, int nx, int ny, int nz, iglb200_grid **out) {
+  API_BEGIN
+  if (!GV || !out) throw std::invalid_argument("null pointer");
+  if (nx < 1 || ny < 1 || nz < 1 || gv_rs <= 0 || gv_cs <= 0) throw std::invalid_argument("bad grid dimensions or strides");
+  const int64_t n = (int64_t)nx * ny * nz;
+  if (n > 0x7FFFFFFF) throw std::invalid_argument("more than 2^31-1 grid vertices");
+  require_device();
+  std::unique_ptr<iglb200_grid> g(new iglb200_grid);
+  g->side[0] = nx; g->side[1] = ny; g->side[2] = nz; g->n = n;
+  g->GV.alloc((size_t)3 * n); g->S.alloc((size_t)n);
+  const size_t span = (size_t)((n - 1) * gv_rs + 2 * gv_cs + 1);
+  DevBuf<double> raw(span);
+  plat::h2d(raw.p, GV, span * 8, nullptr);
+  plat::for_n(n, ToCanon3<double>{raw.p, gv_rs, gv_cs, n, g->GV.p}, nullptr);
+  plat::sync(nullptr);
+  *out = g.release();
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_destroy(iglb200_grid *g) {
+  API_BEGIN
+  delete g;
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_info(const iglb200_grid *g, int side[3], int64_t *n, double corners[6]) {
+  API_BEGIN
+  check_grid(g);
+  if (side) for (int c = 0; c < 3; ++c) side[c] = g->side[c];
+  if (n) *n = g->n;
+  if (corners) {   // first and last grid vertex
+    for (int c = 0; c < 3; ++c) {
+      plat::d2h(&corners[c], g->GV.p + (size_t)c * g->n, 8, nullptr);
+      plat::d2h(&corners[3 + c], g->GV.p + (size_t)c * g->n + (g->n - 1), 8, nullptr);
+    }
+    plat::sync(nullptr);
+  }
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_device(iglb200_grid *g, const double **GV_colmajor, double **S) {
+  API_BEGIN
+  check_grid(g);
+  if (GV_colmajor) *GV_colmajor = g->GV.p;
+  if (S) *S = g->S.p;
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_get_GV(const iglb200_grid *g, double *GV, int64_t gv_rs, int64_t gv_cs) {
+  API_BEGIN
+  check_grid(g);
+  if (!GV || gv_rs <= 0 || gv_cs <= 0) throw std::invalid_argument("bad output");
+  const int64_t n = g->n;
+  if (gv_rs == 1 && gv_cs == n) { plat::d2h(GV, g->GV.p, (size_t)24 * n, nullptr); plat::sync(nullptr); return IGLB200_OK; }
+  const size_t span = (size_t)((n - 1) * gv_rs + 2 * gv_cs + 1);
+  if (span != (size_t)3 * n) throw std::invalid_argument("GV output must be dense (row- or column-major)");
+  DevBuf<double> tmp(span);
+  plat::for_n(n, ColsToStrided{g->GV.p, n, tmp.p, gv_rs, gv_cs}, nullptr);
+  plat::d2h(GV, tmp.p, span * 8, nullptr);
+  plat::sync(nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_set_S(iglb200_grid *g, const double *S) {
+  API_BEGIN
+  check_grid(g);
+  if (!S) throw std::invalid_argument("null pointer");
+  plat::h2d(g->S.p, S, (size_t)8 * g->n, nullptr);
+  plat::sync(nullptr);
+  g->has_S = true;
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_get_S(const iglb200_grid *g, double *S) {
+  API_BEGIN
+  check_grid(g);
+  if (!S) throw std::invalid_argument("null pointer");
+  if (!g->has_S) throw std::invalid_argument("the grid holds no values yet");
+  plat::d2h(S, g->S.p, (size_t)8 * g->n, nullptr);
+  plat::sync(nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_signed_distance(iglb200_grid *g, const iglb200_mesh *m, int sign_type, double lower, double upper) {
+  API_BEGIN
+  check_grid(g); check_mesh(m);
+  require_device();
+  const int64_t n = g->n;
+  DevBuf<int32_t> I((size_t)n);
+  DevBuf<double> C((size_t)3 * n);
+  DevBuf<char> scratch(iglb200_query_scratch_bytes(n));
+  plat::launch_counter() = 0;
+  run_signed_distance(m, g->GV.p, n, sign_type, lower, upper, g->S.p, I.p, C.p, nullptr, nullptr, scratch.p, 1, nullptr);
+  plat::sync(nullptr);
+  throw_if_overflow(nullptr);
+  g->has_S = true;
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_flood_fill(iglb200_grid *g) {
+  API_BEGIN
+  check_grid(g);
+  if (!g->has_S) throw std::invalid_argument("the grid holds no values yet");
+  require_device();
+  grid::flood_fill(g->side, g->S.p, nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_grid_marching_cubes(const iglb200_grid *g, double shift, double isovalue, iglb200_surface **out) {
+  API_BEGIN
+  check_grid(g);
+  if (!out) throw std::invalid_argument("null pointer");
+  if (!g->has_S) throw std::invalid_argument("the grid holds no values yet");
+  require_device();
+  *out = grid::marching_cubes(g->S.p, g->GV.p, g->side[0], g->side[1], g->side[2], shift, isovalue, nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_surface_info(const iglb200_surface *s, int64_t *nV, int64_t *nF) {
+  API_BEGIN
+  check_surface(s);
+  if (nV) *nV = s->nV;
+  if (nF) *nF = s->nF;
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_surface_get(const iglb200_surface *s, double *V, int32_t *F, int32_t *E) {
+  API_BEGIN
+  check_surface(s);
+  if (V && s->nV) plat::d2h(V, s->V.p, (size_t)24 * s->nV, nullptr);
+  if (F && s->nF) plat::d2h(F, s->F.p, (size_t)12 * s->nF, nullptr);
+  if (E && s->nV) plat::d2h(E, s->E.p, (size_t)8 * s->nV, nullptr);
+  plat::sync(nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_surface_device(const iglb200_surface *s, const double **V, const int32_t **F, const int32_t **E) {
+  API_BEGIN
+  check_surface(s);
+  if (V) *V = s->V.p;
+  if (F) *F = s->F.p;
+  if (E) *E = s->E.p;
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_surface_destroy(iglb200_surface *s) {
+  API_BEGIN
+  delete s;
+  return IGLB200_OK;
+  API_END
+}
+// host-pointer one-shots with the reference's argument meaning
+int iglb200_flood_fill(const int res[3], double *S) {
+  API_BEGIN
+  if (!res || !S) throw std::invalid_argument("null pointer");
+  if (res[0] < 1 || res[1] < 1 || res[2] < 1) throw std::invalid_argument("empty grid");
+  const int64_t n = (int64_t)res[0] * res[1] * res[2];
+  require_device();
+  DevBuf<double> d((size_t)n);
+  plat::h2d(d.p, S, (size_t)8 * n, nullptr);
+  grid::flood_fill(res, d.p, nullptr);
+  plat::d2h(S, d.p, (size_t)8 * n, nullptr);
+  plat::sync(nullptr);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_marching_cubes(const double *S, const double *GV, int64_t gv_rs, int64_t gv_cs, int nx, int ny, int nz,
+                           double isovalue, iglb200_surface **out) {
+  API_BEGIN
+  if (!S || !GV || !out) throw std::invalid_argument("null pointer");
+  iglb200_grid *g = nullptr;
+  if (iglb200_grid_create_from(GV, gv_rs, gv_cs, nx, ny, nz, &g) != IGLB200_OK) throw std::invalid_argument(g_err);
+  std::unique_ptr<iglb200_grid> hold(g);
+  plat::h2d(g->S.p, S, (size_t)8 * g->n, nullptr);
+  plat::sync(nullptr);
+  *out = grid::marching_cubes(g->S.p, g->GV.p, nx, ny, nz, 0.0, isovalue, nullptr);
+  return IGLB200_OK;
+  API_END
+}
+
 int iglb200_cloud_create(const void *P, const void *N, const void *A, int is_f64, int64_t nP, int expansion_order,
                          iglb200_cloud **out) {
   API_BEGIN

@@ -336,3 +336,88 @@ class PortCloud:
         WN = np.empty(Q.shape[0])
         port().port_cloud_eval(self.h, _dp(Q), Q.shape[0], float(beta), _dp(WN))
         return WN
+
+
+# ---------------------------------------------------------------------------
+# voxel grids around the path: grid / voxel_grid / flood_fill / marching_cubes / offset_surface
+def mc_tables():
+    """(edge_flags[256], edge_conn[12,2], tri[256,16]) as the genuine reference header defines them."""
+    L = ref()
+    ef = np.empty(256, np.int32); cn = np.empty((12, 2), np.int32); tr = np.empty((256, 16), np.int32)
+    L.ref_mc_tables.argtypes = [_c_ip, _c_ip, _c_ip]
+    L.ref_mc_tables(_ip(ef), _ip(cn), _ip(tr))
+    return ef, cn, tr
+
+
+def grid(res):
+    """igl::grid (grid.cpp:12-45): (prod(res), 3) positions in [0,1]^3, x fastest."""
+    res = np.ascontiguousarray(res, dtype=np.int32)
+    GV = np.empty((int(np.prod(res.astype(np.int64))), 3))
+    L = port()
+    L.port_grid.argtypes = [_c_ip, _c_dp]
+    L.port_grid(_ip(res), _dp(GV))
+    return GV
+
+
+def voxel_grid(bmin, bmax, s, pad_count):
+    """igl::voxel_grid(box, s, pad_count, GV, side) (voxel_grid.cpp:14-66) -> GV (n,3), side (3,)."""
+    bmin = np.ascontiguousarray(bmin, dtype=np.float64); bmax = np.ascontiguousarray(bmax, dtype=np.float64)
+    side = np.zeros(3, np.int32)
+    L = port()
+    L.port_voxel_grid.argtypes = [_c_dp, _c_dp, C.c_int, C.c_int, _c_ip, _c_dp]
+    L.port_voxel_grid(_dp(bmin), _dp(bmax), int(s), int(pad_count), _ip(side), None)
+    GV = np.empty((int(np.prod(side.astype(np.int64))), 3))
+    L.port_voxel_grid(_dp(bmin), _dp(bmax), int(s), int(pad_count), _ip(side), _dp(GV))
+    return GV, side
+
+
+def voxel_grid_mesh(V, offset, s, pad_count):
+    """The (V, offset) overload (voxel_grid.cpp:68-88)."""
+    V = np.asarray(V, np.float64)
+    return voxel_grid(V.min(0) - offset, V.max(0) + offset, s, pad_count)
+
+
+def flood_fill(res, S):
+    """igl::flood_fill (flood_fill.cpp:11-98); returns the filled copy."""
+    res = np.ascontiguousarray(res, dtype=np.int32)
+    S = np.array(S, dtype=np.float64, copy=True).ravel()
+    assert S.size == int(np.prod(res.astype(np.int64)))
+    L = port()
+    L.port_flood_fill.argtypes = [_c_ip, _c_dp]
+    L.port_flood_fill(_ip(res), _dp(S))
+    return S
+
+
+def marching_cubes(S, GV, nx, ny, nz, isovalue=0.0, tables=None):
+    """igl::marching_cubes(S,GV,nx,ny,nz,isovalue,V,F[,E2V]) -> V (n,3), F (m,3), E (n,2) = E2V keys by vertex."""
+    S = np.ascontiguousarray(S, dtype=np.float64).ravel(); GV = np.ascontiguousarray(GV, dtype=np.float64)
+    ef, cn, tr = tables or mc_tables()
+    ef = np.ascontiguousarray(ef, np.int32); cn = np.ascontiguousarray(cn, np.int32); tr = np.ascontiguousarray(tr, np.int32)
+    L = port()
+    L.port_marching_cubes.restype = C.c_void_p
+    L.port_marching_cubes.argtypes = [_c_dp, _c_dp, C.c_int, C.c_int, C.c_int, C.c_double, _c_ip, _c_ip, _c_ip, _c_lp, _c_lp]
+    L.port_mc_get.argtypes = [C.c_void_p, _c_dp, _c_ip, _c_ip]
+    L.port_mc_destroy.argtypes = [C.c_void_p]
+    nV = C.c_int64(); nF = C.c_int64()
+    h = L.port_marching_cubes(_dp(S), _dp(GV), int(nx), int(ny), int(nz), float(isovalue), _ip(ef), _ip(cn), _ip(tr),
+                              C.byref(nV), C.byref(nF))
+    V = np.empty((nV.value, 3)); F = np.empty((nF.value, 3), np.int32); E = np.empty((nV.value, 2), np.int32)
+    L.port_mc_get(h, _dp(V), _ip(F), _ip(E))
+    L.port_mc_destroy(h)
+    return V, F, E
+
+
+def offset_surface(V, F, isolevel, s, sign_type="fwn"):
+    """igl::offset_surface (offset_surface.cpp:18-48) -> SV, SF, GV, side, S (S after flood_fill)."""
+    GV, side = voxel_grid_mesh(V, isolevel, s, 1)
+    h = (GV[:, 0].max() - GV[:, 0].min()) / float(side[0] - 1)
+    lower, upper = isolevel - np.sqrt(3.0) * h, isolevel + np.sqrt(3.0) * h
+    if sign_type == "fwn":
+        S = signed_distance_fwn(GV, V, F, lower, upper)[0]
+    elif sign_type == "pseudonormal":
+        S = signed_distance_pseudonormal(GV, V, F, lower, upper)[0]
+    else:
+        raise ValueError(sign_type)
+    S = flood_fill(side, S)
+    SV, SF, _ = marching_cubes(S - isolevel, GV, side[0], side[1], side[2], 0.0)
+    return SV, SF, GV, side, S

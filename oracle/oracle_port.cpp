@@ -30,6 +30,7 @@
 #include <numeric>
 #include <thread>
 #include <vector>
+#include <unordered_map>
 
 namespace {
 
@@ -801,5 +802,134 @@ void port_pseudo_test(void *p, const double *Q, const int *I, const double *C, i
     pseudonormal_test(ps, Q + 3 * k, I[k], C + 3 * k, S[k], N + 3 * k);
   }, 10000);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Voxel grids around the path: restated, sequential, double precision.
+// ---------------------------------------------------------------------------------------------
+
+// igl::grid (grid.cpp:12-45): x fastest; GV(gi,c) = sub_c / (res_c - 1).  GV row-major n x 3.
+void port_grid(const int *res, double *GV) {
+  const int64_t n = (int64_t)res[0] * res[1] * res[2];
+  int sub[3] = {0, 0, 0};
+  for (int64_t gi = 0; gi < n; ++gi) {
+    for (int c = 0; c < 2; ++c)
+      if (sub[c] >= res[c]) { sub[c] = 0; sub[c + 1]++; }
+    for (int c = 0; c < 3; ++c) GV[3 * gi + c] = (double)sub[c] / (double)(res[c] - 1);
+    sub[0]++;
+  }
+}
+
+// igl::voxel_grid, box overload (voxel_grid.cpp:14-66).  Phase 1 (GV == nullptr): side only.
+// The column mean (:64) is a plain running sum here; Eigen's reduction order is not defined by the
+// reference's sources, so positions are pinned to ~1e-13 relative, not to the bit.
+void port_voxel_grid(const double *bmin, const double *bmax, int in_s, int pad_count, int *side, double *GV) {
+  double diag[3];
+  for (int c = 0; c < 3; ++c) diag[c] = bmax[c] - bmin[c];
+  int si = 0;
+  for (int c = 1; c < 3; ++c) if (diag[c] > diag[si]) si = c;   // maxCoeff: first maximum
+  const double s_len = diag[si];
+  const double s = in_s - 2 * pad_count;
+  side[si] = (int)s;
+  for (int i = 0; i < 3; ++i)
+    if (i != si) side[i] = (int)std::ceil(s * (bmax[i] - bmin[i]) / s_len);
+  for (int i = 0; i < 3; ++i) side[i] += 2 * pad_count;
+  if (!GV) return;
+  port_grid(side, GV);
+  double ps[3], A[3];
+  for (int c = 0; c < 3; ++c) { ps[c] = (double)pad_count / ((double)side[c] - 1.); A[c] = diag[c] / (1.0 - 2. * ps[c]); }
+  int ai = 0;
+  for (int c = 1; c < 3; ++c) if (A[c] > A[ai]) ai = c;
+  const double a = A[ai];
+  double ratio[3];
+  for (int c = 0; c < 3; ++c) ratio[c] = a * ((double)side[c] - 1.0) / (double)(side[ai] - 1.0);
+  const int64_t n = (int64_t)side[0] * side[1] * side[2];
+  double sum[3] = {0, 0, 0};
+  for (int64_t g = 0; g < n; ++g)
+    for (int c = 0; c < 3; ++c) { GV[3 * g + c] *= ratio[c]; sum[c] += GV[3 * g + c]; }
+  double off[3];
+  for (int c = 0; c < 3; ++c) off[c] = (bmin[c] + bmax[c]) / 2.0 - sum[c] / (double)n;
+  for (int64_t g = 0; g < n; ++g)
+    for (int c = 0; c < 3; ++c) GV[3 * g + c] += off[c];
+}
+
+// igl::flood_fill (flood_fill.cpp:11-98), literally sequential
+void port_flood_fill(const int *res, double *S) {
+  const int rx = res[0], ry = res[1], rz = res[2];
+  auto at = [&](int x, int y, int z) -> double & { return S[x + (int64_t)rx * (y + (int64_t)ry * z)]; };
+  int signed_zi = -1;
+  double s = std::numeric_limits<double>::quiet_NaN();
+  for (int zi = 0; zi < rz; zi++) {
+    int signed_yi = -1;
+    if (zi != 0) s = at(0, 0, zi - 1);
+    for (int yi = 0; yi < ry; yi++) {
+      int signed_xi = -1;
+      if (yi != 0) s = at(0, yi - 1, zi);
+      for (int xi = 0; xi < rx; xi++) {
+        double &v = at(xi, yi, zi);
+        if (v != v) { if (s == s) v = s; continue; }
+        s = v;
+        for (int bxi = xi; signed_xi < --bxi;) at(bxi, yi, zi) = s;
+        for (int byi = yi; signed_yi < --byi;)
+          for (int x = 0; x < rx; x++) at(x, byi, zi) = s;
+        for (int bzi = zi; signed_zi < --bzi;)
+          for (int y = 0; y < ry; y++)
+            for (int x = 0; x < rx; x++) at(x, y, bzi) = s;
+        signed_xi = xi; signed_yi = yi; signed_zi = zi;
+      }
+    }
+  }
+}
+
+// igl::marching_cubes on a regular index grid (marching_cubes.cpp:34-112) with igl::march_cube
+// (march_cube.cpp:24-142): cubes x-fastest, a vertex per cut edge created by the first cube that
+// meets it (hash map keyed by the sorted endpoint pair), interpolated FROM that cube's first
+// endpoint, up to five triangles per cube.  Tables are passed in (the genuine ones come from
+// oracle/_ref).  Returns counts; V (n x 3), F (m x 3), E (n x 2: the vertex's E2V key, i < j) are
+// written if the caps allow.
+struct McOut { std::vector<double> V; std::vector<int> F, E; };
+void *port_marching_cubes(const double *S, const double *GV, int nx, int ny, int nz, double isovalue,
+                          const int *edge_flags, const int *conn, const int *tri, int64_t *nV, int64_t *nF) {
+  McOut *o = new McOut;
+  std::unordered_map<int64_t, int> E2V;
+  const int64_t off[8] = {0, 1, 1 + (int64_t)nx, nx, (int64_t)nx * ny, 1 + (int64_t)nx * ny, 1 + nx + (int64_t)nx * ny, nx + (int64_t)nx * ny};
+  for (int z = 0; z < nz - 1; z++)
+    for (int y = 0; y < ny - 1; y++)
+      for (int x = 0; x < nx - 1; x++) {
+        const int64_t i0 = x + (int64_t)nx * (y + (int64_t)ny * z);
+        double cS[8]; int64_t cI[8];
+        int c_flags = 0;
+        for (int c = 0; c < 8; c++) { cI[c] = i0 + off[c]; cS[c] = S[cI[c]]; if (cS[c] > isovalue) c_flags |= 1 << c; }
+        const int e_flags = edge_flags[c_flags];
+        if (e_flags == 0) continue;
+        int ev[12];
+        for (int e = 0; e < 12; e++) {
+          if (!(e_flags & (1 << e))) continue;
+          const int64_t i = cI[conn[2 * e]], j = cI[conn[2 * e + 1]];
+          const int64_t key = (i < j ? i : j) | ((i < j ? j : i) << 32);
+          auto it = E2V.find(key);
+          if (it == E2V.end()) {
+            const int v = (int)(o->V.size() / 3);
+            E2V[key] = v; ev[e] = v;
+            const double a = cS[conn[2 * e]], b = cS[conn[2 * e + 1]];
+            const double t = (isovalue - a) / (b - a);   // the delta==0 branch (:118) is overwritten by :119
+            for (int d = 0; d < 3; ++d) o->V.push_back(GV[3 * i + d] + t * (GV[3 * j + d] - GV[3 * i + d]));
+            o->E.push_back((int)(i < j ? i : j)); o->E.push_back((int)(i < j ? j : i));   // the E2V key (:52-60)
+          } else ev[e] = it->second;
+        }
+        for (int f = 0; f < 5; f++) {
+          if (tri[16 * c_flags + 3 * f] < 0) break;
+          for (int k = 0; k < 3; ++k) o->F.push_back(ev[tri[16 * c_flags + 3 * f + k]]);
+        }
+      }
+  *nV = (int64_t)(o->V.size() / 3); *nF = (int64_t)(o->F.size() / 3);
+  return o;
+}
+void port_mc_get(void *p, double *V, int *F, int *E) {
+  McOut *o = (McOut *)p;
+  if (V) std::memcpy(V, o->V.data(), o->V.size() * 8);
+  if (F) std::memcpy(F, o->F.data(), o->F.size() * 4);
+  if (E) std::memcpy(E, o->E.data(), o->E.size() * 4);
+}
+void port_mc_destroy(void *p) { delete (McOut *)p; }
 
 }  // extern "C"

@@ -114,4 +114,13 @@ int ref_bvh4_build(const float *boxes, int nb, uint32_t *nodes_out, int cap_node
   return n;
 }
 
+// the marching-cubes case tables exactly as the reference compiles them (march_cube.cpp:44 includes this
+// header fragment inside the function body, as done here)
+void ref_mc_tables(int *edge_flags256, int *edge_conn24, int *tri4096) {
+#include <igl/marching_cubes_tables.h>
+  for (int i = 0; i < 256; ++i) edge_flags256[i] = aiCubeEdgeFlags[i];
+  for (int e = 0; e < 12; ++e) { edge_conn24[2 * e] = a2eConnection[e][0]; edge_conn24[2 * e + 1] = a2eConnection[e][1]; }
+  for (int i = 0; i < 256; ++i) for (int k = 0; k < 16; ++k) tri4096[16 * i + k] = a2fConnectionTable[i][k];
+}
+
 }  // extern "C"

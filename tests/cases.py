@@ -448,3 +448,156 @@ def case_segments_points_hausdorff(api):
     dBA = oracle.brute_closest(VB, FB, VA)[0].max()
     dAB = oracle.brute_closest(VA, FA, VB)[0].max()
     assert h == np.sqrt(max(dBA, dAB))
+
+
+# ---------------------------------------------------------------- voxel grids
+def _same(a, b):
+    """bit-for-bit equality that treats NaN == NaN"""
+    a = np.asarray(a); b = np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+
+
+def case_voxel_grid(api):
+    """igl::voxel_grid: `side` exact; positions to 1e-13 of the box size (the reference's column mean is an
+    Eigen reduction whose order its sources do not fix, see oracle_port.cpp::port_voxel_grid)."""
+    boxes = [([0, 0, 0], [1, 1, 1], 10, 0), ([0, 0, 0], [1, 2, 0.5], 20, 1), ([-3.5, 2, 7], [4, 2.25, 9], 33, 2),
+             ([1e3, -1e-3, 0], [1e3 + 1, 1e-3, 1e-6], 17, 1), ([-1, -1, -1], [1, 1, 1], 64, 1)]
+    for bmin, bmax, s, pad in boxes:
+        GVo, so = oracle.voxel_grid(bmin, bmax, s, pad)
+        GV, side = api.voxel_grid((bmin, bmax), s, pad)
+        assert np.array_equal(side, so), (side, so)
+        scale = np.abs(np.array(bmax, float) - np.array(bmin, float)).max() + np.abs(np.array(bmax, float)).max()
+        assert np.array_equal(np.isnan(GV), np.isnan(GVo))   # a 3-vertex padded side divides by zero in the reference too
+        assert np.nanmax(np.abs(GV - GVo), initial=0.0) <= 1e-13 * scale, np.nanmax(np.abs(GV - GVo))
+    V, _ = synth.icosphere(2)
+    GVo, so = oracle.voxel_grid_mesh(V, 0.25, 30, 1)
+    GV, side = api.voxel_grid(V, 0.25, 30, 1)
+    assert np.array_equal(side, so) and np.abs(GV - GVo).max() <= 1e-13 * 3
+    # the reference's own known answer (tests/include/igl/grid.cpp:5-41) through the unit box, no padding
+    GV, side = api.voxel_grid(([0, 0, 0], [1, 1, 1]), 3, 0)
+    assert side.tolist() == [3, 3, 3]
+    want = np.array([[x, y, z] for z in (0, .5, 1) for y in (0, .5, 1) for x in (0, .5, 1)])
+    assert np.abs(GV - want).max() < 1e-15
+    for bad in [(([0, 0, 0], [1, 1, 1]), 3, 1), (([0, 0, 0], [0, 0, 0]), 10, 1), (([0, 0, 0], [np.nan, 1, 1]), 10, 1)]:
+        try:
+            api.voxel_grid(*bad)
+        except IglB200Error:
+            pass
+        else:
+            raise AssertionError(f"voxel_grid{bad} must fail")
+
+
+def case_flood_fill(api, seeds=12):
+    """igl::flood_fill: bit-identical to the sequential sweep for every NaN pattern."""
+    rng = np.random.default_rng(3)
+    shapes = [(5, 4, 3), (1, 7, 2), (8, 1, 1), (1, 1, 1), (2, 2, 2), (9, 6, 5), (16, 3, 7), (3, 11, 4)]
+    n_cases = 0
+    for shape in shapes:
+        n = int(np.prod(shape))
+        for k in range(seeds):
+            S = rng.standard_normal(n)
+            p = [0.0, 0.1, 0.5, 0.9, 0.98, 1.0][k % 6]
+            S[rng.random(n) < p] = np.nan
+            S3 = S.reshape(shape[2], shape[1], shape[0])
+            if k % 4 == 1 and shape[1] > 1:     # whole rows
+                S3[:, rng.integers(0, shape[1]), :] = np.nan
+            if k % 4 == 2 and shape[2] > 1:     # whole sheets, leading / inner / trailing
+                S3[rng.integers(0, shape[2]), :, :] = np.nan
+            if k % 4 == 3:
+                S3[-1, :, :] = np.nan
+                S3[0, :, :] = np.nan
+            got = api.flood_fill(shape, S)
+            want = oracle.flood_fill(shape, S)
+            assert _same(got, want), (shape, k, np.flatnonzero(~((got == want) | (np.isnan(got) & np.isnan(want))))[:5])
+            n_cases += 1
+    return n_cases
+
+
+def _check_mc(api, S, GV, dims, iso, what):
+    nx, ny, nz = dims
+    Vo, Fo, Eo = oracle.marching_cubes(S, GV, nx, ny, nz, iso)
+    V, F, E = api.marching_cubes(S, GV, nx, ny, nz, iso, return_E2V=True)
+    assert V.shape == Vo.shape and F.shape == Fo.shape, f"{what}: {V.shape} {F.shape} vs {Vo.shape} {Fo.shape}"
+    assert _same(F, Fo), f"{what}: faces differ"
+    assert _same(E, Eo), f"{what}: edge keys differ"
+    assert _same(V, Vo), f"{what}: vertices differ (max {np.nanmax(np.abs(V - Vo)) if V.size else 0})"
+    return V.shape[0], F.shape[0]
+
+
+def case_marching_cubes(api):
+    """igl::marching_cubes: V, F and the E2V keys bit-identical to the sequential hash-map sweep."""
+    rng = np.random.default_rng(5)
+    out = {}
+    g = 24
+    GV = oracle.grid([g, g, g]) * 2 - 1
+    S = np.linalg.norm(GV, axis=1) - 0.7
+    nv, nf = _check_mc(api, S, GV, (g, g, g), 0.0, "sphere")
+    assert nv - nf * 3 // 2 + nf == 2      # closed genus-0 surface
+    out["sphere"] = (nv, nf)
+    _check_mc(api, S, GV, (g, g, g), 0.1, "sphere iso 0.1")
+    # every corner configuration, ambiguous ones included; anisotropic, non-uniform positions
+    dims = (13, 9, 11)
+    n = int(np.prod(dims))
+    GVr = oracle.grid(list(dims)) * np.array([1.0, 3.0, 0.5]) + rng.standard_normal((n, 3)) * 0.01
+    Sr = rng.standard_normal(n)
+    out["noise"] = _check_mc(api, Sr, GVr, dims, 0.0, "noise")
+    _check_mc(api, Sr, np.asfortranarray(GVr), dims, 0.3, "noise, column-major GV")
+    # values equal to the isovalue (delta == 0 -> t = +-inf/NaN, march_cube.cpp:117-119), NaN and inf samples
+    Sq = np.round(Sr * 2) / 2
+    _check_mc(api, Sq, GVr, dims, 0.5, "quantised (ties with the isovalue)")
+    Sn = Sr.copy(); Sn[rng.random(n) < 0.1] = np.nan; Sn[rng.random(n) < 0.02] = np.inf
+    _check_mc(api, Sn, GVr, dims, 0.0, "NaN/inf samples")
+    # degenerate grids: no cubes at all, a single cube, flat slabs
+    for d in [(1, 1, 1), (5, 1, 4), (2, 2, 2), (2, 7, 2), (3, 2, 6)]:
+        m = int(np.prod(d))
+        _check_mc(api, rng.standard_normal(m), oracle.grid(list(d)) if min(d) > 1 else rng.standard_normal((m, 3)), d, 0.0, f"dims {d}")
+    _check_mc(api, np.full(n, 1.0), GVr, dims, 0.0, "all above")
+    _check_mc(api, np.full(n, -1.0), GVr, dims, 0.0, "all below")
+    return out
+
+
+def case_offset_surface(api, V, F, isolevel, s, sign_type, what):
+    """igl::offset_surface = voxel_grid -> signed_distance(bounded) -> flood_fill -> marching_cubes.
+    Stage by stage: the raw S obeys the signed-distance parity rules (rows the reference itself leaves
+    order-dependent, SURVEY A.1, excluded); flood fill and marching cubes of that S are bit-identical to
+    the sequential reference algorithms; the one-call result equals the staged one."""
+    from libigl_b200.api import Grid, Mesh, SIGNED_DISTANCE_TYPE_PSEUDONORMAL
+    pseudo = int(sign_type) == SIGNED_DISTANCE_TYPE_PSEUDONORMAL
+    GVo, side_o = oracle.voxel_grid_mesh(V, isolevel, s, 1)
+    g = Grid(api, V.min(0) - isolevel, V.max(0) + isolevel, s, 1)
+    m = Mesh(api, V, F, 2, pseudonormals=pseudo)
+    assert np.array_equal(g.side, side_o)
+    GV = g.GV()
+    diag = np.linalg.norm(V.max(0) - V.min(0))
+    assert np.abs(GV - GVo).max() <= 1e-13 * (diag + np.abs(V).max())
+    c = g.corners()
+    h = (c[3] - c[0]) / float(g.side[0] - 1)
+    assert h == (GV[:, 0].max() - GV[:, 0].min()) / float(g.side[0] - 1)
+    lower, upper = isolevel - np.sqrt(3.0) * h, isolevel + np.sqrt(3.0) * h
+    g.signed_distance(m, sign_type, lower, upper)
+    S_raw = g.S()
+    # the signed-distance stage on the product's own grid vertices
+    if pseudo:
+        So = oracle.signed_distance_pseudonormal(GV, V, F, lower, upper)[0]
+    else:
+        So = oracle.signed_distance_fwn(GV, V, F, lower, upper)[0]
+    low2, _ = oracle.signed_distance_bounds(lower, upper)
+    d2 = oracle.PortAABB(V, F).squared_distance(GV)[0]
+    care = d2 > low2 * (1 + 1e-12)                     # below the lower bound the reference is order-dependent
+    assert np.array_equal(np.isnan(S_raw[care]), np.isnan(So[care])), f"{what}: NaN pattern"
+    ok = care & ~np.isnan(So)
+    assert np.abs(S_raw[ok] - So[ok]).max() <= 1e-5 * max(diag, 1.0), f"{what}: S"
+    g.flood_fill()
+    S_fill = g.S()
+    assert _same(S_fill, oracle.flood_fill(g.side, S_raw)), f"{what}: flood_fill"
+    SV, SF, E = g.marching_cubes(0.0, shift=isolevel, return_E2V=True)
+    Vo, Fo, Eo = oracle.marching_cubes(S_fill - isolevel, GV, g.side[0], g.side[1], g.side[2], 0.0)
+    assert _same(SF, Fo) and _same(E, Eo) and _same(SV, Vo), f"{what}: marching_cubes"
+    m.close(); g.close()
+    SV1, SF1, GV1, side1, S1 = api.offset_surface(V, F, isolevel, s, sign_type)
+    assert _same(SV1, SV) and _same(SF1, SF) and _same(GV1, GV) and _same(side1, side_o) and _same(S1, S_fill), f"{what}: one call"
+    # the offset surface really is at distance `isolevel` from the mesh
+    if SV.shape[0]:
+        dist = np.sqrt(oracle.PortAABB(V, F).squared_distance(SV)[0])
+        assert np.abs(dist - abs(isolevel)).max() < 1.5 * h, f"{what}: surface off by {np.abs(dist - abs(isolevel)).max()} (h={h})"
+    return dict(nV=int(SV.shape[0]), nF=int(SF.shape[0]), side=side_o.tolist())

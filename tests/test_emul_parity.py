@@ -92,3 +92,25 @@ def test_pseudonormal_sign(emul_api):
 
 def test_segments_points_hausdorff(emul_api):
     cases.case_segments_points_hausdorff(emul_api)
+
+
+def test_voxel_grid(emul_api):
+    cases.case_voxel_grid(emul_api)
+
+
+def test_flood_fill(emul_api):
+    assert cases.case_flood_fill(emul_api) > 90
+
+
+def test_marching_cubes(emul_api):
+    cases.case_marching_cubes(emul_api)
+
+
+def test_offset_surface(emul_api):
+    from libigl_b200.api import SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER as FWN, SIGNED_DISTANCE_TYPE_PSEUDONORMAL as PN
+    V, F = synth.icosphere(2)
+    r = cases.case_offset_surface(emul_api, V, F, 0.2, 20, FWN, "ico2 +0.2 fwn")
+    assert r["nF"] > 500
+    cases.case_offset_surface(emul_api, V, F, 0.15, 18, PN, "ico2 +0.15 pseudonormal")
+    V, F = synth.torus_knot(120, 10)
+    cases.case_offset_surface(emul_api, V, F, 0.05, 28, FWN, "knot +0.05 fwn")
