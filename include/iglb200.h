@@ -188,9 +188,9 @@ int iglb200_grid_destroy(iglb200_grid *g);
 int iglb200_grid_info(const iglb200_grid *g, int side[3], int64_t *n, double corners[6]);
 /* device pointers: GV column-major (x[n], y[n], z[n]) and S[n]; valid until destroy */
 int iglb200_grid_device(iglb200_grid *g, const double **GV_colmajor, double **S);
-int iglb200_grid_get_GV(const iglb200_grid *g, double *GV, int64_t gv_row_stride, int64_t gv_col_stride);
-int iglb200_grid_set_S(iglb200_grid *g, const double *S);
-int iglb200_grid_get_S(const iglb200_grid *g, double *S);
+int iglb200_grid_get_gv(const iglb200_grid *g, double *GV, int64_t gv_row_stride, int64_t gv_col_stride);
+int iglb200_grid_set_s(iglb200_grid *g, const double *S);
+int iglb200_grid_get_s(const iglb200_grid *g, double *S);
 /* S = igl::signed_distance(GV, mesh, sign_type, lower, upper) (signed_distance.cpp:28-139); I, C, N are not kept */
 int iglb200_grid_signed_distance(iglb200_grid *g, const iglb200_mesh *m, int sign_type, double lower, double upper);
 /* igl::flood_fill(side, S) */

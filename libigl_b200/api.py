@@ -66,7 +66,7 @@ class Api:
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
         "iglb200_grid_create", "iglb200_grid_create_from", "iglb200_grid_destroy", "iglb200_grid_info", "iglb200_grid_device",
-        "iglb200_grid_get_GV", "iglb200_grid_set_S", "iglb200_grid_get_S", "iglb200_grid_signed_distance",
+        "iglb200_grid_get_gv", "iglb200_grid_set_s", "iglb200_grid_get_s", "iglb200_grid_signed_distance",
         "iglb200_grid_flood_fill", "iglb200_grid_marching_cubes", "iglb200_surface_info", "iglb200_surface_get",
         "iglb200_surface_device", "iglb200_surface_destroy", "iglb200_flood_fill", "iglb200_marching_cubes",
     ]
@@ -112,9 +112,9 @@ class Api:
         L.iglb200_grid_destroy.argtypes = [_vp]
         L.iglb200_grid_info.argtypes = [_vp, _vp, C.POINTER(_i64), _vp]
         L.iglb200_grid_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp)]
-        L.iglb200_grid_get_GV.argtypes = [_vp, _vp, _i64, _i64]
-        L.iglb200_grid_set_S.argtypes = [_vp, _vp]
-        L.iglb200_grid_get_S.argtypes = [_vp, _vp]
+        L.iglb200_grid_get_gv.argtypes = [_vp, _vp, _i64, _i64]
+        L.iglb200_grid_set_s.argtypes = [_vp, _vp]
+        L.iglb200_grid_get_s.argtypes = [_vp, _vp]
         L.iglb200_grid_signed_distance.argtypes = [_vp, _vp, _int, _dbl, _dbl]
         L.iglb200_grid_flood_fill.argtypes = [_vp]
         L.iglb200_grid_marching_cubes.argtypes = [_vp, _dbl, _dbl, C.POINTER(_vp)]
@@ -511,19 +511,19 @@ class Grid:
 
     def GV(self):
         out = np.empty((self.n, 3), np.float64)
-        self.api.check(self.api.lib.iglb200_grid_get_GV(self.h, out.ctypes.data_as(_vp), 3, 1))
+        self.api.check(self.api.lib.iglb200_grid_get_gv(self.h, out.ctypes.data_as(_vp), 3, 1))
         return out
 
     def S(self):
         out = np.empty(self.n, np.float64)
-        self.api.check(self.api.lib.iglb200_grid_get_S(self.h, out.ctypes.data_as(_vp)))
+        self.api.check(self.api.lib.iglb200_grid_get_s(self.h, out.ctypes.data_as(_vp)))
         return out
 
     def set_S(self, S):
         S = np.ascontiguousarray(S, dtype=np.float64).reshape(-1)
         if S.size != self.n:
             raise ValueError("S must hold one value per grid vertex")
-        self.api.check(self.api.lib.iglb200_grid_set_S(self.h, S.ctypes.data_as(_vp)))
+        self.api.check(self.api.lib.iglb200_grid_set_s(self.h, S.ctypes.data_as(_vp)))
 
     def signed_distance(self, mesh, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower_bound=None, upper_bound=None):
         if lower_bound is None:

@@ -1080,7 +1080,7 @@ int iglb200_grid_device(iglb200_grid *g, const double **GV_colmajor, double **S)
   return IGLB200_OK;
   API_END
 }
-int iglb200_grid_get_GV(const iglb200_grid *g, double *GV, int64_t gv_rs, int64_t gv_cs) {
+int iglb200_grid_get_gv(const iglb200_grid *g, double *GV, int64_t gv_rs, int64_t gv_cs) {
   API_BEGIN
   check_grid(g);
   if (!GV || gv_rs <= 0 || gv_cs <= 0) throw std::invalid_argument("bad output");
@@ -1095,7 +1095,7 @@ int iglb200_grid_get_GV(const iglb200_grid *g, double *GV, int64_t gv_rs, int64_
   return IGLB200_OK;
   API_END
 }
-int iglb200_grid_set_S(iglb200_grid *g, const double *S) {
+int iglb200_grid_set_s(iglb200_grid *g, const double *S) {
   API_BEGIN
   check_grid(g);
   if (!S) throw std::invalid_argument("null pointer");
@@ -1105,7 +1105,7 @@ int iglb200_grid_set_S(iglb200_grid *g, const double *S) {
   return IGLB200_OK;
   API_END
 }
-int iglb200_grid_get_S(const iglb200_grid *g, double *S) {
+int iglb200_grid_get_s(const iglb200_grid *g, double *S) {
   API_BEGIN
   check_grid(g);
   if (!S) throw std::invalid_argument("null pointer");

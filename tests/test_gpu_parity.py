@@ -160,3 +160,64 @@ def test_pseudonormal_sign(gpu_api):
 
 def test_segments_points_hausdorff(gpu_api):
     cases.case_segments_points_hausdorff(gpu_api)
+
+
+# ---- voxel grids around the path ----
+def test_voxel_grid(gpu_api):
+    cases.case_voxel_grid(gpu_api)
+
+
+def test_flood_fill(gpu_api):
+    assert cases.case_flood_fill(gpu_api) > 90
+    # a large volume with every kind of gap: a signed band around a sphere, everything else NaN
+    g = 160
+    GV = oracle.grid([g, g, g]) * 2 - 1
+    S = np.linalg.norm(GV, axis=1) - 0.6
+    S[np.abs(S) > 0.05] = np.nan
+    got = gpu_api.flood_fill([g, g, g], S)
+    assert np.array_equal(got, oracle.flood_fill([g, g, g], S), equal_nan=True)
+    assert not np.isnan(got).any()
+
+
+def test_marching_cubes(gpu_api):
+    cases.case_marching_cubes(gpu_api)
+    # 1.7 M cubes, 100k+ triangles: still the reference's vertex order to the bit
+    g = 120
+    GV = oracle.grid([g, g, g]) * 2 - 1
+    S = np.sin(7 * GV[:, 0]) * np.cos(5 * GV[:, 1]) + GV[:, 2]
+    Vo, Fo, Eo = oracle.marching_cubes(S, GV, g, g, g, 0.0)
+    V, F, E = gpu_api.marching_cubes(S, GV, g, g, g, 0.0, return_E2V=True)
+    assert Fo.shape[0] > 50_000
+    assert np.array_equal(F, Fo) and np.array_equal(E, Eo) and np.array_equal(V, Vo)
+
+
+def test_offset_surface(gpu_api):
+    from libigl_b200.api import SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER as FWN, SIGNED_DISTANCE_TYPE_PSEUDONORMAL as PN
+    V, F = synth.icosphere(2)
+    cases.case_offset_surface(gpu_api, V, F, 0.2, 20, FWN, "ico2 +0.2 fwn")
+    cases.case_offset_surface(gpu_api, V, F, 0.15, 18, PN, "ico2 +0.15 pseudonormal")
+    V, F = synth.torus_knot(400, 24)
+    r = cases.case_offset_surface(gpu_api, V, F, 0.04, 96, FWN, "knot19k +0.04 fwn, 96 grid")
+    assert r["nF"] > 20_000
+
+
+def test_grid_pipeline_stays_on_device_tutorial_705(gpu_api):
+    """tutorial/705_MarchingCubes/main.cpp:24-44: voxel_grid(V,0,s,1) -> signed_distance (default bounds) ->
+    marching_cubes at 0 re-creates the input surface: every vertex within one cell of the mesh."""
+    from libigl_b200.api import Grid, Mesh, SIGNED_DISTANCE_TYPE_PSEUDONORMAL as PN
+    V, F = synth.torus_knot(600, 30)
+    g = Grid(gpu_api, V.min(0), V.max(0), 128, 1)
+    m = Mesh(gpu_api, V, F, 2, pseudonormals=True)
+    g.signed_distance(m, PN)
+    SV, SF = g.marching_cubes(0.0)
+    S, GV = g.S(), g.GV()
+    Vo, Fo, _ = oracle.marching_cubes(S, GV, g.side[0], g.side[1], g.side[2], 0.0)
+    assert np.array_equal(SF, Fo) and np.array_equal(SV, Vo)
+    h = (g.corners()[3] - g.corners()[0]) / (g.side[0] - 1)
+    d = np.sqrt(oracle.PortAABB(V, F).squared_distance(SV)[0])
+    assert SF.shape[0] > 10_000 and d.max() < h
+    # closed surface: every edge shared by exactly two triangles
+    e = np.sort(np.concatenate([SF[:, [0, 1]], SF[:, [1, 2]], SF[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert (cnt == 2).all()
+    m.close(); g.close()
