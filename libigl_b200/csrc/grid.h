@@ -113,6 +113,7 @@ inline iglb200_grid *create(const double bmin[3], const double bmax[3], int s, i
     g->n = n;
     g->GV.alloc((size_t)3 * n);
     g->S.alloc((size_t)n);
+    plat::Span sp("voxel_grid", st);
     plat::for_n(n, FillGrid{vp.side[0], vp.side[1], n, (double)(vp.side[0] - 1), (double)(vp.side[1] - 1), (double)(vp.side[2] - 1),
                             vp.ratio[0], vp.ratio[1], vp.ratio[2], vp.off[0], vp.off[1], vp.off[2], g->GV.p}, st);
     plat::sync(st);
@@ -182,10 +183,11 @@ inline void flood_fill(const int side[3], double *S, stream_t st) {
   const int64_t rows = (int64_t)ny * nz, n = rows * nx;
   if (n <= 0) return;
   plat::DevBuf<double> rowval((size_t)rows), rowfill((size_t)rows), sheetval((size_t)nz), sheetfill((size_t)nz);
+  { plat::Span sp("flood_fill", st);
   plat::for_n(rows, FloodRows{nx, S, rowval.p}, st);
   plat::for_n(nz, FloodSheets{ny, rowval.p, rowfill.p, sheetval.p}, st);
   plat::for_n(1, FloodVolume{nz, sheetval.p, sheetfill.p}, st);
-  plat::for_n(n, FloodFill{nx, ny, S, rowval.p, rowfill.p, sheetfill.p}, st);
+  plat::for_n(n, FloodFill{nx, ny, S, rowval.p, rowfill.p, sheetfill.p}, st); }
   plat::sync(st);
 }
 
@@ -333,6 +335,7 @@ inline iglb200_surface *marching_cubes(const double *S, const double *GV, int nx
     const McDims d{nx, ny, nz};
     const int64_t nc = (nx > 1 && ny > 1 && nz > 1) ? d.cubes() : 0;
     if (nc > 0) {
+      plat::Span sp("marching_cubes", st);
       plat::DevBuf<uint32_t> info((size_t)nc), vcount((size_t)nc + 1), fcount((size_t)nc + 1), vbase((size_t)nc + 1), fbase((size_t)nc + 1);
       plat::for_n(nc, McClassify{d, S, shift, iso, info.p, vcount.p, fcount.p}, st);
       plat::dev_memset(vcount.p + nc, 0, 4, st);

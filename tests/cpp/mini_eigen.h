@@ -14,6 +14,7 @@ template <class T, int Options = ColMajor> class Matrix {
   Matrix() = default;
   Matrix(int64_t r, int64_t c) { resize(r, c); }
   void resize(int64_t r, int64_t c) { r_ = r; c_ = c; d_.assign((size_t)(r * c), T()); }
+  void resize(int64_t n) { resize(n, 1); }   // vectors
   int64_t rows() const { return r_; }
   int64_t cols() const { return c_; }
   int64_t size() const { return r_ * c_; }

@@ -11,6 +11,7 @@
 #include "iglb200/signed_distance.h"
 #include "iglb200/point_mesh_squared_distance.h"
 #include "iglb200/hausdorff.h"
+#include "iglb200/offset_surface.h"
 
 using namespace mini;
 #define REQUIRE(x) do { if (!(x)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #x); std::exit(1); } } while (0)
@@ -119,6 +120,39 @@ int main() {
     iglb200::fast_winding_number(Pc, Nc, A, Q, WN2);
     const double gold[4] = {0.38779369004261133, -0.00041235296362485, -0.00362978253577090, -0.00041235296362485};
     for (int i = 0; i < 4; ++i) { REQUIRE(std::fabs(WN(i) - gold[i]) < 1e-15); REQUIRE(WN2(i) == WN(i)); }
+  }
+  // voxel_grid / flood_fill / marching_cubes / offset_surface (tutorials 705, 909; offset_surface.cpp)
+  {
+    MatrixXd GV; VectorXi side;
+    iglb200::voxel_grid(V, 0.25, 12, 1, GV, side);
+    REQUIRE(side(0) == 12 && side(1) == 12 && side(2) == 12 && GV.rows() == 12 * 12 * 12 && GV.cols() == 3);
+    RowMatrixXd GVr; VectorXi side2;
+    iglb200::voxel_grid(V, 0.25, 12, 1, GVr, side2);
+    for (int64_t i = 0; i < GV.rows(); i += 97) for (int d = 0; d < 3; ++d) REQUIRE(GV(i, d) == GVr(i, d));
+    // sphere of radius 0.45 about the grid centre, NaN away from a band: fill, then polygonise
+    VectorXd S(GV.rows(), 1);
+    double c[3];
+    for (int d = 0; d < 3; ++d) c[d] = 0.5 * (GV(0, d) + GV(GV.rows() - 1, d));
+    for (int64_t i = 0; i < GV.rows(); ++i) {
+      const double r = std::sqrt((GV(i, 0) - c[0]) * (GV(i, 0) - c[0]) + (GV(i, 1) - c[1]) * (GV(i, 1) - c[1]) + (GV(i, 2) - c[2]) * (GV(i, 2) - c[2]));
+      S(i) = std::fabs(r - 0.45) < 0.3 ? r - 0.45 : std::nan("");
+    }
+    iglb200::flood_fill(side, S);
+    for (int64_t i = 0; i < S.rows(); ++i) REQUIRE(S(i) == S(i));
+    REQUIRE(S(0) > 0);
+    MatrixXd SV; MatrixXi SF;
+    std::unordered_map<std::int64_t, int> E2V;
+    iglb200::marching_cubes(S, GV, side(0), side(1), side(2), 0.0, SV, SF, E2V);
+    REQUIRE(SV.rows() > 100 && SF.rows() == 2 * SV.rows() - 4);          // closed genus-0 surface
+    REQUIRE((int64_t)E2V.size() == SV.rows());
+    for (int64_t i = 0; i < SV.rows(); ++i) {
+      const double r = std::sqrt((SV(i, 0) - c[0]) * (SV(i, 0) - c[0]) + (SV(i, 1) - c[1]) * (SV(i, 1) - c[1]) + (SV(i, 2) - c[2]) * (SV(i, 2) - c[2]));
+      REQUIRE(std::fabs(r - 0.45) < 0.02);
+    }
+    MatrixXd SV2, GV2; MatrixXi SF2; VectorXi side3; VectorXd S2;
+    iglb200::offset_surface(V, F, 0.2, 16, iglb200::SIGNED_DISTANCE_TYPE_PSEUDONORMAL, SV2, SF2, GV2, side3, S2);
+    REQUIRE(SV2.rows() > 50 && SF2.rows() == 2 * SV2.rows() - 4 && GV2.rows() == S2.rows());
+    for (int64_t i = 0; i < S2.rows(); ++i) REQUIRE(S2(i) == S2(i));
   }
   std::printf("OK\n");
   return 0;
