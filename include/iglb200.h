@@ -38,9 +38,10 @@ extern "C" {
 #define IGLB200_ERR_UNSUPPORTED (-4)
 #define IGLB200_ERR_INTERNAL (-5)
 
-/* igl::SignedDistanceType, signed_distance.h:20-34.  UNSIGNED, FAST_WINDING_NUMBER and
- * PSEUDONORMAL (mesh created with IGLB200_MESH_PSEUDONORMALS) are implemented;
- * WINDING_NUMBER / DEFAULT return IGLB200_ERR_UNSUPPORTED (no silent fallback). */
+/* igl::SignedDistanceType, signed_distance.h:20-34.  All five run on the device: UNSIGNED,
+ * FAST_WINDING_NUMBER, PSEUDONORMAL (mesh created with IGLB200_MESH_PSEUDONORMALS) and
+ * WINDING_NUMBER = DEFAULT in 3-D (mesh created with IGLB200_MESH_WINDING_NUMBER); a mesh that
+ * lacks the tables a sign type needs returns IGLB200_ERR_ARG (no silent fallback). */
 #define IGLB200_SIGN_PSEUDONORMAL 0
 #define IGLB200_SIGN_WINDING_NUMBER 1
 #define IGLB200_SIGN_DEFAULT 2
@@ -68,6 +69,10 @@ int iglb200_mesh_create(const void *V, int v_is_f64, int64_t nV, int64_t v_row_s
 /* flags: IGLB200_MESH_PSEUDONORMALS also precomputes face / angle-weighted vertex / uniform edge
  * normals (signed_distance.cpp:68-76: per_face_normals, per_vertex_normals, per_edge_normals). */
 #define IGLB200_MESH_PSEUDONORMALS 1
+/* IGLB200_MESH_WINDING_NUMBER also builds the boundary chains of the exact hierarchical winding number
+ * (WindingNumberAABB::set_mesh + grow, signed_distance.cpp:60-64), needed by sign types WINDING_NUMBER / DEFAULT
+ * and by iglb200_winding_number. */
+#define IGLB200_MESH_WINDING_NUMBER 2
 int iglb200_mesh_create_ex(const void *V, int v_is_f64, int64_t nV, int64_t v_row_stride, int64_t v_col_stride,
                            const int32_t *F, int64_t nF, int64_t f_row_stride, int64_t f_col_stride,
                            int fwn_order, int flags, iglb200_mesh **out);
@@ -133,6 +138,15 @@ int iglb200_squared_distance_dev(const iglb200_mesh *m, const double *P, int64_t
                                  void *scratch, int sort_queries, void *stream);
 int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, float accuracy_scale,
                          double *W, void *scratch, int sort_queries, void *stream);
+
+/* igl::winding_number(V,F,O,W) for triangle meshes (winding_number.h:35-43, winding_number.cpp:17-52): the exact
+ * generalised winding number, double precision, evaluated hierarchically (WindingNumberTree.h:262-335).
+ * The mesh must have been created with IGLB200_MESH_WINDING_NUMBER. */
+int iglb200_winding_number(const iglb200_mesh *m,
+                           const void *O, int o_is_f64, int64_t nO, int64_t o_row_stride, int64_t o_col_stride,
+                           void *W, int w_is_f64);
+int iglb200_winding_number_dev(const iglb200_mesh *m, const double *O, int64_t nO, double *W, void *scratch,
+                               int sort_queries, void *stream);
 /* After synchronising a stream that ran *_dev calls: 0, or an error if a device-side
  * condition (traversal stack overflow) invalidated their results.  The host-pointer
  * entry points check this themselves. */

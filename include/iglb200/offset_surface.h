@@ -140,7 +140,8 @@ inline void offset_surface(const DerivedV &V, const DerivedF &F, const isolevelT
   const double h = (corners[3] - corners[0]) / ((double)(side(0) - 1));                    // offset_surface.cpp:31-32
   const double lower_bound = (double)isolevel - std::sqrt(3.0) * h, upper_bound = (double)isolevel + std::sqrt(3.0) * h;
   const bool pseudo = signed_distance_type == SIGNED_DISTANCE_TYPE_PSEUDONORMAL;
-  iglb200_mesh *m = detail::make_mesh(V, F, 2, pseudo ? IGLB200_MESH_PSEUDONORMALS : 0);
+  const bool exact = signed_distance_type == SIGNED_DISTANCE_TYPE_WINDING_NUMBER || signed_distance_type == SIGNED_DISTANCE_TYPE_DEFAULT;
+  iglb200_mesh *m = detail::make_mesh(V, F, 2, (pseudo ? IGLB200_MESH_PSEUDONORMALS : 0) | (exact ? IGLB200_MESH_WINDING_NUMBER : 0));
   int rc = iglb200_grid_signed_distance(g.g, m, (int)signed_distance_type, lower_bound, upper_bound);
   iglb200_mesh_destroy(m);
   check(rc);

@@ -1,8 +1,8 @@
 // igl::signed_distance with the reference's Eigen signatures, computed on the GPU.
 //   /root/reference/include/igl/signed_distance.h:20-34 (enum), :61-89 and :91-110 (signed_distance),
 //   :283-312 (signed_distance_fast_winding_number); semantics signed_distance.cpp:28-139, 372-440.
-// SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, _UNSIGNED and _PSEUDONORMAL run on the device;
-// _WINDING_NUMBER / _DEFAULT throw iglb200::Error(IGLB200_ERR_UNSUPPORTED) — there is no CPU fallback.
+// All five sign types run on the device (there is no CPU fallback): FAST_WINDING_NUMBER, UNSIGNED, PSEUDONORMAL,
+// and WINDING_NUMBER = DEFAULT (exact hierarchical winding number, csrc/wn.h).
 #pragma once
 #include "AABB.h"
 
@@ -75,7 +75,8 @@ inline void signed_distance(const DerivedP &P, const DerivedV &V, const DerivedF
     return;
   }
   const bool pseudo = sign_type == SIGNED_DISTANCE_TYPE_PSEUDONORMAL;
-  iglb200_mesh *m = detail::make_mesh(V, F, 2, pseudo ? IGLB200_MESH_PSEUDONORMALS : 0);
+  const bool exact = sign_type == SIGNED_DISTANCE_TYPE_WINDING_NUMBER || sign_type == SIGNED_DISTANCE_TYPE_DEFAULT;
+  iglb200_mesh *m = detail::make_mesh(V, F, 2, (pseudo ? IGLB200_MESH_PSEUDONORMALS : 0) | (exact ? IGLB200_MESH_WINDING_NUMBER : 0));
   try {
     detail::sd_query<DerivedP, DerivedS, DerivedI, DerivedC, DerivedS, DerivedN>(m, P, (int)sign_type, (double)lower_bound,
                                                                                (double)upper_bound, S, I, C, nullptr, pseudo ? &N : nullptr);

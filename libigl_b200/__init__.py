@@ -66,6 +66,10 @@ def cloud(P, N, A, order=2) -> Cloud:
     return lib().Cloud(P, N, A, order)
 
 
+def winding_number(V, F, O):
+    return lib().winding_number(V, F, O)
+
+
 def voxel_grid(*args):
     return lib().voxel_grid(*args)
 

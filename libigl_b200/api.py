@@ -65,6 +65,7 @@ class Api:
         "iglb200_debug_visit_counts", "iglb200_poll_device_error", "iglb200_debug_fp32_peak_tflops",
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
+        "iglb200_winding_number", "iglb200_winding_number_dev",
         "iglb200_grid_create", "iglb200_grid_create_from", "iglb200_grid_destroy", "iglb200_grid_info", "iglb200_grid_device",
         "iglb200_grid_get_gv", "iglb200_grid_set_s", "iglb200_grid_get_s", "iglb200_grid_signed_distance",
         "iglb200_grid_flood_fill", "iglb200_grid_marching_cubes", "iglb200_surface_info", "iglb200_surface_get",
@@ -107,6 +108,8 @@ class Api:
         L.iglb200_cloud_info.argtypes = [_vp, C.POINTER(_i64)]
         L.iglb200_cloud_eval.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _dbl, _vp, _int]
         L.iglb200_cloud_eval_dev.argtypes = [_vp, _vp, _i64, _dbl, _vp, _vp]
+        L.iglb200_winding_number.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _vp, _int]
+        L.iglb200_winding_number_dev.argtypes = [_vp, _vp, _i64, _vp, _vp, _int, _vp]
         L.iglb200_grid_create.argtypes = [_vp, _vp, _int, _int, C.POINTER(_vp)]
         L.iglb200_grid_create_from.argtypes = [_vp, _i64, _i64, _int, _int, _int, C.POINTER(_vp)]
         L.iglb200_grid_destroy.argtypes = [_vp]
@@ -157,8 +160,8 @@ class Api:
         return out
 
     # -- handles ----------------------------------------------------------
-    def Mesh(self, V, F, order=2, pseudonormals=False):
-        return Mesh(self, V, F, order, pseudonormals=pseudonormals)
+    def Mesh(self, V, F, order=2, pseudonormals=False, winding_number=False):
+        return Mesh(self, V, F, order, pseudonormals=pseudonormals, winding_number=winding_number)
 
     def Cloud(self, P, N, A, order=2):
         return Cloud(self, P, N, A, order)
@@ -212,8 +215,9 @@ class Api:
         (offset_surface.cpp:18-48); the grid never leaves the device between the stages."""
         V = np.asarray(V, np.float64)
         pseudo = int(sign_type) == SIGNED_DISTANCE_TYPE_PSEUDONORMAL
+        exact = int(sign_type) in (SIGNED_DISTANCE_TYPE_WINDING_NUMBER, SIGNED_DISTANCE_TYPE_DEFAULT)
         g = Grid(self, V.min(0) - isolevel, V.max(0) + isolevel, s, 1)     # voxel_grid(V, isolevel, s, 1, GV, side)
-        m = Mesh(self, V, F, 2, pseudonormals=pseudo)
+        m = Mesh(self, V, F, 2, pseudonormals=pseudo, winding_number=exact)
         try:
             c = g.corners()
             h = (c[3] - c[0]) / float(g.side[0] - 1)                        # :31-32
@@ -237,7 +241,8 @@ class Api:
             if pseudo:
                 out = out + (np.full((n, 3), np.nan),)
             return out + (np.full(n, np.nan),) if return_W else out
-        m = Mesh(self, V, F, 2, pseudonormals=pseudo)
+        exact = int(sign_type) in (SIGNED_DISTANCE_TYPE_WINDING_NUMBER, SIGNED_DISTANCE_TYPE_DEFAULT)
+        m = Mesh(self, V, F, 2, pseudonormals=pseudo, winding_number=exact)
         try:
             return m.signed_distance(P, sign_type, lower_bound, upper_bound, return_W)
         finally:
@@ -247,6 +252,14 @@ class Api:
         m = Mesh(self, V, Ele, 0)
         try:
             return m.squared_distance(P)
+        finally:
+            m.close()
+
+    def winding_number(self, V, F, O):
+        """igl::winding_number(V,F,O,W) for triangle meshes (winding_number.cpp:17-52): exact, double."""
+        m = Mesh(self, V, F, 2, winding_number=True)
+        try:
+            return m.winding_number(O)
         finally:
             m.close()
 
@@ -281,7 +294,7 @@ class Api:
 class Mesh:
     """AABB<MatrixXd,3> + FastWindingNumberBVH built on the device (one handle)."""
 
-    def __init__(self, api: Api, V, F, order=2, _handle=None, pseudonormals=False):
+    def __init__(self, api: Api, V, F, order=2, _handle=None, pseudonormals=False, winding_number=False):
         self.api = api
         self.h = _vp()
         if _handle is not None:
@@ -301,7 +314,8 @@ class Mesh:
             F = np.ascontiguousarray(F)
         api.check(api.lib.iglb200_mesh_create_ex(vp, vf64, nV, vrs, vcs, F.ctypes.data_as(_vp), F.shape[0],
                                                  F.strides[0] // 4 if F.shape[0] else 3, F.strides[1] // 4 if F.shape[0] else 1,
-                                                 int(order), 1 if pseudonormals else 0, C.byref(self.h)))
+                                                 int(order), (1 if pseudonormals else 0) | (2 if winding_number else 0),
+                                                 C.byref(self.h)))
 
     def close(self):
         if self.h:
@@ -381,6 +395,13 @@ class Mesh:
         return D, I, Cc
 
     # fast_winding_number(fwn_bvh, accuracy_scale, Q, W)
+    def winding_number(self, O):
+        """Exact generalised winding number at the rows of O (mesh created with winding_number=True)."""
+        Ok, op, of64, n, ors, ocs = _mat(O, "O")
+        W = np.empty(n, np.float64)
+        self.api.check(self.api.lib.iglb200_winding_number(self.h, op, of64, n, ors, ocs, W.ctypes.data_as(_vp), 1))
+        return W
+
     def fast_winding_number(self, Q, accuracy_scale=2.0):
         Qk, qp, qf64, n, qrs, qcs = _mat(Q, "Q")
         W = np.empty(n, np.float64)

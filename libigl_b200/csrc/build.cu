@@ -4,6 +4,7 @@
 // reference must be reproduced bit for bit.
 #define IGLB200_BUILDER_TU 1
 #include "mesh.h"
+#include "wn.h"
 
 namespace fwn {
 
@@ -238,11 +239,29 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
     m->h.off_cnodes = off; off = align(off + (uint64_t)sizeof(CpNode) * nn);
     m->h.off_pn = 0;
     if (flags & 1) { m->h.off_pn = off; off = align(off + (uint64_t)8 * PN_STRIDE * nF); }
+    m->h.off_wn_cnt = m->h.off_wn_start = m->h.off_wn_bstart = m->h.off_wn_bent = m->h.off_wn_leafface = m->h.n_wn_bent = 0;
+    wn::Built wb;
+    if ((flags & 2) && nn) {
+      wn::build(tree, dF.p, f_rs, f_cs, nF, wb, s);
+      m->h.n_wn_bent = wb.nent;
+      m->h.off_wn_cnt = off; off = align(off + (uint64_t)16 * nn);
+      m->h.off_wn_start = off; off = align(off + (uint64_t)16 * nn);
+      m->h.off_wn_bstart = off; off = align(off + (uint64_t)4 * (4 * nn + 1));
+      m->h.off_wn_bent = off; off = align(off + (uint64_t)8 * (wb.nent + 1));
+      m->h.off_wn_leafface = off; off = align(off + (uint64_t)4 * nF);
+    }
     m->h.bytes = off;
     m->arena = (char *)plat::dev_alloc(off);
     plat::d2d(m->arena + m->h.off_tri64, tri64.p, (size_t)72 * nF, s);
     plat::d2d(m->arena + m->h.off_tri32, tri32.p, (size_t)16 * TRI32_STRIDE * nF, s);
     plat::d2d(m->arena + m->h.off_triq, triq.p, (size_t)16 * TRIQ_STRIDE * nF, s);
+    if (m->h.off_wn_cnt) {
+      plat::d2d(m->arena + m->h.off_wn_cnt, wb.cnt.p, (size_t)16 * nn, s);
+      plat::d2d(m->arena + m->h.off_wn_start, wb.start.p, (size_t)16 * nn, s);
+      plat::d2d(m->arena + m->h.off_wn_bstart, wb.bstart.p, (size_t)4 * (4 * nn + 1), s);
+      plat::d2d(m->arena + m->h.off_wn_bent, wb.bent.p, (size_t)8 * wb.nent, s);
+      plat::d2d(m->arena + m->h.off_wn_leafface, wb.leafface.p, (size_t)4 * (nF - tree.nexcluded), s);
+    }
     if (nn) {
       DevBuf<Local> locals((size_t)nn);
       for (int l = tree_levels(tree) - 1; l >= 0; --l) {

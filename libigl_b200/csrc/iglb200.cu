@@ -3,6 +3,7 @@
 #include "mesh.h"
 #include "cloud.h"
 #include "grid.h"
+#include "wn.h"
 #include <chrono>
 #include <memory>
 
@@ -170,7 +171,10 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
 void launch_closest(const ClosestArgs &a, stream_t) {
   for (int64_t base = 0; base < a.n; base += 32) closest_packet_emul(a, base);
 }
-void throw_if_overflow(stream_t) {}
+uint32_t *overflow_flag() { static thread_local uint32_t f = 0; return &f; }
+void throw_if_overflow(stream_t) {
+  if (*overflow_flag()) { *overflow_flag() = 0; throw std::runtime_error("traversal stack overflow (tree too deep)"); }
+}
 #else
 DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -328,7 +332,7 @@ void throw_if_overflow(stream_t s) {
   uint32_t h = 0;
   plat::d2h(&h, overflow_flag(), 4, s);
   plat::sync(s);
-  if (h) { cudaMemset(overflow_flag(), 0, 4); throw std::runtime_error("closest-point traversal stack overflow (tree too deep)"); }
+  if (h) { cudaMemset(overflow_flag(), 0, 4); throw std::runtime_error("traversal stack overflow (tree too deep)"); }
 }
 void launch_closest(const ClosestArgs &a, stream_t s) {
   if (a.n <= 0) return;
@@ -383,6 +387,34 @@ struct CountWinding {
     uint32_t w[2] = {0, 0};
     fwn::winding_solid_angle(fnodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], 4.0f, order, sn, w);
     plat::atomic_add(&acc[0], w[0]); plat::atomic_add(&acc[1], w[1]);
+  }
+};
+
+// exact winding number (wn.h) and, optionally, the epilogue of signed_distance.cpp:107-113, 611-629:
+// s = 1 - 2 w, S = s * sqrt(sqrd); out-of-bounds rows as :99-105
+struct ExactWindingQuery {
+  const fwn::CpNode *nodes; const double *tri64; wn::View v;
+  const double *P; int64_t n; const uint32_t *perm;
+  int mode;   // 0: W only (winding_number.cpp:44-50); 1: signed distance
+  double up, low; int32_t nF;
+  double *W; double *S; int32_t *I; double *C;   // S holds sqrD on entry when mode 1
+  uint32_t *overflow;
+  DEVFN void operator()(int64_t t) const {
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    if (mode == 1) {
+      const double sqrd = S[i];
+      if (sqrd >= up || sqrd < low) {
+        S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
+        if (W) W[i] = NAN;
+        return;
+      }
+    }
+    uint32_t stack[wn::STACK];
+    bool ovf = false;
+    const double w = wn::winding_number(nodes, tri64, v, P[i], P[n + i], P[2 * n + i], stack, ovf);
+    if (ovf) plat::atomic_max(overflow, 1u);
+    if (W) W[i] = w;
+    if (mode == 1) S[i] = fwn::dmul(fwn::dsub(1.0, fwn::dmul(2.0, w)), sqrt(S[i]));
   }
 };
 
@@ -476,6 +508,14 @@ void launch_query(const char *, int64_t n, WindingQuery f, stream_t s) {
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }
+__global__ void __launch_bounds__(128) exact_winding_kernel(int64_t n, ExactWindingQuery f) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+}
+void launch_query(const char *, int64_t n, ExactWindingQuery f, stream_t s) {
+  exact_winding_kernel<<<query_grid(n, 128), 128, 0, s>>>(n, f);
+  plat::launch_counter()++;
+  PLAT_CHECK(cudaGetLastError());
+}
 #endif
 
 // scratch layout: [keys_in | keys_out | vals_in | vals_out(perm) | cub temp]
@@ -519,11 +559,19 @@ void bounds_to_sqr(double lower, double upper, double &low, double &up) {  // si
   low = std::pow(std::max(max_abs - (upper - lower), 0.0), 2.0);
 }
 
+wn::View wn_view(const iglb200_mesh *m) {
+  const char *a = m->arena;
+  return wn::View{(const uint32_t *)(a + m->h.off_wn_cnt), (const uint32_t *)(a + m->h.off_wn_start),
+                  (const uint32_t *)(a + m->h.off_wn_bstart), (const uint32_t *)(a + m->h.off_wn_leafface),
+                  (const uint64_t *)(a + m->h.off_wn_bent)};
+}
+
 void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int sign_type, double lower, double upper,
                          double *S, int32_t *I, double *C, double *W, double *N, void *scratch, int sort_queries, stream_t s) {
-  if (sign_type != IGLB200_SIGN_FAST_WINDING_NUMBER && sign_type != IGLB200_SIGN_UNSIGNED && sign_type != IGLB200_SIGN_PSEUDONORMAL) {
-    throw std::domain_error("sign type not implemented on the device (only UNSIGNED, FAST_WINDING_NUMBER and PSEUDONORMAL); no CPU fallback");
-  }
+  if (sign_type < 0 || sign_type > IGLB200_SIGN_FAST_WINDING_NUMBER) throw std::domain_error("unknown signed distance type");
+  const bool exact_wn = sign_type == IGLB200_SIGN_WINDING_NUMBER || sign_type == IGLB200_SIGN_DEFAULT;
+  if (exact_wn && m->h.nnodes > 0 && !m->h.off_wn_cnt)
+    throw std::invalid_argument("mesh was created without IGLB200_MESH_WINDING_NUMBER");
   if (sign_type == IGLB200_SIGN_PSEUDONORMAL && m->h.nF > 0 && !m->pn())
     throw std::invalid_argument("mesh was created without IGLB200_MESH_PSEUDONORMALS");
   if (n == 0) return;
@@ -548,9 +596,26 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
     if (W) plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, NAN, 0, 0.0}, s);
     return;
   }
+  if (exact_wn) {
+    plat::Span sp("exact_winding", s);
+    launch_query("exact_winding", n, ExactWindingQuery{m->cnodes(), m->tri64(), wn_view(m), P, n, perm, 1, up, low, (int32_t)m->h.nF,
+                                                       W, S, I, C, overflow_flag()}, s);
+    return;
+  }
   { plat::Span sp("winding", s);
     launch_query("winding", n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
                                             sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s); }
+}
+
+// igl::winding_number(V,F,O,W) for triangle meshes (winding_number.cpp:38-52)
+void run_exact_winding(const iglb200_mesh *m, const double *O, int64_t n, double *W, void *scratch, int sort_queries, stream_t s) {
+  if (n == 0) return;
+  if (m->h.nnodes == 0) { plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, 0.0, 0, 0.0}, s); return; }
+  if (!m->h.off_wn_cnt) throw std::invalid_argument("mesh was created without IGLB200_MESH_WINDING_NUMBER");
+  const uint32_t *perm = morton_perm(m, O, n, scratch, sort_queries, s);
+  plat::Span sp("exact_winding", s);
+  launch_query("exact_winding", n, ExactWindingQuery{m->cnodes(), m->tri64(), wn_view(m), O, n, perm, 0, 0.0, 0.0, (int32_t)m->h.nF,
+                                                     W, nullptr, nullptr, nullptr, overflow_flag()}, s);
 }
 
 void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, double *sqrD, int32_t *I, double *C,
@@ -1012,6 +1077,37 @@ int iglb200_fwn_eval(const iglb200_mesh *m, const void *Q, int q_is_f64, int64_t
   run_fwn(m, dQ.p, nQ, accuracy_scale, dW.p, scratch.p, 1, s);
   download_scalar(dW, nQ, W, w_is_f64, s);
   plat::sync(s);
+  return IGLB200_OK;
+  API_END
+}
+
+// igl::winding_number(V,F,O,W) (winding_number.cpp:17-52): exact, hierarchical, double precision
+int iglb200_winding_number(const iglb200_mesh *m, const void *O, int o_is_f64, int64_t nO, int64_t o_rs, int64_t o_cs,
+                           void *W, int w_is_f64) {
+  API_BEGIN
+  check_mesh(m);
+  if (nO < 0 || (nO > 0 && (!O || !W))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  stream_t s = nullptr;
+  DevBuf<double> dO, dW((size_t)nO);
+  DevBuf<char> scratch(iglb200_query_scratch_bytes(nO));
+  upload_points(O, o_is_f64, nO, o_rs, o_cs, dO, s);
+  run_exact_winding(m, dO.p, nO, dW.p, scratch.p, 1, s);
+  download_scalar(dW, nO, W, w_is_f64, s);
+  plat::sync(s);
+  throw_if_overflow(s);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_winding_number_dev(const iglb200_mesh *m, const double *O, int64_t nO, double *W, void *scratch, int sort_queries,
+                               void *stream) {
+  API_BEGIN
+  check_mesh(m);
+  if (nO < 0 || (nO > 0 && (!O || !W))) throw std::invalid_argument("null pointer");
+  require_device();
+  plat::launch_counter() = 0;
+  run_exact_winding(m, O, nO, W, scratch, sort_queries, (stream_t)stream);
   return IGLB200_OK;
   API_END
 }

@@ -3,7 +3,8 @@
 // broadcast of [arena, arena+bytes).
 //
 //   [ArenaHeader | tri64 (9 f64 / face) | tri32 (3 float4 / face) | triq (4 float4 / face) |
-//    fwn nodes (384 B) | closest-point nodes (128 B) | optional pseudonormals (21 f64 / face)]
+//    fwn nodes (384 B) | closest-point nodes (128 B) | optional pseudonormals (21 f64 / face) |
+//    optional exact-winding-number tables (wn.h)]
 //
 // tri64/tri32 are the faces' vertices gathered once at build time (the
 // reference dereferences V through F for every leaf test: AABB.cpp:1413-1432,
@@ -22,7 +23,9 @@ struct ArenaHeader {
   float absmax, padf;             // max |coordinate| (slack of the fp32 box tests)
   uint64_t off_tri64, off_tri32, off_fnodes, off_cnodes, off_triq;
   uint64_t off_pn;  // 21 f64 / face: face normal, 3 corner (vertex) normals, 3 edge normals; 0 = absent
-  uint64_t reserved[6];
+  // exact winding number (wn.h), 0 = absent: per cluster (4 per node) face count, first leaf slot, first chain
+  // entry (4*nnodes+1 entries); chain entries; faces in depth-first leaf order
+  uint64_t off_wn_cnt, off_wn_start, off_wn_bstart, off_wn_bent, off_wn_leafface, n_wn_bent;
 };
 
 struct iglb200_mesh {

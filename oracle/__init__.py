@@ -421,3 +421,40 @@ def offset_surface(V, F, isolevel, s, sign_type="fwn"):
     S = flood_fill(side, S)
     SV, SF, _ = marching_cubes(S - isolevel, GV, side[0], side[1], side[2], 0.0)
     return SV, SF, GV, side, S
+
+
+# ---------------------------------------------------------------------------
+def winding_number(V, F, O):
+    """igl::winding_number(V,F,O,W) for triangles: the exact generalised winding number, summed face by face
+    (winding_number.cpp:62-89, solid_angle.cpp:10-55).  O(#O * #F): keep the product below ~1e10."""
+    V = np.ascontiguousarray(V, dtype=np.float64); F = np.ascontiguousarray(F, dtype=np.int32)
+    O = np.ascontiguousarray(O, dtype=np.float64)
+    W = np.empty(O.shape[0])
+    L = port()
+    L.port_winding_number.argtypes = [_c_dp, _c_ip, C.c_int64, _c_dp, C.c_int64, _c_dp]
+    L.port_winding_number(_dp(V), _ip(F), F.shape[0], _dp(O), O.shape[0], _dp(W))
+    return W
+
+
+def signed_distance_winding_number(P, V, F, lower=None, upper=None, tree=None):
+    """igl::signed_distance(..., SIGNED_DISTANCE_TYPE_WINDING_NUMBER / _DEFAULT, ...): S, I, C, W
+    (signed_distance.cpp:60-64, 107-113, 611-629: s = 1 - 2 w, S = s * sqrt(sqrd))."""
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    F = np.ascontiguousarray(F, dtype=np.int32)
+    if lower is None:
+        lower = np.finfo(np.float64).tiny
+    if upper is None:
+        upper = np.finfo(np.float64).max
+    low, up = signed_distance_bounds(lower, upper)
+    tree = tree or PortAABB(V, F)
+    sqrD, I, Cc = tree.squared_distance(P, low, up)
+    oob = (sqrD >= up) | (sqrD < low)
+    w = np.full(P.shape[0], np.nan)
+    if (~oob).any():
+        w[~oob] = winding_number(V, F, P[~oob])
+    S = (1.0 - 2.0 * w) * np.sqrt(sqrD)
+    S[oob] = np.nan
+    I = I.copy()
+    I[oob] = F.shape[0] + 1
+    Cc[oob] = 0.0
+    return S, I, Cc, w

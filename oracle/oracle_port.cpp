@@ -932,4 +932,31 @@ void port_mc_get(void *p, double *V, int *F, int *E) {
 }
 void port_mc_destroy(void *p) { delete (McOut *)p; }
 
+// ---------------------------------------------------------------------------------------------
+// Exact winding number: igl::solid_angle (solid_angle.cpp:10-55) summed over every face as
+// igl::winding_number(V,F,p) does (winding_number.cpp:62-89).  The reference's hierarchy
+// (WindingNumberAABB / WindingNumberTree.h:262-335) returns this same quantity: for a query outside a
+// sub-mesh's box it sums the sub-mesh's cap instead of its faces, which is the same number in exact
+// arithmetic (closed surface, outside point) and differs by rounding only.
+static double port_solid_angle(const double *A, const double *B, const double *C, const double *P) {
+  double v[3][3], vl[3];
+  for (int d = 0; d < 3; d++) { v[0][d] = A[d] - P[d]; v[1][d] = B[d] - P[d]; v[2][d] = C[d] - P[d]; }
+  for (int r = 0; r < 3; ++r) vl[r] = std::sqrt(v[r][0] * v[r][0] + v[r][1] * v[r][1] + v[r][2] * v[r][2]);
+  const double detf = v[0][0] * v[1][1] * v[2][2] + v[1][0] * v[2][1] * v[0][2] + v[2][0] * v[0][1] * v[1][2] -
+                      v[2][0] * v[1][1] * v[0][2] - v[1][0] * v[0][1] * v[2][2] - v[0][0] * v[2][1] * v[1][2];
+  double dp[3];
+  dp[0] = v[1][0] * v[2][0]; dp[0] += v[1][1] * v[2][1]; dp[0] += v[1][2] * v[2][2];
+  dp[1] = v[2][0] * v[0][0]; dp[1] += v[2][1] * v[0][1]; dp[1] += v[2][2] * v[0][2];
+  dp[2] = v[0][0] * v[1][0]; dp[2] += v[0][1] * v[1][1]; dp[2] += v[0][2] * v[1][2];
+  return std::atan2(detf, vl[0] * vl[1] * vl[2] + dp[0] * vl[0] + dp[1] * vl[1] + dp[2] * vl[2]) / (2. * 3.1415926535897932384626433832795);
+}
+void port_winding_number(const double *V, const int *F, int64_t nF, const double *O, int64_t n, double *W) {
+  port_parallel_for(n, [&](int64_t o) {
+    double w = 0;
+    for (int64_t f = 0; f < nF; ++f)
+      w += port_solid_angle(V + 3 * F[3 * f], V + 3 * F[3 * f + 1], V + 3 * F[3 * f + 2], O + 3 * o);
+    W[o] = w;
+  }, 1);
+}
+
 }  // extern "C"

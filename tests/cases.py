@@ -145,9 +145,13 @@ def case_bounds_and_sentinels(api):
     m = api.Mesh(V, F, 2)
     S, I, C = m.signed_distance(np.zeros((0, 3)))
     assert S.shape == (0,) and I.shape == (0,) and C.shape == (0, 3)
-    # other sign types fail loudly (no CPU fallback)
+    # sign types whose tables the mesh was built without fail loudly (no CPU fallback); unknown types too
+    for t in (1, 2):   # SIGNED_DISTANCE_TYPE_WINDING_NUMBER, _DEFAULT
+        with pytest.raises(IglB200Error) as e:
+            m.signed_distance(P[:5], t)
+        assert e.value.code == -1
     with pytest.raises(IglB200Error) as e:
-        m.signed_distance(P[:5], 1)   # SIGNED_DISTANCE_TYPE_WINDING_NUMBER
+        m.signed_distance(P[:5], 7)
     assert e.value.code == -4
     with pytest.raises(IglB200Error) as e:   # pseudonormals need the precomputed normals
         m.signed_distance(P[:5], SIGNED_DISTANCE_TYPE_PSEUDONORMAL)
@@ -601,3 +605,71 @@ def case_offset_surface(api, V, F, isolevel, s, sign_type, what):
         dist = np.sqrt(oracle.PortAABB(V, F).squared_distance(SV)[0])
         assert np.abs(dist - abs(isolevel)).max() < 1.5 * h, f"{what}: surface off by {np.abs(dist - abs(isolevel)).max()} (h={h})"
     return dict(nV=int(SV.shape[0]), nF=int(SF.shape[0]), side=side_o.tolist())
+
+
+# ---------------------------------------------------------------- exact winding number
+def open_and_messy_meshes():
+    """closed, open, non-manifold, inconsistently oriented and duplicated soups: the generalised winding number
+    is defined for all of them and fractional for most."""
+    rng = np.random.default_rng(11)
+    ms = {}
+    V, F = synth.icosphere(3)
+    ms["closed sphere"] = (V, F)
+    ms["hemisphere (open)"] = (V, F[V[F].mean(1)[:, 2] > 0.1])
+    ms["sphere with holes"] = (V, F[rng.random(F.shape[0]) > 0.2])
+    Ff = F.copy(); flip = rng.random(F.shape[0]) < 0.3; Ff[flip] = Ff[flip][:, ::-1]
+    ms["inconsistent orientation"] = (V, Ff)
+    ms["duplicated faces"] = (V, np.concatenate([F, F[: F.shape[0] // 3], F[: F.shape[0] // 5][:, ::-1]]))
+    ms["random soup"] = (rng.standard_normal((300, 3)), rng.integers(0, 300, (500, 3)).astype(np.int32))
+    Vk, Fk = synth.torus_knot(200, 12)
+    ms["knot (closed)"] = (Vk, Fk)
+    ms["knot (cut open)"] = (Vk, Fk[: Fk.shape[0] * 2 // 3])
+    Vt, Ft = synth.tetrahedron()
+    ms["tet"] = (Vt, Ft)
+    ms["one triangle"] = (Vt, Ft[:1])
+    Fd = F.copy(); Fd[::7, 2] = Fd[::7, 1]          # degenerate rows [i j j]
+    ms["with degenerate faces"] = (V, Fd)
+    # shuffled rows: the tree no longer follows the surface, chains get long
+    ms["shuffled sphere"] = (V, F[rng.permutation(F.shape[0])])
+    return ms
+
+
+def case_winding_number(api, n_queries=1500, meshes=None):
+    """igl::winding_number / hierarchical evaluation vs the face-by-face sum: |dW| <= 1e-10."""
+    rng = np.random.default_rng(13)
+    out = {}
+    for name, (V, F) in (meshes or open_and_messy_meshes()).items():
+        lo, hi = V.min(0), V.max(0)
+        O = np.concatenate([lo + (hi - lo) * (rng.random((n_queries, 3)) * 1.6 - 0.3),      # around and inside
+                            V[rng.integers(0, V.shape[0], 50)] + 1e-3 * rng.standard_normal((50, 3)),   # next to vertices
+                            10.0 * (hi - lo) * rng.standard_normal((20, 3))])                     # far away
+        Wo = oracle.winding_number(V, F, O)
+        W = api.winding_number(V, F, O)
+        d = np.abs(W - Wo).max()
+        assert d <= 1e-10, f"{name}: winding number differs by {d}"
+        out[name] = float(d)
+    return out
+
+
+def case_signed_distance_exact_winding(api, V, F, P, what, lower=None, upper=None):
+    """SIGNED_DISTANCE_TYPE_WINDING_NUMBER and _DEFAULT (the same in 3-D, signed_distance.cpp:60-64)."""
+    So, Io, Co, Wo = oracle.signed_distance_winding_number(P, V, F, lower, upper)
+    res = {}
+    for t in (1, 2):
+        S, I, C, W = api.signed_distance(P, V, F, t, lower, upper, return_W=True)
+        nan = np.isnan(So)
+        assert np.array_equal(np.isnan(S), nan), f"{what}: NaN rows"
+        ok = ~nan
+        assert np.abs(W[ok] - Wo[ok]).max(initial=0.0) <= 1e-10, f"{what}: W"
+        scale = max(np.linalg.norm(V.max(0) - V.min(0)), 1.0)
+        assert np.abs(S[ok] - So[ok]).max(initial=0.0) <= 1e-9 * scale, f"{what}: S"
+        assert np.array_equal(C[nan], Co[nan]) and np.array_equal(I[nan], Io[nan]), f"{what}: sentinels"
+        # closest face / point: identical except on exact ties (same squared distance to several faces)
+        diff = ok & (I != Io)
+        if diff.any():
+            assert np.array_equal(oracle.face_distance(V, F, P[diff], I[diff]), oracle.face_distance(V, F, P[diff], Io[diff])), \
+                f"{what}: closest face differs off ties"
+        same = ok & (I == Io)
+        assert np.array_equal(C[same], Co[same]), f"{what}: C"
+        res[t] = int(ok.sum())
+    return res

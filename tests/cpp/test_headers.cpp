@@ -29,8 +29,10 @@ int main() {
   MatrixXd P(1, 3);
   P(0, 0) = P(0, 1) = P(0, 2) = 0.5;
   // signed_distance: single_tet
+  // (the reference test loops over exactly these five: tests/include/igl/signed_distance.cpp:23-30)
   for (auto type : {iglb200::SIGNED_DISTANCE_TYPE_PSEUDONORMAL, iglb200::SIGNED_DISTANCE_TYPE_UNSIGNED,
-                    iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER}) {
+                    iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, iglb200::SIGNED_DISTANCE_TYPE_WINDING_NUMBER,
+                    iglb200::SIGNED_DISTANCE_TYPE_DEFAULT}) {
     VectorXd S; VectorXi I; MatrixXd C, N;
     iglb200::signed_distance(P, V, F, type, S, I, C, N);
     REQUIRE(S.rows() == 1 && I.rows() == 1 && C.rows() == 1 && C.cols() == 3);
@@ -44,11 +46,11 @@ int main() {
       REQUIRE(N.rows() == 0);   // untouched, as in the reference
     }
   }
-  // other sign types must fail loudly
+  // an unknown sign type must fail loudly
   {
     VectorXd S; VectorXi I; MatrixXd C, N;
     bool threw = false;
-    try { iglb200::signed_distance(P, V, F, iglb200::SIGNED_DISTANCE_TYPE_WINDING_NUMBER, S, I, C, N); }
+    try { iglb200::signed_distance(P, V, F, (iglb200::SignedDistanceType)9, S, I, C, N); }
     catch (const iglb200::Error &e) { threw = (e.code == IGLB200_ERR_UNSUPPORTED); }
     REQUIRE(threw);
   }

@@ -114,3 +114,15 @@ def test_offset_surface(emul_api):
     cases.case_offset_surface(emul_api, V, F, 0.15, 18, PN, "ico2 +0.15 pseudonormal")
     V, F = synth.torus_knot(120, 10)
     cases.case_offset_surface(emul_api, V, F, 0.05, 28, FWN, "knot +0.05 fwn")
+
+
+def test_exact_winding_number(emul_api):
+    cases.case_winding_number(emul_api, 400)
+
+
+def test_signed_distance_winding_number_and_default(emul_api):
+    V, F = synth.icosphere(3)
+    P = synth.grid_points(*synth.bbox(V), 12, 1.4)
+    cases.case_signed_distance_exact_winding(emul_api, V, F, P, "ico3")
+    cases.case_signed_distance_exact_winding(emul_api, V, F[V[F].mean(1)[:, 2] > 0.0], P, "open hemisphere")
+    cases.case_signed_distance_exact_winding(emul_api, V, F, P, "ico3 bounded", 0.1, 0.4)

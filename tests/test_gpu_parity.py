@@ -221,3 +221,30 @@ def test_grid_pipeline_stays_on_device_tutorial_705(gpu_api):
     _, cnt = np.unique(e, axis=0, return_counts=True)
     assert (cnt == 2).all()
     m.close(); g.close()
+
+
+# ---- exact winding number: SIGNED_DISTANCE_TYPE_WINDING_NUMBER / _DEFAULT, igl::winding_number ----
+def test_exact_winding_number(gpu_api):
+    cases.case_winding_number(gpu_api, 1500)
+    # a 320k-face closed knot: integers inside/outside to 1e-9, and the face-by-face sum on a sample
+    V, F = synth.torus_knot(*synth.knot_dims(320_000))
+    m = gpu_api.Mesh(V, F, 2, winding_number=True)
+    P = synth.grid_points(*synth.bbox(V), 64, 1.1)
+    W = m.winding_number(P)
+    assert np.abs(W - np.round(W)).max() < 1e-9 and set(np.unique(np.round(W)).tolist()) <= {0.0, 1.0}
+    k = np.arange(0, P.shape[0], 997)
+    assert np.abs(W[k] - oracle.winding_number(V, F, P[k])).max() < 1e-10
+    # the fast winding number agrees with it to its own truncation error
+    Wf = m.fast_winding_number(P)
+    assert np.abs(Wf - W).max() < 2e-2
+    m.close()
+
+
+def test_signed_distance_winding_number_and_default(gpu_api):
+    V, F = synth.icosphere(4)
+    P = synth.grid_points(*synth.bbox(V), 24, 1.4)
+    cases.case_signed_distance_exact_winding(gpu_api, V, F, P, "ico4")
+    cases.case_signed_distance_exact_winding(gpu_api, V, F[V[F].mean(1)[:, 2] > 0.0], P, "open hemisphere")
+    cases.case_signed_distance_exact_winding(gpu_api, V, F, P, "ico4 bounded", 0.1, 0.4)
+    V, F = synth.torus_knot(300, 16)
+    cases.case_signed_distance_exact_winding(gpu_api, V, F, synth.grid_points(*synth.bbox(V), 20, 1.1), "knot")
