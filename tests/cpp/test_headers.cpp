@@ -12,6 +12,7 @@
 #include "iglb200/point_mesh_squared_distance.h"
 #include "iglb200/hausdorff.h"
 #include "iglb200/offset_surface.h"
+#include "iglb200/winding_number.h"
 
 using namespace mini;
 #define REQUIRE(x) do { if (!(x)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #x); std::exit(1); } } while (0)
@@ -122,6 +123,17 @@ int main() {
     iglb200::fast_winding_number(Pc, Nc, A, Q, WN2);
     const double gold[4] = {0.38779369004261133, -0.00041235296362485, -0.00362978253577090, -0.00041235296362485};
     for (int i = 0; i < 4; ++i) { REQUIRE(std::fabs(WN(i) - gold[i]) < 1e-15); REQUIRE(WN2(i) == WN(i)); }
+  }
+  // exact winding number (igl::winding_number): 1 inside the tet, 0 outside
+  {
+    MatrixXd O(3, 3); VectorXd W;
+    O(0, 0) = O(0, 1) = O(0, 2) = 0.1; O(1, 0) = O(1, 1) = O(1, 2) = 2.0; O(2, 0) = O(2, 1) = O(2, 2) = -0.2;
+    iglb200::winding_number(V, F, O, W);
+    REQUIRE(std::fabs(W(0) - 1.0) < 1e-14 && std::fabs(W(1)) < 1e-14 && std::fabs(W(2)) < 1e-14);
+    MatrixXi F1(1, 3); F1(0, 0) = 1; F1(0, 1) = 2; F1(0, 2) = 3;       // the slanted face alone, seen from the origin:
+    MatrixXd O1(1, 3); O1(0, 0) = O1(0, 1) = O1(0, 2) = 0.0;            // one octant of the sphere = 1/8
+    iglb200::winding_number(V, F1, O1, W);
+    REQUIRE(std::fabs(std::fabs(W(0)) - 0.125) < 1e-14);
   }
   // voxel_grid / flood_fill / marching_cubes / offset_surface (tutorials 705, 909; offset_surface.cpp)
   {

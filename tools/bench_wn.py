@@ -1,0 +1,20 @@
+import sys, time, numpy as np
+sys.path.insert(0, "/root/repo")
+import libigl_b200 as ig
+from libigl_b200 import synth
+api = ig.lib()
+api.profile_enable(True)
+for nf, g in ((100_000, 96), (1_000_000, 128)):
+    V, F = synth.torus_knot(*synth.knot_dims(nf))
+    t0 = time.perf_counter(); m = api.Mesh(V, F, 2, winding_number=True); tb = time.perf_counter() - t0
+    info = m.info()
+    P = synth.grid_points(*synth.bbox(V), g, 1.1)
+    m.winding_number(P[:1000])
+    api.profile_collect()
+    t0 = time.perf_counter(); W = m.winding_number(P); t1 = time.perf_counter() - t0
+    prof = api.profile_collect()
+    S, I, C = m.signed_distance(P, 2)
+    prof2 = api.profile_collect()
+    print(nf, g, "build_s", round(tb, 3), "arena_MB", info["device_bytes"] / 1e6, "wn wall_s", round(t1, 3), prof, "sd default", prof2,
+          "q/s", P.shape[0] / (prof["exact_winding"] / 1e3), "Wrange", W.min(), W.max(), flush=True)
+    m.close()
