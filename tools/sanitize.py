@@ -25,4 +25,16 @@ Pc, N, A = synth.oriented_cloud(V, F, 3000, 2)
 c = api.Cloud(Pc, N, A, 2)
 Wc = c.eval(P[:2000], 2.0)
 c.close()
+# exact winding number (open soup: chains with every kind of multiplicity) and the grid pipeline
+rng = np.random.default_rng(0)
+Fo = np.concatenate([F[rng.random(F.shape[0]) > 0.2], F[:50], F[:30][:, ::-1]])
+mw = api.Mesh(V, Fo, 2, winding_number=True)
+Wx = mw.winding_number(P[:3000])
+Sx = mw.signed_distance(P[:3000], 2)[0]
+mw.close()
+SV, SF, GV, side, Sg = api.offset_surface(V, F, 0.05, 24)
+Sn = Sg.copy(); Sn[rng.random(Sn.size) < 0.5] = np.nan
+Sf = api.flood_fill(side, Sn)
+V2, F2, E2 = api.marching_cubes(Sf, GV, side[0], side[1], side[2], 0.01, return_E2V=True)
+print("grid", side.tolist(), SV.shape, SF.shape, V2.shape, float(np.abs(Wx).max()), float(np.nanmax(Sx)))
 print("ok", float(np.nanmax(np.abs(S))), int(I.max()), float(Wc.max()))
