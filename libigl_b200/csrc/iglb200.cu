@@ -126,11 +126,11 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     float d2[32][4];
     for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) d2[l][i] = lane_box_d2(n, i, L[l]);
     // faces first: they tighten the bounds the internal children are judged by
-    uint32_t wt = 0;
-    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) if (d2[l][i] <= L[l].thr2) wt |= 1u << i;
-    wt &= tmask;
     for (int i = 0; i < 4; ++i) {
-      if (!((wt >> i) & 1u)) continue;
+      if (!((tmask >> i) & 1u)) continue;
+      bool any = false;   // judged by the bounds as tightened by the faces before it
+      for (int l = 0; l < 32; ++l) any = any || (d2[l][i] <= L[l].thr2);
+      if (!any) continue;
       ++ntri;
       const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
       for (int l = 0; l < 32; ++l) {
@@ -220,9 +220,6 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       const CpNode n = *np;
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
       const uint32_t imask = n.pad.x, tmask = n.pad.y;
-#ifndef CP_FACE_UNROLL
-#define CP_FACE_UNROLL 1   // measured: 97.1 vs 100.8 ms on c2
-#endif
 #ifndef CP_PREFETCH
 #define CP_PREFETCH 0   // measured: the extra instructions cost more than the L1 misses they save
 #endif
@@ -246,6 +243,10 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
 #pragma unroll
       for (int i = 0; i < 4; ++i) d2[i] = lane_box_d2(n, i, L);
       // faces first: they tighten the bounds the internal children are judged by
+#ifndef CP_VOTE
+#define CP_VOTE 1   // bit 0: per-face __any_sync (95.7 vs 97.0 ms); bit 1: the same for internal children (99.2 ms: worse)
+#endif
+#if !(CP_VOTE & 1)
       uint32_t wt = 0;
       if (tmask) {   // warp-uniform
         uint32_t mine = 0;
@@ -253,11 +254,16 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         for (int i = 0; i < 4; ++i) mine |= (d2[i] <= L.thr2) ? (1u << i) : 0u;
         wt = __reduce_or_sync(FULL, mine) & tmask;
       }
-#if CP_FACE_UNROLL
+#endif
       // one guarded copy per lane: the child id is a plain register in each (no select chain, no ffs)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+#if CP_VOTE & 1
+        if (!((tmask >> i) & 1u)) continue;                      // warp-uniform
+        if (!__any_sync(FULL, d2[i] <= L.thr2)) continue;        // judged by the bounds as tightened so far
+#else
         if (!((wt >> i) & 1u)) continue;   // warp-uniform
+#endif
         const uint32_t f = ch[i];
         if (COUNT) ++ntri;
         const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)f;
@@ -265,25 +271,17 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
         if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, f, d32, err);   // few lanes
       }
-#else
-      // one face at a time (not unrolled: four faces in flight would double the register count)
-#pragma unroll 1
-      while (wt) {     // warp-uniform
-        const int i = __ffs(wt) - 1;
-        wt &= wt - 1;
-        const uint32_t f = i == 0 ? ch[0] : i == 1 ? ch[1] : i == 2 ? ch[2] : ch[3];
-#ifdef CP_COUNT_LANES
-        if (COUNT) ntri += __popc(__ballot_sync(FULL, d2[i] <= L.thr2));
-#else
-        if (COUNT) ++ntri;
-#endif
-        const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)f;
-        const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3];
-        float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
-        if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, f, d32, err);   // few lanes
-      }
-#endif
       if (imask) {   // warp-uniform
+#if CP_VOTE & 2
+        uint32_t wi = 0, mykey = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!((imask >> i) & 1u)) continue;   // warp-uniform
+          const bool w = d2[i] <= L.thr2;
+          if (__any_sync(FULL, w)) wi |= 1u << i;
+          mykey = w ? min(mykey, (__float_as_uint(d2[i]) & ~3u) | (uint32_t)i) : mykey;
+        }
+#else
         uint32_t mine = 0, mykey = 0xFFFFFFFFu;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -292,6 +290,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
           mykey = w ? min(mykey, (__float_as_uint(d2[i]) & ~3u) | (uint32_t)i) : mykey;
         }
         const uint32_t wi = __reduce_or_sync(FULL, mine);
+#endif
         if (wi) {
           const uint32_t best = __reduce_min_sync(FULL, mykey);
           const int nb = (int)(best & 3u);
