@@ -181,6 +181,12 @@ DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" 
 #ifndef CP_MIN_BLOCKS
 #define CP_MIN_BLOCKS 5
 #endif
+#ifndef CP_PUSH_ALL
+// 1: every lane stores the (identical) stack entries itself and the loop needs no __syncwarp: 93.3 vs 95.7 ms
+// on c2, but the same-value stores are write-write races in racecheck's eyes -> off.  (Lane 0 owning the stack
+// and broadcasting pops by shuffle is race-free too, and slower: 96.1 ms.)
+#define CP_PUSH_ALL 0
+#endif
 // One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
@@ -298,17 +304,27 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
           const int npush = __popc(push);
           if (sp + npush > CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); }
           else if (push) {
+#if CP_PUSH_ALL
+            // every lane stores the same entries (it holds all four child ids) and later reads back its own
+            // store: no cross-lane dependency through shared memory, so no __syncwarp in the loop
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if ((push >> j) & 1u) stack[sp + __popc(push & ((1u << j) - 1u))] = ch[j] & ~INTERNAL_BIT;   // warp-uniform
+#else
             if (lane < 4 && ((push >> lane) & 1u)) {
               const uint32_t c = lane == 0 ? ch[0] : lane == 1 ? ch[1] : lane == 2 ? ch[2] : ch[3];
               stack[sp + __popc(push & ((1u << lane) - 1u))] = c & ~INTERNAL_BIT;
             }
+#endif
             sp += npush;
           }
           cur = (nb == 0 ? ch[0] : nb == 1 ? ch[1] : nb == 2 ? ch[2] : ch[3]) & ~INTERNAL_BIT;
           have = true;
         }
       }
+#if !CP_PUSH_ALL
       __syncwarp();
+#endif
     }
     if (valid) {
       CpResult r;
