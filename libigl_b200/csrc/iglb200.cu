@@ -179,8 +179,8 @@ void throw_if_overflow(stream_t) {
 DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 #ifndef CP_MIN_BLOCKS
-#define CP_MIN_BLOCKS 5
-#endif
+#define CP_MIN_BLOCKS 24   // with one-warp blocks: 80 registers, 25 warps per SM (measured best: 92.8 ms on c2;
+#endif                     // 96 regs/20 warps 95.6, 72 regs/28 warps 99.2, 64 regs/32 warps 100.1)
 #ifndef CP_PUSH_ALL
 // 1: every lane stores the (identical) stack entries itself and the loop needs no __syncwarp: 93.3 vs 95.7 ms
 // on c2, but the same-value stores are write-write races in racecheck's eyes -> off.  (Lane 0 owning the stack
@@ -191,7 +191,7 @@ DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" 
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
 #ifndef CP_WARPS
-#define CP_WARPS 4
+#define CP_WARPS 1         // a block is one packet: a finished packet frees its slot at once (4 warps/block: 94.6 ms)
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
