@@ -144,24 +144,23 @@ DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, cons
   return sqrt_fast(d2 + z * z);
 }
 
-// running state of one query during the walk (kept in registers: no dynamic indexing)
+// running state of one query during the walk (registers)
 struct CpLane {
   float px, py, pz;
   float xm, ym, zm, xp, yp, zp;  // p -/+ slack: the box tests absorb their own rounding this way
   float u;        // 2^-24 * max(|p|, |mesh|)
   float best_ub;  // fp32 upper bound of the distance to the nearest face seen so far
   float thr2;     // prune a box when its squared lower bound exceeds this
-  float min_lb;   // smallest lower bound among the listed candidates
-  int ncand;
-  uint32_t cf0, cf1, cf2;  // candidate faces
-  float cl0, cl1, cl2;     // their lower bounds
 };
 // exact best among the candidates already evaluated in fp64 (touched only by the rare fp64
 // stage: lives in shared memory on the device so it does not cost registers in the walk)
 struct CpExact {
   double d2;
   int32_t face;
-  int32_t pad;
+  int32_t ncand;
+  float min_lb;             // smallest lower bound among the listed candidates
+  uint32_t cf[CP_NCAND];    // candidate faces of the fp32 stage (touched by the few lanes a face is close to)
+  float cl[CP_NCAND];       // their lower bounds
 };
 // where the query itself can be re-read by the fp64 stage
 struct CpQueryRef { const double *P; int64_t n, qi; };
@@ -179,10 +178,8 @@ DEVFN void lane_init(CpLane &L, CpExact &X, D3 p, double up_sqr_d, float absmax)
   L.xm = L.px - slack; L.ym = L.py - slack; L.zm = L.pz - slack;
   L.xp = L.px + slack; L.yp = L.py + slack; L.zp = L.pz + slack;
   L.u = M * 5.9604645e-8f * 1.0000002f;
-  L.ncand = 0; L.min_lb = INFINITY;
-  L.cf0 = L.cf1 = L.cf2 = 0u;
-  L.cl0 = L.cl1 = L.cl2 = INFINITY;
-  X.d2 = up_sqr_d; X.face = -1; X.pad = 0;
+  X.ncand = 0; X.min_lb = INFINITY;
+  X.d2 = up_sqr_d; X.face = -1;
   const float ub = (up_sqr_d < 3.0e38) ? f_up(sqrt(up_sqr_d)) * 1.0000002f : INFINITY;
   L.best_ub = ub;
   L.thr2 = (up_sqr_d < 3.0e38) ? f_up(up_sqr_d) * 1.000001f : INFINITY;
@@ -212,10 +209,10 @@ static __device__ __noinline__
 #endif
 void lane_flush(CpLane &L, CpExact &X, const double *tri64, CpQueryRef q) {
   const D3 p = load_query(q);
-  if (L.ncand > 0 && L.cl0 <= L.best_ub) lane_exact(X, tri64, p, L.cf0);
-  if (L.ncand > 1 && L.cl1 <= L.best_ub) lane_exact(X, tri64, p, L.cf1);
-  if (L.ncand > 2 && L.cl2 <= L.best_ub) lane_exact(X, tri64, p, L.cf2);
-  L.ncand = 0; L.min_lb = INFINITY;
+  const int nc = X.ncand;
+  for (int k = 0; k < nc; ++k)
+    if (X.cl[k] <= L.best_ub) lane_exact(X, tri64, p, X.cf[k]);
+  X.ncand = 0; X.min_lb = INFINITY;
   if (X.face >= 0) {
     const float ub = f_up(sqrt(X.d2)) * 1.0000002f;
     if (ub < L.best_ub) lane_set_ub(L, ub);
@@ -227,16 +224,18 @@ DEVFN void lane_offer(CpLane &L, CpExact &X, const double *tri64, const CpQueryR
   const float lb = d32 - err;
   if (!(lb <= L.best_ub)) return;
   const float ub = d32 + err;
-  if (ub < L.min_lb) { L.ncand = 0; L.min_lb = INFINITY; }   // every listed candidate is now out of the band
-  if (L.ncand == CP_NCAND) {
+  int nc = X.ncand;
+  float mlb = X.min_lb;
+  if (ub < mlb) { nc = 0; mlb = INFINITY; }   // every listed candidate is now out of the band
+  if (nc == CP_NCAND) {
+    X.ncand = nc;
     lane_flush(L, X, tri64, q);
     if (!(lb <= L.best_ub)) return;
+    nc = 0; mlb = INFINITY;
   }
-  if (L.ncand == 0) { L.cf0 = f; L.cl0 = lb; }
-  else if (L.ncand == 1) { L.cf1 = f; L.cl1 = lb; }
-  else { L.cf2 = f; L.cl2 = lb; }
-  ++L.ncand;
-  L.min_lb = fminf(L.min_lb, lb);
+  X.cf[nc] = f; X.cl[nc] = lb;
+  X.ncand = nc + 1;
+  X.min_lb = fminf(mlb, lb);
   if (ub < L.best_ub) lane_set_ub(L, ub);
 }
 
