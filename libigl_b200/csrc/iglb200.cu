@@ -126,11 +126,11 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     float d2[32][4];
     for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) d2[l][i] = lane_box_d2(n, i, L[l]);
     // faces first: they tighten the bounds the internal children are judged by
+    bool want[4] = {false, false, false, false};   // voted before any face of the node is tested, as the kernel does
+    for (int i = 0; i < 4; ++i)
+      if ((tmask >> i) & 1u) for (int l = 0; l < 32; ++l) want[i] = want[i] || (d2[l][i] <= L[l].thr2);
     for (int i = 0; i < 4; ++i) {
-      if (!((tmask >> i) & 1u)) continue;
-      bool any = false;   // judged by the bounds as tightened by the faces before it
-      for (int l = 0; l < 32; ++l) any = any || (d2[l][i] <= L[l].thr2);
-      if (!any) continue;
+      if (!want[i]) continue;
       ++ntri;
       const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i];
       for (int l = 0; l < 32; ++l) {
@@ -179,8 +179,9 @@ void throw_if_overflow(stream_t) {
 DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 #ifndef CP_MIN_BLOCKS
-#define CP_MIN_BLOCKS 24   // with one-warp blocks: 80 registers, 25 warps per SM (measured best: 92.8 ms on c2;
-#endif                     // 96 regs/20 warps 95.6, 72 regs/28 warps 99.2, 64 regs/32 warps 100.1)
+#define CP_MIN_BLOCKS 20   // with one-warp blocks: 96 registers, 20 warps per SM.  Before two face records were kept in
+#endif                     // flight 80 regs/25 warps was best (92.8 ms; 96/20 95.6, 72/28 99.2, 64/32 100.1); with them
+                           // 96/20 gives 89.4 ms and 80/25 89.9 ms
 #ifndef CP_PUSH_ALL
 // 1: every lane stores the (identical) stack entries itself and the loop needs no __syncwarp: 93.3 vs 95.7 ms
 // on c2, but the same-value stores are write-write races in racecheck's eyes -> off.  (Lane 0 owning the stack
@@ -261,6 +262,31 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         wt = __reduce_or_sync(FULL, mine) & tmask;
       }
 #endif
+#ifndef CP_PAIR
+#define CP_PAIR 1   // 89.4 vs 91.4 ms on c2 (with 96 registers / 20 warps per SM)
+#endif
+#if CP_PAIR
+      if (tmask) {   // warp-uniform
+        // two face records in flight where two neighbouring lanes are wanted: one load round trip instead of two
+        bool w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = ((tmask >> i) & 1u) && __any_sync(FULL, d2[i] <= L.thr2);
+#define CP_FACE1(i) { const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i]; \
+          const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3]; if (COUNT) ++ntri; \
+          float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err); \
+          if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); }
+#define CP_FACE2(i, j) { const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i], *tr = a.triq + TRIQ_STRIDE * (size_t)ch[j]; \
+          const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3], U0 = tr[0], U1 = tr[1], U2 = tr[2], U3 = tr[3]; if (COUNT) ntri += 2; \
+          float err, erq; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err); \
+          const float e32 = tri_dist_f32(U0, U1, U2, U3, L.px, L.py, L.pz, L.u, erq); \
+          if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); \
+          if (e32 - erq <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[j], e32, erq); }
+        if (w[0] && w[1]) CP_FACE2(0, 1) else if (w[0]) CP_FACE1(0) else if (w[1]) CP_FACE1(1)
+        if (w[2] && w[3]) CP_FACE2(2, 3) else if (w[2]) CP_FACE1(2) else if (w[3]) CP_FACE1(3)
+#undef CP_FACE1
+#undef CP_FACE2
+      }
+#else
       // one guarded copy per lane: the child id is a plain register in each (no select chain, no ffs)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -277,6 +303,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
         if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, f, d32, err);   // few lanes
       }
+#endif
       if (imask) {   // warp-uniform
 #if CP_VOTE & 2
         uint32_t wi = 0, mykey = 0xFFFFFFFFu;
