@@ -151,7 +151,7 @@ def reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
         "config": config_dict(args, F.shape[0], P.shape[0]),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference+port",
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": r["sample"] + "; genuine UT_SolidAngle (oracle/_ref) + restated f64 igl::AABB (oracle port)",
                          "build_s": r["build_s"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -322,7 +322,7 @@ def ours(args):
     }
     if world == 1 and not args.no_cpu:
         r = run_cpu(V, F, P, args.grid, budget_s=args.cpu_seconds)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference+port",
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"] + "; genuine UT_SolidAngle (oracle/_ref) + restated f64 igl::AABB (oracle port)",
                                 "build_s": r["build_s"]}
         # algorithmic flops from the instrumented oracle on a small sample
