@@ -728,7 +728,7 @@ void download_scalar(const DevBuf<double> &src, int64_t n, void *dst, int is_f64
 // k-1's download run concurrently on two streams with a grow-only per-thread device workspace
 // (no cudaMalloc/cudaFree on the call path).
 struct Pipeline {
-  static constexpr int64_t CHUNK = int64_t(1) << 21;
+  static constexpr int64_t CHUNK_MAX = int64_t(1) << 22, CHUNK_MIN = int64_t(1) << 20;   // measured on c2: 4 M-query chunks 149 M q/s e2e, 2 M 141, 8 M 145, 1 M 135
   cudaStream_t st[2] = {nullptr, nullptr};
   char *buf[2] = {nullptr, nullptr};
   size_t cap = 0;
@@ -747,7 +747,9 @@ Pipeline &pipeline() { static thread_local Pipeline p; return p; }
 void run_streamed(const iglb200_mesh *m, int mode, const double *P, int64_t n, int sign_type, double lower, double upper,
                   float accuracy_scale, double *S, int32_t *I, double *C, double *W, double *N = nullptr) {
   Pipeline &pl = pipeline();
-  const int64_t chunk = std::min<int64_t>(Pipeline::CHUNK, n);
+  static const int64_t chunk_cfg = [] { const char *e = std::getenv("IGLB200_STREAM_CHUNK"); const long long v = e ? std::atoll(e) : 0; return v > 0 ? (int64_t)v : 0; }();
+  // a quarter of the batch, so that uploads, kernels and downloads overlap, within [1 M, 4 M] queries
+  const int64_t chunk = std::min<int64_t>(chunk_cfg ? chunk_cfg : std::min(Pipeline::CHUNK_MAX, std::max(Pipeline::CHUNK_MIN, (n + 3) / 4)), n);
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   const size_t oP = 0, oS = oP + al(24 * chunk), oC = oS + al(8 * chunk), oW = oC + al(24 * chunk), oI = oW + al(8 * chunk),
                oN = oI + al(4 * chunk), oX = oN + al(N ? 24 * chunk : 0), total = oX + al(iglb200_query_scratch_bytes(chunk));
