@@ -26,6 +26,7 @@ struct iglb200_cloud {
   int order = 2, nterms = 39;
   int64_t ncells = 0, nlevels = 0;
   uint64_t bytes = 0;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the points
   // sorted points: position, area*normal
   plat::DevBuf<double> P, AN;
   // cells
@@ -268,6 +269,7 @@ struct EvalQuery {  // helper() of fast_winding_number.cpp:233-292, depth-first
   const double *CM, *R, *EC;
   int nterms; int64_t ncloud;
   const double *Q; int64_t nq; double beta; double *WN;
+  const uint32_t *perm;   // queries in Morton order: a warp walks (nearly) the same cells
   DEVFN double leaf_sum(uint32_t c, const double *q) const {
     double wn = 0;
     const uint32_t b = cbegin[c], e = b + ccount[c];
@@ -278,7 +280,8 @@ struct EvalQuery {  // helper() of fast_winding_number.cpp:233-292, depth-first
     }
     return wn;
   }
-  DEVFN void operator()(int64_t i) const {
+  DEVFN void operator()(int64_t t) const {
+    const int64_t i = perm ? (int64_t)perm[t] : t;
     const double q[3] = {Q[i], Q[nq + i], Q[2 * nq + i]};
     double wn = 0;
     if (ncloud == 0) { WN[i] = 0.0; return; }
@@ -351,7 +354,7 @@ inline iglb200_cloud *create(const void *P, const void *N, const void *A, int is
     plat::d2h(hb, bb.p, sizeof(hb), s);
     plat::sync(s);
     double lo[3], hi[3];
-    for (int d = 0; d < 3; ++d) { lo[d] = plat::ord2d(hb[d]); hi[d] = plat::ord2d(hb[3 + d]); }
+    for (int d = 0; d < 3; ++d) { lo[d] = plat::ord2d(hb[d]); hi[d] = plat::ord2d(hb[3 + d]); c->lo[d] = lo[d]; c->hi[d] = hi[d]; }
     // octree.cpp:143-150
     const double cen[3] = {(lo[0] + hi[0]) / 2.0, (lo[1] + hi[1]) / 2.0, (lo[2] + hi[2]) / 2.0};
     const double width = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
@@ -443,10 +446,56 @@ inline void info(const iglb200_cloud *c, int64_t *out) {
   out[5] = out[6] = out[7] = 0;
 }
 
+struct QueryKeys {   // 30-bit Morton code of a query inside the cloud's box doubled about its centre
+  const double *Q; int64_t n;
+  double lo[3], inv[3];
+  uint32_t *keys, *vals;
+  static DEVFN uint32_t spread(uint32_t v) {
+    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+    return v;
+  }
+  DEVFN void operator()(int64_t i) const {
+    uint32_t c[3];
+    for (int d = 0; d < 3; ++d) {
+      double t = (Q[d * n + i] - lo[d]) * inv[d];
+      t = t < 0.0 ? 0.0 : (t > 1023.0 ? 1023.0 : t);
+      if (!(t == t)) t = 0.0;
+      c[d] = (uint32_t)t;
+    }
+    keys[i] = spread(c[0]) | (spread(c[1]) << 1) | (spread(c[2]) << 2);
+    vals[i] = (uint32_t)i;
+  }
+};
+
 inline void eval(const iglb200_cloud *c, const double *Q, int64_t nq, double beta, double *WN, stream_t s) {
   if (nq <= 0) return;
-  plat::Span sp("cloud_eval", s);
-  plat::for_n(nq, EvalQuery{c->P.p, c->AN.p, c->cbegin.p, c->ccount.p, c->cchild.p, c->CM.p, c->R.p, c->EC.p, c->nterms, c->n, Q, nq, beta, WN}, s);
+  using plat::DevBuf;
+  DevBuf<uint32_t> kin, kout, vin, perm;
+  DevBuf<char> tmp;
+  const bool sort = nq >= 1024 && c->n > 0 && beta > 0;
+  if (sort) {
+    plat::Span sp("morton_sort", s);
+    kin.alloc((size_t)nq); kout.alloc((size_t)nq); vin.alloc((size_t)nq); perm.alloc((size_t)nq);
+    const size_t tb = plat::sort_pairs_temp_bytes(nq);
+    tmp.alloc(tb);
+    QueryKeys qk;
+    qk.Q = Q; qk.n = nq; qk.keys = kin.p; qk.vals = vin.p;
+    for (int d = 0; d < 3; ++d) {
+      const double cen = 0.5 * (c->lo[d] + c->hi[d]);
+      double ext = c->hi[d] - c->lo[d];
+      if (!(ext > 0.0)) ext = 1.0;
+      qk.lo[d] = cen - ext; qk.inv[d] = 1024.0 / (2.0 * ext);
+    }
+    plat::for_n(nq, qk, s);
+    plat::sort_pairs_u32(tmp.p, tb, kin.p, kout.p, vin.p, perm.p, nq, 30, s);
+  }
+  {
+    plat::Span sp("cloud_eval", s);
+    plat::for_n(nq, EvalQuery{c->P.p, c->AN.p, c->cbegin.p, c->ccount.p, c->cchild.p, c->CM.p, c->R.p, c->EC.p, c->nterms, c->n, Q, nq, beta, WN,
+                              sort ? perm.p : nullptr}, s);
+  }
+  plat::sync(s);   // the sort buffers are released on return
 }
 
 }  // namespace cloud
