@@ -113,13 +113,16 @@ def main():
             tb = time.perf_counter() - t0
             dQ = dev_cols(Q)
             dW = torch.empty(nq, dtype=torch.float64, device="cuda")
+            api.profile_enable(True)
             ms = timed(lambda: api.check(api.lib.iglb200_cloud_eval_dev(cl.h, dQ.data_ptr(), nq, 2.0, dW.data_ptr(), None)), reps=2)
+            spans = {k: v / 3 for k, v in api.profile_collect().items()}
+            api.profile_enable(False)
             k = np.arange(0, nq, max(1, nq // 20000))
             Wo = oracle.PortCloud(Pc, N, A, 2).eval(Q[k], 2.0)
             d = np.abs(dW.cpu().numpy()[k] - Wo).max()
             assert d < 1e-10, d
             res.append(dict(config=f"c4 cloud {npts} points, {nq} queries", points=npts, queries=nq, ms=ms, qps=nq / ms * 1e3,
-                            build_s=tb, cells=cl.info()["n_cells"], levels=cl.info()["n_levels"], parity_sample=dict(n=len(k), dW=float(d))))
+                            kernel_ms=spans, build_s=tb, cells=cl.info()["n_cells"], levels=cl.info()["n_levels"], parity_sample=dict(n=len(k), dW=float(d))))
             cl.close()
         elif c == "c5":
             nf, g = (400_000, 128) if a.small else (10_000_000, 512)
