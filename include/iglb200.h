@@ -55,6 +55,8 @@ const char *iglb200_last_error(void);
 const char *iglb200_version(void);
 int iglb200_device_count(void);          /* <0 on error, 0 when no GPU */
 int iglb200_set_device(int device);      /* device used by the calling thread */
+int iglb200_init(int n_gpus);            /* optional: checks that n_gpus devices exist and creates their contexts */
+void iglb200_shutdown(void);             /* optional: waits for the calling thread's device to go idle */
 
 /* pinned host memory for fast transfers (optional; any host pointer works) */
 int iglb200_host_alloc(void **out, uint64_t bytes);

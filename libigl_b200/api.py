@@ -55,7 +55,7 @@ class Api:
     libigl_b200/libiglb200.so; nothing here knows about any other library."""
 
     SYMBOLS = [
-        "iglb200_last_error", "iglb200_version", "iglb200_device_count", "iglb200_set_device",
+        "iglb200_last_error", "iglb200_version", "iglb200_device_count", "iglb200_set_device", "iglb200_init", "iglb200_shutdown",
         "iglb200_host_alloc", "iglb200_host_free",
         "iglb200_mesh_create", "iglb200_mesh_create_ex", "iglb200_mesh_destroy", "iglb200_mesh_info", "iglb200_mesh_build_ms",
         "iglb200_mesh_arena", "iglb200_mesh_arena_download", "iglb200_mesh_from_arena",

@@ -815,6 +815,31 @@ int iglb200_set_device(int device) {
   API_END
 #endif
 }
+// one process drives n_gpus devices (one per host thread or one per process under torchrun): checks that they exist
+// and creates their contexts up front so that the first query does not pay for it
+int iglb200_init(int n_gpus) {
+  API_BEGIN
+  if (n_gpus < 1) throw std::invalid_argument("n_gpus must be >= 1");
+  require_device();
+#ifndef IGLB200_EMUL
+  int have = 0, cur = 0;
+  PLAT_CHECK(cudaGetDeviceCount(&have));
+  if (have < n_gpus) throw std::invalid_argument("fewer CUDA devices than requested");
+  PLAT_CHECK(cudaGetDevice(&cur));
+  for (int d = 0; d < n_gpus; ++d) { PLAT_CHECK(cudaSetDevice(d)); PLAT_CHECK(cudaFree(nullptr)); }
+  PLAT_CHECK(cudaSetDevice(cur));
+#endif
+  return IGLB200_OK;
+  API_END
+}
+// waits for outstanding work of the calling thread's device; handles stay valid (they are destroyed one by one)
+void iglb200_shutdown(void) {
+#ifndef IGLB200_EMUL
+  int n = 0;
+  if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) cudaDeviceSynchronize();
+  cudaGetLastError();
+#endif
+}
 int iglb200_host_alloc(void **out, uint64_t bytes) {
   if (!out) return fail(IGLB200_ERR_ARG, "null out");
 #ifdef IGLB200_EMUL
