@@ -90,3 +90,65 @@ def test_oracle_reproduces_golden_fixtures():
         o = oracle.PortCloud(g["P"], g["N"], g["A"], order)
         assert o.num_cells() == int(g[f"ncells_order{order}"])
         assert np.abs(o.eval(g["Q"], 2.0) - g[f"WN_order{order}"]).max() < 1e-15
+
+
+# ---- the checker's grid functions and the product's marching-cubes tables, pinned to the reference -------------
+def test_grid_known_answer():
+    """tests/include/igl/grid.cpp:5-41 ("grid: 3d") re-created against the restated igl::grid."""
+    GV = oracle.grid([3, 3, 3])
+    want = np.array([[x, y, z] for z in (0, .5, 1) for y in (0, .5, 1) for x in (0, .5, 1)], float)
+    assert np.array_equal(GV, want)
+
+
+def test_marching_cubes_tables_are_the_reference_s():
+    """libigl_b200/csrc/mc_tables.h (packed, generated) and the corner/edge numbering in csrc/grid.h against
+    the genuine header as march_cube.cpp:44 compiles it (exported by oracle/_ref)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ef, conn, tri = oracle.mc_tables()
+    txt = open(os.path.join(root, "libigl_b200", "csrc", "mc_tables.h")).read()
+    words = [int(w, 16) for w in re.findall(r"0x([0-9A-Fa-f]{16})ULL", txt)]
+    assert len(words) == 256
+    for c in range(256):
+        got = [(words[c] >> (4 * k)) & 0xF for k in range(16)]
+        assert got == [0xF if e < 0 else int(e) for e in tri[c]], c
+    g = open(os.path.join(root, "libigl_b200", "csrc", "grid.h")).read()
+
+    def arr(name):
+        m = re.search(name + r"\[\d+\] = \{([^}]*)\}", g)
+        return [int(x) for x in m.group(1).split(",")]
+    assert list(zip(arr("MC_EA"), arr("MC_EB"))) == [tuple(r) for r in conn.tolist()]
+    # an edge is cut iff its corners lie on different sides: the header's edge-flag table is exactly that
+    derived = [sum(1 << e for e, (a, b) in enumerate(conn) if ((c >> a) ^ (c >> b)) & 1) for c in range(256)]
+    assert derived == ef.tolist()
+    # corner offsets in the order of marching_cubes.cpp:52 (ioffset = {0,1,1+nx,nx,nx*ny,...})
+    cx, cy, cz = arr("MC_CX"), arr("MC_CY"), arr("MC_CZ")
+    nx, ny = 7, 5
+    assert [x + nx * (y + ny * z) for x, y, z in zip(cx, cy, cz)] == [0, 1, 1 + nx, nx, nx * ny, 1 + nx * ny, 1 + nx + nx * ny, nx + nx * ny]
+
+
+def test_restated_flood_fill_and_marching_cubes_properties():
+    g = 20
+    GV = oracle.grid([g, g, g]) * 2 - 1
+    S = np.linalg.norm(GV, axis=1) - 0.6
+    Sn = S.copy()
+    Sn[np.abs(S) > 0.15] = np.nan
+    Sf = oracle.flood_fill([g, g, g], Sn)
+    assert not np.isnan(Sf).any() and np.array_equal(np.sign(Sf), np.sign(S))      # the fill keeps every sign
+    V, F, E = oracle.marching_cubes(Sf, GV, g, g, g, 0.0)
+    assert V.shape[0] - F.shape[0] * 3 // 2 + F.shape[0] == 2                        # closed, genus 0
+    assert np.abs(np.linalg.norm(V, axis=1) - 0.6).max() < 0.02
+    assert (E[:, 0] < E[:, 1]).all() and len({tuple(e) for e in E.tolist()}) == E.shape[0]   # one vertex per grid edge
+
+
+def test_exact_winding_number_known_values():
+    """winding_number.cpp + solid_angle.cpp restated: 1 inside / 0 outside a closed mesh, 1/8 for one octant."""
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    F = np.array([[0, 1, 3], [0, 2, 1], [0, 3, 2], [1, 2, 3]], np.int32)
+    W = oracle.winding_number(V, F, np.array([[0.1, 0.1, 0.1], [2, 2, 2], [-0.2, -0.2, -0.2]], float))
+    assert np.abs(W - [1, 0, 0]).max() < 1e-15
+    w = oracle.winding_number(V, F[3:], np.zeros((1, 3)))
+    assert abs(abs(w[0]) - 0.125) < 1e-15
+    S, I, C, Wd = oracle.signed_distance_winding_number(np.array([[0.5, 0.5, 0.5]]), V, F)
+    assert abs(S[0] - np.sqrt(1. / 12.)) < 1e-15 and I[0] == 3        # tests/include/igl/signed_distance.cpp:4-43
