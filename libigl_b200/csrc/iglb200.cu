@@ -90,6 +90,13 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   double up, low; float absmax;
   double *sqrD; int32_t *I; double *C;
   uint32_t *counters;  // nullable: [0] node visits, [1] face tests (summed over warps)
+  unsigned long long *sched = nullptr;   // nullable: work distribution state of the persistent schedule (CP_PERSIST)
+};
+
+static constexpr int64_t SCHED_WORDS = 1 + 2 * 1024;   // next chunk; per SM id: state, refill lock
+struct InitSched {   // every SM starts with an exhausted chunk
+  unsigned long long *w;
+  DEVFN void operator()(int64_t i) const { w[i] = (i >= 1 && (i & 1)) ? 0x7F7F7F7Full : 0ull; }
 };
 
 DEVFN void closest_store(const ClosestArgs &a, int64_t i, const fwn::CpResult &r) {
@@ -203,8 +210,44 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   CpExact &X = exact[threadIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *stack = stacks[warp];
+#ifndef CP_PERSIST
+#define CP_PERSIST 1   // 81.5 vs 89.3 ms on c2
+#endif
+#ifndef CP_CHUNK
+#define CP_CHUNK 16   // measured: 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2
+#endif
+#if CP_PERSIST
+  // Persistent schedule: every SM hands out the packets of one chunk of CP_CHUNK Morton-consecutive packets to its
+  // resident warps, so the packets that share an L1 are neighbours; chunks are taken from a global counter, so the
+  // chunks in flight still form one window of the query set (L2).  sched[0] = next chunk, sched[1 + 2*smid] =
+  // (chunk << 32 | packets handed out), sched[2 + 2*smid] = refill lock.
+  unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  const uint32_t npackets = (uint32_t)((a.n + 31) / 32);
+  while (true) {
+    uint32_t packet = 0xFFFFFFFFu;
+    if (lane == 0) {
+      unsigned long long *st = a.sched + 1 + 2 * smid, *lock = st + 1;
+      while (true) {
+        const unsigned long long old = atomicAdd(st, 1ull);
+        if ((uint32_t)old < CP_CHUNK) { packet = (uint32_t)(old >> 32) * CP_CHUNK + (uint32_t)old; break; }
+        if (atomicCAS(lock, 0ull, 1ull) == 0ull) {   // this warp refills the SM's chunk
+          if ((uint32_t)(*(volatile unsigned long long *)st) >= CP_CHUNK) {
+            const unsigned long long nc = atomicAdd(a.sched, 1ull);
+            atomicExch(st, nc << 32);
+          }
+          __threadfence();
+          atomicExch(lock, 0ull);
+        }
+      }
+    }
+    packet = __shfl_sync(FULL, packet, 0);
+    if (packet >= npackets) break;   // the SM's chunk lies past the last packet: this warp is done
+    const int64_t base = (int64_t)packet * 32;
+    const int64_t t = base + lane;
+#else
   for (int64_t base = ((int64_t)blockIdx.x * CP_WARPS + warp) * 32; base < a.n; base += (int64_t)gridDim.x * (32 * CP_WARPS)) {
     const int64_t t = base + lane;
+#endif
     const bool valid = t < a.n;
     const int64_t qi = valid ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
     CpLane L;
@@ -381,9 +424,21 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   const int64_t warps = (a.n + 31) / 32;
   // one packet per warp, blocks in Morton order: the packets in flight form one sliding window of the
   // query set, so the tree region they touch stays L2-resident (a grid-stride loop spreads it over ~14 regions)
-  const int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)0x7FFFFFFF);
+  int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)0x7FFFFFFF);
+#if CP_PERSIST
+  static_assert(CP_WARPS == 1, "the persistent schedule hands out packets to one-warp blocks");
+  DevBuf<unsigned long long> own;
+  ClosestArgs b = a;
+  if (!b.sched) { own.alloc(SCHED_WORDS); b.sched = own.p; }   // no caller scratch: a private state for this launch
+  plat::for_n(SCHED_WORDS, InitSched{b.sched}, s);
+  blocks = std::min<int64_t>(blocks, (int64_t)plat::sm_count() * CP_MIN_BLOCKS);
+  if (b.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
+  else closest_packet_kernel<false><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
+  if (own.p) plat::sync(s);
+#else
   if (a.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
   else closest_packet_kernel<false><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
+#endif
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }
@@ -563,9 +618,9 @@ void launch_query(const char *, int64_t n, ExactWindingQuery f, stream_t s) {
 }
 #endif
 
-// scratch layout: [keys_in | keys_out | vals_in | vals_out(perm) | cub temp]
+// scratch layout: [keys_in | keys_out | vals_in | vals_out(perm) | cub temp | schedule state of the search kernel]
 struct Scratch {
-  uint32_t *kin, *kout, *vin, *perm; void *temp; size_t temp_bytes;
+  uint32_t *kin, *kout, *vin, *perm; void *temp; size_t temp_bytes; unsigned long long *sched;
 };
 Scratch carve(void *scratch, int64_t n) {
   Scratch s;
@@ -573,6 +628,7 @@ Scratch carve(void *scratch, int64_t n) {
   char *p = (char *)scratch;
   s.kin = (uint32_t *)p; s.kout = (uint32_t *)(p + a); s.vin = (uint32_t *)(p + 2 * a); s.perm = (uint32_t *)(p + 3 * a);
   s.temp = p + 4 * a; s.temp_bytes = plat::sort_pairs_temp_bytes(n);
+  s.sched = (unsigned long long *)(p + 4 * a + ((s.temp_bytes + 255) & ~size_t(255)));
   return s;
 }
 
@@ -634,7 +690,8 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   bounds_to_sqr(lower, upper, low, up);
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   { plat::Span sp("closest", s);
-    launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr}, s); }
+    launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr,
+                               scratch ? carve(scratch, n).sched : nullptr}, s); }
   if (sign_type == IGLB200_SIGN_PSEUDONORMAL) {
     plat::Span sp("pseudonormal", s);
     plat::for_n(n, PseudonormalQuery{m->tri64(), m->pn(), P, n, up, low, (int32_t)m->h.nF, S, I, C, N}, s);
@@ -672,7 +729,8 @@ void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, dou
   }
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   plat::Span sp("closest", s);
-  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr}, s);
+  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr,
+                             scratch ? carve(scratch, n).sched : nullptr}, s);
 }
 
 void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_scale, double *W, void *scratch,
@@ -957,7 +1015,7 @@ int iglb200_mesh_from_arena(const void *device_ptr, uint64_t bytes, int copy, ig
 uint64_t iglb200_query_scratch_bytes(int64_t nP) {
   if (nP <= 0) return 256;
   const size_t a = ((size_t)nP * 4 + 255) & ~size_t(255);
-  return 4 * a + plat::sort_pairs_temp_bytes(nP) + 256;
+  return 4 * a + ((plat::sort_pairs_temp_bytes(nP) + 255) & ~size_t(255)) + 8 * (size_t)SCHED_WORDS + 256;
 }
 
 int iglb200_last_launch_count(void) { return plat::launch_counter(); }
@@ -1020,7 +1078,8 @@ int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colma
   plat::h2d(dP.p, P_host_colmajor, (size_t)24 * n, nullptr);
   plat::dev_memset(acc.p, 0, 16, nullptr);
   const uint32_t *perm = morton_perm(m, dP.p, n, scratch.p, 1, nullptr);
-  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p}, nullptr);
+  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p,
+                             carve(scratch.p, n).sched}, nullptr);
   plat::for_n(n, CountWinding{m->fnodes(), m->tri32(), dP.p, n, m->h.order, acc.p + 2}, nullptr);
   uint32_t h[4];
   plat::d2h(h, acc.p, 16, nullptr);
