@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   // chunks in flight still form one window of the query set (L2).  sched[0] = next chunk, sched[1 + 2*smid] =
   // (chunk << 32 | packets handed out), sched[2 + 2*smid] = refill lock.
   unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  smid &= 1023u;   // the state array has 1024 slots
   const uint32_t npackets = (uint32_t)((a.n + 31) / 32);
   while (true) {
     uint32_t packet = 0xFFFFFFFFu;
@@ -427,6 +428,7 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)0x7FFFFFFF);
 #if CP_PERSIST
   static_assert(CP_WARPS == 1, "the persistent schedule hands out packets to one-warp blocks");
+  if (warps > (int64_t)0xFFF00000) throw std::invalid_argument("too many queries in one call (packet index is 32 bits)");
   DevBuf<unsigned long long> own;
   ClosestArgs b = a;
   if (!b.sched) { own.alloc(SCHED_WORDS); b.sched = own.p; }   // no caller scratch: a private state for this launch
