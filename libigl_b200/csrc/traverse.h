@@ -264,7 +264,10 @@ DEVFN float lane_box_d2(const CpNode &n, int i, const CpLane &L) {
 // Morton order) share one stack and visit a node when ANY of them still needs it,
 // so every box and face test runs on all 32 lanes at once (iglb200.cu:
 // closest_packet_kernel; host emulation: closest_packet_emul).
-static constexpr int CP_STACK = 192;   // node ids per warp (3 per level at most)
+// node ids per warp (3 per level at most: 42 levels).  128 entries keep a block at 2 KB of shared memory, so that 20
+// blocks fit the 64 KB carve-out and L1 keeps 192 KB (192 entries -> 100 KB carve-out, 156 KB L1: +1.5 % time; the
+// search is sensitive to L1: 124 KB +4.5 %, 92 KB +14 %).  Overflow raises an error, never a wrong answer.
+static constexpr int CP_STACK = 128;
 
 // ---------------------------------------------------------------------------
 // UTsignedSolidAngleTri (FastWindingNumberForSoups.h:6070-6110), un-fused fp32
