@@ -1,5 +1,13 @@
-import sys, time, numpy as np
-sys.path.insert(0, "/root/repo")
+#!/usr/bin/env python
+"""Times the exact hierarchical winding number (sign types WINDING_NUMBER / DEFAULT, igl::winding_number) on one GPU:
+build of the boundary chains with the tree, iglb200_winding_number and signed_distance(DEFAULT) on a grid."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import libigl_b200 as ig
 from libigl_b200 import synth
 api = ig.lib()
