@@ -1261,9 +1261,7 @@ int iglb200_grid_create(const double box_min[3], const double box_max[3], int s,
   return IGLB200_OK;
   API_END
 }
-int iglb200_grid_create_from(const double *GV, int64_t gv_rs, int64_t gv_cs, int nx, int ny, int nz, iglb200_grid **out) {
-  API_BEGIN
-  if (!GV || !out) throw std::invalid_argument("null pointer");
+static iglb200_grid *grid_from_host(const double *GV, int64_t gv_rs, int64_t gv_cs, int nx, int ny, int nz) {
   if (nx < 1 || ny < 1 || nz < 1 || gv_rs <= 0 || gv_cs <= 0) throw std::invalid_argument("bad grid dimensions or strides");
   const int64_t n = (int64_t)nx * ny * nz;
   if (n > 0x7FFFFFFF) throw std::invalid_argument("more than 2^31-1 grid vertices");
@@ -1276,7 +1274,12 @@ int iglb200_grid_create_from(const double *GV, int64_t gv_rs, int64_t gv_cs, int
   plat::h2d(raw.p, GV, span * 8, nullptr);
   plat::for_n(n, ToCanon3<double>{raw.p, gv_rs, gv_cs, n, g->GV.p}, nullptr);
   plat::sync(nullptr);
-  *out = g.release();
+  return g.release();
+}
+int iglb200_grid_create_from(const double *GV, int64_t gv_rs, int64_t gv_cs, int nx, int ny, int nz, iglb200_grid **out) {
+  API_BEGIN
+  if (!GV || !out) throw std::invalid_argument("null pointer");
+  *out = grid_from_host(GV, gv_rs, gv_cs, nx, ny, nz);
   return IGLB200_OK;
   API_END
 }
@@ -1431,9 +1434,8 @@ int iglb200_marching_cubes(const double *S, const double *GV, int64_t gv_rs, int
                            double isovalue, iglb200_surface **out) {
   API_BEGIN
   if (!S || !GV || !out) throw std::invalid_argument("null pointer");
-  iglb200_grid *g = nullptr;
-  if (iglb200_grid_create_from(GV, gv_rs, gv_cs, nx, ny, nz, &g) != IGLB200_OK) throw std::invalid_argument(g_err);
-  std::unique_ptr<iglb200_grid> hold(g);
+  std::unique_ptr<iglb200_grid> hold(grid_from_host(GV, gv_rs, gv_cs, nx, ny, nz));
+  iglb200_grid *g = hold.get();
   plat::h2d(g->S.p, S, (size_t)8 * g->n, nullptr);
   plat::sync(nullptr);
   *out = grid::marching_cubes(g->S.p, g->GV.p, nx, ny, nz, 0.0, isovalue, nullptr);

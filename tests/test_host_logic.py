@@ -46,6 +46,20 @@ def test_no_cpu_fallback_without_a_gpu():
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
     with pytest.raises(libigl_b200.IglB200Error):
         libigl_b200.signed_distance(np.zeros((1, 3)), V, F)
+    # every other compute entry point refuses the same way: cloud, grids, flood fill, marching cubes, winding number
+    calls = [
+        lambda: api.Cloud(V, V, np.ones(4)),
+        lambda: api.voxel_grid(V, 0.1, 8, 1),
+        lambda: api.flood_fill([2, 2, 2], np.zeros(8)),
+        lambda: api.marching_cubes(np.zeros(8), np.zeros((8, 3)), 2, 2, 2),
+        lambda: api.offset_surface(V, F, 0.1, 8),
+        lambda: api.winding_number(V, F, np.zeros((1, 3))),
+        lambda: api.check(api.lib.iglb200_init(1)),
+    ]
+    for c in calls:
+        with pytest.raises(libigl_b200.IglB200Error) as e:
+            c()
+        assert e.value.code == -2, str(e.value)
 
 
 def test_product_never_references_the_oracle_or_the_emulation():
