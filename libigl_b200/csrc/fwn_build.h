@@ -320,7 +320,7 @@ struct InitRoot {
       counters[0] = 0;
       return;
     }
-    Task t;
+    Task t{};
     t.node = 0; t.nsub = 1; t.bnd[0] = 0; t.bnd[1] = n; t.choice = 0; t.sarea[0] = 0.f;
     for (int a = 0; a < 3; ++a) { t.sbox[0].lo[a] = plat::ord2f(acc[a]); t.sbox[0].hi[a] = plat::ord2f(acc[3 + a]); }
     tasks[0] = t;
@@ -782,7 +782,7 @@ struct EmitChildren {  // initNode's tail (:4942-4949, :5036-5045)
       if (c <= 4) {
         for (uint32_t k = 0; k < 4; ++k) nodes[4 * id + k] = (k < c) ? idx[b + k] : EMPTY;
       } else {
-        Task ch;
+        Task ch{};   // zero-filled: the whole record is read back by PhasePrepare
         ch.node = id; ch.nsub = 1; ch.bnd[0] = b; ch.bnd[1] = b + c; ch.sbox[0] = t.sbox[i]; ch.choice = 0; ch.sarea[0] = 0.f;
         next[nt++] = ch;
       }
