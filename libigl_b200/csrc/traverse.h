@@ -147,7 +147,7 @@ DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, cons
 // running state of one query during the walk (registers)
 struct CpLane {
   float px, py, pz;
-  float xm, ym, zm, xp, yp, zp;  // p -/+ slack: the box tests absorb their own rounding this way
+  float slack3;   // sqrt(3) * rounding allowance of one fp32 box test, folded into thr2
   float u;        // 2^-24 * max(|p|, |mesh|)
   float best_ub;  // fp32 upper bound of the distance to the nearest face seen so far
   float thr2;     // prune a box when its squared lower bound exceeds this
@@ -168,21 +168,22 @@ DEVFN D3 load_query(const CpQueryRef &q) { return D3{q.P[q.qi], q.P[q.n + q.qi],
 
 DEVFN void lane_set_ub(CpLane &L, float ub) {
   L.best_ub = ub;
-  L.thr2 = ub * ub * 1.000001f;  // rounded up, and absorbs the rounding of a box test's sum of squares
+  const float t = ub + L.slack3;
+  L.thr2 = t * t * 1.000001f;  // rounded up; absorbs the rounding of a box test (slack3) and of its sum of squares
 }
 
 DEVFN void lane_init(CpLane &L, CpExact &X, D3 p, double up_sqr_d, float absmax) {
   L.px = (float)p.x; L.py = (float)p.y; L.pz = (float)p.z;
   const float M = fmaxf(fmaxf(fabsf(L.px), fabsf(L.py)), fmaxf(fabsf(L.pz), absmax));
-  const float slack = M * 2.3841858e-7f;   // rounding allowance of the fp32 box tests
-  L.xm = L.px - slack; L.ym = L.py - slack; L.zm = L.pz - slack;
-  L.xp = L.px + slack; L.yp = L.py + slack; L.zp = L.pz + slack;
+  // each difference lo - p / p - hi of a box test is off by <= 2^-24 * M; the norm of the three by sqrt(3) times
+  // that; four times as much is allowed for and added to the pruning threshold instead of widening the query
+  L.slack3 = M * (2.3841858e-7f * 1.7320509f);
   L.u = M * 5.9604645e-8f * 1.0000002f;
   X.ncand = 0; X.min_lb = INFINITY;
   X.d2 = up_sqr_d; X.face = -1;
   const float ub = (up_sqr_d < 3.0e38) ? f_up(sqrt(up_sqr_d)) * 1.0000002f : INFINITY;
   L.best_ub = ub;
-  L.thr2 = (up_sqr_d < 3.0e38) ? f_up(up_sqr_d) * 1.000001f : INFINITY;
+  if (up_sqr_d < 3.0e38) lane_set_ub(L, ub); else L.thr2 = INFINITY;
 }
 
 DEVFN double face_sqr_distance(const double *tri64, D3 p, uint32_t f, D3 &cc) {
@@ -246,13 +247,13 @@ DEVFN void lane_finish(CpLane &L, CpExact &X, const double *tri64, const CpQuery
   face_sqr_distance(tri64, load_query(q), (uint32_t)res.face, res.c);   // closest point of the winner
 }
 
-// Lower bound of the squared distance from the query to a box: the query is widened by
-// `slack` (xm..xp) so that fp32 rounding can only make the result smaller; the rounding of the
-// sum itself is absorbed by thr2 (lane_set_ub).
+// Squared distance from the query to a box in plain fp32; its rounding (of the differences and of the sum) is
+// allowed for in the threshold it is compared with (thr2, lane_set_ub), so the comparison never prunes a box that
+// the exact distance would keep.
 DEVFN float box_lb2(float lx, float ly, float lz, float hx, float hy, float hz, const CpLane &L) {
-  const float dx = fmaxf(fmaxf(lx - L.xp, L.xm - hx), 0.f);
-  const float dy = fmaxf(fmaxf(ly - L.yp, L.ym - hy), 0.f);
-  const float dz = fmaxf(fmaxf(lz - L.zp, L.zm - hz), 0.f);
+  const float dx = fmaxf(fmaxf(lx - L.px, L.px - hx), 0.f);
+  const float dy = fmaxf(fmaxf(ly - L.py, L.py - hy), 0.f);
+  const float dz = fmaxf(fmaxf(lz - L.pz, L.pz - hz), 0.f);
   return dx * dx + dy * dy + dz * dz;
 }
 DEVFN float lane_box_d2(const CpNode &n, int i, const CpLane &L) {
