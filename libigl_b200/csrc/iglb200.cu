@@ -184,6 +184,15 @@ void throw_if_overflow(stream_t) {
 }
 #else
 DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef CP_LD256
+#define CP_LD256 1   // 78.6 vs 79.2 ms on c2
+#endif
+// 256-bit global load (sm_100: LDG.E.256): half the load instructions for the 128-byte node and the 64-byte face record
+DEVFN void ld256(const void *p, float4 &a, float4 &b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 
 #ifndef CP_MIN_BLOCKS
 #define CP_MIN_BLOCKS 20   // with one-warp blocks: 96 registers, 20 warps per SM.  Before two face records were kept in
@@ -268,7 +277,15 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       have = false;
       if (COUNT) ++nvis;
       const CpNode *np = a.nodes + cur;
+#if CP_LD256
+      CpNode n;
+      { float4 c4, p4;
+        ld256(&np->lox, n.lox, n.loy); ld256(&np->loz, n.loz, n.hix); ld256(&np->hiy, n.hiy, n.hiz); ld256(&np->child, c4, p4);
+        n.child = make_uint4(__float_as_uint(c4.x), __float_as_uint(c4.y), __float_as_uint(c4.z), __float_as_uint(c4.w));
+        n.pad = make_uint4(__float_as_uint(p4.x), __float_as_uint(p4.y), 0u, 0u); }
+#else
       const CpNode n = *np;
+#endif
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
       const uint32_t imask = n.pad.x, tmask = n.pad.y;
 #ifndef CP_PREFETCH
@@ -315,12 +332,17 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         bool w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] = ((tmask >> i) & 1u) && __any_sync(FULL, d2[i] <= L.thr2);
+#if CP_LD256
+#define CP_LOADQ(p, A, B, C, D) { ld256((p), A, B); ld256((p) + 2, C, D); }
+#else
+#define CP_LOADQ(p, A, B, C, D) { A = (p)[0]; B = (p)[1]; C = (p)[2]; D = (p)[3]; }
+#endif
 #define CP_FACE1(i) { const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i]; \
-          const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3]; if (COUNT) ++ntri; \
+          float4 T0, T1, T2, T3; CP_LOADQ(tq, T0, T1, T2, T3); if (COUNT) ++ntri; \
           float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err); \
           if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); }
 #define CP_FACE2(i, j) { const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i], *tr = a.triq + TRIQ_STRIDE * (size_t)ch[j]; \
-          const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3], U0 = tr[0], U1 = tr[1], U2 = tr[2], U3 = tr[3]; if (COUNT) ntri += 2; \
+          float4 T0, T1, T2, T3, U0, U1, U2, U3; CP_LOADQ(tq, T0, T1, T2, T3); CP_LOADQ(tr, U0, U1, U2, U3); if (COUNT) ntri += 2; \
           float err, erq; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err); \
           const float e32 = tri_dist_f32(U0, U1, U2, U3, L.px, L.py, L.pz, L.u, erq); \
           if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); \
