@@ -20,9 +20,10 @@
  *  - Return value 0 = ok, negative = error; iglb200_last_error() gives the
  *    message (thread local).  There is NO CPU fallback: without a CUDA device
  *    every compute entry point returns IGLB200_ERR_CUDA.
- *  - Handles are immutable after creation and may be queried from several
- *    host threads at once (the reference structures are const-queried from
- *    igl::parallel_for threads: AABB.h:569-574).
+ *  - Mesh and cloud handles are immutable after creation and may be queried
+ *    from several host threads at once (the reference structures are
+ *    const-queried from igl::parallel_for threads: AABB.h:569-574).  A grid
+ *    handle carries state (its values S): use it from one thread at a time.
  */
 #ifndef IGLB200_H
 #define IGLB200_H
