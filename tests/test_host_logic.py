@@ -119,3 +119,23 @@ def test_query_sharding_world_size_2_gloo(tmp_path):
            "--master-port", "29611", str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "SHARDED_OK 2" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/iglb200.h is what an FFI binds: it must compile as C99 and link against the library from C."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "iglb200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%s %d\\n", iglb200_version(), iglb200_device_count() >= 0); return 0; }\n')
+    import libigl_b200
+    from libigl_b200 import build
+    build.build()
+    libdir = os.path.dirname(libigl_b200.LIB_PATH)
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L" + libdir, "-liglb200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("iglb200"), r.stdout + r.stderr
