@@ -225,6 +225,11 @@ int iglb200_surface_destroy(iglb200_surface *s);
 int iglb200_flood_fill(const int res[3], double *S);
 int iglb200_marching_cubes(const double *S, const double *GV, int64_t gv_row_stride, int64_t gv_col_stride,
                            int nx, int ny, int nz, double isovalue, iglb200_surface **out);
+/* igl::marching_cubes(S, GV, GI, isovalue, V, F, E2V) (marching_cubes.h:68-92, marching_cubes.cpp:114-176): cube c has
+ * the corners GI(c, 0..7), vertex indices into the n rows of GV / entries of S (e.g. a sparse voxel grid). */
+int iglb200_marching_cubes_sparse(const double *S, const double *GV, int64_t n, int64_t gv_row_stride, int64_t gv_col_stride,
+                                  const int32_t *GI, int64_t n_cubes, int64_t gi_row_stride, int64_t gi_col_stride,
+                                  double isovalue, iglb200_surface **out);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@
 //   igl::marching_cubes  /root/reference/include/igl/marching_cubes.h:39-66    (marching_cubes.cpp:19-112)
 //   igl::offset_surface  /root/reference/include/igl/offset_surface.h          (offset_surface.cpp:18-48)
 // Values are double precision (the reference's templates also instantiate float; those are not offered:
-// results would not be bit-identical).  The sparse-cube overload marching_cubes(S,GV,GI,...) is not covered.
+// results would not be bit-identical).
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -115,6 +115,30 @@ inline void marching_cubes(const DerivedS &S, const DerivedGV &GV, const unsigne
                            const typename DerivedS::Scalar isovalue, DerivedV &V, DerivedF &F) {
   std::unordered_map<std::int64_t, int> E2V;
   marching_cubes(S, GV, nx, ny, nz, isovalue, V, F, E2V);
+}
+
+// marching_cubes(S, GV, GI, isovalue, V, F[, E2V]): cubes listed by their 8 corner indices (marching_cubes.h:68-92)
+template <class DerivedS, class DerivedGV, class DerivedGI, class DerivedV, class DerivedF>
+inline typename std::enable_if<!std::is_arithmetic<DerivedGI>::value>::type
+marching_cubes(const DerivedS &S, const DerivedGV &GV, const DerivedGI &GI, const typename DerivedS::Scalar isovalue, DerivedV &V,
+               DerivedF &F, std::unordered_map<std::int64_t, int> &E2V) {
+  detail::require_double<DerivedS>(); detail::require_double<DerivedGV>();
+  static_assert(sizeof(typename DerivedGI::Scalar) == 4, "iglb200: GI must hold 32-bit ints");
+  if (GV.cols() != 3 || (int64_t)S.rows() * (int64_t)S.cols() != (int64_t)GV.rows() || (GI.rows() && GI.cols() != 8))
+    throw Error(IGLB200_ERR_ARG, "iglb200: GV must be #GV x 3, S #GV, GI #cubes x 8");
+  detail::SurfaceHandle h;
+  check(iglb200_marching_cubes_sparse((const double *)S.data(), (const double *)GV.data(), (int64_t)GV.rows(),
+                                      GV.rows() ? detail::row_stride(GV) : 3, GV.rows() ? detail::col_stride(GV) : 1,
+                                      (const int32_t *)GI.data(), (int64_t)GI.rows(), GI.rows() ? detail::row_stride(GI) : 8,
+                                      GI.rows() ? detail::col_stride(GI) : 1, (double)isovalue, &h.s));
+  detail::fetch_surface(h.s, V, F, &E2V);
+}
+template <class DerivedS, class DerivedGV, class DerivedGI, class DerivedV, class DerivedF>
+inline typename std::enable_if<!std::is_arithmetic<DerivedGI>::value>::type
+marching_cubes(const DerivedS &S, const DerivedGV &GV, const DerivedGI &GI, const typename DerivedS::Scalar isovalue, DerivedV &V,
+               DerivedF &F) {
+  std::unordered_map<std::int64_t, int> E2V;
+  marching_cubes(S, GV, GI, isovalue, V, F, E2V);
 }
 
 // offset_surface(V, F, isolevel, s, signed_distance_type, SV, SF, GV, side, S)

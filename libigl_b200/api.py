@@ -70,6 +70,7 @@ class Api:
         "iglb200_grid_get_gv", "iglb200_grid_set_s", "iglb200_grid_get_s", "iglb200_grid_signed_distance",
         "iglb200_grid_flood_fill", "iglb200_grid_marching_cubes", "iglb200_surface_info", "iglb200_surface_get",
         "iglb200_surface_device", "iglb200_surface_destroy", "iglb200_flood_fill", "iglb200_marching_cubes",
+        "iglb200_marching_cubes_sparse",
     ]
 
     def __init__(self, lib: C.CDLL):
@@ -127,6 +128,7 @@ class Api:
         L.iglb200_surface_destroy.argtypes = [_vp]
         L.iglb200_flood_fill.argtypes = [_vp, _vp]
         L.iglb200_marching_cubes.argtypes = [_vp, _vp, _i64, _i64, _int, _int, _int, _dbl, C.POINTER(_vp)]
+        L.iglb200_marching_cubes_sparse.argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _dbl, C.POINTER(_vp)]
 
     # -- plumbing ---------------------------------------------------------
     def check(self, rc):
@@ -204,6 +206,26 @@ class Api:
         h = _vp()
         self.check(self.lib.iglb200_marching_cubes(S.ctypes.data_as(_vp), GV.ctypes.data_as(_vp), GV.strides[0] // 8,
                                                    GV.strides[1] // 8, int(nx), int(ny), int(nz), float(isovalue), C.byref(h)))
+        sf = Surface(self, h)
+        try:
+            return sf.get(return_E2V)
+        finally:
+            sf.close()
+
+    def marching_cubes_sparse(self, S, GV, GI, isovalue=0.0, return_E2V=False):
+        """igl::marching_cubes(S, GV, GI, isovalue, V, F[, E2V]): cubes listed by their 8 corner indices
+        (marching_cubes.cpp:114-176)."""
+        S = np.ascontiguousarray(S, dtype=np.float64).reshape(-1)
+        GV = np.asarray(GV, np.float64)
+        GI = np.ascontiguousarray(GI, dtype=np.int32)
+        if GV.ndim != 2 or GV.shape[1] != 3 or GV.shape[0] != S.size or GI.ndim != 2 or (GI.shape[0] and GI.shape[1] != 8):
+            raise ValueError("GV must be #GV x 3, S #GV, GI #cubes x 8")
+        if not (GV.flags.c_contiguous or GV.flags.f_contiguous):
+            GV = np.ascontiguousarray(GV)
+        h = _vp()
+        self.check(self.lib.iglb200_marching_cubes_sparse(S.ctypes.data_as(_vp), GV.ctypes.data_as(_vp), S.size,
+                                                          GV.strides[0] // 8 if S.size else 3, GV.strides[1] // 8 if S.size else 1,
+                                                          GI.ctypes.data_as(_vp), GI.shape[0], 8, 1, float(isovalue), C.byref(h)))
         sf = Surface(self, h)
         try:
             return sf.get(return_E2V)

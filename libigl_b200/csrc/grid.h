@@ -358,4 +358,160 @@ inline iglb200_surface *marching_cubes(const double *S, const double *GV, int nx
   return out;
 }
 
+struct Iota32 { uint32_t *v; DEVFN void operator()(int64_t i) const { v[i] = (uint32_t)i; } };
+// ------------------------------------------------------------------ marching_cubes over an explicit cube list
+// igl::marching_cubes(S, GV, GI, isovalue, V, F, E2V) (marching_cubes.cpp:114-160): cube c has the corners
+// GI(c, 0..7) (any vertex indices, e.g. of a sparse voxel grid).  There is no grid structure to derive the first
+// cube of an edge from, so the hash map is replaced by a sort: every cube emits its cut edges in order (cube, edge),
+// a stable radix sort by the edge key (i < j packed) groups the occurrences of an edge with its first visitor in
+// front, and the groups ranked by that first visitor's emission index are the reference's vertex ids.
+struct SpClassify {
+  const double *S; const int32_t *GI; int64_t gi_rs, gi_cs; double iso;
+  unsigned char *cf8; uint32_t *ecount, *fcount;
+  DEVFN void operator()(int64_t c) const {
+    uint32_t cf = 0;
+    for (int k = 0; k < 8; ++k) if (S[GI[c * gi_rs + k * gi_cs]] > iso) cf |= 1u << k;
+    int ne = 0;
+    for (int e = 0; e < 12; ++e) ne += (int)(((cf >> MC_EA[e]) ^ (cf >> MC_EB[e])) & 1u);
+    const uint64_t w = MC_TRI[cf];
+    int nf = 0;
+    while (nf < 5 && ((w >> (12 * nf)) & 0xF) != 0xF) ++nf;
+    cf8[c] = (unsigned char)cf; ecount[c] = (uint32_t)ne; fcount[c] = (uint32_t)nf;
+  }
+};
+struct SpEmitEdges {   // emission index = ebase[c] + rank of the edge among the cube's cut edges
+  const int32_t *GI; int64_t gi_rs, gi_cs;
+  const unsigned char *cf8; const uint32_t *ebase;
+  uint64_t *key; uint32_t *val, *cube_edge;
+  DEVFN void operator()(int64_t c) const {
+    const uint32_t cf = cf8[c];
+    uint32_t idx = ebase[c];
+    for (int e = 0; e < 12; ++e) {
+      if ((((cf >> MC_EA[e]) ^ (cf >> MC_EB[e])) & 1u) == 0) continue;
+      const uint32_t i = (uint32_t)GI[c * gi_rs + MC_EA[e] * gi_cs], j = (uint32_t)GI[c * gi_rs + MC_EB[e] * gi_cs];
+      key[idx] = i < j ? ((uint64_t)i | ((uint64_t)j << 32)) : ((uint64_t)j | ((uint64_t)i << 32));   // march_cube.cpp:52-60
+      val[idx] = idx;
+      cube_edge[idx] = (uint32_t)(c * 12 + e);
+      ++idx;
+    }
+  }
+};
+struct SpHeads { const uint64_t *skey; uint32_t *head; DEVFN void operator()(int64_t p) const { head[p] = (p == 0 || skey[p - 1] != skey[p]) ? 1u : 0u; } };
+struct SpOwners {   // group g = number of heads before p; its owner is the emission index at the head
+  const uint32_t *head, *gscan, *sval; uint32_t *owner, *gid_of_entry;
+  DEVFN void operator()(int64_t p) const {
+    const uint32_t g = gscan[p] + head[p] - 1u;
+    if (head[p]) owner[g] = sval[p];
+    gid_of_entry[sval[p]] = g;
+  }
+};
+struct SpRank { const uint32_t *gsorted; uint32_t *vid; DEVFN void operator()(int64_t r) const { vid[gsorted[r]] = (uint32_t)r; } };
+struct SpVertices {
+  const double *S; const double *GV; int64_t n; const int32_t *GI; int64_t gi_rs, gi_cs; double iso;
+  const uint32_t *owner, *vid, *cube_edge;
+  double *V; int32_t *E;
+  DEVFN void operator()(int64_t g) const {
+    const uint32_t ce = cube_edge[owner[g]], v = vid[g];
+    const int64_t c = ce / 12; const int e = (int)(ce % 12);
+    const int64_t i = GI[c * gi_rs + MC_EA[e] * gi_cs], j = GI[c * gi_rs + MC_EB[e] * gi_cs];
+    const double a = S[i], b = S[j];
+    const double t = ddiv(dsub(iso, a), dsub(b, a));
+    for (int k = 0; k < 3; ++k) {
+      const double gi = GV[k * n + i], gj = GV[k * n + j];
+      V[3 * (size_t)v + k] = dadd(gi, dmul(t, dsub(gj, gi)));
+    }
+    E[2 * (size_t)v] = (int32_t)(i < j ? i : j);
+    E[2 * (size_t)v + 1] = (int32_t)(i < j ? j : i);
+  }
+};
+struct SpFaces {
+  const unsigned char *cf8; const uint32_t *ebase, *fbase, *gid_of_entry, *vid;
+  int32_t *F;
+  DEVFN void operator()(int64_t c) const {
+    const uint32_t cf = cf8[c];
+    const uint64_t w = MC_TRI[cf];
+    if ((w & 0xF) == 0xF) return;
+    int32_t ev[12];
+    uint32_t idx = ebase[c];
+    for (int e = 0; e < 12; ++e) {
+      ev[e] = -1;
+      if ((((cf >> MC_EA[e]) ^ (cf >> MC_EB[e])) & 1u) == 0) continue;
+      ev[e] = (int32_t)vid[gid_of_entry[idx++]];
+    }
+    size_t f = fbase[c];
+    for (int t = 0; t < 5; ++t) {
+      if (((w >> (12 * t)) & 0xF) == 0xF) break;
+      for (int k = 0; k < 3; ++k) F[3 * f + k] = ev[(w >> (12 * t + 4 * k)) & 0xF];
+      ++f;
+    }
+  }
+};
+struct SpCheckIndices { const int32_t *GI; int64_t gi_rs, gi_cs, n; uint32_t *bad; DEVFN void operator()(int64_t q) const {
+  const int32_t v = GI[(q / 8) * gi_rs + (q % 8) * gi_cs]; if (v < 0 || v >= n) plat::atomic_max(bad, 1u); } };
+
+// S: n values; GV: column-major 3 x n; GI: m x 8 device int32 with the given strides
+inline iglb200_surface *marching_cubes_sparse(const double *S, const double *GV, int64_t n, const int32_t *GI, int64_t gi_rs, int64_t gi_cs,
+                                              int64_t m, double iso, stream_t st) {
+  using plat::DevBuf;
+  if (m < 0 || n < 0 || n > 0x7FFFFFFF || m > (int64_t)(0xFFFFFFFFu / 12)) throw std::invalid_argument("marching_cubes: too many cubes or vertices");
+  iglb200_surface *out = new iglb200_surface;
+  try {
+    if (m == 0) return out;
+    plat::Span sp("marching_cubes", st);
+    DevBuf<uint32_t> bad(1);
+    plat::dev_memset(bad.p, 0, 4, st);
+    plat::for_n(8 * m, SpCheckIndices{GI, gi_rs, gi_cs, n, bad.p}, st);
+    uint32_t hbad = 0;
+    plat::d2h(&hbad, bad.p, 4, st);
+    plat::sync(st);
+    if (hbad) throw std::invalid_argument("marching_cubes: GI contains a vertex index outside [0, #GV)");
+    DevBuf<unsigned char> cf8((size_t)m);
+    DevBuf<uint32_t> ecount((size_t)m + 1), fcount((size_t)m + 1), ebase((size_t)m + 1), fbase((size_t)m + 1);
+    plat::for_n(m, SpClassify{S, GI, gi_rs, gi_cs, iso, cf8.p, ecount.p, fcount.p}, st);
+    plat::dev_memset(ecount.p + m, 0, 4, st);
+    plat::dev_memset(fcount.p + m, 0, 4, st);
+    plat::exclusive_scan_u32(ecount.p, ebase.p, m + 1, st);
+    plat::exclusive_scan_u32(fcount.p, fbase.p, m + 1, st);
+    uint32_t tot[2];
+    plat::d2h(&tot[0], ebase.p + m, 4, st);
+    plat::d2h(&tot[1], fbase.p + m, 4, st);
+    plat::sync(st);
+    const int64_t ne = tot[0];
+    out->nF = tot[1];
+    ecount.release(); fcount.release();
+    if (ne == 0) return out;
+    DevBuf<uint64_t> key((size_t)ne), skey((size_t)ne);
+    DevBuf<uint32_t> val((size_t)ne), sval((size_t)ne), cube_edge((size_t)ne);
+    plat::for_n(m, SpEmitEdges{GI, gi_rs, gi_cs, cf8.p, ebase.p, key.p, val.p, cube_edge.p}, st);
+    {
+      const size_t tb = plat::sort_pairs64_temp_bytes(ne);
+      DevBuf<char> tmp(tb);
+      plat::sort_pairs_u64(tmp.p, tb, key.p, skey.p, val.p, sval.p, ne, st);   // stable: first visitor first in its group
+    }
+    key.release(); val.release();
+    DevBuf<uint32_t> head((size_t)ne + 1), gscan((size_t)ne + 1), gid((size_t)ne);
+    plat::for_n(ne, SpHeads{skey.p, head.p}, st);
+    plat::dev_memset(head.p + ne, 0, 4, st);
+    plat::exclusive_scan_u32(head.p, gscan.p, ne + 1, st);
+    uint32_t ng = 0;
+    plat::d2h(&ng, gscan.p + ne, 4, st);
+    plat::sync(st);
+    out->nV = ng;
+    DevBuf<uint32_t> owner((size_t)ng), gidx((size_t)ng), owner_sorted((size_t)ng), gsorted((size_t)ng), vid((size_t)ng);
+    plat::for_n(ne, SpOwners{head.p, gscan.p, sval.p, owner.p, gid.p}, st);
+    plat::for_n(ng, Iota32{gidx.p}, st);
+    {
+      const size_t tb = plat::sort_pairs_temp_bytes(ng);
+      DevBuf<char> tmp(tb);
+      plat::sort_pairs_u32(tmp.p, tb, owner.p, owner_sorted.p, gidx.p, gsorted.p, ng, 32, st);   // vertex ids in order of first visit
+    }
+    plat::for_n(ng, SpRank{gsorted.p, vid.p}, st);
+    out->V.alloc((size_t)3 * ng); out->E.alloc((size_t)2 * ng); out->F.alloc((size_t)3 * out->nF + 1);
+    plat::for_n(ng, SpVertices{S, GV, n, GI, gi_rs, gi_cs, iso, owner.p, vid.p, cube_edge.p, out->V.p, out->E.p}, st);
+    if (out->nF) plat::for_n(m, SpFaces{cf8.p, ebase.p, fbase.p, gid.p, vid.p, out->F.p}, st);
+    plat::sync(st);
+  } catch (...) { delete out; throw; }
+  return out;
+}
+
 }  // namespace grid

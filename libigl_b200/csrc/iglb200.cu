@@ -1236,6 +1236,36 @@ int iglb200_fwn_eval(const iglb200_mesh *m, const void *Q, int q_is_f64, int64_t
   API_END
 }
 
+// igl::marching_cubes(S, GV, GI, isovalue, V, F[, E2V]) (marching_cubes.cpp:114-176): cubes given by their 8 corner ids
+int iglb200_marching_cubes_sparse(const double *S, const double *GV, int64_t n, int64_t gv_rs, int64_t gv_cs,
+                                  const int32_t *GI, int64_t n_cubes, int64_t gi_rs, int64_t gi_cs, double isovalue,
+                                  iglb200_surface **out) {
+  API_BEGIN
+  if (!out || n < 0 || n_cubes < 0 || (n > 0 && (!S || !GV)) || (n_cubes > 0 && !GI)) throw std::invalid_argument("null pointer or negative size");
+  if (n > 0 && (gv_rs <= 0 || gv_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  if (n_cubes > 0 && (gi_rs <= 0 || gi_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  if (n > 0x7FFFFFFF) throw std::invalid_argument("more than 2^31-1 grid vertices");
+  require_device();
+  DevBuf<double> dS((size_t)n + 1), dGV((size_t)3 * n + 1);
+  DevBuf<int32_t> dGI;
+  size_t gspan = 0;
+  if (n > 0) {
+    plat::h2d(dS.p, S, (size_t)8 * n, nullptr);
+    const size_t span = (size_t)((n - 1) * gv_rs + 2 * gv_cs + 1);
+    DevBuf<double> raw(span);
+    plat::h2d(raw.p, GV, span * 8, nullptr);
+    plat::for_n(n, ToCanon3<double>{raw.p, gv_rs, gv_cs, n, dGV.p}, nullptr);
+    plat::sync(nullptr);
+  }
+  if (n_cubes > 0) {
+    gspan = (size_t)((n_cubes - 1) * gi_rs + 7 * gi_cs + 1);
+    dGI.alloc(gspan);
+    plat::h2d(dGI.p, GI, gspan * 4, nullptr);
+  }
+  *out = grid::marching_cubes_sparse(dS.p, dGV.p, n, dGI.p, gi_rs, gi_cs, n_cubes, isovalue, nullptr);
+  return IGLB200_OK;
+  API_END
+}
 // igl::winding_number(V,F,O,W) (winding_number.cpp:17-52): exact, hierarchical, double precision
 int iglb200_winding_number(const iglb200_mesh *m, const void *O, int o_is_f64, int64_t nO, int64_t o_rs, int64_t o_cs,
                            void *W, int w_is_f64) {

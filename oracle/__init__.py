@@ -407,6 +407,26 @@ def marching_cubes(S, GV, nx, ny, nz, isovalue=0.0, tables=None):
     return V, F, E
 
 
+def marching_cubes_sparse(S, GV, GI, isovalue=0.0, tables=None):
+    """igl::marching_cubes(S,GV,GI,isovalue,V,F[,E2V]) (marching_cubes.cpp:114-176) -> V, F, E."""
+    S = np.ascontiguousarray(S, dtype=np.float64).ravel(); GV = np.ascontiguousarray(GV, dtype=np.float64)
+    GI = np.ascontiguousarray(GI, dtype=np.int32)
+    ef, cn, tr = tables or mc_tables()
+    ef = np.ascontiguousarray(ef, np.int32); cn = np.ascontiguousarray(cn, np.int32); tr = np.ascontiguousarray(tr, np.int32)
+    L = port()
+    L.port_marching_cubes_sparse.restype = C.c_void_p
+    L.port_marching_cubes_sparse.argtypes = [_c_dp, _c_dp, _c_ip, C.c_int64, C.c_double, _c_ip, _c_ip, _c_ip, _c_lp, _c_lp]
+    L.port_mc_get.argtypes = [C.c_void_p, _c_dp, _c_ip, _c_ip]
+    L.port_mc_destroy.argtypes = [C.c_void_p]
+    nV = C.c_int64(); nF = C.c_int64()
+    h = L.port_marching_cubes_sparse(_dp(S), _dp(GV), _ip(GI), GI.shape[0], float(isovalue), _ip(ef), _ip(cn), _ip(tr),
+                                     C.byref(nV), C.byref(nF))
+    V = np.empty((nV.value, 3)); F = np.empty((nF.value, 3), np.int32); E = np.empty((nV.value, 2), np.int32)
+    L.port_mc_get(h, _dp(V), _ip(F), _ip(E))
+    L.port_mc_destroy(h)
+    return V, F, E
+
+
 def offset_surface(V, F, isolevel, s, sign_type="fwn"):
     """igl::offset_surface (offset_surface.cpp:18-48) -> SV, SF, GV, side, S (S after flood_fill)."""
     GV, side = voxel_grid_mesh(V, isolevel, s, 1)

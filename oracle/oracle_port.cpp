@@ -924,6 +924,40 @@ void *port_marching_cubes(const double *S, const double *GV, int nx, int ny, int
   *nV = (int64_t)(o->V.size() / 3); *nF = (int64_t)(o->F.size() / 3);
   return o;
 }
+// igl::marching_cubes over an explicit cube list GI (m x 8) (marching_cubes.cpp:114-160): the same march_cube per row
+void *port_marching_cubes_sparse(const double *S, const double *GV, const int *GI, int64_t m, double isovalue,
+                                 const int *edge_flags, const int *conn, const int *tri, int64_t *nV, int64_t *nF) {
+  McOut *o = new McOut;
+  std::unordered_map<int64_t, int> E2V;
+  for (int64_t c = 0; c < m; c++) {
+    double cS[8]; int64_t cI[8];
+    int c_flags = 0;
+    for (int v = 0; v < 8; v++) { cI[v] = GI[8 * c + v]; cS[v] = S[cI[v]]; if (cS[v] > isovalue) c_flags |= 1 << v; }
+    const int e_flags = edge_flags[c_flags];
+    if (e_flags == 0) continue;
+    int ev[12];
+    for (int e = 0; e < 12; e++) {
+      if (!(e_flags & (1 << e))) continue;
+      const int64_t i = cI[conn[2 * e]], j = cI[conn[2 * e + 1]];
+      const int64_t key = (i < j ? i : j) | ((i < j ? j : i) << 32);
+      auto it = E2V.find(key);
+      if (it == E2V.end()) {
+        const int v = (int)(o->V.size() / 3);
+        E2V[key] = v; ev[e] = v;
+        const double a = cS[conn[2 * e]], b = cS[conn[2 * e + 1]];
+        const double t = (isovalue - a) / (b - a);
+        for (int d = 0; d < 3; ++d) o->V.push_back(GV[3 * i + d] + t * (GV[3 * j + d] - GV[3 * i + d]));
+        o->E.push_back((int)(i < j ? i : j)); o->E.push_back((int)(i < j ? j : i));
+      } else ev[e] = it->second;
+    }
+    for (int f = 0; f < 5; f++) {
+      if (tri[16 * c_flags + 3 * f] < 0) break;
+      for (int k = 0; k < 3; ++k) o->F.push_back(ev[tri[16 * c_flags + 3 * f + k]]);
+    }
+  }
+  *nV = (int64_t)(o->V.size() / 3); *nF = (int64_t)(o->F.size() / 3);
+  return o;
+}
 void port_mc_get(void *p, double *V, int *F, int *E) {
   McOut *o = (McOut *)p;
   if (V) std::memcpy(V, o->V.data(), o->V.size() * 8);

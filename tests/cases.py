@@ -673,3 +673,38 @@ def case_signed_distance_exact_winding(api, V, F, P, what, lower=None, upper=Non
         assert np.array_equal(C[same], Co[same]), f"{what}: C"
         res[t] = int(ok.sum())
     return res
+
+
+def case_marching_cubes_sparse(api):
+    """igl::marching_cubes(S,GV,GI,...) over an explicit cube list: V, F, E2V keys bit-identical to the sequential
+    hash-map sweep, for a full grid listed as cubes (must equal the grid overload), a random subset in random order
+    (a sparse voxel grid), repeated cubes, and arbitrary corner ids."""
+    rng = np.random.default_rng(21)
+    dims = (11, 9, 10)
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    GV = oracle.grid(list(dims)) * np.array([1.0, 2.0, 0.7]) + 0.01 * rng.standard_normal((n, 3))
+    S = rng.standard_normal(n)
+    off = np.array([0, 1, 1 + nx, nx, nx * ny, 1 + nx * ny, 1 + nx + nx * ny, nx + nx * ny])
+    x, y, z = np.meshgrid(np.arange(nx - 1), np.arange(ny - 1), np.arange(nz - 1), indexing="ij")
+    base = (x + nx * (y + ny * z)).transpose(2, 1, 0).ravel()          # x fastest, as the grid overload walks
+    GI = (base[:, None] + off[None, :]).astype(np.int32)
+
+    def check(GI_, S_, iso, what):
+        Vo, Fo, Eo = oracle.marching_cubes_sparse(S_, GV, GI_, iso)
+        V, F, E = api.marching_cubes_sparse(S_, GV, GI_, iso, return_E2V=True)
+        assert _same(F, Fo) and _same(E, Eo) and _same(V, Vo), what
+        return V, F
+    V, F = check(GI, S, 0.0, "all cubes in grid order")
+    Vg, Fg = api.marching_cubes(S, GV, nx, ny, nz, 0.0)
+    assert _same(V, Vg) and _same(F, Fg), "cube list in grid order == grid overload"
+    sub = rng.permutation(GI.shape[0])[: GI.shape[0] // 3]
+    check(GI[sub], S, 0.2, "random third of the cubes, random order")
+    check(np.concatenate([GI[sub[:50]], GI[sub[:50]], GI[sub[25:80]]]), S, 0.0, "repeated cubes")
+    check(rng.integers(0, n, (400, 8)).astype(np.int32), S, 0.0, "arbitrary corner ids")
+    Sn = S.copy(); Sn[rng.random(n) < 0.1] = np.nan; Sn[::17] = 0.0
+    check(GI[sub], Sn, 0.0, "NaN samples and values equal to the isovalue")
+    check(GI[:0], S, 0.0, "no cubes")
+    check(GI, np.full(n, 1.0), 0.0, "nothing cut")
+    with pytest.raises(IglB200Error):
+        api.marching_cubes_sparse(S, GV, np.full((1, 8), n, np.int32), 0.0)

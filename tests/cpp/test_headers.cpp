@@ -163,6 +163,19 @@ int main() {
       const double r = std::sqrt((SV(i, 0) - c[0]) * (SV(i, 0) - c[0]) + (SV(i, 1) - c[1]) * (SV(i, 1) - c[1]) + (SV(i, 2) - c[2]) * (SV(i, 2) - c[2]));
       REQUIRE(std::fabs(r - 0.45) < 0.02);
     }
+    {   // the same surface from an explicit list of all cubes (marching_cubes(S,GV,GI,...))
+      const int nx = side(0), ny = side(1), nz = side(2);
+      RowMatrixXi GI((nx - 1) * (ny - 1) * (nz - 1), 8);
+      const int off[8] = {0, 1, 1 + nx, nx, nx * ny, 1 + nx * ny, 1 + nx + nx * ny, nx + nx * ny};
+      int64_t c = 0;
+      for (int z = 0; z < nz - 1; ++z) for (int y = 0; y < ny - 1; ++y) for (int x = 0; x < nx - 1; ++x, ++c)
+        for (int k = 0; k < 8; ++k) GI(c, k) = x + nx * (y + ny * z) + off[k];
+      MatrixXd SVs; MatrixXi SFs;
+      iglb200::marching_cubes(S, GV, GI, 0.0, SVs, SFs);
+      REQUIRE(SVs.rows() == SV.rows() && SFs.rows() == SF.rows());
+      for (int64_t i = 0; i < SV.rows(); ++i) for (int d = 0; d < 3; ++d) REQUIRE(SVs(i, d) == SV(i, d));
+      for (int64_t i = 0; i < SF.rows(); ++i) for (int d = 0; d < 3; ++d) REQUIRE(SFs(i, d) == SF(i, d));
+    }
     MatrixXd SV2, GV2; MatrixXi SF2; VectorXi side3; VectorXd S2;
     iglb200::offset_surface(V, F, 0.2, 16, iglb200::SIGNED_DISTANCE_TYPE_PSEUDONORMAL, SV2, SF2, GV2, side3, S2);
     REQUIRE(SV2.rows() > 50 && SF2.rows() == 2 * SV2.rows() - 4 && GV2.rows() == S2.rows());

@@ -126,3 +126,7 @@ def test_signed_distance_winding_number_and_default(emul_api):
     cases.case_signed_distance_exact_winding(emul_api, V, F, P, "ico3")
     cases.case_signed_distance_exact_winding(emul_api, V, F[V[F].mean(1)[:, 2] > 0.0], P, "open hemisphere")
     cases.case_signed_distance_exact_winding(emul_api, V, F, P, "ico3 bounded", 0.1, 0.4)
+
+
+def test_marching_cubes_sparse(emul_api):
+    cases.case_marching_cubes_sparse(emul_api)

@@ -248,3 +248,7 @@ def test_signed_distance_winding_number_and_default(gpu_api):
     cases.case_signed_distance_exact_winding(gpu_api, V, F, P, "ico4 bounded", 0.1, 0.4)
     V, F = synth.torus_knot(300, 16)
     cases.case_signed_distance_exact_winding(gpu_api, V, F, synth.grid_points(*synth.bbox(V), 20, 1.1), "knot")
+
+
+def test_marching_cubes_sparse(gpu_api):
+    cases.case_marching_cubes_sparse(gpu_api)
