@@ -352,6 +352,12 @@ def case_golden_fixtures(api):
         assert c.info()["n_cells"] == int(g[f"ncells_order{order}"])
         assert np.abs(c.eval(g["Q"], 2.0) - g[f"WN_order{order}"]).max() < 1e-12
         c.close()
+    g = np.load(os.path.join(gold, "grid.npz"))
+    dims = [int(x) for x in g["dims"]]
+    assert np.array_equal(api.flood_fill(dims, g["S_nan"]), g["S_filled"], equal_nan=True)
+    Vm, Fm, Em = api.marching_cubes(g["S"], g["GV"], dims[0], dims[1], dims[2], float(g["iso"]), return_E2V=True)
+    assert np.array_equal(Vm, g["mc_V"]) and np.array_equal(Fm, g["mc_F"]) and np.array_equal(Em, g["mc_E"])
+    assert np.abs(api.winding_number(g["wn_V"], g["wn_F"], g["wn_O"]) - g["wn_W"]).max() < 1e-12
 
 
 def _soup_at(rng, centers, size):

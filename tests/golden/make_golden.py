@@ -50,6 +50,22 @@ def main():
         out[f"ncells_order{order}"] = o.num_cells()
     out["WN_brute"] = oracle.PortCloud(Pc, N, A, 2).eval(Q, 0.0)
     np.savez_compressed(os.path.join(HERE, "cloud.npz"), **out)
+    # 4. grids: flood fill and marching cubes of the restated sequential sweeps (case tables from the genuine header),
+    #    exact winding number (face-by-face sum) on an open soup
+    rng = np.random.default_rng(9)
+    dims = (9, 7, 8)
+    n = int(np.prod(dims))
+    GV = oracle.grid(list(dims)) * np.array([1.0, 1.5, 0.8]) + 0.01 * rng.standard_normal((n, 3))
+    S = rng.standard_normal(n)
+    Sn = S.copy()
+    Sn[rng.random(n) < 0.6] = np.nan
+    Sn.reshape(dims[2], dims[1], dims[0])[2] = np.nan
+    Vm, Fm, Em = oracle.marching_cubes(S, GV, dims[0], dims[1], dims[2], 0.1)
+    V, F = synth.icosphere(2)
+    Fo = F[V[F].mean(1)[:, 2] > -0.2]
+    O = synth.random_points(200, -1.5, 1.5, 6)
+    np.savez_compressed(os.path.join(HERE, "grid.npz"), dims=np.array(dims), GV=GV, S=S, S_nan=Sn, S_filled=oracle.flood_fill(dims, Sn),
+                        iso=0.1, mc_V=Vm, mc_F=Fm, mc_E=Em, wn_V=V, wn_F=Fo, wn_O=O, wn_W=oracle.winding_number(V, Fo, O))
     print("fixtures written to", HERE)
 
 

@@ -90,6 +90,12 @@ def test_oracle_reproduces_golden_fixtures():
         o = oracle.PortCloud(g["P"], g["N"], g["A"], order)
         assert o.num_cells() == int(g[f"ncells_order{order}"])
         assert np.abs(o.eval(g["Q"], 2.0) - g[f"WN_order{order}"]).max() < 1e-15
+    g = np.load(os.path.join(GOLD, "grid.npz"))
+    dims = [int(x) for x in g["dims"]]
+    assert np.array_equal(oracle.flood_fill(dims, g["S_nan"]), g["S_filled"], equal_nan=True)
+    V, F, E = oracle.marching_cubes(g["S"], g["GV"], dims[0], dims[1], dims[2], float(g["iso"]))
+    assert np.array_equal(V, g["mc_V"]) and np.array_equal(F, g["mc_F"]) and np.array_equal(E, g["mc_E"])
+    assert np.abs(oracle.winding_number(g["wn_V"], g["wn_F"], g["wn_O"]) - g["wn_W"]).max() < 1e-15
 
 
 # ---- the checker's grid functions and the product's marching-cubes tables, pinned to the reference -------------
