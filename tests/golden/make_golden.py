@@ -5,7 +5,9 @@ Run in the build container (needs /root/reference to build oracle/_ref):
 The winding numbers, tree topology and per-node moments come from the unmodified
 UT_SolidAngle<float,float> / UT_BVH<4> in /root/reference/include/igl/FastWindingNumberForSoups.h
 (through oracle/ref_fwn.cpp); distances come from the restated f64 AABB cross-checked against
-brute force.  The fixtures travel to the GPU box, /root/reference does not.
+brute force; grid.npz holds flood fill / marching cubes of the restated sequential sweeps (case tables from the
+genuine header) and the face-by-face exact winding number.  The fixtures travel to the GPU box,
+/root/reference does not.
 """
 import os
 import sys
