@@ -810,6 +810,7 @@ void download_scalar(const DevBuf<double> &src, int64_t n, void *dst, int is_f64
 // k-1's download run concurrently on two streams with a grow-only per-thread device workspace
 // (no cudaMalloc/cudaFree on the call path).
 struct Pipeline {
+  static constexpr int64_t EDGE = int64_t(1) << 20;   // first / last chunk of a long batch (e2e on c2: off 165.4, 0.5 M 167.4, 1 M 170.0, 2 M 170.1 M q/s)
   static constexpr int64_t CHUNK_MAX = int64_t(1) << 22, CHUNK_MIN = int64_t(1) << 20;   // measured on c2: 4 M-query chunks 149 M q/s e2e, 2 M 141, 8 M 145, 1 M 135
   cudaStream_t st[2] = {nullptr, nullptr};
   char *buf[2] = {nullptr, nullptr};
@@ -836,8 +837,18 @@ void run_streamed(const iglb200_mesh *m, int mode, const double *P, int64_t n, i
   const size_t oP = 0, oS = oP + al(24 * chunk), oC = oS + al(8 * chunk), oW = oC + al(24 * chunk), oI = oW + al(8 * chunk),
                oN = oI + al(4 * chunk), oX = oN + al(N ? 24 * chunk : 0), total = oX + al(iglb200_query_scratch_bytes(chunk));
   pl.ensure(total);
-  for (int64_t b = 0, k = 0; b < n; b += chunk, ++k) {
-    const int64_t mcount = std::min(chunk, n - b);
+  // the first upload and the last download cannot overlap with anything: make the first and the last chunk small
+  static const int64_t edge_cfg = [] { const char *e = std::getenv("IGLB200_STREAM_EDGE"); const long long v = e ? std::atoll(e) : -1; return (int64_t)v; }();
+  const int64_t edge = edge_cfg >= 0 ? edge_cfg : Pipeline::EDGE;
+  const bool shaped = edge > 0 && n >= 2 * chunk && edge < chunk;
+  int64_t mcount = 0;
+  for (int64_t b = 0, k = 0; b < n; b += mcount, ++k) {
+    mcount = std::min(chunk, n - b);
+    if (shaped) {
+      if (k == 0) mcount = edge;
+      else if (n - b - mcount > 0 && n - b - mcount < edge) mcount = n - b - edge;   // leave exactly `edge` for the last chunk
+      else if (n - b > edge && n - b <= chunk) mcount = n - b - edge;
+    }
     cudaStream_t s = pl.st[k & 1];
     char *base = pl.buf[k & 1];
     double *dP = (double *)(base + oP), *dS = (double *)(base + oS), *dC = (double *)(base + oC), *dW = (double *)(base + oW);
