@@ -90,7 +90,7 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   double up, low; float absmax;
   double *sqrD; int32_t *I; double *C;
   uint32_t *counters;  // nullable: [0] node visits, [1] face tests (summed over warps)
-  unsigned long long *sched = nullptr;   // nullable: work distribution state of the persistent schedule (CP_PERSIST)
+  unsigned long long *sched = nullptr;   // work distribution state of the persistent schedule (launch_closest supplies one if null)
 };
 
 static constexpr int64_t SCHED_WORDS = 1 + 2 * 1024;   // next chunk; per SM id: state, refill lock
@@ -183,10 +183,6 @@ void throw_if_overflow(stream_t) {
   if (*overflow_flag()) { *overflow_flag() = 0; throw std::runtime_error("traversal stack overflow (tree too deep)"); }
 }
 #else
-DEVFN void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#ifndef CP_LD256
-#define CP_LD256 1   // 78.6 vs 79.2 ms on c2
-#endif
 // 256-bit global load (sm_100: LDG.E.256): half the load instructions for the 128-byte node and the 64-byte face record
 DEVFN void ld256(const void *p, float4 &a, float4 &b) {
   asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -195,14 +191,7 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 }
 
 #ifndef CP_MIN_BLOCKS
-#define CP_MIN_BLOCKS 20   // with one-warp blocks: 96 registers, 20 warps per SM.  Before two face records were kept in
-#endif                     // flight 80 regs/25 warps was best (92.8 ms; 96/20 95.6, 72/28 99.2, 64/32 100.1); with them
-                           // 96/20 gives 89.4 ms and 80/25 89.9 ms
-#ifndef CP_PUSH_ALL
-// 1: every lane stores the (identical) stack entries itself and the loop needs no __syncwarp: 93.3 vs 95.7 ms
-// on c2, but the same-value stores are write-write races in racecheck's eyes -> off.  (Lane 0 owning the stack
-// and broadcasting pops by shuffle is race-free too, and slower: 96.1 ms.)
-#define CP_PUSH_ALL 0
+#define CP_MIN_BLOCKS 20   // one-warp blocks at 96 registers: 20 warps per SM (measured optimum, profiles/README_r1.md)
 #endif
 // One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
@@ -219,13 +208,9 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   CpExact &X = exact[threadIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *stack = stacks[warp];
-#ifndef CP_PERSIST
-#define CP_PERSIST 1   // 81.5 vs 89.3 ms on c2
-#endif
 #ifndef CP_CHUNK
 #define CP_CHUNK 16   // measured: 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2
 #endif
-#if CP_PERSIST
   // Persistent schedule: every SM hands out the packets of one chunk of CP_CHUNK Morton-consecutive packets to its
   // resident warps, so the packets that share an L1 are neighbours; chunks are taken from a global counter, so the
   // chunks in flight still form one window of the query set (L2).  sched[0] = next chunk, sched[1 + 2*smid] =
@@ -254,10 +239,6 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     if (packet >= npackets) break;   // the SM's chunk lies past the last packet: this warp is done
     const int64_t base = (int64_t)packet * 32;
     const int64_t t = base + lane;
-#else
-  for (int64_t base = ((int64_t)blockIdx.x * CP_WARPS + warp) * 32; base < a.n; base += (int64_t)gridDim.x * (32 * CP_WARPS)) {
-    const int64_t t = base + lane;
-#endif
     const bool valid = t < a.n;
     const int64_t qi = valid ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
     CpLane L;
@@ -277,66 +258,23 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       have = false;
       if (COUNT) ++nvis;
       const CpNode *np = a.nodes + cur;
-#if CP_LD256
       CpNode n;
       { float4 c4, p4;
         ld256(&np->lox, n.lox, n.loy); ld256(&np->loz, n.loz, n.hix); ld256(&np->hiy, n.hiy, n.hiz); ld256(&np->child, c4, p4);
         n.child = make_uint4(__float_as_uint(c4.x), __float_as_uint(c4.y), __float_as_uint(c4.z), __float_as_uint(c4.w));
         n.pad = make_uint4(__float_as_uint(p4.x), __float_as_uint(p4.y), 0u, 0u); }
-#else
-      const CpNode n = *np;
-#endif
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
       const uint32_t imask = n.pad.x, tmask = n.pad.y;
-#ifndef CP_PREFETCH
-#define CP_PREFETCH 0   // measured: the extra instructions cost more than the L1 misses they save
-#endif
-#if CP_PREFETCH == 1
-      // lanes 0..3 start pulling "their" child (node or face record) into L1
-      if (lane < 4 && ((imask | tmask) >> lane) & 1u) {
-        const uint32_t c = lane == 0 ? ch[0] : lane == 1 ? ch[1] : lane == 2 ? ch[2] : ch[3];
-        prefetch_l1((c & INTERNAL_BIT) ? (const void *)(a.nodes + (c & ~INTERNAL_BIT)) : (const void *)(a.triq + TRIQ_STRIDE * (size_t)c));
-      }
-#elif CP_PREFETCH == 2
-      if (lane < 16) {   // lane = 4*sector + child
-        const int j = lane & 3, sec = lane >> 2;
-        if (((imask | tmask) >> j) & 1u) {
-          const uint32_t c = j == 0 ? ch[0] : j == 1 ? ch[1] : j == 2 ? ch[2] : ch[3];
-          if (c & INTERNAL_BIT) prefetch_l1((const char *)(a.nodes + (c & ~INTERNAL_BIT)) + 32 * sec);
-          else if (sec < 2) prefetch_l1((const char *)(a.triq + TRIQ_STRIDE * (size_t)c) + 32 * sec);
-        }
-      }
-#endif
       float d2[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) d2[i] = lane_box_d2(n, i, L);
       // faces first: they tighten the bounds the internal children are judged by
-#ifndef CP_VOTE
-#define CP_VOTE 1   // bit 0: per-face __any_sync (95.7 vs 97.0 ms); bit 1: the same for internal children (99.2 ms: worse)
-#endif
-#if !(CP_VOTE & 1)
-      uint32_t wt = 0;
-      if (tmask) {   // warp-uniform
-        uint32_t mine = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mine |= (d2[i] <= L.thr2) ? (1u << i) : 0u;
-        wt = __reduce_or_sync(FULL, mine) & tmask;
-      }
-#endif
-#ifndef CP_PAIR
-#define CP_PAIR 1   // 89.4 vs 91.4 ms on c2 (with 96 registers / 20 warps per SM)
-#endif
-#if CP_PAIR
       if (tmask) {   // warp-uniform
         // two face records in flight where two neighbouring lanes are wanted: one load round trip instead of two
         bool w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] = ((tmask >> i) & 1u) && __any_sync(FULL, d2[i] <= L.thr2);
-#if CP_LD256
 #define CP_LOADQ(p, A, B, C, D) { ld256((p), A, B); ld256((p) + 2, C, D); }
-#else
-#define CP_LOADQ(p, A, B, C, D) { A = (p)[0]; B = (p)[1]; C = (p)[2]; D = (p)[3]; }
-#endif
 #define CP_FACE1(i) { const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i]; \
           float4 T0, T1, T2, T3; CP_LOADQ(tq, T0, T1, T2, T3); if (COUNT) ++ntri; \
           float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err); \
@@ -352,35 +290,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
 #undef CP_FACE1
 #undef CP_FACE2
       }
-#else
-      // one guarded copy per lane: the child id is a plain register in each (no select chain, no ffs)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#if CP_VOTE & 1
-        if (!((tmask >> i) & 1u)) continue;                      // warp-uniform
-        if (!__any_sync(FULL, d2[i] <= L.thr2)) continue;        // judged by the bounds as tightened so far
-#else
-        if (!((wt >> i) & 1u)) continue;   // warp-uniform
-#endif
-        const uint32_t f = ch[i];
-        if (COUNT) ++ntri;
-        const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)f;
-        const float4 T0 = tq[0], T1 = tq[1], T2 = tq[2], T3 = tq[3];
-        float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
-        if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, f, d32, err);   // few lanes
-      }
-#endif
       if (imask) {   // warp-uniform
-#if CP_VOTE & 2
-        uint32_t wi = 0, mykey = 0xFFFFFFFFu;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (!((imask >> i) & 1u)) continue;   // warp-uniform
-          const bool w = d2[i] <= L.thr2;
-          if (__any_sync(FULL, w)) wi |= 1u << i;
-          mykey = w ? min(mykey, (__float_as_uint(d2[i]) & ~3u) | (uint32_t)i) : mykey;
-        }
-#else
         uint32_t mine = 0, mykey = 0xFFFFFFFFu;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -389,7 +299,6 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
           mykey = w ? min(mykey, (__float_as_uint(d2[i]) & ~3u) | (uint32_t)i) : mykey;
         }
         const uint32_t wi = __reduce_or_sync(FULL, mine);
-#endif
         if (wi) {
           const uint32_t best = __reduce_min_sync(FULL, mykey);
           const int nb = (int)(best & 3u);
@@ -397,27 +306,17 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
           const int npush = __popc(push);
           if (sp + npush > CP_STACK) { if (lane == 0) atomicExch(overflow, 1u); }
           else if (push) {
-#if CP_PUSH_ALL
-            // every lane stores the same entries (it holds all four child ids) and later reads back its own
-            // store: no cross-lane dependency through shared memory, so no __syncwarp in the loop
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if ((push >> j) & 1u) stack[sp + __popc(push & ((1u << j) - 1u))] = ch[j] & ~INTERNAL_BIT;   // warp-uniform
-#else
             if (lane < 4 && ((push >> lane) & 1u)) {
               const uint32_t c = lane == 0 ? ch[0] : lane == 1 ? ch[1] : lane == 2 ? ch[2] : ch[3];
               stack[sp + __popc(push & ((1u << lane) - 1u))] = c & ~INTERNAL_BIT;
             }
-#endif
             sp += npush;
           }
           cur = (nb == 0 ? ch[0] : nb == 1 ? ch[1] : nb == 2 ? ch[2] : ch[3]) & ~INTERNAL_BIT;
           have = true;
         }
       }
-#if !CP_PUSH_ALL
       __syncwarp();
-#endif
     }
     if (valid) {
       CpResult r;
@@ -448,7 +347,6 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   // one packet per warp, blocks in Morton order: the packets in flight form one sliding window of the
   // query set, so the tree region they touch stays L2-resident (a grid-stride loop spreads it over ~14 regions)
   int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)0x7FFFFFFF);
-#if CP_PERSIST
   static_assert(CP_WARPS == 1, "the persistent schedule hands out packets to one-warp blocks");
   if (warps > (int64_t)0xFFF00000) throw std::invalid_argument("too many queries in one call (packet index is 32 bits)");
   DevBuf<unsigned long long> own;
@@ -459,10 +357,6 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   if (b.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
   else closest_packet_kernel<false><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
   if (own.p) plat::sync(s);
-#else
-  if (a.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
-  else closest_packet_kernel<false><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(a, overflow_flag());
-#endif
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }
