@@ -119,4 +119,21 @@ inline void signed_distance_fast_winding_number(const DerivedP &P, const Derived
                                                          (double)std::numeric_limits<Scalar>::max(), S, I, C, nullptr);
 }
 
+// signed_distance_pseudonormal(P,V,F,tree,FN,VN,EN,EMAP,S,I,C,N): batch overload with prebuilt structures
+// (signed_distance.h:135-147, signed_distance.cpp:468-512).  The device keeps its own copy of the angle-weighted
+// vertex, uniform edge and face normals, computed from V and F exactly as per_face_normals / per_vertex_normals /
+// per_edge_normals do (face and edge normals bit-identical, vertex normals to one ulp), so FN, VN, EN and EMAP are
+// accepted for signature compatibility and not read: callers who pass normals of their own making get the standard
+// ones.
+template <class DerivedP, class DerivedV, class DerivedF, class DerivedFN, class DerivedVN, class DerivedEN, class DerivedEMAP,
+          class DerivedS, class DerivedI, class DerivedC, class DerivedN>
+inline void signed_distance_pseudonormal(const DerivedP &P, const DerivedV &V, const DerivedF &F, const AABB<DerivedV, 3> & /*tree*/,
+                                         const DerivedFN & /*FN*/, const DerivedVN & /*VN*/, const DerivedEN & /*EN*/,
+                                         const DerivedEMAP & /*EMAP*/, DerivedS &S, DerivedI &I, DerivedC &C, DerivedN &N) {
+  using Scalar = typename DerivedV::Scalar;
+  // the reference searches without bounds here (:500-511)
+  signed_distance(P, V, F, SIGNED_DISTANCE_TYPE_PSEUDONORMAL, std::numeric_limits<Scalar>::min(), std::numeric_limits<Scalar>::max(), S, I,
+                  C, N);
+}
+
 }  // namespace iglb200

@@ -47,6 +47,13 @@ int main() {
       REQUIRE(N.rows() == 0);   // untouched, as in the reference
     }
   }
+  // batch pseudonormal overload with prebuilt structures (normals arguments are accepted, not read)
+  {
+    iglb200::AABB<MatrixXd, 3> tree; tree.init(V, F);
+    MatrixXd FN, VN, EN, C, N; VectorXi EMAP, I; VectorXd S;
+    iglb200::signed_distance_pseudonormal(P, V, F, tree, FN, VN, EN, EMAP, S, I, C, N);
+    REQUIRE(std::fabs(S(0) - std::sqrt(1. / 12.)) <= 1e-15 && I(0) == 3 && N.rows() == 1);
+  }
   // an unknown sign type must fail loudly
   {
     VectorXd S; VectorXi I; MatrixXd C, N;
