@@ -89,6 +89,12 @@ int main() {
     VectorXd sqrD; VectorXi I;
     tree.squared_distance(V, F, BC, sqrD, I, C);
     for (int f = 0; f < 4; ++f) { REQUIRE(I(f) == f); REQUIRE(sqrD(f) <= 1e-30); }
+    {   // single-query overload
+      MatrixXd q(1, 3), c1; q(0) = BC(3, 0); q(1) = BC(3, 1); q(2) = BC(3, 2);
+      int i1 = -1;
+      const double d1 = tree.squared_distance(V, F, q, i1, c1);
+      REQUIRE(i1 == 3 && d1 == sqrD(3) && c1(0) == C(3, 0) && c1(1) == C(3, 1) && c1(2) == C(3, 2));
+    }
     VectorXd sqrD2; VectorXi I2; MatrixXd C2;
     iglb200::point_mesh_squared_distance(BC, V, F, sqrD2, I2, C2);
     for (int f = 0; f < 4; ++f) REQUIRE(I2(f) == I(f) && sqrD2(f) == sqrD(f));
