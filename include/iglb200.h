@@ -12,7 +12,9 @@
  *    strides in ELEMENTS, which covers Eigen column-major (rs=1, cs=rows),
  *    row-major (rs=cols, cs=1) and Map<..., Stride<>> views.
  *  - All pointers in the non-_dev entry points are HOST pointers (pageable or
- *    pinned); the library copies to/from the current CUDA device.
+ *    pinned); the library copies to/from the device(s) holding the handle.  Batches are
+ *    cut into chunks and streamed by worker threads, so uploads, kernels and downloads
+ *    overlap; pageable arrays go through a page-locked staging ring.
  *  - The caller owns every array (AABB.h:20-21: "The mesh (V,Ele) is stored and
  *    managed by the caller").  A mesh handle COPIES V and F at creation, so the
  *    inputs may be freed afterwards (unlike UT_SolidAngle, which keeps raw
@@ -56,7 +58,18 @@ const char *iglb200_last_error(void);
 const char *iglb200_version(void);
 int iglb200_device_count(void);          /* <0 on error, 0 when no GPU */
 int iglb200_set_device(int device);      /* device used by the calling thread */
-int iglb200_init(int n_gpus);            /* optional: checks that n_gpus devices exist and creates their contexts */
+/* One process, several GPUs.  iglb200_init(n) makes devices 0..n-1 the process's GROUP: every mesh created
+ * afterwards is built once (on the calling thread's device) and its arena is replicated to all devices of the
+ * group with ncclBroadcast over NVLink (NCCL is loaded at run time; peer-to-peer DMA when it cannot be), and every
+ * host-pointer query on such a mesh is dealt — chunk by chunk, one atomic counter — to all of those devices, each
+ * of which DMA-writes its chunks straight into the caller's output arrays.  This is the loop igl::signed_distance
+ * runs over igl::parallel_for threads (signed_distance.cpp:90-138; AABB.cpp:1241-1265;
+ * fast_winding_number.cpp:429-436): queries are independent, the structures read-only.
+ * iglb200_init(1) returns to single-device operation.  Optional: without it the group is the current device. */
+int iglb200_init(int n_gpus);
+/* info = {devices in the group, 1 if NCCL replicates, 1 if peer access is on, microseconds of the last replication};
+ * transport (may be NULL) names what the last replication used */
+int iglb200_group_info(int64_t info[4], char *transport, uint64_t cap);
 void iglb200_shutdown(void);             /* optional: waits for the calling thread's device to go idle */
 
 /* pinned host memory for fast transfers (optional; any host pointer works) */
@@ -80,7 +93,10 @@ int iglb200_mesh_create_ex(const void *V, int v_is_f64, int64_t nV, int64_t v_ro
                            const int32_t *F, int64_t nF, int64_t f_row_stride, int64_t f_col_stride,
                            int fwn_order, int flags, iglb200_mesh **out);
 int iglb200_mesh_destroy(iglb200_mesh *m);
-/* info[0]=#faces, [1]=#tree nodes, [2]=#levels, [3]=device bytes, [4]=#faces excluded (NaN/Inf boxes) */
+/* (re)replicate a mesh onto the devices of the current group (meshes created after iglb200_init are already) */
+int iglb200_mesh_replicate(iglb200_mesh *m);
+/* info[0]=#faces, [1]=#tree nodes, [2]=#levels, [3]=device bytes, [4]=#faces excluded (NaN/Inf boxes),
+ * [5]=fwn order, [6]=has pseudonormals, [7]=#devices holding a copy */
 int iglb200_mesh_info(const iglb200_mesh *m, int64_t info[8]);
 /* device build time of the last create on this handle, milliseconds (CUDA events) */
 double iglb200_mesh_build_ms(const iglb200_mesh *m);
@@ -111,6 +127,21 @@ int iglb200_signed_distance(const iglb200_mesh *m,
                             void *C, int c_is_f64, int64_t c_row_stride, int64_t c_col_stride,
                             void *W, int w_is_f64,
                             void *N, int n_is_f64, int64_t n_row_stride, int64_t n_col_stride);
+
+/* The same call made COOPERATIVELY by several processes (one per GPU, e.g. under torchrun) on ONE query set: all
+ * of them map the same host arrays (shared memory) and pass the same arguments; each takes chunks of `chunk_rows`
+ * rows off `shared_chunk_counter` (an int64 in that shared memory, zeroed before the first call starts) until the
+ * rows run out, and writes only the rows of its chunks.  Matrices must be column-major or dense row-major. */
+int iglb200_signed_distance_coop(const iglb200_mesh *m,
+                                 const void *P, int p_is_f64, int64_t nP, int64_t p_row_stride, int64_t p_col_stride,
+                                 int sign_type, double lower_bound, double upper_bound,
+                                 void *S, int s_is_f64, int32_t *I,
+                                 void *C, int c_is_f64, int64_t c_row_stride, int64_t c_col_stride,
+                                 void *W, int w_is_f64,
+                                 void *N, int n_is_f64, int64_t n_row_stride, int64_t n_col_stride,
+                                 int64_t *shared_chunk_counter, int64_t chunk_rows);
+/* the chunk size the library itself would use for nP rows on n_devices devices */
+int64_t iglb200_host_chunk_rows(int64_t nP, int n_devices);
 
 /* ---- AABB::squared_distance(V,Ele,P,sqrD,I,C) batch, AABB.h:722-728,
  *      AABB.cpp:1241-1265; also point_mesh_squared_distance.h:54-60. */

@@ -56,6 +56,7 @@ class Api:
 
     SYMBOLS = [
         "iglb200_last_error", "iglb200_version", "iglb200_device_count", "iglb200_set_device", "iglb200_init", "iglb200_shutdown",
+        "iglb200_group_info", "iglb200_mesh_replicate", "iglb200_signed_distance_coop", "iglb200_host_chunk_rows",
         "iglb200_host_alloc", "iglb200_host_free",
         "iglb200_mesh_create", "iglb200_mesh_create_ex", "iglb200_mesh_destroy", "iglb200_mesh_info", "iglb200_mesh_build_ms",
         "iglb200_mesh_arena", "iglb200_mesh_arena_download", "iglb200_mesh_from_arena",
@@ -92,6 +93,12 @@ class Api:
         L.iglb200_mesh_from_arena.argtypes = [_vp, C.c_uint64, _int, C.POINTER(_vp)]
         L.iglb200_signed_distance.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _int, _dbl, _dbl,
                                               _vp, _int, _vp, _vp, _int, _i64, _i64, _vp, _int, _vp, _int, _i64, _i64]
+        L.iglb200_signed_distance_coop.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _int, _dbl, _dbl,
+                                                   _vp, _int, _vp, _vp, _int, _i64, _i64, _vp, _int, _vp, _int, _i64, _i64, _vp, _i64]
+        L.iglb200_host_chunk_rows.argtypes = [_i64, _int]
+        L.iglb200_host_chunk_rows.restype = _i64
+        L.iglb200_group_info.argtypes = [C.POINTER(_i64), C.c_char_p, C.c_uint64]
+        L.iglb200_mesh_replicate.argtypes = [_vp]
         L.iglb200_squared_distance.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _int, _i64, _i64]
         L.iglb200_fwn_eval.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, C.c_float, _vp, _int]
         L.iglb200_query_scratch_bytes.argtypes = [_i64]
@@ -143,6 +150,17 @@ class Api:
 
     def set_device(self, d):
         self.check(self.lib.iglb200_set_device(int(d)))
+
+    def init(self, n_gpus):
+        """iglb200_init: devices 0..n_gpus-1 become the process's group (meshes are replicated, host queries dealt)."""
+        self.check(self.lib.iglb200_init(int(n_gpus)))
+
+    def group_info(self):
+        info = (_i64 * 4)()
+        buf = C.create_string_buffer(128)
+        self.check(self.lib.iglb200_group_info(info, buf, 128))
+        return {"devices": int(info[0]), "nccl": bool(info[1]), "peer": bool(info[2]), "replicate_ms": info[3] / 1000.0,
+                "transport": buf.value.decode()}
 
     def last_launch_count(self):
         return int(self.lib.iglb200_last_launch_count())
@@ -350,7 +368,7 @@ class Mesh:
         a = (_i64 * 8)()
         self.api.check(self.api.lib.iglb200_mesh_info(self.h, a))
         return dict(n_faces=a[0], n_nodes=a[1], n_levels=a[2], device_bytes=a[3], n_excluded=a[4], order=a[5],
-                    pseudonormals=bool(a[6]),
+                    pseudonormals=bool(a[6]), n_devices=int(a[7]),
                     build_ms=float(self.api.lib.iglb200_mesh_build_ms(self.h)))
 
     def arena(self):
@@ -400,6 +418,20 @@ class Mesh:
             N.ctypes.data_as(_vp) if pseudo else None, 1, 1, max(n, 1)))
         out = (S, I, Cc, N) if pseudo else (S, I, Cc)
         return out + (W,) if return_W else out
+
+    def signed_distance_coop(self, sh, chunk_rows, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower_bound=None,
+                             upper_bound=None):
+        """This process's share of ONE query set held in memory shared between processes (dist.SharedArrays):
+        chunks of `chunk_rows` rows are taken off sh.counter until the rows run out."""
+        if lower_bound is None:
+            lower_bound = np.finfo(np.float64).tiny
+        if upper_bound is None:
+            upper_bound = np.finfo(np.float64).max
+        n = sh.n
+        self.api.check(self.api.lib.iglb200_signed_distance_coop(
+            self.h, sh.P.ctypes.data_as(_vp), 1, n, 1, n, int(sign_type), float(lower_bound), float(upper_bound),
+            sh.S.ctypes.data_as(_vp), 1, sh.I.ctypes.data_as(_vp), sh.C.ctypes.data_as(_vp), 1, 1, n,
+            sh.W.ctypes.data_as(_vp), 1, None, 1, 1, n, sh.counter.ctypes.data_as(_vp), int(chunk_rows)))
 
     # igl::signed_distance_fast_winding_number(P,V,F,tree,fwn_bvh,S): S only
     def signed_distance_fast_winding_number(self, P):

@@ -482,8 +482,10 @@ static __global__ void __launch_bounds__(CLOUD_THREADS, CLOUD_MIN_BLOCKS) cloud_
 
 inline void eval(const iglb200_cloud *c, const double *Q, int64_t nq, double beta, double *WN, stream_t s) {
   if (nq <= 0) return;
+  if (nq > (int64_t)0x7FFFFFFF) throw std::invalid_argument("more than 2^31-1 queries in one call");
   // grow-only per-thread workspace for the sort (no cudaMalloc on the steady-state call path)
-  static thread_local plat::DevBuf<char> ws;
+  struct Ws { plat::DevBuf<char> b; };
+  plat::DevBuf<char> &ws = plat::per_device<Ws>().b;
   const bool sort = nq >= 1024 && c->n > 0 && beta > 0;
   uint32_t *perm_p = nullptr;
   if (sort) {

@@ -4,8 +4,12 @@
 #include "cloud.h"
 #include "grid.h"
 #include "wn.h"
+#include "group.h"
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <memory>
+#include <thread>
 
 using plat::DevBuf;
 
@@ -179,6 +183,7 @@ void launch_closest(const ClosestArgs &a, stream_t) {
   for (int64_t base = 0; base < a.n; base += 32) closest_packet_emul(a, base);
 }
 uint32_t *overflow_flag() { static thread_local uint32_t f = 0; return &f; }
+void reset_overflow(stream_t) { *overflow_flag() = 0; }
 void throw_if_overflow(stream_t) {
   if (*overflow_flag()) { *overflow_flag() = 0; throw std::runtime_error("traversal stack overflow (tree too deep)"); }
 }
@@ -328,18 +333,20 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     __syncwarp();
   }
 }
-struct OverflowFlag { uint32_t *d = nullptr; ~OverflowFlag() { plat::dev_free(d); } };
-uint32_t *overflow_flag() {
-  static thread_local OverflowFlag f;
-  if (!f.d) { f.d = (uint32_t *)plat::dev_alloc(4); cudaMemset(f.d, 0, 4); }
-  return f.d;
-}
+// one flag per (host thread, device); zeroed before any kernel of any stream can see it
+struct OverflowFlag {
+  uint32_t *d = nullptr;
+  OverflowFlag() { d = (uint32_t *)plat::dev_alloc(4); PLAT_CHECK(cudaMemset(d, 0, 4)); PLAT_CHECK(cudaDeviceSynchronize()); }
+  ~OverflowFlag() { plat::dev_free(d); }
+};
+uint32_t *overflow_flag() { return plat::per_device<OverflowFlag>().d; }
+void reset_overflow(stream_t s) { plat::dev_memset(overflow_flag(), 0, 4, s); plat::sync(s); }
 // stack overflow in a walk (tree deeper than the per-warp stack can follow) must never pass silently
 void throw_if_overflow(stream_t s) {
   uint32_t h = 0;
   plat::d2h(&h, overflow_flag(), 4, s);
   plat::sync(s);
-  if (h) { cudaMemset(overflow_flag(), 0, 4); throw std::runtime_error("traversal stack overflow (tree too deep)"); }
+  if (h) { reset_overflow(s); throw std::runtime_error("traversal stack overflow (tree too deep)"); }
 }
 void launch_closest(const ClosestArgs &a, stream_t s) {
   if (a.n <= 0) return;
@@ -370,6 +377,7 @@ struct WindingQuery {
   int mode;  // 0: W only (fast_winding_number.cpp:435); 1: signed distance FWN; 2: unsigned
   double up, low; int32_t nF;
   double *W; double *S; int32_t *I; double *C;  // S holds sqrD on entry when mode!=0
+  uint32_t *overflow;
   DEVFN void operator()(int64_t t) const {
     const int64_t i = perm ? (int64_t)perm[t] : t;
     const double FOUR_PI = 4.0 * 3.1415926535897932384626433832795;
@@ -383,7 +391,7 @@ struct WindingQuery {
       if (mode == 2) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return; }
     }
     uint32_t stack[fwn::FWN_STACK];
-    const float om = fwn::winding_solid_angle(nodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], acc2, order, stack, nullptr);
+    const float om = fwn::winding_solid_angle(nodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], acc2, order, stack, nullptr, overflow);
     const double w = (double)om / FOUR_PI;
     if (mode == 0) { W[i] = w; return; }
     const double wf = (double)(float)w;  // narrowed to float by fast_winding_number.cpp:452
@@ -397,10 +405,11 @@ struct CountWinding {
   const fwn::FwnNode *fnodes; const float4 *tri32;
   const double *P; int64_t n; int order;
   uint32_t *acc;  // [2] fwn nodes, fwn tris (sums; n must keep them < 2^32)
+  uint32_t *overflow;
   DEVFN void operator()(int64_t i) const {
     uint32_t sn[fwn::FWN_STACK];
     uint32_t w[2] = {0, 0};
-    fwn::winding_solid_angle(fnodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], 4.0f, order, sn, w);
+    fwn::winding_solid_angle(fnodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], 4.0f, order, sn, w, overflow);
     plat::atomic_add(&acc[0], w[0]); plat::atomic_add(&acc[1], w[1]);
   }
 };
@@ -571,6 +580,16 @@ const uint32_t *morton_perm(const iglb200_mesh *m, const double *P, int64_t n, v
 void check_mesh(const iglb200_mesh *m) {
   if (!m || m->h.magic != IGLB200_ARENA_MAGIC) throw std::invalid_argument("invalid mesh handle");
 }
+// *_dev entry points take pointers of the calling thread's current device: the copy of the mesh on that device answers
+const iglb200_mesh *mesh_here(const iglb200_mesh *m) {
+  check_mesh(m);
+  const iglb200_mesh *r = m->on(plat::current_device());
+  if (!r) throw std::invalid_argument("the mesh has no copy on the calling thread's current device (iglb200_set_device / iglb200_init)");
+  return r;
+}
+void check_count(int64_t n) {
+  if (n > (int64_t)0x7FFFFFFF) throw std::invalid_argument("more than 2^31-1 queries in one device-resident call (host-pointer calls chunk internally)");
+}
 
 void bounds_to_sqr(double lower, double upper, double &low, double &up) {  // signed_distance.cpp:81-84
   const double max_abs = std::max(std::fabs(lower), std::fabs(upper));
@@ -624,7 +643,7 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   }
   { plat::Span sp("winding", s);
     launch_query("winding", n, WindingQuery{m->fnodes(), m->tri32(), P, n, perm, 4.0f, m->h.order,
-                                            sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C}, s); }
+                                            sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1, up, low, (int32_t)m->h.nF, W, S, I, C, overflow_flag()}, s); }
 }
 
 // igl::winding_number(V,F,O,W) for triangle meshes (winding_number.cpp:38-52)
@@ -658,7 +677,7 @@ void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_s
   const uint32_t *perm = morton_perm(m, Q, n, scratch, sort_queries, s);
   plat::Span sp("winding", s);
   launch_query("winding", n, WindingQuery{m->fnodes(), m->tri32(), Q, n, perm, accuracy_scale * accuracy_scale, m->h.order, 0, 0.0, 0.0,
-                              (int32_t)m->h.nF, W, nullptr, nullptr, nullptr}, s);
+                              (int32_t)m->h.nF, W, nullptr, nullptr, nullptr, overflow_flag()}, s);
 }
 
 // upload a strided host matrix n x 3 as canonical column-major doubles
@@ -698,73 +717,298 @@ void download_scalar(const DevBuf<double> &src, int64_t n, void *dst, int is_f64
 }
 
 
-#ifndef IGLB200_EMUL
-// Host-pointer calls in the canonical layout (column-major doubles — Eigen's default) are
-// streamed: the batch is cut into chunks, and chunk k+1's upload, chunk k's kernels and chunk
-// k-1's download run concurrently on two streams with a grow-only per-thread device workspace
-// (no cudaMalloc/cudaFree on the call path).
-struct Pipeline {
-  static constexpr int64_t EDGE = int64_t(1) << 20;   // first / last chunk of a long batch (e2e on c2: off 165.4, 0.5 M 167.4, 1 M 170.0, 2 M 170.1 M q/s)
-  static constexpr int64_t CHUNK_MAX = int64_t(1) << 22, CHUNK_MIN = int64_t(1) << 20;   // measured on c2: 4 M-query chunks 149 M q/s e2e, 2 M 141, 8 M 145, 1 M 135
-  cudaStream_t st[2] = {nullptr, nullptr};
-  char *buf[2] = {nullptr, nullptr};
-  size_t cap = 0;
-  ~Pipeline() { for (int k = 0; k < 2; ++k) { if (buf[k]) cudaFree(buf[k]); if (st[k]) cudaStreamDestroy(st[k]); } }
-  void ensure(size_t bytes) {
-    for (int k = 0; k < 2; ++k) if (!st[k]) PLAT_CHECK(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
-    if (bytes <= cap) return;
-    for (int k = 0; k < 2; ++k) { if (buf[k]) { PLAT_CHECK(cudaFree(buf[k])); buf[k] = nullptr; } }
-    for (int k = 0; k < 2; ++k) buf[k] = (char *)plat::dev_alloc(bytes);
-    cap = bytes;
+// ---------------------------------------------------------------------------------------------------
+// Host-pointer calls.  The batch is cut into chunks that are dealt — one atomic counter — to worker
+// threads: IGLB200_HOST_WORKERS (default 3) per device, for every device that holds a copy of the mesh
+// (group.h).  A worker owns one stream, one grow-only device workspace and one grow-only pinned staging
+// buffer (no cudaMalloc on the steady-state call path) and takes a chunk through
+//     [pageable input: memcpy into pinned staging] -> H2D -> layout shim -> sort + kernels -> layout shim
+//     -> D2H [-> memcpy out of pinned staging]
+// so that one worker's copies overlap the other workers' kernels, on one GPU as on eight.  Each device
+// DMA-writes its chunks straight into the caller's S/I/C when those are page-locked.  The chunk counter
+// may also live in memory shared between PROCESSES (the *_coop entry points: one process per GPU under
+// torchrun, all of them mapping the same host arrays).
+// This is the loop of signed_distance.cpp:90-138 / AABB.cpp:1241-1265 / fast_winding_number.cpp:429-436.
+// ---------------------------------------------------------------------------------------------------
+struct WorkerCtx {
+  int device = 0;
+  stream_t s = nullptr;
+  char *dbuf = nullptr; size_t dcap = 0;
+  char *hbuf = nullptr; size_t hcap = 0;
+  ~WorkerCtx() { plat::dev_free(dbuf); plat::pinned_free(hbuf); plat::stream_destroy(s); }
+  void ensure(size_t dbytes, size_t hbytes) {
+    if (!s) s = plat::stream_create();
+    if (dbytes > dcap) { plat::sync(s); plat::dev_free(dbuf); dbuf = nullptr; dcap = 0; dbuf = (char *)plat::dev_alloc(dbytes); dcap = dbytes; }
+    if (hbytes > hcap) { plat::sync(s); plat::pinned_free(hbuf); hbuf = nullptr; hcap = 0; hbuf = (char *)plat::pinned_alloc(hbytes); hcap = hbytes; }
   }
 };
-Pipeline &pipeline() { static thread_local Pipeline p; return p; }
 
-// mode 0: signed distance (S,I,C,W), 1: squared distance (S=sqrD,I,C), 2: winding number only (W)
-void run_streamed(const iglb200_mesh *m, int mode, const double *P, int64_t n, int sign_type, double lower, double upper,
-                  float accuracy_scale, double *S, int32_t *I, double *C, double *W, double *N = nullptr) {
-  Pipeline &pl = pipeline();
-  static const int64_t chunk_cfg = [] { const char *e = std::getenv("IGLB200_STREAM_CHUNK"); const long long v = e ? std::atoll(e) : 0; return v > 0 ? (int64_t)v : 0; }();
-  // a quarter of the batch, so that uploads, kernels and downloads overlap, within [1 M, 4 M] queries
-  const int64_t chunk = std::min<int64_t>(chunk_cfg ? chunk_cfg : std::min(Pipeline::CHUNK_MAX, std::max(Pipeline::CHUNK_MIN, (n + 3) / 4)), n);
-  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  const size_t oP = 0, oS = oP + al(24 * chunk), oC = oS + al(8 * chunk), oW = oC + al(24 * chunk), oI = oW + al(8 * chunk),
-               oN = oI + al(4 * chunk), oX = oN + al(N ? 24 * chunk : 0), total = oX + al(iglb200_query_scratch_bytes(chunk));
-  pl.ensure(total);
-  // the first upload and the last download cannot overlap with anything: make the first and the last chunk small
-  static const int64_t edge_cfg = [] { const char *e = std::getenv("IGLB200_STREAM_EDGE"); const long long v = e ? std::atoll(e) : -1; return (int64_t)v; }();
-  const int64_t edge = edge_cfg >= 0 ? edge_cfg : Pipeline::EDGE;
-  const bool shaped = edge > 0 && n >= 2 * chunk && edge < chunk;
-  int64_t mcount = 0;
-  for (int64_t b = 0, k = 0; b < n; b += mcount, ++k) {
-    mcount = std::min(chunk, n - b);
-    if (shaped) {
-      if (k == 0) mcount = edge;
-      else if (n - b - mcount > 0 && n - b - mcount < edge) mcount = n - b - edge;   // leave exactly `edge` for the last chunk
-      else if (n - b > edge && n - b <= chunk) mcount = n - b - edge;
-    }
-    cudaStream_t s = pl.st[k & 1];
-    char *base = pl.buf[k & 1];
-    double *dP = (double *)(base + oP), *dS = (double *)(base + oS), *dC = (double *)(base + oC), *dW = (double *)(base + oW);
-    int32_t *dI = (int32_t *)(base + oI);
-    for (int d = 0; d < 3; ++d) plat::h2d(dP + d * mcount, P + d * n + b, (size_t)8 * mcount, s);
-    double *dN = N ? (double *)(base + oN) : nullptr;
-    if (mode == 0) run_signed_distance(m, dP, mcount, sign_type, lower, upper, dS, dI, dC, W ? dW : nullptr, dN, base + oX, 1, s);
-    else if (mode == 1) run_squared_distance(m, dP, mcount, dS, dI, dC, base + oX, 1, s);
-    else run_fwn(m, dP, mcount, accuracy_scale, dW, base + oX, 1, s);
-    if (mode != 2) {
-      plat::d2h(S + b, dS, (size_t)8 * mcount, s);
-      plat::d2h(I + b, dI, (size_t)4 * mcount, s);
-      for (int d = 0; d < 3; ++d) plat::d2h(C + d * n + b, dC + d * mcount, (size_t)8 * mcount, s);
-    }
-    if (W && mode != 1) plat::d2h(W + b, dW, (size_t)8 * mcount, s);
-    if (N && mode == 0) for (int d = 0; d < 3; ++d) plat::d2h(N + d * n + b, dN + d * mcount, (size_t)8 * mcount, s);
-  }
-  plat::sync(pl.st[0]);
-  plat::sync(pl.st[1]);
-  throw_if_overflow(nullptr);
+// an n x 3 host matrix as the chunk pipeline sees it
+enum MatKind { MAT_NONE = 0, MAT_COLS, MAT_ROWS, MAT_OTHER };
+struct HostMat {
+  char *p = nullptr; int f64 = 1; int64_t rs = 0, cs = 0; MatKind kind = MAT_NONE; bool pinned = false;
+  size_t esz() const { return f64 ? 8 : 4; }
+};
+HostMat host_mat(const void *p, int f64, int64_t n, int64_t rs, int64_t cs) {
+  HostMat m; m.p = (char *)p; m.f64 = f64; m.rs = rs; m.cs = cs;
+  if (!p) { m.kind = MAT_NONE; return m; }
+  if (rs == 1 && (cs >= n || n <= 1)) m.kind = MAT_COLS;        // column-major (Eigen's default), any leading dimension
+  else if (cs == 1 && rs == 3) m.kind = MAT_ROWS;               // dense row-major (numpy's default)
+  else m.kind = MAT_OTHER;
+  m.pinned = plat::host_is_pinned(p);
+  return m;
 }
-#endif
+struct HostVec { char *p = nullptr; int f64 = 1; bool pinned = false; size_t esz() const { return f64 ? 8 : 4; } };
+HostVec host_vec(const void *p, int f64) { HostVec v; v.p = (char *)p; v.f64 = f64; v.pinned = p ? plat::host_is_pinned(p) : false; return v; }
+
+struct ToFloat3Cols { const double *src; float *dst; DEVFN void operator()(int64_t i) const { dst[i] = (float)src[i]; } };
+struct FromFloatCols { const float *src; double *dst; DEVFN void operator()(int64_t i) const { dst[i] = (double)src[i]; } };
+
+struct HostQuery {
+  const iglb200_mesh *m = nullptr;
+  int mode = 0;   // 0: signed distance (S,I,C[,W][,N]); 1: squared distance (S=sqrD,I,C); 2: fast winding number (W); 3: exact winding number (W)
+  HostMat P, C, N;
+  HostVec S, W;
+  int32_t *I = nullptr; bool i_pinned = false;
+  int64_t n = 0;
+  int sign_type = 0; double lower = 0, upper = 0; float acc = 2.0f;
+  int64_t chunk = 0;
+  int64_t *counter = nullptr;       // chunks handed out so far (process-local or shared between processes)
+  std::atomic<int> failed{0};
+  std::atomic<long long> launches{0};
+  std::mutex err_mu; std::string err; int err_code = 0;
+};
+
+// device workspace of one chunk
+struct ChunkBufs { size_t oP, oS, oC, oW, oI, oN, oRaw, oX, oFlag, total; };
+ChunkBufs chunk_bufs(const HostQuery &q, int64_t c) {
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  ChunkBufs b;
+  b.oP = 0; b.oS = b.oP + al(24 * c); b.oC = b.oS + al(8 * c); b.oW = b.oC + al(24 * c); b.oI = b.oW + al(8 * c);
+  b.oN = b.oI + al(4 * c); b.oRaw = b.oN + al(q.N.p ? 24 * c : 0);
+  b.oX = b.oRaw + al(24 * c);                                   // raw: one strided/float matrix or vector at a time
+  b.oFlag = b.oX + al(iglb200_query_scratch_bytes(c));
+  b.total = b.oFlag + 256;
+  return b;
+}
+// pinned staging of one chunk: [raw input | S | I | C | W | N | flag]
+struct StageBufs { size_t oIn, oS, oI, oC, oW, oN, oFlag, total; };
+StageBufs stage_bufs(int64_t c) {
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  StageBufs b;
+  b.oIn = 0; b.oS = al(24 * c); b.oI = b.oS + al(8 * c); b.oC = b.oI + al(4 * c); b.oW = b.oC + al(24 * c); b.oN = b.oW + al(8 * c);
+  b.oFlag = b.oN + al(24 * c); b.total = b.oFlag + 256;
+  return b;
+}
+
+// upload rows [lo, lo+c) of a host matrix into canonical column-major doubles dP[3][c]
+void chunk_upload(WorkerCtx &w, const HostMat &M, int64_t lo, int64_t c, double *dP, char *draw, char *hin) {
+  const size_t e = M.esz();
+  if (M.kind == MAT_COLS) {
+    for (int d = 0; d < 3; ++d) {
+      const char *src = M.p + (size_t)(d * M.cs + lo) * e;
+      char *dst = M.f64 ? (char *)(dP + d * c) : draw + (size_t)d * c * e;
+      if (!M.pinned) { std::memcpy(hin + (size_t)d * c * e, src, (size_t)c * e); src = hin + (size_t)d * c * e; }
+      plat::h2d(dst, src, (size_t)c * e, w.s);
+    }
+    if (!M.f64) plat::for_n(3 * c, FromFloatCols{(const float *)draw, dP}, w.s);
+  } else {   // dense row-major rows are one contiguous byte range
+    const char *src = M.p + (size_t)lo * 3 * e;
+    if (!M.pinned) { std::memcpy(hin, src, (size_t)c * 3 * e); src = hin; }
+    plat::h2d(draw, src, (size_t)c * 3 * e, w.s);
+    if (M.f64) plat::for_n(c, ToCanon3<double>{(const double *)draw, 3, 1, c, dP}, w.s);
+    else plat::for_n(c, ToCanon3<float>{(const float *)draw, 3, 1, c, dP}, w.s);
+  }
+}
+// enqueue the download of canonical dC[3][c] into rows [lo, lo+c) of a host matrix (through `hst` when it is pageable);
+// `draw` is device scratch for the layout change (consumed by the D2H copy that follows on the same stream)
+void chunk_download3(WorkerCtx &w, const HostMat &M, int64_t lo, int64_t c, const double *dC, char *draw, char *hst) {
+  const size_t e = M.esz();
+  if (M.kind == MAT_COLS) {
+    if (!M.f64) plat::for_n(3 * c, ToFloat3Cols{dC, (float *)draw}, w.s);
+    for (int d = 0; d < 3; ++d) {
+      const char *src = M.f64 ? (const char *)(dC + d * c) : draw + (size_t)d * c * e;
+      char *dst = M.pinned ? M.p + (size_t)(d * M.cs + lo) * e : hst + (size_t)d * c * e;
+      plat::d2h(dst, src, (size_t)c * e, w.s);
+    }
+  } else {
+    if (M.f64) plat::for_n(c, FromCanon3<double>{dC, c, (double *)draw, 3, 1}, w.s);
+    else plat::for_n(c, FromCanon3<float>{dC, c, (float *)draw, 3, 1}, w.s);
+    char *dst = M.pinned ? M.p + (size_t)lo * 3 * e : hst;
+    plat::d2h(dst, draw, (size_t)c * 3 * e, w.s);
+  }
+}
+void chunk_unstage3(const HostMat &M, int64_t lo, int64_t c, const char *hst) {
+  if (M.pinned) return;
+  const size_t e = M.esz();
+  if (M.kind == MAT_COLS) for (int d = 0; d < 3; ++d) std::memcpy(M.p + (size_t)(d * M.cs + lo) * e, hst + (size_t)d * c * e, (size_t)c * e);
+  else std::memcpy(M.p + (size_t)lo * 3 * e, hst, (size_t)c * 3 * e);
+}
+
+int64_t take_chunk(int64_t *counter) { return __atomic_fetch_add(counter, (int64_t)1, __ATOMIC_RELAXED); }
+
+// One worker's share of a host query: chunks until the counter runs past the end.
+void host_worker(WorkerCtx &w, HostQuery &q) {
+  const iglb200_mesh *m = q.m->on(w.device);
+  if (!m) return;
+  const int64_t nchunks = (q.n + q.chunk - 1) / q.chunk;
+  const ChunkBufs B = chunk_bufs(q, q.chunk);
+  const StageBufs H = stage_bufs(q.chunk);
+  plat::launch_counter() = 0;
+  bool sized = false;
+  // three device scratch areas for layout shims are needed at most (C, N raw at once are sequenced on one stream, so one suffices)
+  while (!q.failed.load(std::memory_order_relaxed)) {
+    const int64_t k = take_chunk(q.counter);
+    if (k >= nchunks) break;
+    if (!sized) { w.ensure(B.total, H.total); sized = true; }
+    const int64_t lo = k * q.chunk, c = std::min(q.chunk, q.n - lo);
+    char *base = w.dbuf, *hb = w.hbuf;
+    double *dP = (double *)(base + B.oP), *dS = (double *)(base + B.oS), *dC = (double *)(base + B.oC), *dW = (double *)(base + B.oW);
+    double *dN = q.N.p ? (double *)(base + B.oN) : nullptr;
+    int32_t *dI = (int32_t *)(base + B.oI);
+    char *draw = base + B.oRaw;
+    chunk_upload(w, q.P, lo, c, dP, draw, hb + H.oIn);
+    if (q.mode == 0) run_signed_distance(m, dP, c, q.sign_type, q.lower, q.upper, dS, dI, dC, q.W.p ? dW : nullptr, dN, base + B.oX, 1, w.s);
+    else if (q.mode == 1) run_squared_distance(m, dP, c, dS, dI, dC, base + B.oX, 1, w.s);
+    else if (q.mode == 2) run_fwn(m, dP, c, q.acc, dW, base + B.oX, 1, w.s);
+    else run_exact_winding(m, dP, c, dW, base + B.oX, 1, w.s);
+    // downloads (each layout shim reuses `draw`: stream order keeps them apart)
+    if (q.S.p) {
+      const size_t e = q.S.esz();
+      const char *src = (const char *)dS;
+      if (!q.S.f64) { plat::for_n(c, ToFloat1{dS, (float *)draw}, w.s); src = draw; }
+      plat::d2h(q.S.pinned ? q.S.p + (size_t)lo * e : hb + H.oS, src, (size_t)c * e, w.s);
+    }
+    if (q.I) plat::d2h(q.i_pinned ? (char *)(q.I + lo) : hb + H.oI, dI, (size_t)4 * c, w.s);
+    if (q.C.p) chunk_download3(w, q.C, lo, c, dC, draw, hb + H.oC);
+    if (q.W.p) {
+      const size_t e = q.W.esz();
+      const char *src = (const char *)dW;
+      if (!q.W.f64) { plat::for_n(c, ToFloat1{dW, (float *)draw}, w.s); src = draw; }
+      plat::d2h(q.W.pinned ? q.W.p + (size_t)lo * e : hb + H.oW, src, (size_t)c * e, w.s);
+    }
+    if (q.N.p && dN) chunk_download3(w, q.N, lo, c, dN, draw, hb + H.oN);
+    plat::d2h(hb + H.oFlag, overflow_flag(), 4, w.s);
+    plat::sync(w.s);
+    if (*(const uint32_t *)(hb + H.oFlag)) { reset_overflow(w.s); throw std::runtime_error("traversal stack overflow (tree too deep)"); }
+    if (q.S.p && !q.S.pinned) std::memcpy(q.S.p + (size_t)lo * q.S.esz(), hb + H.oS, (size_t)c * q.S.esz());
+    if (q.I && !q.i_pinned) std::memcpy(q.I + lo, hb + H.oI, (size_t)4 * c);
+    if (q.C.p) chunk_unstage3(q.C, lo, c, hb + H.oC);
+    if (q.W.p && !q.W.pinned) std::memcpy(q.W.p + (size_t)lo * q.W.esz(), hb + H.oW, (size_t)c * q.W.esz());
+    if (q.N.p && dN) chunk_unstage3(q.N, lo, c, hb + H.oN);
+  }
+  q.launches += plat::launch_counter();
+}
+
+// Worker threads, IGLB200_HOST_WORKERS per device, created on first use and never destroyed (the process's exit
+// must not wait for, or free CUDA resources under, a thread).  One fork-join at a time.
+struct Pool {
+  struct W { std::thread t; WorkerCtx ctx; uint64_t seen = 0; };
+  std::mutex mu, call_mu;
+  std::condition_variable cv, cv_done;
+  std::vector<W *> ws;
+  uint64_t gen = 0;
+  int pending = 0;
+  HostQuery *job = nullptr;
+  int per_dev = 3;
+  Pool() {
+    const char *e = std::getenv("IGLB200_HOST_WORKERS");
+    const int v = e ? std::atoi(e) : 0;
+    if (v > 0 && v <= 16) per_dev = v;
+  }
+  void loop(W *w) {
+    try { plat::set_device(w->ctx.device); plat::pin_thread_near_device(w->ctx.device); } catch (...) {}
+    std::unique_lock<std::mutex> lk(mu);
+    while (true) {
+      cv.wait(lk, [&] { return gen != w->seen; });
+      w->seen = gen;
+      HostQuery *q = job;
+      if (!q || !q->m->on(w->ctx.device)) continue;   // not taking part (pending does not count it)
+      lk.unlock();
+      try { host_worker(w->ctx, *q); }
+      catch (const std::exception &ex) {
+        std::lock_guard<std::mutex> g(q->err_mu);
+        if (!q->failed.exchange(1)) {
+          q->err = ex.what();
+          q->err_code = dynamic_cast<const std::invalid_argument *>(&ex) ? IGLB200_ERR_ARG
+                        : dynamic_cast<const std::bad_alloc *>(&ex) ? IGLB200_ERR_OOM : IGLB200_ERR_CUDA;
+        }
+      } catch (...) {
+        std::lock_guard<std::mutex> g(q->err_mu);
+        if (!q->failed.exchange(1)) { q->err = "unknown error in a worker"; q->err_code = IGLB200_ERR_INTERNAL; }
+      }
+      lk.lock();
+      if (--pending == 0) cv_done.notify_all();
+    }
+  }
+  void run(HostQuery &q) {
+    std::lock_guard<std::mutex> call(call_mu);
+    std::unique_lock<std::mutex> lk(mu);
+    // workers for every device that holds a copy
+    const int maxdev = std::max<int>(q.m->device + 1, (int)q.m->reps.size());
+    for (int d = 0; d < maxdev; ++d) {
+      if (!q.m->on(d)) continue;
+      int have = 0;
+      for (W *w : ws) have += w->ctx.device == d;
+      for (; have < per_dev; ++have) {
+        W *w = new W; w->ctx.device = d; w->seen = gen;
+        ws.push_back(w);
+        w->t = std::thread([this, w] { loop(w); });
+        w->t.detach();
+      }
+    }
+    int takers = 0;
+    for (W *w : ws) takers += q.m->on(w->ctx.device) ? 1 : 0;
+    job = &q; pending = takers; ++gen;
+    cv.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+    job = nullptr;
+  }
+};
+Pool &pool() { static Pool *p = new Pool; return *p; }
+
+static int64_t env_i64(const char *name, int64_t dflt) { const char *e = std::getenv(name); const long long v = e ? std::atoll(e) : 0; return v > 0 ? (int64_t)v : dflt; }
+
+// rows per chunk of a host query of n rows on ndev devices
+int64_t host_chunk_rows(int64_t n, int ndev) {
+  static const int64_t cfg = env_i64("IGLB200_STREAM_CHUNK", 0);
+  if (cfg) return std::min(cfg, std::max<int64_t>(n, 1));
+  const int64_t want = (n + (int64_t)ndev * 12 - 1) / ((int64_t)ndev * 12);    // >= 4 chunks per worker
+  int64_t c = std::min<int64_t>(int64_t(1) << 20, std::max<int64_t>(int64_t(1) << 16, want));
+  c = (c + 31) & ~int64_t(31);
+  return std::min(c, std::max<int64_t>(n, 1));
+}
+
+void run_host_query(HostQuery &q, int64_t *shared_counter, int64_t shared_chunk) {
+  if (q.n <= 0) return;
+  if (q.P.kind == MAT_OTHER || q.C.kind == MAT_OTHER || q.N.kind == MAT_OTHER)
+    throw std::invalid_argument("host matrices must be column-major (row stride 1) or dense row-major (strides 3, 1)");
+  if (q.n > (int64_t)0x7FFFFFFF * 1024) throw std::invalid_argument("too many queries");
+  int64_t local_counter = 0;
+  const int ndev = q.m->n_devices();
+  if (shared_counter) {
+    if (shared_chunk <= 0) throw std::invalid_argument("chunk_rows must be positive");
+    q.counter = shared_counter; q.chunk = std::min<int64_t>(shared_chunk, int64_t(1) << 24);
+  } else {
+    q.counter = &local_counter; q.chunk = host_chunk_rows(q.n, ndev);
+  }
+  static const int64_t inline_rows = env_i64("IGLB200_INLINE_ROWS", 1 << 15);
+  if (!shared_counter && ndev == 1 && q.n <= inline_rows) {
+    // small call: on the calling thread, with its own per-device context (no fork-join latency)
+    plat::DeviceGuard dg(q.m->device);
+    WorkerCtx &w = plat::per_device<WorkerCtx>();
+    w.device = q.m->device;
+    host_worker(w, q);
+  } else {
+    pool().run(q);
+    if (q.failed.load()) {
+      if (q.err_code == IGLB200_ERR_ARG) throw std::invalid_argument(q.err);
+      if (q.err_code == IGLB200_ERR_OOM) throw std::bad_alloc();
+      throw std::runtime_error(q.err);
+    }
+  }
+  plat::launch_counter() = (int)q.launches.load();
+}
 
 }  // namespace iglq
 using namespace iglq;
@@ -802,20 +1046,22 @@ int iglb200_set_device(int device) {
   API_END
 #endif
 }
-// one process drives n_gpus devices (one per host thread or one per process under torchrun): checks that they exist
-// and creates their contexts up front so that the first query does not pay for it
+// One process drives n_gpus devices: devices 0..n_gpus-1 become the process's group (group.h).  Meshes created
+// afterwards are replicated to every device of the group (ncclBroadcast / P2P) and host-pointer queries on them are
+// dealt to all of those devices.  n_gpus == 1 returns to single-device operation.
 int iglb200_init(int n_gpus) {
   API_BEGIN
   if (n_gpus < 1) throw std::invalid_argument("n_gpus must be >= 1");
   require_device();
-#ifndef IGLB200_EMUL
-  int have = 0, cur = 0;
-  PLAT_CHECK(cudaGetDeviceCount(&have));
-  if (have < n_gpus) throw std::invalid_argument("fewer CUDA devices than requested");
-  PLAT_CHECK(cudaGetDevice(&cur));
-  for (int d = 0; d < n_gpus; ++d) { PLAT_CHECK(cudaSetDevice(d)); PLAT_CHECK(cudaFree(nullptr)); }
-  PLAT_CHECK(cudaSetDevice(cur));
-#endif
+  grp::init(n_gpus);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_group_info(int64_t info[4], char *transport, uint64_t cap) {
+  API_BEGIN
+  grp::State &g = grp::state();
+  if (info) { info[0] = g.n; info[1] = g.nccl ? 1 : 0; info[2] = g.peer ? 1 : 0; info[3] = (int64_t)(g.last_replicate_ms * 1000.0); }
+  if (transport && cap) { std::strncpy(transport, g.transport.c_str(), (size_t)cap - 1); transport[cap - 1] = 0; }
   return IGLB200_OK;
   API_END
 }
@@ -871,10 +1117,21 @@ int iglb200_mesh_create_ex(const void *V, int v_is_f64, int64_t nV, int64_t v_rs
   t.start(nullptr);
   iglb200_mesh *m = fwn::create_mesh(V, v_is_f64, nV, v_rs, v_cs, F, nF, f_rs, f_cs, fwn_order, flags, nullptr);
   m->build_ms = t.stop(nullptr);
-#ifndef IGLB200_EMUL
-  cudaGetDevice(&m->device);
-#endif
+  m->device = plat::current_device();
   *out = m;
+  if (grp::size() > 1 && m->device < grp::size()) {
+    try { grp::replicate(m); }
+    catch (...) { iglb200_mesh_destroy(m); *out = nullptr; throw; }
+  }
+  return IGLB200_OK;
+  API_END
+}
+
+int iglb200_mesh_replicate(iglb200_mesh *m) {
+  API_BEGIN
+  check_mesh(m);
+  require_device();
+  grp::replicate(m);
   return IGLB200_OK;
   API_END
 }
@@ -883,6 +1140,11 @@ int iglb200_mesh_destroy(iglb200_mesh *m) {
   API_BEGIN
   if (!m) return IGLB200_OK;
   check_mesh(m);
+  for (iglb200_mesh *r : m->reps) {
+    if (!r) continue;
+    if (r->owns && r->arena) plat::dev_free(r->arena);
+    delete r;
+  }
   if (m->owns && m->arena) plat::dev_free(m->arena);
   m->h.magic = 0;
   delete m;
@@ -894,7 +1156,7 @@ int iglb200_mesh_info(const iglb200_mesh *m, int64_t info[8]) {
   API_BEGIN
   check_mesh(m);
   info[0] = m->h.nF; info[1] = m->h.nnodes; info[2] = m->h.nlevels; info[3] = (int64_t)m->h.bytes; info[4] = m->h.nexcluded;
-  info[5] = m->h.order; info[6] = m->h.off_pn ? 1 : 0; info[7] = 0;
+  info[5] = m->h.order; info[6] = m->h.off_pn ? 1 : 0; info[7] = m->n_devices();
   return IGLB200_OK;
   API_END
 }
@@ -936,6 +1198,7 @@ int iglb200_mesh_from_arena(const void *device_ptr, uint64_t bytes, int copy, ig
     m->arena = (char *)device_ptr;
     m->owns = false;
   }
+  m->device = plat::current_device();
   *out = m;
   return IGLB200_OK;
   API_END
@@ -997,7 +1260,7 @@ int iglb200_poll_device_error(void) {
 
 int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colmajor, int64_t n, double out[4]) {
   API_BEGIN
-  check_mesh(m);
+  m = mesh_here(m);
   if (n <= 0 || !P_host_colmajor || !out || m->h.nnodes == 0) throw std::invalid_argument("bad arguments");
   require_device();
   DevBuf<double> dP((size_t)3 * n), dD((size_t)n), dC((size_t)3 * n);
@@ -1009,7 +1272,7 @@ int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colma
   const uint32_t *perm = morton_perm(m, dP.p, n, scratch.p, 1, nullptr);
   launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p,
                              carve(scratch.p, n).sched}, nullptr);
-  plat::for_n(n, CountWinding{m->fnodes(), m->tri32(), dP.p, n, m->h.order, acc.p + 2}, nullptr);
+  plat::for_n(n, CountWinding{m->fnodes(), m->tri32(), dP.p, n, m->h.order, acc.p + 2, overflow_flag()}, nullptr);
   uint32_t h[4];
   plat::d2h(h, acc.p, 16, nullptr);
   plat::sync(nullptr);
@@ -1025,9 +1288,10 @@ int iglb200_profile_collect(char *out, uint64_t cap) { return plat::prof_collect
 int iglb200_signed_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP, int sign_type, double lower, double upper,
                                 double *S, int32_t *I, double *C, double *W, double *N, void *scratch, int sort_queries, void *stream) {
   API_BEGIN
-  check_mesh(m);
+  m = mesh_here(m);
   if (nP < 0 || (nP > 0 && (!P || !S || !I || !C))) throw std::invalid_argument("null pointer");
   require_device();
+  check_count(nP);
   plat::launch_counter() = 0;
   run_signed_distance(m, P, nP, sign_type, lower, upper, S, I, C, W, N, scratch, sort_queries, (stream_t)stream);
   return IGLB200_OK;
@@ -1036,9 +1300,10 @@ int iglb200_signed_distance_dev(const iglb200_mesh *m, const double *P, int64_t 
 int iglb200_squared_distance_dev(const iglb200_mesh *m, const double *P, int64_t nP, double *sqrD, int32_t *I, double *C,
                                  void *scratch, int sort_queries, void *stream) {
   API_BEGIN
-  check_mesh(m);
+  m = mesh_here(m);
   if (nP < 0 || (nP > 0 && (!P || !sqrD || !I || !C))) throw std::invalid_argument("null pointer");
   require_device();
+  check_count(nP);
   plat::launch_counter() = 0;
   run_squared_distance(m, P, nP, sqrD, I, C, scratch, sort_queries, (stream_t)stream);
   return IGLB200_OK;
@@ -1047,32 +1312,22 @@ int iglb200_squared_distance_dev(const iglb200_mesh *m, const double *P, int64_t
 int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, float accuracy_scale, double *W, void *scratch,
                          int sort_queries, void *stream) {
   API_BEGIN
-  check_mesh(m);
+  m = mesh_here(m);
   if (nQ < 0 || (nQ > 0 && (!Q || !W))) throw std::invalid_argument("null pointer");
   require_device();
+  check_count(nQ);
   plat::launch_counter() = 0;
   run_fwn(m, Q, nQ, accuracy_scale, W, scratch, sort_queries, (stream_t)stream);
   return IGLB200_OK;
   API_END
 }
 
-int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
-                            int sign_type, double lower, double upper, void *S, int s_is_f64, int32_t *I, void *C, int c_is_f64,
-                            int64_t c_rs, int64_t c_cs, void *W, int w_is_f64, void *N, int n_is_f64, int64_t n_rs, int64_t n_cs) {
-  API_BEGIN
-  check_mesh(m);
-  if (nP < 0 || (nP > 0 && (!P || !S || !I || !C))) throw std::invalid_argument("null pointer");
-  if (nP > 0 && (c_rs <= 0 || c_cs <= 0)) throw std::invalid_argument("strides must be positive");
-  require_device();
-  plat::launch_counter() = 0;
-#ifndef IGLB200_EMUL
-  if (N && nP > 0 && (n_rs <= 0 || n_cs <= 0)) throw std::invalid_argument("strides must be positive");
-  if (nP > 0 && p_is_f64 && p_rs == 1 && p_cs == nP && s_is_f64 && c_is_f64 && c_rs == 1 && c_cs == nP && (!W || w_is_f64) &&
-      (!N || (n_is_f64 && n_rs == 1 && n_cs == nP))) {
-    run_streamed(m, 0, (const double *)P, nP, sign_type, lower, upper, 2.0f, (double *)S, I, (double *)C, (double *)W, (double *)N);
-    return IGLB200_OK;
-  }
-#endif
+// whole-batch path for layouts the chunk pipeline does not take (arbitrary strides): synchronous, per-call allocations
+static void slow_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
+                                 int sign_type, double lower, double upper, void *S, int s_is_f64, int32_t *I, void *C, int c_is_f64,
+                                 int64_t c_rs, int64_t c_cs, void *W, int w_is_f64, void *N, int n_is_f64, int64_t n_rs, int64_t n_cs) {
+  check_count(nP);
+  plat::DeviceGuard dg(m->device);
   stream_t s = nullptr;
   DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP), dW(W ? (size_t)nP : 0), dN(N ? (size_t)3 * nP : 0);
   DevBuf<int32_t> dI((size_t)nP);
@@ -1085,60 +1340,117 @@ int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, 
   download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);
   if (W) download_scalar(dW, nP, W, w_is_f64, s);
   throw_if_overflow(s);
+}
+
+static int signed_distance_host(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
+                                int sign_type, double lower, double upper, void *S, int s_is_f64, int32_t *I, void *C, int c_is_f64,
+                                int64_t c_rs, int64_t c_cs, void *W, int w_is_f64, void *N, int n_is_f64, int64_t n_rs, int64_t n_cs,
+                                int64_t *shared_counter, int64_t shared_chunk) {
+  API_BEGIN
+  check_mesh(m);
+  if (nP < 0 || (nP > 0 && (!P || !S || !I || !C))) throw std::invalid_argument("null pointer");
+  if (nP > 0 && (c_rs <= 0 || c_cs <= 0 || p_rs <= 0 || p_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  if (N && nP > 0 && (n_rs <= 0 || n_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  if (sign_type < 0 || sign_type > IGLB200_SIGN_FAST_WINDING_NUMBER) throw std::domain_error("unknown signed distance type");
+  require_device();
+  plat::launch_counter() = 0;
+  // N is an output of PSEUDONORMAL only (signed_distance.cpp:125-131); with #F == 0 it is NaN for every type (:403)
+  if (sign_type != IGLB200_SIGN_PSEUDONORMAL && m->h.nF != 0) N = nullptr;
+  HostQuery q;
+  q.m = m; q.mode = 0; q.n = nP; q.sign_type = sign_type; q.lower = lower; q.upper = upper;
+  q.P = host_mat(P, p_is_f64, nP, p_rs, p_cs); q.C = host_mat(C, c_is_f64, nP, c_rs, c_cs); q.N = host_mat(N, n_is_f64, nP, n_rs, n_cs);
+  q.S = host_vec(S, s_is_f64); q.W = host_vec(W, w_is_f64); q.I = I; q.i_pinned = nP > 0 && plat::host_is_pinned(I);
+  if (nP > 0 && (q.P.kind == MAT_OTHER || q.C.kind == MAT_OTHER || q.N.kind == MAT_OTHER)) {
+    if (shared_counter) throw std::invalid_argument("cooperative calls need column-major or dense row-major matrices");
+    slow_signed_distance(m, P, p_is_f64, nP, p_rs, p_cs, sign_type, lower, upper, S, s_is_f64, I, C, c_is_f64, c_rs, c_cs, W, w_is_f64,
+                         N, n_is_f64, n_rs, n_cs);
+    return IGLB200_OK;
+  }
+  run_host_query(q, shared_counter, shared_chunk);
   return IGLB200_OK;
   API_END
 }
+
+int iglb200_signed_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
+                            int sign_type, double lower, double upper, void *S, int s_is_f64, int32_t *I, void *C, int c_is_f64,
+                            int64_t c_rs, int64_t c_cs, void *W, int w_is_f64, void *N, int n_is_f64, int64_t n_rs, int64_t n_cs) {
+  return signed_distance_host(m, P, p_is_f64, nP, p_rs, p_cs, sign_type, lower, upper, S, s_is_f64, I, C, c_is_f64, c_rs, c_cs, W, w_is_f64,
+                              N, n_is_f64, n_rs, n_cs, nullptr, 0);
+}
+int iglb200_signed_distance_coop(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
+                                 int sign_type, double lower, double upper, void *S, int s_is_f64, int32_t *I, void *C, int c_is_f64,
+                                 int64_t c_rs, int64_t c_cs, void *W, int w_is_f64, void *N, int n_is_f64, int64_t n_rs, int64_t n_cs,
+                                 int64_t *shared_chunk_counter, int64_t chunk_rows) {
+  if (!shared_chunk_counter) return fail(IGLB200_ERR_ARG, "null chunk counter");
+  return signed_distance_host(m, P, p_is_f64, nP, p_rs, p_cs, sign_type, lower, upper, S, s_is_f64, I, C, c_is_f64, c_rs, c_cs, W, w_is_f64,
+                              N, n_is_f64, n_rs, n_cs, shared_chunk_counter, chunk_rows);
+}
+int64_t iglb200_host_chunk_rows(int64_t nP, int n_devices) { return host_chunk_rows(nP, n_devices < 1 ? 1 : n_devices); }
 
 int iglb200_squared_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
                              void *sqrD, int d_is_f64, int32_t *I, void *C, int c_is_f64, int64_t c_rs, int64_t c_cs) {
   API_BEGIN
   check_mesh(m);
   if (nP < 0 || (nP > 0 && (!P || !sqrD || !I || !C))) throw std::invalid_argument("null pointer");
-  if (nP > 0 && (c_rs <= 0 || c_cs <= 0)) throw std::invalid_argument("strides must be positive");
+  if (nP > 0 && (c_rs <= 0 || c_cs <= 0 || p_rs <= 0 || p_cs <= 0)) throw std::invalid_argument("strides must be positive");
   require_device();
   plat::launch_counter() = 0;
-#ifndef IGLB200_EMUL
-  if (nP > 0 && p_is_f64 && p_rs == 1 && p_cs == nP && d_is_f64 && c_is_f64 && c_rs == 1 && c_cs == nP) {
-    run_streamed(m, 1, (const double *)P, nP, 0, 0.0, 0.0, 2.0f, (double *)sqrD, I, (double *)C, nullptr);
+  HostQuery q;
+  q.m = m; q.mode = 1; q.n = nP;
+  q.P = host_mat(P, p_is_f64, nP, p_rs, p_cs); q.C = host_mat(C, c_is_f64, nP, c_rs, c_cs);
+  q.S = host_vec(sqrD, d_is_f64); q.I = I; q.i_pinned = nP > 0 && plat::host_is_pinned(I);
+  if (nP > 0 && (q.P.kind == MAT_OTHER || q.C.kind == MAT_OTHER)) {
+    check_count(nP);
+    plat::DeviceGuard dg(m->device);
+    stream_t s = nullptr;
+    DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP);
+    DevBuf<int32_t> dI((size_t)nP);
+    DevBuf<char> scratch(iglb200_query_scratch_bytes(nP));
+    upload_points(P, p_is_f64, nP, p_rs, p_cs, dP, s);
+    run_squared_distance(m, dP.p, nP, dS.p, dI.p, dC.p, scratch.p, 1, s);
+    download_scalar(dS, nP, sqrD, d_is_f64, s);
+    plat::d2h(I, dI.p, (size_t)4 * nP, s);
+    download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);
+    throw_if_overflow(s);
     return IGLB200_OK;
   }
-#endif
-  stream_t s = nullptr;
-  DevBuf<double> dP, dS((size_t)nP), dC((size_t)3 * nP);
-  DevBuf<int32_t> dI((size_t)nP);
-  DevBuf<char> scratch(iglb200_query_scratch_bytes(nP));
-  upload_points(P, p_is_f64, nP, p_rs, p_cs, dP, s);
-  run_squared_distance(m, dP.p, nP, dS.p, dI.p, dC.p, scratch.p, 1, s);
-  download_scalar(dS, nP, sqrD, d_is_f64, s);
-  plat::d2h(I, dI.p, (size_t)4 * nP, s);
-  download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);
-  throw_if_overflow(s);
+  run_host_query(q, nullptr, 0);
   return IGLB200_OK;
   API_END
 }
 
-int iglb200_fwn_eval(const iglb200_mesh *m, const void *Q, int q_is_f64, int64_t nQ, int64_t q_rs, int64_t q_cs,
-                     float accuracy_scale, void *W, int w_is_f64) {
+static int winding_host(const iglb200_mesh *m, int mode, const void *Q, int q_is_f64, int64_t nQ, int64_t q_rs, int64_t q_cs,
+                        float accuracy_scale, void *W, int w_is_f64) {
   API_BEGIN
   check_mesh(m);
   if (nQ < 0 || (nQ > 0 && (!Q || !W))) throw std::invalid_argument("null pointer");
+  if (nQ > 0 && (q_rs <= 0 || q_cs <= 0)) throw std::invalid_argument("strides must be positive");
   require_device();
   plat::launch_counter() = 0;
-#ifndef IGLB200_EMUL
-  if (nQ > 0 && q_is_f64 && q_rs == 1 && q_cs == nQ && w_is_f64) {
-    run_streamed(m, 2, (const double *)Q, nQ, 0, 0.0, 0.0, accuracy_scale, nullptr, nullptr, nullptr, (double *)W);
+  HostQuery q;
+  q.m = m; q.mode = mode; q.n = nQ; q.acc = accuracy_scale;
+  q.P = host_mat(Q, q_is_f64, nQ, q_rs, q_cs); q.W = host_vec(W, w_is_f64);
+  if (nQ > 0 && q.P.kind == MAT_OTHER) {
+    check_count(nQ);
+    plat::DeviceGuard dg(m->device);
+    stream_t s = nullptr;
+    DevBuf<double> dQ, dW((size_t)nQ);
+    DevBuf<char> scratch(iglb200_query_scratch_bytes(nQ));
+    upload_points(Q, q_is_f64, nQ, q_rs, q_cs, dQ, s);
+    if (mode == 2) run_fwn(m, dQ.p, nQ, accuracy_scale, dW.p, scratch.p, 1, s);
+    else run_exact_winding(m, dQ.p, nQ, dW.p, scratch.p, 1, s);
+    download_scalar(dW, nQ, W, w_is_f64, s);
+    plat::sync(s);
+    throw_if_overflow(s);
     return IGLB200_OK;
   }
-#endif
-  stream_t s = nullptr;
-  DevBuf<double> dQ, dW((size_t)nQ);
-  DevBuf<char> scratch(iglb200_query_scratch_bytes(nQ));
-  upload_points(Q, q_is_f64, nQ, q_rs, q_cs, dQ, s);
-  run_fwn(m, dQ.p, nQ, accuracy_scale, dW.p, scratch.p, 1, s);
-  download_scalar(dW, nQ, W, w_is_f64, s);
-  plat::sync(s);
+  run_host_query(q, nullptr, 0);
   return IGLB200_OK;
   API_END
+}
+int iglb200_fwn_eval(const iglb200_mesh *m, const void *Q, int q_is_f64, int64_t nQ, int64_t q_rs, int64_t q_cs,
+                     float accuracy_scale, void *W, int w_is_f64) {
+  return winding_host(m, 2, Q, q_is_f64, nQ, q_rs, q_cs, accuracy_scale, W, w_is_f64);
 }
 
 // igl::marching_cubes(S, GV, GI, isovalue, V, F[, E2V]) (marching_cubes.cpp:114-176): cubes given by their 8 corner ids
@@ -1174,28 +1486,15 @@ int iglb200_marching_cubes_sparse(const double *S, const double *GV, int64_t n, 
 // igl::winding_number(V,F,O,W) (winding_number.cpp:17-52): exact, hierarchical, double precision
 int iglb200_winding_number(const iglb200_mesh *m, const void *O, int o_is_f64, int64_t nO, int64_t o_rs, int64_t o_cs,
                            void *W, int w_is_f64) {
-  API_BEGIN
-  check_mesh(m);
-  if (nO < 0 || (nO > 0 && (!O || !W))) throw std::invalid_argument("null pointer");
-  require_device();
-  plat::launch_counter() = 0;
-  stream_t s = nullptr;
-  DevBuf<double> dO, dW((size_t)nO);
-  DevBuf<char> scratch(iglb200_query_scratch_bytes(nO));
-  upload_points(O, o_is_f64, nO, o_rs, o_cs, dO, s);
-  run_exact_winding(m, dO.p, nO, dW.p, scratch.p, 1, s);
-  download_scalar(dW, nO, W, w_is_f64, s);
-  plat::sync(s);
-  throw_if_overflow(s);
-  return IGLB200_OK;
-  API_END
+  return winding_host(m, 3, O, o_is_f64, nO, o_rs, o_cs, 0.f, W, w_is_f64);
 }
 int iglb200_winding_number_dev(const iglb200_mesh *m, const double *O, int64_t nO, double *W, void *scratch, int sort_queries,
                                void *stream) {
   API_BEGIN
-  check_mesh(m);
+  m = mesh_here(m);
   if (nO < 0 || (nO > 0 && (!O || !W))) throw std::invalid_argument("null pointer");
   require_device();
+  check_count(nO);
   plat::launch_counter() = 0;
   run_exact_winding(m, O, nO, W, scratch, sort_queries, (stream_t)stream);
   return IGLB200_OK;
@@ -1306,7 +1605,7 @@ int iglb200_grid_get_s(const iglb200_grid *g, double *S) {
 }
 int iglb200_grid_signed_distance(iglb200_grid *g, const iglb200_mesh *m, int sign_type, double lower, double upper) {
   API_BEGIN
-  check_grid(g); check_mesh(m);
+  check_grid(g); m = mesh_here(m);
   require_device();
   const int64_t n = g->n;
   DevBuf<int32_t> I((size_t)n);

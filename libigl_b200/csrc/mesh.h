@@ -34,6 +34,15 @@ struct iglb200_mesh {
   bool owns = true;
   double build_ms = 0.0;
   int device = 0;
+  // copies of the arena on the other devices of the process's group (group.h), indexed by device; the entry of
+  // `device` itself is null.  Empty for a single-device handle.
+  std::vector<iglb200_mesh *> reps;
+  // the handle whose arena lives on device `d`, or null
+  const iglb200_mesh *on(int d) const {
+    if (d == device) return this;
+    return (d >= 0 && (size_t)d < reps.size()) ? reps[(size_t)d] : nullptr;
+  }
+  int n_devices() const { int k = 1; for (const iglb200_mesh *r : reps) k += r ? 1 : 0; return k; }
   const double *tri64() const { return (const double *)(arena + h.off_tri64); }
   const float4 *tri32() const { return (const float4 *)(arena + h.off_tri32); }
   const float4 *triq() const { return (const float4 *)(arena + h.off_triq); }

@@ -17,10 +17,12 @@
 #include <stdexcept>
 #include <vector>
 #include <algorithm>
+#include <memory>
 
 namespace plat {
 // kernels (ours + cub passes) enqueued by the calling thread; reset by the C ABI per call
 inline int &launch_counter() { static thread_local int c = 0; return c; }
+static constexpr int MAX_DEVICES = 64;
 }  // namespace plat
 
 #ifdef IGLB200_EMUL
@@ -52,6 +54,18 @@ inline void d2h(void *h, const void *d, size_t n, stream_t) { std::memcpy(h, d, 
 inline void d2d(void *d, const void *s, size_t n, stream_t) { std::memcpy(d, s, n); }
 inline void dev_memset(void *d, int v, size_t n, stream_t) { std::memset(d, v, n); }
 inline void sync(stream_t) {}
+// "devices" of the emulation are virtual: memory is host memory, the current device is a per-thread integer
+inline int &emul_dev() { static thread_local int d = 0; return d; }
+inline int current_device() { return emul_dev(); }
+inline void set_device(int d) { emul_dev() = d; }
+inline int device_count() { return 16; }
+inline void *pinned_alloc(size_t bytes) { void *p = std::malloc(bytes ? bytes : 1); if (!p) throw std::bad_alloc(); return p; }
+inline void pinned_free(void *p) { std::free(p); }
+inline bool host_is_pinned(const void *) { return false; }   // every host buffer is staged: the emulation exercises that path
+inline stream_t stream_create() { return nullptr; }
+inline void stream_destroy(stream_t) {}
+inline void peer_copy(void *d, int, const void *s_, int, size_t n, stream_t) { std::memcpy(d, s_, n); }
+inline void pin_thread_near_device(int) {}
 // f(i) for i in [0,n)
 template <class F> void for_n(int64_t n, F f, stream_t) { for (int64_t i = 0; i < n; ++i) f(i); }
 // f(i) for i in [0,*count) with the count living in "device" memory
@@ -82,6 +96,8 @@ inline void sort_pairs_u64(void *, size_t, const uint64_t *kin, uint64_t *kout, 
 // ------------------------------------------------------------------ CUDA
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <sched.h>
+#include <cctype>
 #define HD __host__ __device__ __forceinline__
 #define DEVFN __device__ __forceinline__
 typedef cudaStream_t stream_t;
@@ -124,9 +140,52 @@ inline void d2d(void *d, const void *s_, size_t n, stream_t s) { if (n) PLAT_CHE
 inline void dev_memset(void *d, int v, size_t n, stream_t s) { if (n) PLAT_CHECK(cudaMemsetAsync(d, v, n, s)); }
 inline void sync(stream_t s) { PLAT_CHECK(cudaStreamSynchronize(s)); }
 
-inline int sm_count() {
-  static int n = [] { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
-  return n;
+inline int current_device() { int d = 0; PLAT_CHECK(cudaGetDevice(&d)); return d; }
+inline void set_device(int d) { PLAT_CHECK(cudaSetDevice(d)); }
+inline int device_count() { int n = 0; PLAT_CHECK(cudaGetDeviceCount(&n)); return n; }
+inline void *pinned_alloc(size_t bytes) { void *p = nullptr; PLAT_CHECK(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable)); return p; }
+inline void pinned_free(void *p) { if (p) cudaFreeHost(p); }
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory can be the source/target of truly asynchronous copies
+inline bool host_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+inline stream_t stream_create() { cudaStream_t s = nullptr; PLAT_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
+inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
+inline void peer_copy(void *d, int ddev, const void *s_, int sdev, size_t n, stream_t s) {
+  if (n) PLAT_CHECK(cudaMemcpyPeerAsync(d, ddev, s_, sdev, n, s));
+}
+// run the calling thread on the CPUs next to the GPU (pinned staging buffers are then first-touched on that NUMA node)
+inline void pin_thread_near_device(int dev) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) { cudaGetLastError(); return; }
+  for (char *c = bus; *c; ++c) *c = (char)tolower(*c);
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  FILE *f = fopen(path.c_str(), "r");
+  if (!f) return;
+  char line[4096] = {0};
+  const bool ok = fgets(line, sizeof(line), f) != nullptr;
+  fclose(f);
+  if (!ok) return;
+  cpu_set_t set; CPU_ZERO(&set);
+  int any = 0;
+  char *save = nullptr;
+  for (char *tok = strtok_r(line, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); ++any; }
+  }
+  if (any) sched_setaffinity(0, sizeof(set), &set);
+}
+
+inline int sm_count() {   // of the current device (cached per device)
+  static int cache[64] = {0};
+  int d = 0, v = 148;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return v;
+  if (!cache[d]) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); cache[d] = v; }
+  return cache[d];
 }
 
 template <class F> __global__ void __launch_bounds__(256) k_for_n(int64_t n, F f) {
@@ -159,11 +218,13 @@ template <class F> void tiles_dyn(const uint32_t *ntiles, F f, stream_t s) {
   launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }
-// scratch for cub, grown on demand (one per thread; builds are serialised per handle)
+// scratch for cub, grown on demand (one per thread and device; builds are serialised per handle)
 struct ScanTemp { void *p = nullptr; size_t cap = 0; ~ScanTemp() { dev_free(p); } };
 inline void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, stream_t s) {
   if (n <= 0) return;
-  static thread_local ScanTemp tmp;
+  if (n > 0x7FFFFFFF) throw std::invalid_argument("scan of more than 2^31-1 items");
+  static thread_local ScanTemp tmps[MAX_DEVICES];
+  ScanTemp &tmp = tmps[current_device() % MAX_DEVICES];
   size_t need = 0;
   PLAT_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, s));
   if (need > tmp.cap) { sync(s); dev_free(tmp.p); tmp.p = dev_alloc(need); tmp.cap = need; }
@@ -181,10 +242,12 @@ inline size_t sort_pairs64_temp_bytes(int64_t n) {
   return need + 256;
 }
 inline void sort_pairs_u64(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, stream_t s) {
+  if (n > 0x7FFFFFFF) throw std::invalid_argument("sort of more than 2^31-1 items");
   PLAT_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 64, s));
   launch_counter() += 9;
 }
 inline void sort_pairs_u32(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, stream_t s) {
+  if (n > 0x7FFFFFFF) throw std::invalid_argument("sort of more than 2^31-1 items");
   PLAT_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
   launch_counter() += 4;
 }
@@ -232,6 +295,23 @@ inline int prof_collect(char *out, size_t cap) {
 #endif
 
 namespace plat {
+// one T per (host thread, device): streams, workspaces and flags must never be used on a device other than the one
+// they were created on
+template <class T> T &per_device() {
+  static thread_local std::unique_ptr<T> slot[MAX_DEVICES];
+  const int d = current_device();
+  if (d < 0 || d >= MAX_DEVICES) throw std::invalid_argument("device index out of range");
+  if (!slot[d]) slot[d].reset(new T());
+  return *slot[d];
+}
+// make `device` current for the lifetime of the guard
+struct DeviceGuard {
+  int prev; bool switched;
+  explicit DeviceGuard(int device) : prev(current_device()), switched(device != prev) { if (switched) set_device(device); }
+  ~DeviceGuard() { if (switched) { try { set_device(prev); } catch (...) {} } }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 // RAII device array
 template <class T> struct DevBuf {
   T *p = nullptr;

@@ -371,8 +371,10 @@ DEVFN void node_omega4(const FwnNode &n, const Lanes4 &NX, Lanes4 q0, Lanes4 q1,
 DEVFN bool finite_f(float x) { return (plat::f2u(x) & 0x7F800000u) != 0x7F800000u; }
 
 // Solid angle (not yet divided by 4 pi) of the whole soup seen from q.
+// `overflow` (nullable) is raised when the stack cannot hold a pushed child: the caller turns it into an error, the
+// truncated sum is never returned as a result.
 DEVFN float winding_solid_angle(const FwnNode *nodes, const float4 *tri32, float qx, float qy, float qz, float acc2,
-                                int order, uint32_t *stack, uint32_t *visits /*nullable: [nodes, tris]*/) {
+                                int order, uint32_t *stack, uint32_t *visits /*nullable: [nodes, tris]*/, uint32_t *overflow = nullptr) {
   float sum = 0.f;
   int sp = 0;
   stack[sp++] = 0;
@@ -409,7 +411,10 @@ DEVFN float winding_solid_angle(const FwnNode *nodes, const float4 *tri32, float
       if (!((descend >> i) & 1u)) continue;
       const uint32_t c = ch[i];
       if (c == EMPTY) continue;
-      if (c & INTERNAL_BIT) { if (sp < FWN_STACK) stack[sp++] = c & ~INTERNAL_BIT; }
+      if (c & INTERNAL_BIT) {
+        if (sp < FWN_STACK) stack[sp++] = c & ~INTERNAL_BIT;
+        else if (overflow) *overflow = 1u;   // plain store of the same value by every thread that overflows
+      }
       else { sum += tri_solid_angle(tri32, c, qx, qy, qz); if (visits) visits[1]++; }
     }
   }

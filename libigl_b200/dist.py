@@ -78,3 +78,62 @@ def gather_rows(local: np.ndarray, n_total: int, dst: int = 0, group=None):
     out = np.concatenate(parts, axis=0)
     assert out.shape[0] == n_total
     return out
+
+
+class SharedArrays:
+    """ONE query set and its outputs in POSIX shared memory, mapped by every process of the job (one per GPU):
+    P [3, n] and C [3, n] doubles (column-major n x 3), S, W [n] doubles, I [n] int32, and the int64 chunk counter the
+    cooperative C-ABI calls (iglb200_signed_distance_coop) deal work from.  The mapping can be page-locked
+    (cudaHostRegister) so that every GPU DMA-writes its chunks straight into it."""
+
+    def __init__(self, name: str, n: int, create: bool):
+        from multiprocessing import shared_memory
+        self.n = int(n)
+        al = lambda x: (x + 4095) & ~4095
+        self._off = {}
+        off = 4096
+        for key, nbytes in (("P", 24 * n), ("S", 8 * n), ("I", 4 * n), ("C", 24 * n), ("W", 8 * n)):
+            self._off[key] = off
+            off += al(nbytes)
+        self.nbytes = off
+        if create:
+            try:
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=self.nbytes)
+        else:
+            import time
+            for _ in range(600):
+                try:
+                    self.shm = shared_memory.SharedMemory(name=name)
+                    if self.shm.size >= self.nbytes:
+                        break
+                    self.shm.close()
+                except FileNotFoundError:
+                    pass
+                time.sleep(0.05)
+            else:
+                raise RuntimeError("shared query set never appeared")
+        buf = self.shm.buf
+        self.counter = np.frombuffer(buf, np.int64, 1, 0)
+        self.P = np.frombuffer(buf, np.float64, 3 * n, self._off["P"]).reshape(3, n)
+        self.S = np.frombuffer(buf, np.float64, n, self._off["S"])
+        self.I = np.frombuffer(buf, np.int32, n, self._off["I"])
+        self.C = np.frombuffer(buf, np.float64, 3 * n, self._off["C"]).reshape(3, n)
+        self.W = np.frombuffer(buf, np.float64, n, self._off["W"])
+        self._registered = False
+
+    def address(self):
+        return self.counter.ctypes.data
+
+    def close(self, unlink=False):
+        self.counter = self.P = self.S = self.I = self.C = self.W = None
+        try:
+            self.shm.close()
+            if unlink:
+                self.shm.unlink()
+        except Exception:
+            pass

@@ -139,3 +139,123 @@ def test_c_abi_header_is_plain_c(tmp_path):
                     "-L" + libdir, "-liglb200", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("iglb200"), r.stdout + r.stderr
+
+
+def _sd_arrays(n):
+    return (np.empty(n), np.empty(n, np.int32), np.empty((n, 3), order="F"), np.empty(n))
+
+
+def test_device_group_deals_chunks_to_every_device(emul_api, monkeypatch):
+    """iglb200_init(n): the mesh is replicated, host queries are dealt chunk by chunk to the workers of every device,
+    and the result is bit-identical to the single-device call — in every host layout the chunk pipeline takes."""
+    from libigl_b200 import synth
+    api = emul_api
+    V, F = synth.icosphere(3)
+    P = synth.grid_points(*synth.bbox(V), 36, 1.5)           # 46 656 rows: above the inline threshold
+    api.init(1)
+    m1 = api.Mesh(V, F, 2)
+    assert m1.info()["n_devices"] == 1
+    ref = m1.signed_distance(P, return_W=True)
+    D1 = m1.squared_distance(P)
+    W1 = m1.fast_winding_number(P)
+    m1.close()
+    try:
+        api.init(3)
+        assert api.group_info()["devices"] == 3
+        m = api.Mesh(V, F, 2)
+        assert m.info()["n_devices"] == 3
+        for layout in ("C", "F"):
+            for dt in (np.float64, np.float32):
+                Pl = np.array(P, dtype=dt, order=layout)
+                out = m.signed_distance(Pl, return_W=True)
+                if dt == np.float64:
+                    for a, b in zip(out, ref):
+                        assert np.array_equal(a, b, equal_nan=True), (layout, dt)
+                else:
+                    out64 = m.signed_distance(Pl.astype(np.float64), return_W=True)
+                    for a, b in zip(out, out64):
+                        assert np.array_equal(a, b, equal_nan=True), (layout, dt)
+        for a, b in zip(m.squared_distance(np.ascontiguousarray(P)), D1):
+            assert np.array_equal(a, b)
+        assert np.array_equal(m.fast_winding_number(P), W1)
+        m.close()
+    finally:
+        api.init(1)
+
+
+def test_row_major_outputs_and_float_outputs(emul_api):
+    """C / N as dense row-major matrices and S / C / W as float32 go through the same chunk pipeline."""
+    import ctypes as C
+    from libigl_b200 import synth
+    api = emul_api
+    V, F = synth.icosphere(2)
+    P = synth.random_points(40000, -1.5, 1.5, 3)
+    m = api.Mesh(V, F, 2, pseudonormals=True)
+    S0, I0, C0, N0 = m.signed_distance(P, sign_type=0)
+    n = P.shape[0]
+    vp = C.c_void_p
+    for dt, f64 in ((np.float64, 1), (np.float32, 0)):
+        S = np.empty(n, dt); I = np.empty(n, np.int32); Cr = np.empty((n, 3), dt); Nr = np.empty((n, 3), dt)
+        Pr = np.ascontiguousarray(P)
+        api.check(api.lib.iglb200_signed_distance(m.h, Pr.ctypes.data_as(vp), 1, n, 3, 1, 0, float(np.finfo(float).tiny),
+                                                  float(np.finfo(float).max), S.ctypes.data_as(vp), f64, I.ctypes.data_as(vp),
+                                                  Cr.ctypes.data_as(vp), f64, 3, 1, None, 1, Nr.ctypes.data_as(vp), f64, 3, 1))
+        assert np.array_equal(I, I0)
+        assert np.array_equal(S, S0.astype(dt)) and np.array_equal(Cr, np.asarray(C0).astype(dt)) and np.array_equal(Nr, np.asarray(N0).astype(dt))
+    # N is an output of PSEUDONORMAL only: other sign types leave the caller's array untouched
+    Nr = np.full((n, 3), 7.0)
+    S = np.empty(n); I = np.empty(n, np.int32); Cr = np.empty((n, 3))
+    api.check(api.lib.iglb200_signed_distance(m.h, Pr.ctypes.data_as(vp), 1, n, 3, 1, 4, float(np.finfo(float).tiny),
+                                              float(np.finfo(float).max), S.ctypes.data_as(vp), 1, I.ctypes.data_as(vp),
+                                              Cr.ctypes.data_as(vp), 1, 3, 1, None, 1, Nr.ctypes.data_as(vp), 1, 3, 1))
+    assert (Nr == 7.0).all()
+    m.close()
+
+
+COOP_WORKER = r'''
+import os, sys, ctypes as C
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import emul
+from libigl_b200 import synth
+from libigl_b200.dist import broadcast_mesh, SharedArrays
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+api = emul.api()
+V, F = synth.icosphere(3)
+P = synth.grid_points(*synth.bbox(V), 30, 1.5)
+n = P.shape[0]
+mesh = api.Mesh(V, F, 2) if rank == 0 else None
+mesh, keep = broadcast_mesh(api, mesh, src=0)
+# ONE query set in shared host memory; every rank takes chunks off one shared counter
+sh = SharedArrays("iglb200_coop_test", n, create=(rank == 0))
+if rank == 0:
+    sh.P[:] = P.T
+    sh.counter[0] = 0
+    sh.S[:] = -777.0
+dist.barrier()
+chunk = 2048
+mesh.signed_distance_coop(sh, chunk)
+dist.barrier()
+if rank == 0:
+    S1, I1, C1, W1 = mesh.signed_distance(P, return_W=True)
+    assert np.array_equal(sh.S, S1, equal_nan=True) and np.array_equal(sh.I, I1) and np.array_equal(sh.C.T, C1)
+    assert np.array_equal(sh.W, W1, equal_nan=True)
+    assert sh.counter[0] >= (n + chunk - 1) // chunk + world - 1     # every rank saw the end of the rows
+    print("COOP_OK", world, n)
+dist.barrier()
+sh.close(unlink=(rank == 0))
+dist.destroy_process_group()
+'''
+
+
+def test_cooperative_processes_share_one_query_set_gloo(tmp_path):
+    import emul
+    emul.build()
+    script = tmp_path / "coop.py"
+    script.write_text(COOP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "COOP_OK 2" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
