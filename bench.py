@@ -1,25 +1,29 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: igl::signed_distance (FAST_WINDING_NUMBER sign)
-on BASELINE.json config c2 — 256^3 grid queries against a 1 M-face torus-knot
-mesh — as queries/second.
+"""Benchmark of the hot path, one BASELINE.json config per run (default c2: igl::signed_distance with the
+FAST_WINDING_NUMBER sign, 256^3 grid queries against a 1 M-face torus-knot mesh), as queries/second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4|c5] [--impl reference]
 
-A "step" is one pass of the hot path over the whole batch of queries.
-  value : device-resident throughput (queries already in HBM), CUDA events on
-          the launching stream, max over ranks.
-  e2e   : the same metric through the host-pointer C ABI call a libigl user
-          makes (pinned host buffers, H2D + kernels + D2H inside the timed region).
-  roofline : the dominant kernel against the measured HBM peak (the path is
-          latency/FP32 bound, not HBM bound — the fp32 fraction is reported too).
-  cpu_baseline : the oracle (genuine reference FWN core + restated f64 AABB)
-          under igl::parallel_for semantics on this box's host cores, bounded sample.
-Under torchrun (N>1) rank 0 builds the trees, the arena is broadcast with NCCL,
-every rank answers its own 256^3 grid (weak scaling), rank 0 prints one JSON line.
+A "step" is one pass of the hot path over ONE FIXED query set (strong scaling: the set does not grow with N).
+  value : device-resident throughput.  The query set and the outputs live in rank 0's HBM.  Per step: rank 0
+          Morton-sorts once; every rank (one process per GPU, torchrun) takes super-chunks of sorted queries off a
+          counter in rank 0's memory (atomics over NVLink), reads them from and writes its results to rank 0's
+          memory directly (CUDA-IPC-mapped peer memory: the gather is the kernels' own epilogue); rank 0 un-sorts.
+          Two tiny NCCL all-reduces per step order the streams.  CUDA events on the launching streams, max over ranks.
+  e2e   : the same metric through the host-pointer C ABI call a libigl user makes, H2D + kernels + D2H inside the
+          timed region, page-locked host arrays.  N > 1: the ranks call iglb200_signed_distance_coop on ONE query set in
+          shared host memory, dealing chunks off one shared counter; each GPU DMA-writes its chunks into the shared
+          S/I/C.  Extra keys: `pageable` (plain malloc'ed arrays, what Eigen::MatrixXd gives) and `single_process`
+          (ONE process driving all N GPUs through iglb200_init(N) — the call a C++ user of the drop-in makes).
+  roofline : the dominant kernel against the FP32 ceiling (executed work; both the theoretical and the
+          micro-benchmarked peak), `roofline_hbm` the same kernel against the measured HBM peak (not the bound).
+  cpu_baseline : the oracle (genuine reference FWN core + restated f64 AABB) under igl::parallel_for semantics on
+          this box's host cores, bounded sample (N = 1 only).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -34,10 +38,25 @@ sys.path.insert(0, ROOT)
 
 from libigl_b200 import synth  # noqa: E402
 
-METRIC = "signed_distance_fwn_queries_per_sec"
 UNIT = "queries/s"
-BYTES_PER_QUERY = 36          # P 12 B in; S 4 + I 4 + C 12 + W 4 out (fp32 SoA accounting)
-FLOP_NODE_FWN, FLOP_TRI_FWN, FLOP_NODE_CP, FLOP_TRI_CP = 372, 100, 50, 85  # SURVEY §8(d)
+# algorithmic HBM bytes per query (fp32 SoA accounting) and flops of the REFERENCE algorithm per unit of work
+BYTES_PER_QUERY = {"sd": 36, "cp": 32, "cloud": 16}
+FLOP_NODE_FWN, FLOP_TRI_FWN, FLOP_NODE_CP, FLOP_TRI_CP = 372, 100, 50, 85
+# flops our search kernel EXECUTES per lane (DESIGN.md "Kernels"): a node visit = 4 child bounds, a face test = tri_dist_f32
+OURS_FLOP_CP_NODE_LANE, OURS_FLOP_CP_FACE_LANE = 68, 76
+
+CONFIGS = {
+    "c1": dict(kind="sd", metric="signed_distance_fwn_queries_per_sec", mesh=("icosphere", 4), grid=64, scale=1.5,
+               name="c1: igl::signed_distance(FAST_WINDING_NUMBER) 64^3 grid vs 4x-upsampled icosahedron sphere"),
+    "c2": dict(kind="sd", metric="signed_distance_fwn_queries_per_sec", mesh=("knot", 1_000_000), grid=256, scale=1.1,
+               name="c2: igl::signed_distance(FAST_WINDING_NUMBER) 256^3 grid vs 1M-face torus-knot mesh"),
+    "c3": dict(kind="cp", metric="aabb_squared_distance_queries_per_sec", mesh=("noisy", 9), nq=10_000_000,
+               name="c3: igl::AABB::squared_distance 10M random points vs 5M-face noisy sphere"),
+    "c4": dict(kind="cloud", metric="cloud_fast_winding_number_queries_per_sec", npts=2_000_000, nq=20_000_000,
+               name="c4: point-cloud fast_winding_number (order 2, beta 2), 2M oriented points, 20M queries"),
+    "c5": dict(kind="sd", metric="signed_distance_fwn_queries_per_sec", mesh=("knot", 10_000_000), grid=512, scale=1.1,
+               name="c5: igl::signed_distance(FAST_WINDING_NUMBER) 512^3 grid vs 10M-face torus-knot mesh, query-sharded"),
+}
 
 
 def peaks():
@@ -88,71 +107,122 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(n_faces, grid, rank=0):
-    V, F = synth.torus_knot(*synth.knot_dims(n_faces))
-    if os.environ.get("IGLB200_BENCH_SHUFFLE_FACES"):   # tuning aid: same mesh, rows of F in random order
-        F = np.ascontiguousarray(F[np.random.default_rng(0).permutation(F.shape[0])])
-    lo, hi = synth.bbox(V)
-    # every rank answers a different grid of the same size (weak scaling): scale 1.1, 1.11, ...
-    P = synth.grid_points(lo, hi, grid, 1.1 + 0.01 * rank)
-    return V, F, P
+# ------------------------------------------------------------------------------------------------ workloads
+def make_mesh(cfg, args):
+    kind, arg = cfg["mesh"]
+    if kind == "icosphere":
+        return synth.icosphere(arg)
+    if kind == "knot":
+        V, F = synth.torus_knot(*synth.knot_dims(args.faces or arg))
+        if os.environ.get("IGLB200_BENCH_SHUFFLE_FACES"):   # tuning aid: same mesh, rows of F in random order
+            F = np.ascontiguousarray(F[np.random.default_rng(0).permutation(F.shape[0])])
+        return V, F
+    if kind == "noisy":
+        return synth.noisy_sphere(arg if not args.faces else max(2, int(round(np.log(args.faces / 20.0) / np.log(4.0)))), 0.01, 0)
+    raise ValueError(kind)
 
 
+def make_queries(cfg, args, V):
+    if cfg["kind"] == "sd":
+        g = args.grid or cfg["grid"]
+        lo, hi = synth.bbox(V)
+        return synth.grid_points(lo, hi, g, cfg["scale"]), g
+    return synth.random_points(args.queries or cfg["nq"], -1.5, 1.5, 1), 0
+
+
+def make_cloud(cfg, args):
+    V, F = synth.icosphere(7)
+    Pc, N, A = synth.oriented_cloud(V, F, args.faces or cfg["npts"], 2)
+    Q = synth.random_points(args.queries or cfg["nq"], -1.5, 1.5, 2)
+    return Pc, N, A, Q
+
+
+def config_dict(cfg, args, n_units, nq, grid, world):
+    d = {"workload": cfg["name"], "config": args.config, "queries": int(nq), "n_gpus": world,
+         "sharding": "one fixed query set; super-chunks of Morton-sorted queries dealt dynamically to the GPUs" if world > 1 else "single GPU",
+         "l2": "inputs+outputs per step exceed the 126 MB L2 (c2: 1.1 GB); no explicit flush", "sort_queries": int(args.sort)}
+    if cfg["kind"] == "cloud":
+        d["points"] = int(n_units)
+    else:
+        d["faces"] = int(n_units)
+    if grid:
+        d["grid"] = int(grid)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_sample(P, grid, target_queries):
-    """A Morton-compact sample of the workload: whole z-slabs from the middle of the grid."""
-    per = grid * grid
-    nsl = max(1, min(grid, int(round(target_queries / per))))
-    z0 = (grid - nsl) // 2
-    return P[z0 * per:(z0 + nsl) * per], f"{nsl} central z-slabs of the {grid}^3 grid = {nsl * per} queries"
+    """A compact sample of the workload: whole z-slabs from the middle of a grid, a leading block of random queries."""
+    if grid:
+        per = grid * grid
+        nsl = max(1, min(grid, int(round(target_queries / per))))
+        z0 = (grid - nsl) // 2
+        return P[z0 * per:(z0 + nsl) * per], f"{nsl} central z-slabs of the {grid}^3 grid = {nsl * per} queries"
+    k = int(max(1000, min(P.shape[0], target_queries)))
+    return P[:k], f"the first {k} of the {P.shape[0]} random queries"
 
 
-def run_cpu(V, F, P, grid, budget_s, steps=1, warmup=0):
-    """oracle = genuine reference FWN (oracle/_ref) + restated f64 AABB (port), timed like
-    signed_distance.cpp:90-138 does the work: one parallel_for pass per structure."""
+def run_cpu(cfg, args, budget_s, steps=1, warmup=0):
+    """kind sd: genuine reference FWN (oracle/_ref) + restated f64 AABB (port), one parallel_for pass per structure as
+    signed_distance.cpp:90-138 does the work; cp: the restated AABB alone; cloud: the restated octree evaluation."""
     import oracle
+    kind = cfg["kind"]
+    build_s = {}
+    if kind == "cloud":
+        Pc, N, A, Q = make_cloud(cfg, args)
+        t0 = time.perf_counter()
+        cl = oracle.PortCloud(Pc, N, A, 2)
+        build_s["octree+precompute"] = time.perf_counter() - t0
+        fn = lambda X: cl.eval(X, 2.0)
+        P, grid, n_units = Q, 0, Pc.shape[0]
+        what = "restated igl::octree + fast_winding_number(P,N,A,...) (oracle port)"
+    else:
+        V, F = make_mesh(cfg, args)
+        P, grid = make_queries(cfg, args, V)
+        n_units = F.shape[0]
+        t0 = time.perf_counter()
+        tree = oracle.PortAABB(V, F)
+        build_s["aabb"] = time.perf_counter() - t0
+        if kind == "sd":
+            t0 = time.perf_counter()
+            fwn = oracle.RefFwn(V, F, 2)
+            build_s["fwn"] = time.perf_counter() - t0
+
+            def fn(X):
+                sqrD, I, C = tree.squared_distance(X)
+                w = fwn.winding(X).astype(np.float32).astype(np.float64)
+                return (1.0 - 2.0 * np.abs(w)) * np.sqrt(sqrD)
+            what = "genuine UT_SolidAngle (oracle/_ref) + restated f64 igl::AABB (oracle port)"
+        else:
+            fn = lambda X: tree.squared_distance(X)
+            what = "restated f64 igl::AABB (oracle port)"
+    probe, _ = cpu_sample(P, grid, max(grid * grid, 20000))
     t0 = time.perf_counter()
-    tree = oracle.PortAABB(V, F)
-    t_tree = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    fwn = oracle.RefFwn(V, F, 2)
-    t_fwn = time.perf_counter() - t0
-    # calibrate on ~1/64 of a slab budget
-    probe, _ = cpu_sample(P, grid, grid * grid)
-    t0 = time.perf_counter()
-    oracle.signed_distance_fwn(probe, V, F, tree=tree, fwn=fwn)
+    fn(probe)
     rate = probe.shape[0] / (time.perf_counter() - t0)
     sample, desc = cpu_sample(P, grid, rate * budget_s)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        _, _, _, _, cnt = cpu_pass(oracle, sample, V, F, tree, fwn)
+        fn(sample)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
-    return dict(value=sample.shape[0] / t, ms_per_step=t * 1e3, sample=desc, n=sample.shape[0], cores=oracle.num_threads(),
-                build_s=dict(aabb=t_tree, fwn=t_fwn), counters=cnt)
-
-
-def cpu_pass(oracle, sample, V, F, tree, fwn):
-    sqrD, I, C = tree.squared_distance(sample)
-    w = fwn.winding(sample).astype(np.float32).astype(np.float64)
-    S = (1.0 - 2.0 * np.abs(w)) * np.sqrt(sqrD)
-    return S, I, C, w, None
+    return dict(value=sample.shape[0] / t, ms_per_step=t * 1e3, sample=desc + "; " + what, n=sample.shape[0],
+                cores=oracle.num_threads(), build_s=build_s, n_units=n_units, nq=P.shape[0], grid=grid)
 
 
 def reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    V, F, P = workload(args.faces, args.grid, 0)
-    r = run_cpu(V, F, P, args.grid, budget_s=args.cpu_seconds, steps=args.steps, warmup=args.warmup)
+    cfg = CONFIGS[args.config]
+    r = run_cpu(cfg, args, budget_s=args.cpu_seconds, steps=args.steps, warmup=args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
-        "config": config_dict(args, F.shape[0], P.shape[0]),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": r["sample"] + "; genuine UT_SolidAngle (oracle/_ref) + restated f64 igl::AABB (oracle port)",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 distance + f32 winding number", "data": "synthetic",
+        "config": config_dict(cfg, args, r["n_units"], r["nq"], r["grid"], args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                          "build_s": r["build_s"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -160,42 +230,110 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def config_dict(args, nF, nQ):
-    return {"workload": f"c2: igl::signed_distance(FAST_WINDING_NUMBER) {args.grid}^3 grid vs {nF}-face torus-knot mesh",
-            "faces": int(nF), "queries_per_gpu": int(nQ), "grid": args.grid,
-            "l2": "inputs+outputs per step (1.1 GB) exceed the 126 MB L2; no explicit flush",
-            "sort_queries": int(args.sort)}
+# ------------------------------------------------------------------------------------------------ our arm
+class Job:
+    """torch.distributed plumbing of one run (NCCL for the device side, gloo for host-side barriers)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.host_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.host_group = dist.new_group(backend="gloo")
+        self.tok = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+    def stream_fence(self):
+        """orders every rank's current stream after every other rank's (a 4-byte NCCL all-reduce on the stream)"""
+        if self.world > 1:
+            self.dist.all_reduce(self.tok)
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.host_group)
+
+    def bcast_obj(self, obj):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0, group=self.host_group)
+        return box[0]
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_floats(self, xs):
+        if self.world == 1:
+            return [list(xs)]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, list(xs), group=self.host_group)
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-def ours(args):
-    import torch
-    import torch.distributed as dist
+def timed_steps(job, stream, step, warmup, steps):
+    torch = job.torch
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+    torch.cuda.synchronize()
+    job.host_barrier()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    with torch.cuda.stream(stream):
+        job.stream_fence()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        job.stream_fence()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    job.host_barrier()
+    return job.max_over_ranks(e0.elapsed_time(e1))
 
+
+def ours_mesh(args, cfg):
+    """configs c1, c2, c3, c5: queries against a triangle mesh (signed distance or squared distance)."""
     import libigl_b200
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    job = Job()
+    torch = job.torch
+    rank, world, dev = job.rank, job.world, job.dev
     api = libigl_b200.lib()
-    api.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    api.set_device(job.local)
+    L = api.lib
+    vp = ctypes.c_void_p
+    mode = 0 if cfg["kind"] == "sd" else 1
+    sign = 4
+    lower, upper = float(np.finfo(np.float64).tiny), float(np.finfo(np.float64).max)
 
-    V, F, P = workload(args.faces, args.grid, rank)
-    nq = P.shape[0]
+    # --- the workload exists on rank 0 only: ONE query set
+    V = F = P = None
+    grid = 0
+    if rank == 0:
+        V, F = make_mesh(cfg, args)
+        P, grid = make_queries(cfg, args, V)
+    nq, nF, grid = job.bcast_obj((P.shape[0], F.shape[0], grid) if rank == 0 else None)
 
     # --- trees: built once on rank 0, replicated with one NCCL broadcast of the flat arena
-    bcast_ms = 0.0
-    keep = None
-    if world == 1:
-        mesh = api.Mesh(V, F, 2)
-    else:
+    bcast_ms, keep = 0.0, None
+    mesh = api.Mesh(V, F, 2) if rank == 0 else None
+    if world > 1:
         from libigl_b200.dist import broadcast_mesh
-        mesh = api.Mesh(V, F, 2) if rank == 0 else None
         torch.cuda.synchronize()
-        dist.barrier()
+        job.host_barrier()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
         mesh, keep = broadcast_mesh(api, mesh, src=0, device=dev)
@@ -204,152 +342,362 @@ def ours(args):
         bcast_ms = e0.elapsed_time(e1)
     info = mesh.info()
 
-    # --- device-resident buffers (canonical layout: column-major doubles)
-    Pcm = np.ascontiguousarray(P.T)                      # [3, n] == column-major n x 3
-    hP = torch.from_numpy(Pcm).pin_memory()
-    dP = hP.to(dev, non_blocking=True)
-    dS = torch.empty(nq, dtype=torch.float64, device=dev)
-    dI = torch.empty(nq, dtype=torch.int32, device=dev)
-    dC = torch.empty((3, nq), dtype=torch.float64, device=dev)
-    dW = torch.empty(nq, dtype=torch.float64, device=dev)
-    scratch = torch.empty(int(api.lib.iglb200_query_scratch_bytes(nq)), dtype=torch.uint8, device=dev)
+    # --- rank 0 owns the device-resident query set, the outputs and the shard scratch (IPC-mapped by the others)
+    sbytes = int(L.iglb200_shard_scratch_bytes(nq))
+    scratch = vp()
+    handle = ctypes.create_string_buffer(64)
+    if rank == 0:
+        api.check(L.iglb200_ipc_alloc(sbytes, ctypes.byref(scratch), handle))
+    hb = job.bcast_obj(bytes(handle.raw) if rank == 0 else None)
+    if rank != 0:
+        api.check(L.iglb200_ipc_open(hb, ctypes.byref(scratch)))
+    super_rows = int(args.super_rows or L.iglb200_shard_super_rows(nq, world))
+    dP = dS = dI = dC = dW = None
+    hP = None
+    if rank == 0:
+        hP = torch.from_numpy(np.ascontiguousarray(P.T)).pin_memory()      # [3, n] == column-major n x 3
+        dP = hP.to(dev, non_blocking=True)
+        dS = torch.empty(nq, dtype=torch.float64, device=dev)
+        dI = torch.empty(nq, dtype=torch.int32, device=dev)
+        dC = torch.empty((3, nq), dtype=torch.float64, device=dev)
+        dW = torch.empty(nq, dtype=torch.float64, device=dev)
     stream = torch.cuda.Stream(device=dev)
-    lower, upper = float(np.finfo(np.float64).tiny), float(np.finfo(np.float64).max)
+    sp = lambda: vp(stream.cuda_stream)
+    launches = [0]
 
     def step():
-        api.check(api.lib.iglb200_signed_distance_dev(mesh.h, dP.data_ptr(), nq, 4, lower, upper, dS.data_ptr(),
-                                                      dI.data_ptr(), dC.data_ptr(), dW.data_ptr(), None, scratch.data_ptr(),
-                                                      int(args.sort), stream.cuda_stream))
+        n_l = 0
+        if rank == 0:
+            api.check(L.iglb200_shard_begin_dev(mesh.h, dP.data_ptr(), nq, scratch, int(args.sort), sp()))
+            n_l += api.last_launch_count()
+        job.stream_fence()
+        api.check(L.iglb200_shard_run_dev(mesh.h, scratch, nq, mode, sign, lower, upper, 2.0, super_rows, 0, sp()))
+        n_l += api.last_launch_count()
+        job.stream_fence()
+        if rank == 0:
+            api.check(L.iglb200_shard_finish_dev(mesh.h, nq, scratch, mode, sign, lower, upper, int(args.sort),
+                                                 dS.data_ptr(), dI.data_ptr(), dC.data_ptr(), dW.data_ptr(), sp()))
+            n_l += api.last_launch_count()
+        launches[0] = n_l
 
-    torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
-    torch.cuda.synchronize()
-    launches_per_step = api.last_launch_count()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
+    # warm-up, then the timed region
+    timed_steps(job, stream, step, args.warmup, 0)
+    sampler = ClockSampler(job.local)
     if rank == 0:
         sampler.start()
     api.profile_enable(True)
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    api.check(api.lib.iglb200_poll_device_error())
+    ms = timed_steps(job, stream, step, 0, args.steps)
+    api.check(L.iglb200_poll_device_error())
     prof = api.profile_collect()
     api.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * nq * args.steps / (ms * 1e-3)
-
-    # --- end to end through the host-pointer C ABI (what igl::signed_distance's caller sees)
-    hS = torch.empty(nq, dtype=torch.float64).pin_memory()
-    hI = torch.empty(nq, dtype=torch.int32).pin_memory()
-    hC = torch.empty((3, nq), dtype=torch.float64).pin_memory()
-
-    def e2e_step():
-        # exactly the outputs of igl::signed_distance(P,V,F,type,S,I,C,N): S, I, C (N is not written for this sign type;
-        # the winding number itself is an extension output and is not asked for)
-        api.check(api.lib.iglb200_signed_distance(mesh.h, hP.data_ptr(), 1, nq, 1, nq, 4, lower, upper,
-                                                  hS.data_ptr(), 1, hI.data_ptr(), hC.data_ptr(), 1, 1, nq,
-                                                  None, 1, None, 1, 1, nq))
-
-    e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = world * nq * args.e2e_steps / t_e2e
-    # device and host paths must agree bit for bit
-    assert torch.equal(hS, dS.cpu()) or bool(torch.isnan(hS).any()), "device-resident and host-pointer paths differ"
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # --- roofline of the dominant kernel
-    hbm, which, sm_max = peaks()
-    dom = max(prof, key=prof.get) if prof else None
+    value = nq * args.steps / (ms * 1e-3)
     kernel_ms = {k: v / args.steps for k, v in prof.items()}
-    roof = None
-    if dom:
-        t_dom = kernel_ms[dom] * 1e-3
-        alg_bytes = BYTES_PER_QUERY * nq + info["device_bytes"]   # per launch: query I/O + one read of the tree
-        ach = alg_bytes / t_dom / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if dom == "closest" and os.path.exists(tp):
-            tj = json.load(open(tp))
-            if tj.get("queries") == nq and tj.get("faces") == int(F.shape[0]):
-                traffic = tj["dram_bytes_per_launch"]   # ncu --set full capture of this kernel on this workload
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": int(alg_bytes),
-                "launch_ms": kernel_ms[dom],
-                "note": "not HBM bound: arithmetic intensity ~1e3 flop/B; see fp32 below and DESIGN.md"}
+    per_rank = job.gather_floats([kernel_ms.get("closest", 0.0), kernel_ms.get("winding", 0.0)])
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 distance + f32 winding number", "data": "synthetic",
-        "config": config_dict(args, F.shape[0], nq),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(24 * nq), "d2h_bytes_per_step": int(36 * nq),
-                "steps": args.e2e_steps},
-        "gpu_launches": int(launches_per_step * args.steps),
-        "kernel_ms_per_step": kernel_ms,
-        "roofline": roof,
-        "clocks": clocks,
-        "tree": {"build_ms": info["build_ms"], "nodes": info["n_nodes"], "levels": info["n_levels"],
-                 "device_bytes": info["device_bytes"], "broadcast_ms": bcast_ms},
-    }
-    if world == 1 and not args.no_cpu:
-        r = run_cpu(V, F, P, args.grid, budget_s=args.cpu_seconds)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                "sample": r["sample"] + "; genuine UT_SolidAngle (oracle/_ref) + restated f64 igl::AABB (oracle port)",
-                                "build_s": r["build_s"]}
-        # algorithmic flops from the instrumented oracle on a small sample
-        try:
-            import oracle
-            samp, _ = cpu_sample(P, args.grid, 200000)
-            tree = oracle.PortAABB(V, F)
-            _, _, _, cnt = tree.squared_distance(samp, count=True)
-            n_cp_node, n_cp_tri = cnt[0] / samp.shape[0], cnt[1] / samp.shape[0]
-            vc = mesh.visit_counts(samp[:65536])   # the winding walk is the reference's own: same nodes, same faces
-            n_fwn_node, n_fwn_tri = vc["fwn_nodes"], vc["fwn_tris"]
-            flops_q = FLOP_NODE_FWN * n_fwn_node + FLOP_TRI_FWN * n_fwn_tri + FLOP_NODE_CP * n_cp_node + FLOP_TRI_CP * n_cp_tri
-            measured = float(api.lib.iglb200_debug_fp32_peak_tflops())
-            fp32_peak = measured * 1e12 if measured > 0 else 2 * 128 * 148 * sm_max * 1e6
-            line["fp32"] = {"flops_per_query": flops_q, "achieved_tflops": flops_q * value / 1e12,
-                            "peak_tflops": fp32_peak / 1e12, "frac": flops_q * value / fp32_peak,
-                            "counts": {"cp_nodes_per_query_reference_tree": n_cp_node, "cp_tris_per_query": n_cp_tri,
-                                       "fwn_nodes_per_query": n_fwn_node, "fwn_tris_per_query": n_fwn_tri,
-                                       "ours_cp_nodes_per_warp": vc["cp_nodes_per_warp"], "ours_cp_faces_per_warp": vc["cp_tris_per_warp"]},
-                            "peak_source": "FMA micro-benchmark on this GPU" if measured > 0 else "2*128*148*sm_max",
-                            "note": "work of the reference algorithm (binary AABB, 1 tri/leaf) per SURVEY §8(d)"}
-        except Exception as ex:  # the flop estimate is informative only
-            line["fp32"] = {"error": str(ex)}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    # N = 1: the fused single-GPU entry point on the same data must give the same bits (and its time is reported)
+    fused_ms = None
+    if world == 1:
+        qs = torch.empty(int(L.iglb200_query_scratch_bytes(nq)), dtype=torch.uint8, device=dev)
+        S2, I2, C2, W2 = torch.empty_like(dS), torch.empty_like(dI), torch.empty_like(dC), torch.empty_like(dW)
+
+        def fused():
+            if mode == 0:
+                api.check(L.iglb200_signed_distance_dev(mesh.h, dP.data_ptr(), nq, sign, lower, upper, S2.data_ptr(), I2.data_ptr(),
+                                                        C2.data_ptr(), W2.data_ptr(), None, qs.data_ptr(), int(args.sort), sp()))
+            else:
+                api.check(L.iglb200_squared_distance_dev(mesh.h, dP.data_ptr(), nq, S2.data_ptr(), I2.data_ptr(), C2.data_ptr(),
+                                                         qs.data_ptr(), int(args.sort), sp()))
+        fused_ms = timed_steps(job, stream, fused, 1, max(2, args.steps // 2)) / max(2, args.steps // 2)
+        same = torch.equal(dI, I2) and torch.equal(dC, C2) and bool(((dS == S2) | (torch.isnan(dS) & torch.isnan(S2))).all())
+        assert same, "sharded and fused device paths differ"
+        del qs, S2, I2, C2, W2
+
+    # --- end to end through the host-pointer C ABI
+    e2e = run_e2e_mesh(job, api, mesh, cfg, args, hP, nq, mode, sign, lower, upper, dS, dI)
+
+    if rank == 0:
+        line = {
+            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 distance + f32 winding number" if mode == 0 else "f64", "data": "synthetic",
+            "config": config_dict(cfg, args, nF, nq, grid, world),
+            "e2e": e2e,
+            "gpu_launches": int(launches[0] * args.steps),
+            "kernel_ms_per_step": kernel_ms,
+            "per_rank_kernel_ms": {"closest": [r[0] for r in per_rank], "winding": [r[1] for r in per_rank]},
+            "super_rows": super_rows,
+            "clocks": clocks,
+            "tree": {"build_ms": info["build_ms"], "nodes": info["n_nodes"], "levels": info["n_levels"],
+                     "device_bytes": info["device_bytes"], "broadcast_ms": bcast_ms},
+        }
+        if fused_ms is not None:
+            line["fused_single_call_ms_per_step"] = fused_ms
+        add_rooflines(line, api, mesh, cfg, args, kernel_ms, info, nq, value, P, grid, world)
+        if world == 1 and not args.no_cpu:
+            r = run_cpu(cfg, args, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                    "build_s": r["build_s"]}
+        print(json.dumps(line), flush=True)
+    job.host_barrier()
+    if rank != 0:
+        L.iglb200_ipc_close(scratch)
+    job.host_barrier()
+    if rank == 0:
+        L.iglb200_ipc_free(scratch)
+    job.close()
+
+
+def run_e2e_mesh(job, api, mesh, cfg, args, hP, nq, mode, sign, lower, upper, dS, dI):
+    """Host-pointer C ABI, H2D + kernels + D2H inside the timed region (wall clock between host barriers, max over ranks)."""
+    torch = job.torch
+    L = api.lib
+    vp = ctypes.c_void_p
+    rank, world = job.rank, job.world
+    steps = args.e2e_steps or args.steps
+    out = {"unit": UNIT, "h2d_bytes_per_step": int(24 * nq), "d2h_bytes_per_step": int(36 * nq), "steps": steps}
+
+    def call(Pp, Sp, Ip, Cp, coop=None):
+        # exactly the outputs of igl::signed_distance(P,V,F,type,S,I,C,N): S, I, C (N is not written for this sign type)
+        if mode == 0 and coop is None:
+            api.check(L.iglb200_signed_distance(mesh.h, Pp, 1, nq, 1, nq, sign, lower, upper, Sp, 1, Ip, Cp, 1, 1, nq,
+                                                None, 1, None, 1, 1, nq))
+        elif mode == 0:
+            api.check(L.iglb200_signed_distance_coop(mesh.h, Pp, 1, nq, 1, nq, sign, lower, upper, Sp, 1, Ip, Cp, 1, 1, nq,
+                                                     None, 1, None, 1, 1, nq, coop[0], coop[1]))
+        else:
+            api.check(L.iglb200_squared_distance(mesh.h, Pp, 1, nq, 1, nq, Sp, 1, Ip, Cp, 1, 1, nq))
+
+    def timed(fn, k):
+        fn(0)
+        job.host_barrier()
+        t0 = time.perf_counter()
+        for i in range(k):
+            fn(i + 1)
+        torch.cuda.synchronize()
+        job.host_barrier()
+        return job.max_over_ranks(time.perf_counter() - t0)
+
+    if world == 1:
+        hS = torch.empty(nq, dtype=torch.float64).pin_memory()
+        hI = torch.empty(nq, dtype=torch.int32).pin_memory()
+        hC = torch.empty((3, nq), dtype=torch.float64).pin_memory()
+        t = timed(lambda i: call(hP.data_ptr(), hS.data_ptr(), hI.data_ptr(), hC.data_ptr()), steps)
+        out["value"] = nq * steps / t
+        out["host_memory"] = "page-locked"
+        # device and host paths must agree bit for bit
+        assert torch.equal(hI, dI.cpu()), "device-resident and host-pointer paths differ (I)"
+        a, b = hS, dS.cpu()
+        assert bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all()), "device-resident and host-pointer paths differ (S)"
+        # the same call from plain pageable arrays (what Eigen::MatrixXd hands over): staged through the pinned ring
+        pP = np.array(hP.numpy(), copy=True)
+        pS, pI, pC = np.empty(nq), np.empty(nq, np.int32), np.empty((3, nq))
+        t = timed(lambda i: call(pP.ctypes.data, pS.ctypes.data, pI.ctypes.data, pC.ctypes.data), steps)
+        out["pageable"] = {"value": nq * steps / t, "unit": UNIT}
+        assert np.array_equal(pI, hI.numpy()), "pageable and pinned host paths differ"
+        return out
+
+    if mode != 0:
+        out["value"] = None
+        out["note"] = "cooperative multi-process host calls exist for signed_distance only"
+        return out
+    # N > 1: ONE query set in shared host memory, page-locked by every rank; chunks dealt off one shared counter
+    from libigl_b200.dist import SharedArrays
+    need = 64 * nq + (1 << 20)
+    st = os.statvfs("/dev/shm")
+    if st.f_bavail * st.f_frsize < need * 1.1 and rank == 0:
+        out["value"] = None
+        out["note"] = f"/dev/shm too small for the shared query set ({need >> 20} MiB)"
+    ok = job.bcast_obj("value" not in out if rank == 0 else None)
+    if ok:
+        name = f"iglb200_bench_{os.environ.get('MASTER_PORT', '0')}"
+        sh = None
+        if rank == 0:
+            sh = SharedArrays(name, nq, create=True)
+            sh.P[:] = hP.numpy()
+            sh.counter[:] = 0
+        job.host_barrier()
+        if rank != 0:
+            sh = SharedArrays(name, nq, create=False)
+        sh.register(api)
+        chunk = int(args.chunk_rows or L.iglb200_host_chunk_rows(nq, world))
+        base = sh.counter.ctypes.data
+
+        def coop_step(i):
+            # ping-pong counters: rank 0 zeroes the one the NEXT step will use; one host barrier per step
+            if rank == 0:
+                sh.counter[(i + 1) & 1] = 0
+            call(sh.P.ctypes.data, sh.S.ctypes.data, sh.I.ctypes.data, sh.C.ctypes.data, coop=(vp(base + 8 * (i & 1)), chunk))
+            job.host_barrier()
+        t = timed(coop_step, steps)
+        out["value"] = nq * steps / t
+        out["host_memory"] = "POSIX shared memory, page-locked by every rank (cudaHostRegister)"
+        out["chunk_rows"] = chunk
+        if rank == 0:
+            assert np.array_equal(sh.I, dI.cpu().numpy()), "cooperative host path and device path differ"
+        job.host_barrier()
+        sh.close(unlink=(rank == 0))
+    # ONE process driving all GPUs (iglb200_init(N)): measured by rank 0 while the other ranks wait on the host
+    if not args.no_single_process:
+        job.torch.cuda.synchronize()
+        job.host_barrier()
+        if rank == 0:
+            try:
+                import libigl_b200
+                V, F = make_mesh(cfg, args)
+                api.init(world)
+                api.set_device(0)
+                m2 = api.Mesh(V, F, 2)
+                gi = api.group_info()
+                hS = torch.empty(nq, dtype=torch.float64).pin_memory()
+                hI = torch.empty(nq, dtype=torch.int32).pin_memory()
+                hC = torch.empty((3, nq), dtype=torch.float64).pin_memory()
+
+                def one(i):
+                    api.check(L.iglb200_signed_distance(m2.h, hP.data_ptr(), 1, nq, 1, nq, sign, lower, upper, hS.data_ptr(), 1,
+                                                        hI.data_ptr(), hC.data_ptr(), 1, 1, nq, None, 1, None, 1, 1, nq))
+                one(0)
+                t0 = time.perf_counter()
+                for i in range(steps):
+                    one(i)
+                t = time.perf_counter() - t0
+                assert torch.equal(hI, dI.cpu()), "single-process multi-GPU path and device path differ"
+                out["single_process"] = {"value": nq * steps / t, "unit": UNIT, "devices": gi["devices"],
+                                         "replication": gi["transport"], "replicate_ms": gi["replicate_ms"]}
+                m2.close()
+                api.init(1)
+                api.set_device(0)
+            except Exception as ex:   # reported, not fatal: the multi-process numbers above stand on their own
+                out["single_process"] = {"error": str(ex)[:300]}
+        job.host_barrier()
+    return out
+
+
+def add_rooflines(line, api, mesh, cfg, args, kernel_ms, info, nq, value, P, grid, world):
+    hbm, which, sm_max = peaks()
+    dom = max(kernel_ms, key=kernel_ms.get) if kernel_ms else None
+    if not dom:
+        return
+    t_dom = kernel_ms[dom] * 1e-3
+    # HBM: algorithmic bytes of one launch on THIS rank = its share of the query I/O + one read of the tree
+    alg_bytes = BYTES_PER_QUERY[cfg["kind"]] * nq / world + info["device_bytes"]
+    ach = alg_bytes / t_dom / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_r2.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("kernel") == dom and tj.get("queries") == nq and tj.get("faces") == int(info["n_faces"]) and world == 1:
+            traffic = tj["dram_bytes_per_launch"]   # ncu --set full capture of this kernel on this workload
+    line["roofline_hbm"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                            "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": int(alg_bytes),
+                            "launch_ms": kernel_ms[dom],
+                            "note": "not the bound: arithmetic intensity ~1e3 flop/B (SURVEY §8d); reported for completeness"}
+    # FP32: work the dominant kernel EXECUTES (its own node/face counters x flops per lane and unit)
+    try:
+        samp, _ = cpu_sample(P, grid, 65536)
+        vc = mesh.visit_counts(samp[:65536])
+        theo = 2 * 128 * 148 * sm_max * 1e6
+        measured = float(api.lib.iglb200_debug_fp32_peak_tflops()) * 1e12
+        if dom == "closest":
+            flops_launch = (vc["cp_nodes_per_warp"] * OURS_FLOP_CP_NODE_LANE + vc["cp_tris_per_warp"] * OURS_FLOP_CP_FACE_LANE) * 32 * (nq / 32.0) / world
+            src = "kernel's own visit counters (65 536-query sample) x flops per lane: node visit 68, face test 76"
+        else:
+            flops_launch = (vc["fwn_nodes"] * FLOP_NODE_FWN + vc["fwn_tris"] * FLOP_TRI_FWN) * nq / world
+            src = "visit counters x 372 flop per node visit, 100 per exact triangle (the reference's own walk)"
+        fj = os.path.join(ROOT, "profiles", "flops_r2.json")
+        ncu_flops = None
+        if os.path.exists(fj):
+            j = json.load(open(fj))
+            if j.get("kernel") == dom and j.get("queries") == nq and world == 1:
+                ncu_flops = j["fp32_flops_per_launch"]    # smsp__sass_thread_inst_executed_op_{ffma x2, fadd, fmul}_pred_on
+        used = ncu_flops if ncu_flops else flops_launch
+        ach_t = used / t_dom
+        line["roofline"] = {"bound": "fp32", "kernel": dom, "achieved": ach_t / 1e12, "peak": theo / 1e12, "unit": "TFLOP/s",
+                            "frac": ach_t / theo, "traffic": traffic,
+                            "peak_source": "2 x 128 lanes x 148 SMs x sm_max_mhz", "peak_microbenchmark": measured / 1e12,
+                            "frac_of_microbenchmark": ach_t / measured if measured > 0 else None,
+                            "executed_flops_per_launch": used,
+                            "numerator": "ncu sass op counters (profiles/flops_r2.json)" if ncu_flops else src,
+                            "launch_ms": kernel_ms[dom],
+                            "counts": {"cp_nodes_per_packet": vc["cp_nodes_per_warp"], "cp_faces_per_packet": vc["cp_tris_per_warp"],
+                                       "fwn_nodes_per_query": vc["fwn_nodes"], "fwn_tris_per_query": vc["fwn_tris"]}}
+    except Exception as ex:
+        line["roofline"] = {"bound": "fp32", "error": str(ex)[:300]}
+
+
+def ours_cloud(args, cfg):
+    """config c4: oriented point cloud.  Every rank builds the (deterministic) octree; N > 1: static contiguous slices of
+    the Morton-uniform random queries, gathered to rank 0 with NCCL (the evaluation cost per query is uniform)."""
+    import libigl_b200
+    job = Job()
+    torch, dist = job.torch, job.dist
+    rank, world, dev = job.rank, job.world, job.dev
+    api = libigl_b200.lib()
+    api.set_device(job.local)
+    L = api.lib
+    Pc, N, A, Q = make_cloud(cfg, args)
+    nq = Q.shape[0]
+    t0 = time.perf_counter()
+    cl = api.Cloud(Pc, N, A, 2)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    from libigl_b200.dist import shard_range
+    lo, hi = shard_range(nq, rank, world)
+    hQ = torch.from_numpy(np.ascontiguousarray(Q.T)).pin_memory()
+    dQ = torch.from_numpy(np.ascontiguousarray(Q[lo:hi].T)).to(dev)
+    dW = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    sizes = [shard_range(nq, r, world) for r in range(world)]
+    parts = [torch.empty(b - a, dtype=torch.float64, device=dev) for a, b in sizes] if (world > 1 and rank == 0) else None
+    stream = torch.cuda.Stream(device=dev)
+
+    def step():
+        api.check(L.iglb200_cloud_eval_dev(cl.h, dQ.data_ptr(), hi - lo, 2.0, dW.data_ptr(), ctypes.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.gather(dW, parts, dst=0)
+    timed_steps(job, stream, step, args.warmup, 0)
+    sampler = ClockSampler(job.local)
+    if rank == 0:
+        sampler.start()
+    api.profile_enable(True)
+    ms = timed_steps(job, stream, step, 0, args.steps)
+    prof = api.profile_collect()
+    api.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = nq * args.steps / (ms * 1e-3)
+    kernel_ms = {k: v / args.steps for k, v in prof.items()}
+    e2e = None
+    if world == 1:
+        hW = torch.empty(nq, dtype=torch.float64).pin_memory()
+        steps = args.e2e_steps or args.steps
+        f = lambda: api.check(L.iglb200_cloud_eval(cl.h, hQ.data_ptr(), 1, nq, 1, nq, 2.0, hW.data_ptr(), 1))
+        f()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            f()
+        t = time.perf_counter() - t0
+        e2e = {"value": nq * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(24 * nq), "d2h_bytes_per_step": int(8 * nq), "steps": steps}
+        assert torch.equal(hW, dW.cpu())
+    if rank == 0:
+        info = cl.info()
+        hbm, which, _ = peaks()
+        dom = "cloud_eval"
+        t_dom = kernel_ms.get(dom, ms / args.steps) * 1e-3
+        alg = BYTES_PER_QUERY["cloud"] * nq / world + info["device_bytes"]
+        line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config_dict(cfg, args, Pc.shape[0], nq, 0, world), "e2e": e2e,
+                "gpu_launches": int(api.last_launch_count() * args.steps), "kernel_ms_per_step": kernel_ms, "clocks": clocks,
+                "roofline_hbm": {"bound": "hbm", "kernel": dom, "achieved": alg / t_dom / 1e9, "peak": hbm, "unit": "GB/s",
+                                 "frac": alg / t_dom / 1e9 / hbm, "traffic": None, "peak_source": which},
+                "tree": {"build_s": build_s, "cells": info["n_cells"], "levels": info["n_levels"], "device_bytes": info["device_bytes"]}}
+        if world == 1 and not args.no_cpu:
+            r = run_cpu(cfg, args, budget_s=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                    "build_s": r["build_s"]}
+        print(json.dumps(line), flush=True)
+    job.host_barrier()
+    cl.close()
+    job.close()
 
 
 def main():
@@ -358,18 +706,26 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--faces", type=int, default=1_000_000)
-    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--faces", type=int, default=0, help="override the mesh size of the config (tuning / smoke runs)")
+    ap.add_argument("--grid", type=int, default=0, help="override the grid resolution of the config")
+    ap.add_argument("--queries", type=int, default=0, help="override the number of random queries (c3, c4)")
     ap.add_argument("--sort", type=int, default=1)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="default: --steps")
+    ap.add_argument("--super-rows", type=int, default=0)
+    ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-single-process", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
         reference_arm(args)
+    elif cfg["kind"] == "cloud":
+        ours_cloud(args, cfg)
     else:
-        ours(args)
+        ours_mesh(args, cfg)
 
 
 if __name__ == "__main__":

@@ -57,7 +57,9 @@ class Api:
     SYMBOLS = [
         "iglb200_last_error", "iglb200_version", "iglb200_device_count", "iglb200_set_device", "iglb200_init", "iglb200_shutdown",
         "iglb200_group_info", "iglb200_mesh_replicate", "iglb200_signed_distance_coop", "iglb200_host_chunk_rows",
-        "iglb200_host_alloc", "iglb200_host_free",
+        "iglb200_shard_scratch_bytes", "iglb200_shard_super_rows", "iglb200_shard_begin_dev", "iglb200_shard_run_dev",
+        "iglb200_shard_finish_dev", "iglb200_ipc_alloc", "iglb200_ipc_open", "iglb200_ipc_close", "iglb200_ipc_free",
+        "iglb200_host_alloc", "iglb200_host_free", "iglb200_host_register", "iglb200_host_unregister",
         "iglb200_mesh_create", "iglb200_mesh_create_ex", "iglb200_mesh_destroy", "iglb200_mesh_info", "iglb200_mesh_build_ms",
         "iglb200_mesh_arena", "iglb200_mesh_arena_download", "iglb200_mesh_from_arena",
         "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
@@ -82,6 +84,8 @@ class Api:
         L.iglb200_version.restype = C.c_char_p
         L.iglb200_host_alloc.argtypes = [C.POINTER(_vp), C.c_uint64]
         L.iglb200_host_free.argtypes = [_vp]
+        L.iglb200_host_register.argtypes = [_vp, C.c_uint64]
+        L.iglb200_host_unregister.argtypes = [_vp]
         L.iglb200_mesh_create.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, C.POINTER(_vp)]
         L.iglb200_mesh_create_ex.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, C.POINTER(_vp)]
         L.iglb200_mesh_destroy.argtypes = [_vp]
@@ -95,6 +99,17 @@ class Api:
                                               _vp, _int, _vp, _vp, _int, _i64, _i64, _vp, _int, _vp, _int, _i64, _i64]
         L.iglb200_signed_distance_coop.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _int, _dbl, _dbl,
                                                    _vp, _int, _vp, _vp, _int, _i64, _i64, _vp, _int, _vp, _int, _i64, _i64, _vp, _i64]
+        L.iglb200_shard_scratch_bytes.argtypes = [_i64]
+        L.iglb200_shard_scratch_bytes.restype = C.c_uint64
+        L.iglb200_shard_super_rows.argtypes = [_i64, _int]
+        L.iglb200_shard_super_rows.restype = _i64
+        L.iglb200_shard_begin_dev.argtypes = [_vp, _vp, _i64, _vp, _int, _vp]
+        L.iglb200_shard_run_dev.argtypes = [_vp, _vp, _i64, _int, _int, _dbl, _dbl, C.c_float, _i64, _i64, _vp]
+        L.iglb200_shard_finish_dev.argtypes = [_vp, _i64, _vp, _int, _int, _dbl, _dbl, _int, _vp, _vp, _vp, _vp, _vp]
+        L.iglb200_ipc_alloc.argtypes = [C.c_uint64, C.POINTER(_vp), C.c_char_p]
+        L.iglb200_ipc_open.argtypes = [C.c_char_p, C.POINTER(_vp)]
+        L.iglb200_ipc_close.argtypes = [_vp]
+        L.iglb200_ipc_free.argtypes = [_vp]
         L.iglb200_host_chunk_rows.argtypes = [_i64, _int]
         L.iglb200_host_chunk_rows.restype = _i64
         L.iglb200_group_info.argtypes = [C.POINTER(_i64), C.c_char_p, C.c_uint64]
@@ -420,7 +435,7 @@ class Mesh:
         return out + (W,) if return_W else out
 
     def signed_distance_coop(self, sh, chunk_rows, sign_type=SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, lower_bound=None,
-                             upper_bound=None):
+                             upper_bound=None, counter_index=0, want_W=True):
         """This process's share of ONE query set held in memory shared between processes (dist.SharedArrays):
         chunks of `chunk_rows` rows are taken off sh.counter until the rows run out."""
         if lower_bound is None:
@@ -431,7 +446,8 @@ class Mesh:
         self.api.check(self.api.lib.iglb200_signed_distance_coop(
             self.h, sh.P.ctypes.data_as(_vp), 1, n, 1, n, int(sign_type), float(lower_bound), float(upper_bound),
             sh.S.ctypes.data_as(_vp), 1, sh.I.ctypes.data_as(_vp), sh.C.ctypes.data_as(_vp), 1, 1, n,
-            sh.W.ctypes.data_as(_vp), 1, None, 1, 1, n, sh.counter.ctypes.data_as(_vp), int(chunk_rows)))
+            sh.W.ctypes.data_as(_vp) if want_W else None, 1, None, 1, 1, n,
+            _vp(sh.counter.ctypes.data + 8 * int(counter_index)), int(chunk_rows)))
 
     # igl::signed_distance_fast_winding_number(P,V,F,tree,fwn_bvh,S): S only
     def signed_distance_fast_winding_number(self, P):

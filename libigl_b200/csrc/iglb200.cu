@@ -95,12 +95,23 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   double *sqrD; int32_t *I; double *C;
   uint32_t *counters;  // nullable: [0] node visits, [1] face tests (summed over warps)
   unsigned long long *sched = nullptr;   // work distribution state of the persistent schedule (launch_closest supplies one if null)
+  // Sharded operation (several GPUs on ONE query set): chunks are not numbered from this launch's own counter but come
+  // in SUPER-chunks of `super_chunks` consecutive chunks taken off a counter in the memory of the device that owns the
+  // query set (a system-scope atomic over NVLink); the super-chunks this device took are listed for the kernels that follow.
+  unsigned long long *remote = nullptr;
+  uint32_t super_chunks = 0;
+  uint32_t *my_supers = nullptr, *my_count = nullptr;
+  int64_t max_supers = 0;   // > 0: take at most this many (static partition / tests)
 };
 
-static constexpr int64_t SCHED_WORDS = 1 + 2 * 1024;   // next chunk; per SM id: state, refill lock
-struct InitSched {   // every SM starts with an exhausted chunk
-  unsigned long long *w;
-  DEVFN void operator()(int64_t i) const { w[i] = (i >= 1 && (i & 1)) ? 0x7F7F7F7Full : 0ull; }
+static constexpr int64_t SCHED_WORDS = 1 + 2 * 1024 + 3;   // next chunk; per SM id: state, refill lock; sharded: lock, block counter, spare
+struct InitSched {   // every SM starts with an exhausted chunk (and, sharded, the device with an exhausted super-chunk)
+  unsigned long long *w; int sharded;
+  DEVFN void operator()(int64_t i) const {
+    if (i == 0) w[i] = sharded ? 0x7F7F7F7Full : 0ull;
+    else if (i >= 1 + 2 * 1024) w[i] = 0ull;
+    else w[i] = (i & 1) ? 0x7F7F7F7Full : 0ull;
+  }
 };
 
 DEVFN void closest_store(const ClosestArgs &a, int64_t i, const fwn::CpResult &r) {
@@ -179,8 +190,17 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
   }
   if (a.counters) { a.counters[0] += nvis; a.counters[1] += ntri; }
 }
+static constexpr int CP_CHUNK = 16;
 void launch_closest(const ClosestArgs &a, stream_t) {
-  for (int64_t base = 0; base < a.n; base += 32) closest_packet_emul(a, base);
+  if (!a.remote) { for (int64_t base = 0; base < a.n; base += 32) closest_packet_emul(a, base); return; }
+  // sharded: super-chunks off the owner's counter, listed for the kernels that follow
+  const int64_t super_rows = (int64_t)a.super_chunks * CP_CHUNK * 32;
+  while (a.max_supers <= 0 || (int64_t)*a.my_count < a.max_supers) {
+    const unsigned long long sc = __atomic_fetch_add(a.remote, 1ull, __ATOMIC_RELAXED);
+    if ((int64_t)sc * super_rows >= a.n) break;
+    a.my_supers[(*a.my_count)++] = (uint32_t)sc;
+    for (int64_t base = (int64_t)sc * super_rows; base < std::min(a.n, ((int64_t)sc + 1) * super_rows); base += 32) closest_packet_emul(a, base);
+  }
 }
 uint32_t *overflow_flag() { static thread_local uint32_t f = 0; return &f; }
 void reset_overflow(stream_t) { *overflow_flag() = 0; }
@@ -204,6 +224,38 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 #ifndef CP_WARPS
 #define CP_WARPS 1         // a block is one packet: a finished packet frees its slot at once (4 warps/block: 94.6 ms)
 #endif
+#ifndef CP_CHUNK
+#define CP_CHUNK 16   // measured: 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2
+#endif
+// Sharded schedule, one level above the per-SM chunks: sched[0] = (super-chunk << 32 | chunks of it handed out).  When a
+// super-chunk is used up, one thread of the device takes the next one off the owner's counter (atomicAdd over NVLink when
+// the owner is a peer) and notes it in my_supers.  Returns a chunk index; chunks past the last packet end the caller's warp.
+static __device__ __noinline__ unsigned long long next_chunk_sharded(const ClosestArgs &a, uint32_t npackets) {
+  unsigned long long *G = a.sched, *glock = a.sched + 1 + 2 * 1024;
+  while (true) {
+    const unsigned long long old = atomicAdd(G, 1ull);
+    if ((uint32_t)old < a.super_chunks) {
+      const unsigned long long sc = old >> 32;
+      const unsigned long long chunk = sc * a.super_chunks + (uint32_t)old;
+      return (sc == 0xFFFFFFFFull || chunk > 0x0FFFFFFFull) ? 0x0FFFFFFFull : chunk;   // sentinel: its packets lie past the end
+    }
+    if (atomicCAS(glock, 0ull, 1ull) == 0ull) {
+      if ((uint32_t)(*(volatile unsigned long long *)G) >= a.super_chunks) {
+        unsigned long long sc = 0xFFFFFFFFull;   // "past the end"
+        const uint32_t have = *(volatile uint32_t *)a.my_count;
+        if (a.max_supers <= 0 || (int64_t)have < a.max_supers) {
+          sc = atomicAdd_system(a.remote, 1ull);
+          if (sc > 0xFFFFFFFFull) sc = 0xFFFFFFFFull;
+          if (sc * a.super_chunks * CP_CHUNK < (unsigned long long)npackets) { a.my_supers[have] = (uint32_t)sc; *(volatile uint32_t *)a.my_count = have + 1; }
+        }
+        __threadfence();
+        atomicExch(G, sc << 32);
+      }
+      __threadfence();
+      atomicExch(glock, 0ull);
+    }
+  }
+}
 template <bool COUNT>
 __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
   using namespace fwn;
@@ -213,9 +265,6 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   CpExact &X = exact[threadIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *stack = stacks[warp];
-#ifndef CP_CHUNK
-#define CP_CHUNK 16   // measured: 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2
-#endif
   // Persistent schedule: every SM hands out the packets of one chunk of CP_CHUNK Morton-consecutive packets to its
   // resident warps, so the packets that share an L1 are neighbours; chunks are taken from a global counter, so the
   // chunks in flight still form one window of the query set (L2).  sched[0] = next chunk, sched[1 + 2*smid] =
@@ -232,7 +281,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         if ((uint32_t)old < CP_CHUNK) { packet = (uint32_t)(old >> 32) * CP_CHUNK + (uint32_t)old; break; }
         if (atomicCAS(lock, 0ull, 1ull) == 0ull) {   // this warp refills the SM's chunk
           if ((uint32_t)(*(volatile unsigned long long *)st) >= CP_CHUNK) {
-            const unsigned long long nc = atomicAdd(a.sched, 1ull);
+            const unsigned long long nc = a.remote ? next_chunk_sharded(a, npackets) : atomicAdd(a.sched, 1ull);
             atomicExch(st, nc << 32);
           }
           __threadfence();
@@ -359,7 +408,7 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   DevBuf<unsigned long long> own;
   ClosestArgs b = a;
   if (!b.sched) { own.alloc(SCHED_WORDS); b.sched = own.p; }   // no caller scratch: a private state for this launch
-  plat::for_n(SCHED_WORDS, InitSched{b.sched}, s);
+  plat::for_n(SCHED_WORDS, InitSched{b.sched, b.remote ? 1 : 0}, s);
   blocks = std::min<int64_t>(blocks, (int64_t)plat::sm_count() * CP_MIN_BLOCKS);
   if (b.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
   else closest_packet_kernel<false><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
@@ -678,6 +727,200 @@ void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_s
   plat::Span sp("winding", s);
   launch_query("winding", n, WindingQuery{m->fnodes(), m->tri32(), Q, n, perm, accuracy_scale * accuracy_scale, m->h.order, 0, 0.0, 0.0,
                               (int32_t)m->h.nF, W, nullptr, nullptr, nullptr, overflow_flag()}, s);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sharded device-resident queries: SEVERAL GPUs answer ONE query set that lives on one of them (the owner).
+//   begin  (owner)      Morton-sort the queries once, gather them in sorted order (Ps), zero the work counter
+//   run    (every GPU)  closest-triangle search + winding number over the super-chunks this GPU takes off the
+//                       owner's counter; queries are read from, and results written in sorted order to, the owner's
+//                       memory directly (peer loads/stores over NVLink: the "gather" is the kernels' own epilogue)
+//   finish (owner)      un-sort + the epilogue of signed_distance.cpp:99-135
+// Between the phases the caller orders the devices' streams (events in one process, a tiny NCCL collective between
+// processes).  The owner's scratch has one layout, computed from nP alone, so that a peer only needs its base pointer.
+// ---------------------------------------------------------------------------------------------------
+struct ShardLayout {
+  size_t oCounter, oSort, oPs, oD, oI, oC, oW, total;
+  explicit ShardLayout(int64_t n) {
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    oCounter = 0; oSort = 256; oPs = oSort + al(iglb200_query_scratch_bytes(n)); oD = oPs + al(24 * (size_t)n); oI = oD + al(8 * (size_t)n);
+    oC = oI + al(4 * (size_t)n); oW = oC + al(24 * (size_t)n); total = oW + al(8 * (size_t)n);
+  }
+};
+struct GatherSorted { const double *P; int64_t n; const uint32_t *perm; double *Ps;
+  DEVFN void operator()(int64_t t) const { const int64_t i = perm ? (int64_t)perm[t] : t; Ps[t] = P[i]; Ps[n + t] = P[n + i]; Ps[2 * n + t] = P[2 * n + i]; } };
+
+// winding number of the sorted queries of the super-chunks listed by the search kernel (or of all rows when list == null)
+struct WindingShard {
+  const fwn::FwnNode *nodes; const float4 *tri32;
+  const double *Ps; int64_t n; float acc2; int order;
+  const double *D; double up, low; int skip_oob;   // skip rows whose squared distance is out of bounds (their W is never read)
+  double *W; uint32_t *overflow;
+  DEVFN void operator()(int64_t t) const {
+    if (skip_oob) { const double sqrd = D[t]; if (sqrd >= up || sqrd < low) { W[t] = NAN; return; } }
+    uint32_t stack[fwn::FWN_STACK];
+    const float om = fwn::winding_solid_angle(nodes, tri32, (float)Ps[t], (float)Ps[n + t], (float)Ps[2 * n + t], acc2, order, stack, nullptr, overflow);
+    W[t] = (double)om / (4.0 * 3.1415926535897932384626433832795);
+  }
+};
+#ifndef IGLB200_EMUL
+__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_shard_kernel(WindingShard f, const uint32_t *my_supers, const uint32_t *my_count,
+                                                                                  int64_t super_rows, unsigned long long *next) {
+  __shared__ unsigned long long item_s;
+  const int64_t per = super_rows / WN_THREADS;           // blocks' worth of rows in a super-chunk
+  const unsigned long long total = (unsigned long long)*my_count * (unsigned long long)per;
+  while (true) {
+    if (threadIdx.x == 0) item_s = atomicAdd(next, 1ull);
+    __syncthreads();
+    const unsigned long long item = item_s;
+    __syncthreads();
+    if (item >= total) return;
+    const int64_t t = (int64_t)my_supers[item / per] * super_rows + (int64_t)(item % per) * WN_THREADS + threadIdx.x;
+    if (t < f.n) f(t);
+  }
+}
+// winding number only: blocks claim pieces of `piece_rows` rows off the owner's counter (system-scope atomic) until
+// the rows run out; `budget` >= 0 caps the pieces this device takes (my_count counts them)
+__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_claim_kernel(WindingShard f, unsigned long long *remote, int64_t piece_rows,
+                                                                                  int64_t budget, uint32_t *my_count) {
+  __shared__ unsigned long long piece_s;
+  while (true) {
+    if (threadIdx.x == 0) {
+      unsigned long long pc = ~0ull;
+      if (budget < 0 || (int64_t)atomicAdd(my_count, 1u) < budget) pc = atomicAdd_system(remote, 1ull);
+      piece_s = pc;
+    }
+    __syncthreads();
+    const unsigned long long pc = piece_s;
+    __syncthreads();
+    if (pc == ~0ull || (int64_t)pc * piece_rows >= f.n) return;
+    const int64_t lo = (int64_t)pc * piece_rows, hi = min(f.n, lo + piece_rows);
+    for (int64_t t = lo + threadIdx.x; t < hi; t += WN_THREADS) f(t);
+  }
+}
+#endif
+
+// epilogue of signed_distance.cpp:99-135 on the sorted intermediate results, written back in the caller's order
+struct ShardFinish {
+  int mode; int sign_type; double up, low; int32_t nF; int64_t n; const uint32_t *perm;
+  const double *D; const int32_t *Is; const double *Cs; const double *Ws;
+  double *S; int32_t *I; double *C; double *W;
+  DEVFN void operator()(int64_t t) const {
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    if (mode == 2) { W[i] = Ws[t]; return; }
+    const double sqrd = D[t];
+    if (mode == 1) { S[i] = sqrd; I[i] = Is[t]; C[i] = Cs[t]; C[n + i] = Cs[n + t]; C[2 * n + i] = Cs[2 * n + t]; return; }
+    if (sqrd >= up || sqrd < low) {
+      S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
+      if (W) W[i] = NAN;
+      return;
+    }
+    I[i] = Is[t]; C[i] = Cs[t]; C[n + i] = Cs[n + t]; C[2 * n + i] = Cs[2 * n + t];
+    if (sign_type == IGLB200_SIGN_UNSIGNED) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return; }
+    const double wf = (double)(float)Ws[t];   // narrowed to float by fast_winding_number.cpp:452
+    if (W) W[i] = wf;
+    S[i] = (1.0 - 2.0 * fabs(wf)) * sqrt(sqrd);
+  }
+};
+
+static constexpr int64_t FWN_PIECE_ROWS = 2048;   // winding-number-only shards: rows per claim
+struct ShardWs {   // per (thread, device) state of shard_run: schedule words, the list of super-chunks taken
+  DevBuf<unsigned long long> sched; DevBuf<uint32_t> supers; size_t cap = 0;
+  void ensure(size_t nsup, stream_t s) {
+    if (!sched.p) sched.alloc(SCHED_WORDS);
+    if (nsup + 1 > cap) { plat::sync(s); supers.alloc(nsup + 1); cap = nsup + 1; }
+  }
+};
+
+int64_t shard_super_rows(int64_t n, int n_shards) {
+  // >= 64 super-chunks per device so that the last ones even out the load, each large enough to keep a device's L2
+  // on one region of the tree: [8 Ki, 256 Ki] rows, a multiple of a chunk (16 packets of 32)
+  const int64_t unit = (int64_t)CP_CHUNK * 32;
+  int64_t r = n / ((int64_t)std::max(n_shards, 1) * 64);
+  r = std::max<int64_t>(int64_t(8) << 10, std::min<int64_t>(int64_t(256) << 10, r));
+  return (r + unit - 1) / unit * unit;
+}
+
+void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int sort_queries, stream_t s) {
+  const ShardLayout L(n);
+  plat::dev_memset(scratch + L.oCounter, 0, 256, s);
+  if (n == 0) return;
+  const uint32_t *perm = morton_perm(m, P, n, scratch + L.oSort, sort_queries, s);
+  plat::for_n(n, GatherSorted{P, n, perm, (double *)(scratch + L.oPs)}, s);
+}
+
+void shard_run(const iglb200_mesh *m, char *scratch, int64_t n, int mode, int sign_type, double lower, double upper, float accuracy_scale,
+               int64_t super_rows, int64_t max_supers, stream_t s) {
+  if (n == 0 || m->h.nF == 0 || m->h.nnodes == 0) return;   // finish fills the sentinels
+  const int64_t unit = (int64_t)CP_CHUNK * 32;
+  if (super_rows <= 0 || super_rows % unit) throw std::invalid_argument("super_rows must be a positive multiple of 512");
+  const ShardLayout L(n);
+  const double *Ps = (const double *)(scratch + L.oPs);
+  double *D = (double *)(scratch + L.oD), *Cs = (double *)(scratch + L.oC), *Ws = (double *)(scratch + L.oW);
+  int32_t *Is = (int32_t *)(scratch + L.oI);
+  unsigned long long *remote = (unsigned long long *)(scratch + L.oCounter);
+  const int64_t nsup = (n + super_rows - 1) / super_rows;
+  ShardWs &ws = plat::per_device<ShardWs>();
+  ws.ensure((size_t)nsup, s);
+  plat::dev_memset(ws.supers.p, 0, 4, s);              // [0] = count, [1..] = list
+  uint32_t *my_count = ws.supers.p, *my_supers = ws.supers.p + 1;
+  double low = 0.0, up = INFINITY;
+  if (mode == 0) bounds_to_sqr(lower, upper, low, up);
+  const bool fwn_sign = mode == 0 && sign_type == IGLB200_SIGN_FAST_WINDING_NUMBER;
+  if (mode == 0 && !fwn_sign && sign_type != IGLB200_SIGN_UNSIGNED) throw std::domain_error("sharded queries support the FAST_WINDING_NUMBER and UNSIGNED sign types");
+  if (mode != 2) {
+    plat::Span sp("closest", s);
+    ClosestArgs a{m->cnodes(), m->tri64(), m->triq(), Ps, n, nullptr, up, low, m->h.absmax, D, Is, Cs, nullptr, ws.sched.p};
+    a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
+    launch_closest(a, s);
+  }
+  if (mode == 2 || fwn_sign) {
+    plat::Span sp("winding", s);
+    const float acc = mode == 2 ? accuracy_scale : 2.0f;
+    WindingShard f{m->fnodes(), m->tri32(), Ps, n, acc * acc, m->h.order, D, up, low, mode == 0 ? 1 : 0, Ws, overflow_flag()};
+#ifdef IGLB200_EMUL
+    if (mode == 2) {   // no search ran: pieces straight off the owner's counter
+      for (int64_t took = 0; max_supers <= 0 || took < max_supers; ++took) {
+        const unsigned long long pc = __atomic_fetch_add(remote, 1ull, __ATOMIC_RELAXED);
+        if ((int64_t)pc * FWN_PIECE_ROWS >= n) break;
+        for (int64_t t = (int64_t)pc * FWN_PIECE_ROWS; t < std::min(n, ((int64_t)pc + 1) * FWN_PIECE_ROWS); ++t) f(t);
+      }
+    } else {
+      for (uint32_t k = 0; k < *my_count; ++k)
+        for (int64_t t = (int64_t)my_supers[k] * super_rows; t < std::min(n, ((int64_t)my_supers[k] + 1) * super_rows); ++t) f(t);
+    }
+#else
+    if (mode == 2) {
+      // winding number only (uniform cost per row): every block claims pieces of the rows straight off the owner's counter
+      winding_claim_kernel<<<plat::sm_count() * WN_MIN_BLOCKS, WN_THREADS, 0, s>>>(f, remote, FWN_PIECE_ROWS, max_supers > 0 ? max_supers : -1, my_count);
+    } else {
+      unsigned long long *next = ws.sched.p + 1 + 2 * 1024 + 1;
+      plat::dev_memset(next, 0, 8, s);
+      winding_shard_kernel<<<plat::sm_count() * WN_MIN_BLOCKS, WN_THREADS, 0, s>>>(f, my_supers, my_count, super_rows, next);
+    }
+    plat::launch_counter()++;
+    PLAT_CHECK(cudaGetLastError());
+#endif
+  }
+}
+
+void shard_finish(const iglb200_mesh *m, int64_t n, char *scratch, int mode, int sign_type, double lower, double upper, int sort_queries,
+                  double *S, int32_t *I, double *C, double *W, stream_t s) {
+  if (n == 0) return;
+  if (mode != 2 && m->h.nF == 0) { plat::for_n(n, FillConst{S, I, C, mode == 0 ? W : nullptr, n, NAN, -1, NAN}, s); return; }
+  if (m->h.nnodes == 0) {
+    if (mode == 2) plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, 0.0, 0, 0.0}, s);
+    else if (mode == 1) plat::for_n(n, FillConst{S, I, C, nullptr, n, INFINITY, -1, 0.0}, s);
+    else plat::for_n(n, FillConst{S, I, C, W, n, NAN, (int32_t)m->h.nF + 1, 0.0}, s);
+    return;
+  }
+  const ShardLayout L(n);
+  double low = 0.0, up = INFINITY;
+  if (mode == 0) bounds_to_sqr(lower, upper, low, up);
+  const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;
+  plat::Span sp("finish", s);
+  plat::for_n(n, ShardFinish{mode, sign_type, up, low, (int32_t)m->h.nF, n, perm, (const double *)(scratch + L.oD), (const int32_t *)(scratch + L.oI),
+                             (const double *)(scratch + L.oC), (const double *)(scratch + L.oW), S, I, C, W}, s);
 }
 
 // upload a strided host matrix n x 3 as canonical column-major doubles
@@ -1096,6 +1339,30 @@ int iglb200_host_free(void *p) {
 #endif
 }
 
+// page-lock memory the caller already owns (e.g. a shared-memory mapping) so that copies to/from it are true DMA
+int iglb200_host_register(void *p, uint64_t bytes) {
+#ifdef IGLB200_EMUL
+  (void)p; (void)bytes; return IGLB200_OK;
+#else
+  API_BEGIN
+  require_device();
+  if (!p) throw std::invalid_argument("null pointer");
+  PLAT_CHECK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return IGLB200_OK;
+  API_END
+#endif
+}
+int iglb200_host_unregister(void *p) {
+#ifdef IGLB200_EMUL
+  (void)p; return IGLB200_OK;
+#else
+  API_BEGIN
+  if (p) PLAT_CHECK(cudaHostUnregister(p));
+  return IGLB200_OK;
+  API_END
+#endif
+}
+
 int iglb200_mesh_create(const void *V, int v_is_f64, int64_t nV, int64_t v_rs, int64_t v_cs, const int32_t *F, int64_t nF,
                         int64_t f_rs, int64_t f_cs, int fwn_order, iglb200_mesh **out) {
   return iglb200_mesh_create_ex(V, v_is_f64, nV, v_rs, v_cs, F, nF, f_rs, f_cs, fwn_order, 0, out);
@@ -1208,6 +1475,97 @@ uint64_t iglb200_query_scratch_bytes(int64_t nP) {
   if (nP <= 0) return 256;
   const size_t a = ((size_t)nP * 4 + 255) & ~size_t(255);
   return 4 * a + ((plat::sort_pairs_temp_bytes(nP) + 255) & ~size_t(255)) + 8 * (size_t)SCHED_WORDS + 256;
+}
+
+
+// ---- sharded device-resident queries + inter-process memory
+uint64_t iglb200_shard_scratch_bytes(int64_t nP) { return ShardLayout(nP < 0 ? 0 : nP).total; }
+int64_t iglb200_shard_super_rows(int64_t nP, int n_shards) { return shard_super_rows(nP, n_shards); }
+int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int sort_queries, void *stream) {
+  API_BEGIN
+  m = mesh_here(m);
+  if (nP < 0 || !shard_scratch || (nP > 0 && !P)) throw std::invalid_argument("null pointer");
+  require_device();
+  check_count(nP);
+  plat::launch_counter() = 0;
+  shard_begin(m, P, nP, (char *)shard_scratch, sort_queries, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_shard_run_dev(const iglb200_mesh *m, void *shard_scratch, int64_t nP, int mode, int sign_type, double lower, double upper,
+                          float accuracy_scale, int64_t super_rows, int64_t max_supers, void *stream) {
+  API_BEGIN
+  m = mesh_here(m);
+  if (nP < 0 || !shard_scratch) throw std::invalid_argument("null pointer");
+  if (mode < 0 || mode > 2) throw std::invalid_argument("mode must be 0 (signed distance), 1 (squared distance) or 2 (fast winding number)");
+  require_device();
+  check_count(nP);
+  plat::launch_counter() = 0;
+  shard_run(m, (char *)shard_scratch, nP, mode, sign_type, lower, upper, accuracy_scale, super_rows, max_supers, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, void *shard_scratch, int mode, int sign_type, double lower, double upper,
+                             int sort_queries, double *S, int32_t *I, double *C, double *W, void *stream) {
+  API_BEGIN
+  m = mesh_here(m);
+  if (nP < 0 || !shard_scratch) throw std::invalid_argument("null pointer");
+  if (mode < 0 || mode > 2) throw std::invalid_argument("mode must be 0, 1 or 2");
+  if (nP > 0 && ((mode != 2 && (!S || !I || !C)) || (mode == 2 && !W))) throw std::invalid_argument("null output");
+  require_device();
+  check_count(nP);
+  plat::launch_counter() = 0;
+  shard_finish(m, nP, (char *)shard_scratch, mode, sign_type, lower, upper, sort_queries, S, I, C, W, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+// device memory another process of the same node can map (cudaIpc*): the owner's shard scratch under torchrun
+int iglb200_ipc_alloc(uint64_t bytes, void **device_ptr, unsigned char handle[64]) {
+  API_BEGIN
+  if (!device_ptr || !handle) throw std::invalid_argument("null pointer");
+  require_device();
+  *device_ptr = plat::dev_alloc((size_t)bytes);
+#ifdef IGLB200_EMUL
+  std::memset(handle, 0, 64); std::memcpy(handle, device_ptr, sizeof(void *));
+#else
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, *device_ptr);
+  if (e != cudaSuccess) { plat::dev_free(*device_ptr); *device_ptr = nullptr; plat::check(e, "cudaIpcGetMemHandle"); }
+  std::memcpy(handle, &h, 64);
+#endif
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_ipc_open(const unsigned char handle[64], void **device_ptr) {
+  API_BEGIN
+  if (!device_ptr || !handle) throw std::invalid_argument("null pointer");
+  require_device();
+#ifdef IGLB200_EMUL
+  std::memcpy(device_ptr, handle, sizeof(void *));
+#else
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  PLAT_CHECK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+#endif
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_ipc_close(void *device_ptr) {
+  API_BEGIN
+#ifndef IGLB200_EMUL
+  if (device_ptr) PLAT_CHECK(cudaIpcCloseMemHandle(device_ptr));
+#else
+  (void)device_ptr;
+#endif
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_ipc_free(void *device_ptr) {
+  API_BEGIN
+  plat::dev_free(device_ptr);
+  return IGLB200_OK;
+  API_END
 }
 
 int iglb200_last_launch_count(void) { return plat::launch_counter(); }

@@ -118,7 +118,7 @@ class SharedArrays:
             else:
                 raise RuntimeError("shared query set never appeared")
         buf = self.shm.buf
-        self.counter = np.frombuffer(buf, np.int64, 1, 0)
+        self.counter = np.frombuffer(buf, np.int64, 8, 0)   # [0], [1]: ping-pong chunk counters
         self.P = np.frombuffer(buf, np.float64, 3 * n, self._off["P"]).reshape(3, n)
         self.S = np.frombuffer(buf, np.float64, n, self._off["S"])
         self.I = np.frombuffer(buf, np.int32, n, self._off["I"])
@@ -129,7 +129,18 @@ class SharedArrays:
     def address(self):
         return self.counter.ctypes.data
 
+    def register(self, api):
+        """Page-lock this process's mapping (cudaHostRegister): every GPU then DMA-reads P and DMA-writes its chunks of
+        S/I/C/W straight from/into the shared arrays."""
+        import ctypes
+        api.check(api.lib.iglb200_host_register(ctypes.c_void_p(self.address()), self.nbytes))
+        self._registered = api
+
     def close(self, unlink=False):
+        if self._registered:
+            import ctypes
+            self._registered.lib.iglb200_host_unregister(ctypes.c_void_p(self.address()))
+            self._registered = False
         self.counter = self.P = self.S = self.I = self.C = self.W = None
         try:
             self.shm.close()

@@ -259,3 +259,52 @@ def test_cooperative_processes_share_one_query_set_gloo(tmp_path):
            "--master-port", "29613", str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "COOP_OK 2" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_sharded_device_queries_match_the_fused_path(emul_api):
+    """begin / run (two devices, super-chunks off one counter) / finish == the single-device fused kernels, bit for bit,
+    for signed distance (FWN and UNSIGNED, bounded and unbounded), squared distance and the winding number alone."""
+    import ctypes as C
+    from libigl_b200 import synth
+    api, L = emul_api, emul_api.lib
+    vp = C.c_void_p
+    V, F = synth.icosphere(3)
+    P = synth.grid_points(*synth.bbox(V), 28, 1.6)
+    n = P.shape[0]
+    Pc = np.ascontiguousarray(P.T)           # [3, n] = column-major n x 3
+    tiny, huge = float(np.finfo(float).tiny), float(np.finfo(float).max)
+    ptr = lambda a: a.ctypes.data_as(vp)
+    try:
+        api.init(2)
+        m = api.Mesh(V, F, 2)
+        scratch = np.zeros(int(L.iglb200_shard_scratch_bytes(n)), np.uint8)
+        qs = np.zeros(int(L.iglb200_query_scratch_bytes(n)), np.uint8)
+        sup = int(L.iglb200_shard_super_rows(n, 2))
+        assert sup % 512 == 0 and sup >= 8192
+        sup = 1024                                    # small super-chunks so that both devices get several
+        for mode, sign, lo, hi in ((0, 4, tiny, huge), (0, 4, 0.05, 0.4), (0, 3, tiny, huge), (1, 0, 0, 0), (2, 0, 0, 0)):
+            S, I, Cc, W = np.full(n, -5.0), np.full(n, -5, np.int32), np.full((3, n), -5.0), np.full(n, -5.0)
+            api.set_device(0)
+            api.check(L.iglb200_shard_begin_dev(m.h, ptr(Pc), n, ptr(scratch), 1, None))
+            api.check(L.iglb200_shard_run_dev(m.h, ptr(scratch), n, mode, sign, lo, hi, 2.0, sup, 5, None))   # device 0: 5 pieces
+            api.set_device(1)
+            api.check(L.iglb200_shard_run_dev(m.h, ptr(scratch), n, mode, sign, lo, hi, 2.0, sup, 0, None))   # device 1: the rest
+            assert int(scratch[:8].view(np.uint64)[0]) > 5
+            api.set_device(0)
+            api.check(L.iglb200_shard_finish_dev(m.h, n, ptr(scratch), mode, sign, lo, hi, 1, ptr(S), ptr(I), ptr(Cc), ptr(W), None))
+            S1, I1, C1, W1 = np.empty(n), np.empty(n, np.int32), np.empty((3, n)), np.empty(n)
+            if mode == 0:
+                api.check(L.iglb200_signed_distance_dev(m.h, ptr(Pc), n, sign, lo, hi, ptr(S1), ptr(I1), ptr(C1), ptr(W1), None, ptr(qs), 1, None))
+                assert np.array_equal(S, S1, equal_nan=True) and np.array_equal(I, I1) and np.array_equal(Cc, C1) and np.array_equal(W, W1, equal_nan=True)
+                if lo > tiny:
+                    assert np.isnan(S).any() and not np.isnan(S).all()
+            elif mode == 1:
+                api.check(L.iglb200_squared_distance_dev(m.h, ptr(Pc), n, ptr(S1), ptr(I1), ptr(C1), ptr(qs), 1, None))
+                assert np.array_equal(S, S1) and np.array_equal(I, I1) and np.array_equal(Cc, C1)
+            else:
+                api.check(L.iglb200_fwn_eval_dev(m.h, ptr(Pc), n, 2.0, ptr(W1), ptr(qs), 1, None))
+                assert np.array_equal(W, W1)
+        m.close()
+    finally:
+        api.set_device(0)
+        api.init(1)
