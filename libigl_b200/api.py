@@ -645,7 +645,7 @@ def parse_arena(buf: np.ndarray):
                     ("nlevels", "<i8"), ("nexcluded", "<i8"), ("order", "<i4"), ("pad", "<i4"),
                     ("bbox_lo", "<f8", 3), ("bbox_hi", "<f8", 3), ("absmax", "<f4"), ("padf", "<f4"),
                     ("off_tri64", "<u8"), ("off_tri32", "<u8"), ("off_fnodes", "<u8"), ("off_cnodes", "<u8"),
-                    ("off_triq", "<u8"), ("off_pn", "<u8"), ("reserved", "<u8", 6)])
+                    ("off_triq", "<u8"), ("off_pn", "<u8"), ("reserved", "<u8", 6), ("off_pnodes", "<u8")])
     h = buf[:hdr.itemsize].view(hdr)[0]
     nF, nn = int(h["nF"]), int(h["nnodes"])
     tri64 = buf[int(h["off_tri64"]):int(h["off_tri64"]) + 72 * nF].view(np.float64).reshape(nF, 3, 3)
@@ -653,11 +653,15 @@ def parse_arena(buf: np.ndarray):
     fn = buf[int(h["off_fnodes"]):int(h["off_fnodes"]) + 384 * nn]
     fchild = fn.view(np.uint32).reshape(nn, 96)[:, :4].copy()
     fdata = fn.view(np.float32).reshape(nn, 96)[:, 4:].reshape(nn, 23, 4).copy()
-    cn = buf[int(h["off_cnodes"]):int(h["off_cnodes"]) + 128 * nn]
-    cbox = cn.view(np.float32).reshape(nn, 32)[:, :24].reshape(nn, 6, 4).copy()
-    cchild = cn.view(np.uint32).reshape(nn, 32)[:, 24:28].copy()
+    pnb = buf[int(h["off_pnodes"]):int(h["off_pnodes"]) + 160 * nn]
+    pill = pnb.view(np.float32).reshape(nn, 40)[:, :32].reshape(nn, 8, 4).copy()     # rows cx cy cz nx ny nz R t, 4 lanes
+    cchild = pnb.view(np.uint32).reshape(nn, 40)[:, 32:36].copy()
+    cbox = None
+    if int(h["off_cnodes"]):
+        cn = buf[int(h["off_cnodes"]):int(h["off_cnodes"]) + 128 * nn]
+        cbox = cn.view(np.float32).reshape(nn, 32)[:, :24].reshape(nn, 6, 4).copy()
     pn = None
     if int(h["off_pn"]):
         pn = buf[int(h["off_pn"]):int(h["off_pn"]) + 168 * nF].view(np.float64).reshape(nF, 7, 3).copy()
-    return dict(header=h, tri64=tri64, tri32=tri32, fwn_child=fchild, fwn_data=fdata, cp_box=cbox, cp_child=cchild,
+    return dict(header=h, tri64=tri64, tri32=tri32, fwn_child=fchild, fwn_data=fdata, cp_box=cbox, cp_pill=pill, cp_child=cchild,
                 pseudonormals=pn)

@@ -5,6 +5,7 @@
 #define IGLB200_BUILDER_TU 1
 #include "mesh.h"
 #include "wn.h"
+#include "pill.h"
 
 namespace fwn {
 
@@ -236,13 +237,21 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
     m->h.off_tri32 = off; off = align(off + (uint64_t)16 * TRI32_STRIDE * nF);
     m->h.off_triq = off; off = align(off + (uint64_t)16 * TRIQ_STRIDE * nF);
     m->h.off_fnodes = off; off = align(off + (uint64_t)sizeof(FwnNode) * nn);
-    m->h.off_cnodes = off; off = align(off + (uint64_t)sizeof(CpNode) * nn);
+    // the box nodes serve the exact winding number only (wn.h descends into clusters whose box holds the query)
+    DevBuf<CpNode> cn_tmp;
+    const bool keep_boxes = (flags & 2) != 0;
+    m->h.off_cnodes = 0;
+    if (keep_boxes) { m->h.off_cnodes = off; off = align(off + (uint64_t)sizeof(CpNode) * nn); }
+    else cn_tmp.alloc((size_t)nn);
+    m->h.off_pnodes = off; off = align(off + (uint64_t)sizeof(PillNode) * nn);
     m->h.off_pn = 0;
     if (flags & 1) { m->h.off_pn = off; off = align(off + (uint64_t)8 * PN_STRIDE * nF); }
     m->h.off_wn_cnt = m->h.off_wn_start = m->h.off_wn_bstart = m->h.off_wn_bent = m->h.off_wn_leafface = m->h.n_wn_bent = 0;
     wn::Built wb;
+    wn::Ranges ranges;
+    if (nn) wn::cluster_ranges(tree, nF, ranges, s);
     if ((flags & 2) && nn) {
-      wn::build(tree, dF.p, f_rs, f_cs, nF, wb, s);
+      wn::build(tree, ranges, dF.p, f_rs, f_cs, nF, wb, s);
       m->h.n_wn_bent = wb.nent;
       m->h.off_wn_cnt = off; off = align(off + (uint64_t)16 * nn);
       m->h.off_wn_start = off; off = align(off + (uint64_t)16 * nn);
@@ -267,8 +276,13 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
       for (int l = tree_levels(tree) - 1; l >= 0; --l) {
         const uint32_t first = tree.level_start[l], cnt = tree.level_start[l + 1] - first;
         plat::for_n(cnt, NodeMoments{tree.nodes.p, (const float4 *)(m->arena + m->h.off_tri32), (const double *)(m->arena + m->h.off_tri64),
-                                     boxes.p, locals.p, (FwnNode *)(m->arena + m->h.off_fnodes), (CpNode *)(m->arena + m->h.off_cnodes), first, order}, s);
+                                     boxes.p, locals.p, (FwnNode *)(m->arena + m->h.off_fnodes),
+                                     keep_boxes ? (CpNode *)(m->arena + m->h.off_cnodes) : cn_tmp.p, first, order}, s);
       }
+      // oriented bounds of the closest-triangle search
+      double scale = (double)m->h.absmax;
+      pill::build(tree, (const double *)(m->arena + m->h.off_tri64), ranges.cnt.p, ranges.start.p, ranges.leafface.p, scale,
+                  (PillNode *)(m->arena + m->h.off_pnodes), s);
       // faces dropped by the NaN/Inf filter = faces not referenced by any node
       plat::sync(s);
     }

@@ -89,7 +89,7 @@ struct MortonKeys {  // 30-bit Morton code of each query inside the doubled scen
 };
 
 struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
-  const fwn::CpNode *nodes; const double *tri64; const float4 *triq;
+  const fwn::PillNode *nodes; const double *tri64; const float4 *triq;
   const double *P; int64_t n; const uint32_t *perm;
   double up, low; float absmax;
   double *sqrD; int32_t *I; double *C;
@@ -142,11 +142,11 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
       cur = stack[sp];
     }
     have = false; ++nvis;
-    const CpNode n = a.nodes[cur];
+    const PillNode n = a.nodes[cur];
     const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
     const uint32_t imask = n.pad.x, tmask = n.pad.y;
     float d2[32][4];
-    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) d2[l][i] = lane_box_d2(n, i, L[l]);
+    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) d2[l][i] = lane_pill_d2(n, i, L[l]);
     // faces first: they tighten the bounds the internal children are judged by
     bool want[4] = {false, false, false, false};   // voted before any face of the node is tested, as the kernel does
     for (int i = 0; i < 4; ++i)
@@ -305,23 +305,23 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       if (!have) {
         if (sp == 0) break;
         --sp;
-        // no re-test against the tightened bounds here: measured slower than simply visiting the
-        // node (its four box tests reject it just as well)
+        // no re-test against the tightened bounds here: for a packet (smallest bound any lane had at the push against the
+        // largest threshold any lane still has) it rejects next to nothing; the node's own tests do it
         cur = stack[sp];
       }
       have = false;
       if (COUNT) ++nvis;
-      const CpNode *np = a.nodes + cur;
-      CpNode n;
+      const PillNode *np = a.nodes + cur;
+      PillNode n;
       { float4 c4, p4;
-        ld256(&np->lox, n.lox, n.loy); ld256(&np->loz, n.loz, n.hix); ld256(&np->hiy, n.hiy, n.hiz); ld256(&np->child, c4, p4);
+        ld256(&np->cx, n.cx, n.cy); ld256(&np->cz, n.cz, n.nx); ld256(&np->ny, n.ny, n.nz); ld256(&np->R, n.R, n.t); ld256(&np->child, c4, p4);
         n.child = make_uint4(__float_as_uint(c4.x), __float_as_uint(c4.y), __float_as_uint(c4.z), __float_as_uint(c4.w));
         n.pad = make_uint4(__float_as_uint(p4.x), __float_as_uint(p4.y), 0u, 0u); }
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
       const uint32_t imask = n.pad.x, tmask = n.pad.y;
       float d2[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) d2[i] = lane_box_d2(n, i, L);
+      for (int i = 0; i < 4; ++i) d2[i] = lane_pill_d2(n, i, L);
       // faces first: they tighten the bounds the internal children are judged by
       if (tmask) {   // warp-uniform
         // two face records in flight where two neighbouring lanes are wanted: one load round trip instead of two
@@ -676,7 +676,7 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   bounds_to_sqr(lower, upper, low, up);
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   { plat::Span sp("closest", s);
-    launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr,
+    launch_closest(ClosestArgs{m->pnodes(), m->tri64(), m->triq(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr,
                                scratch ? carve(scratch, n).sched : nullptr}, s); }
   if (sign_type == IGLB200_SIGN_PSEUDONORMAL) {
     plat::Span sp("pseudonormal", s);
@@ -715,7 +715,7 @@ void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, dou
   }
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   plat::Span sp("closest", s);
-  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr,
+  launch_closest(ClosestArgs{m->pnodes(), m->tri64(), m->triq(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr,
                              scratch ? carve(scratch, n).sched : nullptr}, s);
 }
 
@@ -870,7 +870,7 @@ void shard_run(const iglb200_mesh *m, char *scratch, int64_t n, int mode, int si
   if (mode == 0 && !fwn_sign && sign_type != IGLB200_SIGN_UNSIGNED) throw std::domain_error("sharded queries support the FAST_WINDING_NUMBER and UNSIGNED sign types");
   if (mode != 2) {
     plat::Span sp("closest", s);
-    ClosestArgs a{m->cnodes(), m->tri64(), m->triq(), Ps, n, nullptr, up, low, m->h.absmax, D, Is, Cs, nullptr, ws.sched.p};
+    ClosestArgs a{m->pnodes(), m->tri64(), m->triq(), Ps, n, nullptr, up, low, m->h.absmax, D, Is, Cs, nullptr, ws.sched.p};
     a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
     launch_closest(a, s);
   }
@@ -1628,7 +1628,7 @@ int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colma
   plat::h2d(dP.p, P_host_colmajor, (size_t)24 * n, nullptr);
   plat::dev_memset(acc.p, 0, 16, nullptr);
   const uint32_t *perm = morton_perm(m, dP.p, n, scratch.p, 1, nullptr);
-  launch_closest(ClosestArgs{m->cnodes(), m->tri64(), m->triq(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p,
+  launch_closest(ClosestArgs{m->pnodes(), m->tri64(), m->triq(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p,
                              carve(scratch.p, n).sched}, nullptr);
   plat::for_n(n, CountWinding{m->fnodes(), m->tri32(), dP.p, n, m->h.order, acc.p + 2, overflow_flag()}, nullptr);
   uint32_t h[4];

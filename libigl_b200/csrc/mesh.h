@@ -3,8 +3,8 @@
 // broadcast of [arena, arena+bytes).
 //
 //   [ArenaHeader | tri64 (9 f64 / face) | tri32 (3 float4 / face) | triq (4 float4 / face) |
-//    fwn nodes (384 B) | closest-point nodes (128 B) | optional pseudonormals (21 f64 / face) |
-//    optional exact-winding-number tables (wn.h)]
+//    fwn nodes (384 B) | box nodes (128 B) | optional pseudonormals (21 f64 / face) |
+//    optional exact-winding-number tables (wn.h) | pill nodes (160 B): the closest-triangle search]
 //
 // tri64/tri32 are the faces' vertices gathered once at build time (the
 // reference dereferences V through F for every leaf test: AABB.cpp:1413-1432,
@@ -26,6 +26,7 @@ struct ArenaHeader {
   // exact winding number (wn.h), 0 = absent: per cluster (4 per node) face count, first leaf slot, first chain
   // entry (4*nnodes+1 entries); chain entries; faces in depth-first leaf order
   uint64_t off_wn_cnt, off_wn_start, off_wn_bstart, off_wn_bent, off_wn_leafface, n_wn_bent;
+  uint64_t off_pnodes;   // PillNode (160 B / node): the closest-triangle search walks these; off_cnodes (boxes) serve the exact winding number
 };
 
 struct iglb200_mesh {
@@ -48,6 +49,7 @@ struct iglb200_mesh {
   const float4 *triq() const { return (const float4 *)(arena + h.off_triq); }
   const fwn::FwnNode *fnodes() const { return (const fwn::FwnNode *)(arena + h.off_fnodes); }
   const fwn::CpNode *cnodes() const { return (const fwn::CpNode *)(arena + h.off_cnodes); }
+  const fwn::PillNode *pnodes() const { return (const fwn::PillNode *)(arena + h.off_pnodes); }
   const double *pn() const { return h.off_pn ? (const double *)(arena + h.off_pn) : nullptr; }
 };
 

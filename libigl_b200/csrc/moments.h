@@ -35,6 +35,21 @@ struct alignas(128) CpNode {  // 128 B = one L2 line: child boxes SoA over the 4
   uint4 pad;  // .x = bitmask of lanes that are internal nodes, .y = lanes that are faces
 };
 
+// Node of the closest-triangle search: every child lane (an internal cluster or a single face) is bounded by an
+// ORIENTED CYLINDER ("pill box"): centre c, unit axis n, radius R about the axis, half-height t along it —
+//     lower bound of the distance from p:  sqrt( max(|(p-c).n| - t, 0)^2 + max(|(p-c) - ((p-c).n) n| - R, 0)^2 ).
+// The axis is the cluster's area-weighted mean normal, so t is the cluster's deviation from its mean plane (curvature,
+// noise) — not, as with an axis-aligned box, the height of its tilted faces.  For a query at distance d the candidates
+// are the clusters within ~sqrt(2 d t) of the foot point: independent of the mesh resolution for smooth surfaces
+// (boxes: t ~ face size).  A face lane is the same bound with t ~ 0: a disc.  8 rows x 4 lanes + children + masks = 160 B
+// = five 32-byte sectors.  Absent lanes carry t = -inf (bound = +inf).
+struct alignas(32) PillNode {
+  float4 cx, cy, cz, nx, ny, nz, R, t;
+  uint4 child;
+  uint4 pad;  // .x = bitmask of lanes that are internal nodes, .y = lanes that are faces
+};
+static_assert(sizeof(PillNode) == 160, "PillNode layout");
+
 // tri32: 3 float4 per face, a,b,c = (float)vertex in .xyz — the reference's V.cast<float>()
 // (signed_distance.cpp:66); the winding number and the moments read exactly these.
 static constexpr int TRI32_STRIDE = 3;

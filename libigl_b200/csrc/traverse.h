@@ -147,7 +147,7 @@ DEVFN float tri_dist_f32(const float4 Q0, const float4 Q1, const float4 Q2, cons
 // running state of one query during the walk (registers)
 struct CpLane {
   float px, py, pz;
-  float slack3;   // sqrt(3) * rounding allowance of one fp32 box test, folded into thr2
+  float slack3;   // rounding allowance of one fp32 bound test, folded into thr2
   float u;        // 2^-24 * max(|p|, |mesh|)
   float best_ub;  // fp32 upper bound of the distance to the nearest face seen so far
   float thr2;     // prune a box when its squared lower bound exceeds this
@@ -175,9 +175,9 @@ DEVFN void lane_set_ub(CpLane &L, float ub) {
 DEVFN void lane_init(CpLane &L, CpExact &X, D3 p, double up_sqr_d, float absmax) {
   L.px = (float)p.x; L.py = (float)p.y; L.pz = (float)p.z;
   const float M = fmaxf(fmaxf(fabsf(L.px), fabsf(L.py)), fmaxf(fabsf(L.pz), absmax));
-  // each difference lo - p / p - hi of a box test is off by <= 2^-24 * M; the norm of the three by sqrt(3) times
-  // that; four times as much is allowed for and added to the pruning threshold instead of widening the query
-  L.slack3 = M * (2.3841858e-7f * 1.7320509f);
+  // rounding allowance of one bound test (pill_lb2: < 64 * 2^-24 M); twice as much is added to the pruning threshold
+  // instead of widening the query
+  L.slack3 = M * 7.6293945e-6f;   // 128 * 2^-24
   L.u = M * 5.9604645e-8f * 1.0000002f;
   X.ncand = 0; X.min_lb = INFINITY;
   X.d2 = up_sqr_d; X.face = -1;
@@ -259,6 +259,25 @@ DEVFN float box_lb2(float lx, float ly, float lz, float hx, float hy, float hz, 
 DEVFN float lane_box_d2(const CpNode &n, int i, const CpLane &L) {
   return box_lb2(((const float *)&n.lox)[i], ((const float *)&n.loy)[i], ((const float *)&n.loz)[i],
                  ((const float *)&n.hix)[i], ((const float *)&n.hiy)[i], ((const float *)&n.hiz)[i], L);
+}
+// Squared lower bound of the distance from the query to the oriented cylinder of child lane i (PillNode, moments.h) in
+// plain fp32.  With w = p - c:  z = w.n,  l = w - z n,  bound^2 = max(|z| - t, 0)^2 + max(|l| - R, 0)^2.
+// Rounding: the query is rounded to fp32 (<= u per coordinate, u = 2^-24 M, M = max |coordinate| of query and mesh), the
+// stored axis is unit to 2^-23, the three dot products / differences each lose <= 3 ulp of |w| <= 2 sqrt(3) M, the
+// approximate square root 2 ulp of |l|: |z|, |l| and hence the bound are off by < 64 * 2^-24 M in total.  lane_init folds
+// 128 * 2^-24 M into the pruning threshold, so a cylinder the exact distance would keep is never pruned.
+DEVFN float pill_lb2(float cx, float cy, float cz, float nx, float ny, float nz, float R, float t, const CpLane &L) {
+  const float wx = L.px - cx, wy = L.py - cy, wz = L.pz - cz;
+  const float z = wx * nx + wy * ny + wz * nz;
+  const float lx = wx - z * nx, ly = wy - z * ny, lz = wz - z * nz;
+  const float rho = sqrt_fast(lx * lx + ly * ly + lz * lz);
+  const float a = fmaxf(fabsf(z) - t, 0.f), b = fmaxf(rho - R, 0.f);
+  return a * a + b * b;
+}
+DEVFN float lane_pill_d2(const PillNode &n, int i, const CpLane &L) {
+  return pill_lb2(((const float *)&n.cx)[i], ((const float *)&n.cy)[i], ((const float *)&n.cz)[i],
+                  ((const float *)&n.nx)[i], ((const float *)&n.ny)[i], ((const float *)&n.nz)[i],
+                  ((const float *)&n.R)[i], ((const float *)&n.t)[i], L);
 }
 
 // The walk itself is a PACKET traversal: the 32 queries of a warp (neighbours in

@@ -131,20 +131,31 @@ struct Built {   // temporary device arrays, copied into the arena by create_mes
   uint64_t nent = 0, nleaf = 0;
 };
 
-inline void build(const fwn::Tree &tree, const int32_t *dF, int64_t f_rs, int64_t f_cs, int64_t nF, Built &out, stream_t s) {
+// cluster = child lane (4 per node): number of faces below it and its contiguous range of depth-first leaf slots
+struct Ranges { plat::DevBuf<uint32_t> parent, cnt, start, leafface, leafcluster; };
+inline void cluster_ranges(const fwn::Tree &tree, int64_t nF, Ranges &r, stream_t s) {
+  const int64_t nn = tree.nnodes, nc = 4 * nn;
+  const int levels = (int)tree.level_start.size() - 1;
+  r.parent.alloc((size_t)nn); r.leafcluster.alloc((size_t)nF + 1); r.cnt.alloc((size_t)nc); r.start.alloc((size_t)nc); r.leafface.alloc((size_t)nF + 1);
+  plat::for_n(nn, ParentClusters{tree.nodes.p, r.parent.p}, s);
+  for (int l = levels - 1; l >= 0; --l)
+    plat::for_n(tree.level_start[l + 1] - tree.level_start[l], CountLevel{tree.nodes.p, r.cnt.p, tree.level_start[l]}, s);
+  for (int l = 0; l < levels; ++l)
+    plat::for_n(tree.level_start[l + 1] - tree.level_start[l],
+                StartLevel{tree.nodes.p, r.cnt.p, r.parent.p, r.start.p, r.leafface.p, r.leafcluster.p, tree.level_start[l]}, s);
+}
+
+inline void build(const fwn::Tree &tree, const Ranges &rg, const int32_t *dF, int64_t f_rs, int64_t f_cs, int64_t nF, Built &out, stream_t s) {
   using plat::DevBuf;
   const int64_t nn = tree.nnodes, nc = 4 * nn;
   if (nn == 0) return;
   if (3 * nF > 0xFFFFFFFFll) throw std::invalid_argument("winding number: more than 2^32/3 faces");
-  const int levels = (int)tree.level_start.size() - 1;
-  DevBuf<uint32_t> parent((size_t)nn), leafcluster((size_t)nF);
+  const uint32_t *parent_p = rg.parent.p, *leafcluster_p = rg.leafcluster.p;
   out.cnt.alloc((size_t)nc); out.start.alloc((size_t)nc); out.bstart.alloc((size_t)nc + 1); out.leafface.alloc((size_t)nF);
-  plat::for_n(nn, ParentClusters{tree.nodes.p, parent.p}, s);
-  for (int l = levels - 1; l >= 0; --l)
-    plat::for_n(tree.level_start[l + 1] - tree.level_start[l], CountLevel{tree.nodes.p, out.cnt.p, tree.level_start[l]}, s);
-  for (int l = 0; l < levels; ++l)
-    plat::for_n(tree.level_start[l + 1] - tree.level_start[l],
-                StartLevel{tree.nodes.p, out.cnt.p, parent.p, out.start.p, out.leafface.p, leafcluster.p, tree.level_start[l]}, s);
+  plat::d2d(out.cnt.p, rg.cnt.p, (size_t)4 * nc, s);
+  plat::d2d(out.start.p, rg.start.p, (size_t)4 * nc, s);
+  plat::d2d(out.leafface.p, rg.leafface.p, (size_t)4 * nF, s);
+  struct { const uint32_t *p; } parent{parent_p}, leafcluster{leafcluster_p};
   const int64_t nleaf = nF - tree.nexcluded, nh = 3 * nleaf;
   out.nleaf = (uint64_t)nleaf;
   DevBuf<uint64_t> key((size_t)nh), skey((size_t)nh);
