@@ -230,7 +230,8 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // Sharded schedule, one level above the per-SM chunks: sched[0] = (super-chunk << 32 | chunks of it handed out).  When a
 // super-chunk is used up, one thread of the device takes the next one off the owner's counter (atomicAdd over NVLink when
 // the owner is a peer) and notes it in my_supers.  Returns a chunk index; chunks past the last packet end the caller's warp.
-static __device__ __noinline__ unsigned long long next_chunk_sharded(const ClosestArgs &a, uint32_t npackets) {
+struct ShardSched { unsigned long long *sched, *remote; uint32_t super_chunks; uint32_t *my_supers, *my_count; int64_t max_supers; };
+static __device__ __noinline__ unsigned long long next_chunk_sharded(const ShardSched a, uint32_t npackets) {
   unsigned long long *G = a.sched, *glock = a.sched + 1 + 2 * 1024;
   while (true) {
     const unsigned long long old = atomicAdd(G, 1ull);
@@ -281,7 +282,8 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         if ((uint32_t)old < CP_CHUNK) { packet = (uint32_t)(old >> 32) * CP_CHUNK + (uint32_t)old; break; }
         if (atomicCAS(lock, 0ull, 1ull) == 0ull) {   // this warp refills the SM's chunk
           if ((uint32_t)(*(volatile unsigned long long *)st) >= CP_CHUNK) {
-            const unsigned long long nc = a.remote ? next_chunk_sharded(a, npackets) : atomicAdd(a.sched, 1ull);
+            const unsigned long long nc = a.remote ? next_chunk_sharded(ShardSched{a.sched, a.remote, a.super_chunks, a.my_supers, a.my_count, a.max_supers}, npackets)
+                                                               : atomicAdd(a.sched, 1ull);
             atomicExch(st, nc << 32);
           }
           __threadfence();

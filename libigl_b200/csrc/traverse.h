@@ -202,22 +202,29 @@ DEVFN void lane_exact(CpExact &X, const double *tri64, D3 p, uint32_t f) {
 }
 
 // evaluate every live candidate in fp64 and empty the list (rare: kept out of line so the
-// fp64 code does not sit in the walk's instruction footprint)
+// fp64 code does not sit in the walk's instruction footprint).  Takes and returns the upper bound BY VALUE: the lane
+// state must never have its address taken, or it lives in local memory and every node visit reloads it.
 #ifdef IGLB200_EMUL
 inline
 #else
 static __device__ __noinline__
 #endif
-void lane_flush(CpLane &L, CpExact &X, const double *tri64, CpQueryRef q) {
+float lane_flush_ub(float best_ub, CpExact &X, const double *tri64, const double *P, int64_t n, int64_t qi) {
+  const CpQueryRef q{P, n, qi};
   const D3 p = load_query(q);
   const int nc = X.ncand;
   for (int k = 0; k < nc; ++k)
-    if (X.cl[k] <= L.best_ub) lane_exact(X, tri64, p, X.cf[k]);
+    if (X.cl[k] <= best_ub) lane_exact(X, tri64, p, X.cf[k]);
   X.ncand = 0; X.min_lb = INFINITY;
   if (X.face >= 0) {
     const float ub = f_up(sqrt(X.d2)) * 1.0000002f;
-    if (ub < L.best_ub) lane_set_ub(L, ub);
+    if (ub < best_ub) return ub;
   }
+  return best_ub;
+}
+DEVFN void lane_flush(CpLane &L, CpExact &X, const double *tri64, const CpQueryRef &q) {
+  const float ub = lane_flush_ub(L.best_ub, X, tri64, q.P, q.n, q.qi);
+  if (ub < L.best_ub) lane_set_ub(L, ub);
 }
 
 // stage-1 result for face f (caller has already checked d32 - err <= best_ub)
