@@ -645,7 +645,7 @@ def parse_arena(buf: np.ndarray):
                     ("nlevels", "<i8"), ("nexcluded", "<i8"), ("order", "<i4"), ("pad", "<i4"),
                     ("bbox_lo", "<f8", 3), ("bbox_hi", "<f8", 3), ("absmax", "<f4"), ("padf", "<f4"),
                     ("off_tri64", "<u8"), ("off_tri32", "<u8"), ("off_fnodes", "<u8"), ("off_cnodes", "<u8"),
-                    ("off_triq", "<u8"), ("off_pn", "<u8"), ("reserved", "<u8", 6), ("off_pnodes", "<u8")])
+                    ("off_triq", "<u8"), ("off_pn", "<u8"), ("reserved", "<u8", 6), ("sigma", "<f8"), ("off_pnodes", "<u8")])
     h = buf[:hdr.itemsize].view(hdr)[0]
     nF, nn = int(h["nF"]), int(h["nnodes"])
     tri64 = buf[int(h["off_tri64"]):int(h["off_tri64"]) + 72 * nF].view(np.float64).reshape(nF, 3, 3)

@@ -18,13 +18,11 @@ template <class VT> struct GatherFaces {
   int64_t f_rs, f_cs;
   double *tri64;
   float4 *tri32;
-  float4 *triq;
   uint32_t *err;      // [0] = out-of-range index seen
   uint32_t *absacc;   // order-encoded max |coordinate|
   uint32_t *bbacc;    // [6] order-encoded fp32 hull (rounded outward) of the geometry
   DEVFN void operator()(int64_t f) const {
     float amax = 0.f;
-    double vtx[3][3];
     for (int k = 0; k < 3; ++k) {
       int64_t vi = F[f * f_rs + k * f_cs];
       if (vi < 0 || vi >= nV) { plat::atomic_max(err, 1u); vi = 0; }
@@ -32,7 +30,6 @@ template <class VT> struct GatherFaces {
       for (int d = 0; d < 3; ++d) x[d] = (double)V[vi * v_rs + d * v_cs];
       for (int d = 0; d < 3; ++d) tri64[9 * f + 3 * k + d] = x[d];
       tri32[TRI32_STRIDE * f + k] = make_float4((float)x[0], (float)x[1], (float)x[2], 0.f);
-      for (int d = 0; d < 3; ++d) vtx[k][d] = x[d];
       for (int d = 0; d < 3; ++d) {
         const float up = f_round_up(fabs(x[d]));
         if (up == up) amax = fmaxf(amax, up);
@@ -41,7 +38,16 @@ template <class VT> struct GatherFaces {
       }
     }
     plat::atomic_max(absacc, plat::f2ord(amax));
-    // fp32-stage record of the closest-triangle search (traverse.h: tri_dist_f32): local frame in fp64
+  }
+};
+
+// fp32-stage record of the closest-triangle search (traverse.h: tri_dist_f32): the face in its own orthonormal frame,
+// computed in fp64 from the vertices SCALED by sigma (a power of two, exact)
+struct FaceRecords {
+  const double *tri64; float4 *triq; double sigma;
+  DEVFN void operator()(int64_t f) const {
+    double vtx[3][3];
+    for (int k = 0; k < 3; ++k) for (int d = 0; d < 3; ++d) vtx[k][d] = tri64[9 * f + 3 * k + d] * sigma;
     int k0 = 0;
     double best = -1.0;
     for (int k = 0; k < 3; ++k) {
@@ -209,14 +215,22 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
       plat::h2d(acc.p, init, sizeof(init), s);
     }
     if (v_is_f64)
-      plat::for_n(nF, GatherFaces<double>{(const double *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, triq.p, acc.p, acc.p + 1, acc.p + 2}, s);
+      plat::for_n(nF, GatherFaces<double>{(const double *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, acc.p, acc.p + 1, acc.p + 2}, s);
     else
-      plat::for_n(nF, GatherFaces<float>{(const float *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, triq.p, acc.p, acc.p + 1, acc.p + 2}, s);
+      plat::for_n(nF, GatherFaces<float>{(const float *)dV.p, nV, v_rs, v_cs, dF.p, f_rs, f_cs, tri64.p, tri32.p, acc.p, acc.p + 1, acc.p + 2}, s);
     uint32_t hacc[8];
     plat::d2h(hacc, acc.p, sizeof(hacc), s);
     plat::sync(s);
     if (hacc[0]) throw std::invalid_argument("F contains a vertex index outside [0, #V)");
     m->h.absmax = nF ? plat::ord2f(hacc[1]) : 0.f;
+    {
+      // sigma = 2^-e with absmax = f * 2^e, f in [0.5, 1)
+      int e = 0;
+      const double am = (double)m->h.absmax;
+      m->h.sigma = 1.0;
+      if (am > 0.0 && am < INFINITY) { std::frexp(am, &e); m->h.sigma = std::ldexp(1.0, -e); }
+    }
+    plat::for_n(nF, FaceRecords{tri64.p, triq.p, m->h.sigma}, s);
     for (int d = 0; d < 3; ++d) {
       m->h.bbox_lo[d] = nF ? (double)plat::ord2f(hacc[2 + d]) : 0.0;
       m->h.bbox_hi[d] = nF ? (double)plat::ord2f(hacc[5 + d]) : 0.0;
@@ -280,8 +294,7 @@ iglb200_mesh *create_mesh(const void *V, int v_is_f64, int64_t nV, int64_t v_rs,
                                      keep_boxes ? (CpNode *)(m->arena + m->h.off_cnodes) : cn_tmp.p, first, order}, s);
       }
       // oriented bounds of the closest-triangle search
-      double scale = (double)m->h.absmax;
-      pill::build(tree, (const double *)(m->arena + m->h.off_tri64), ranges.cnt.p, ranges.start.p, ranges.leafface.p, scale,
+      pill::build(tree, (const double *)(m->arena + m->h.off_tri64), ranges.cnt.p, ranges.start.p, ranges.leafface.p, m->h.sigma,
                   (PillNode *)(m->arena + m->h.off_pnodes), s);
       // faces dropped by the NaN/Inf filter = faces not referenced by any node
       plat::sync(s);

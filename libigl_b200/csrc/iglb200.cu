@@ -102,6 +102,9 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   uint32_t super_chunks = 0;
   uint32_t *my_supers = nullptr, *my_count = nullptr;
   int64_t max_supers = 0;   // > 0: take at most this many (static partition / tests)
+  // the fp32 stage works in coordinates scaled by a power of two so that the mesh's max |coordinate| lies in [0.5, 1):
+  // exact, and squares can neither overflow nor go denormal whatever the units of the mesh (absmax above is scaled too)
+  double sigma = 1.0;
 };
 
 static constexpr int64_t SCHED_WORDS = 1 + 2 * 1024 + 3;   // next chunk; per SM id: state, refill lock; sharded: lock, block counter, spare
@@ -129,8 +132,8 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     const int64_t t = base + l;
     valid[l] = t < a.n;
     qi[l] = valid[l] ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
-    qr[l] = CpQueryRef{a.P, a.n, qi[l]};
-    lane_init(L[l], X[l], valid[l] ? load_query(qr[l]) : D3{0.0, 0.0, 0.0}, a.up, a.absmax);
+    qr[l] = CpQueryRef{a.P, a.n, qi[l], a.sigma};
+    lane_init(L[l], X[l], valid[l] ? load_query(qr[l]) : D3{0.0, 0.0, 0.0}, a.up, a.absmax, a.sigma);
     if (!valid[l] || a.low > a.up) { L[l].best_ub = -INFINITY; L[l].thr2 = -1.f; }
   }
   uint32_t nvis = 0, ntri = 0;
@@ -146,7 +149,7 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
     const uint32_t imask = n.pad.x, tmask = n.pad.y;
     float d2[32][4];
-    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) d2[l][i] = lane_pill_d2(n, i, L[l]);
+    for (int l = 0; l < 32; ++l) for (int i = 0; i < 4; ++i) d2[l][i] = lane_pill_d2(n, i, L[l], n.pad.z);
     // faces first: they tighten the bounds the internal children are judged by
     bool want[4] = {false, false, false, false};   // voted before any face of the node is tested, as the kernel does
     for (int i = 0; i < 4; ++i)
@@ -298,8 +301,8 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     const bool valid = t < a.n;
     const int64_t qi = valid ? (a.perm ? (int64_t)a.perm[t] : t) : 0;
     CpLane L;
-    const CpQueryRef qr{a.P, a.n, qi};
-    lane_init(L, X, valid ? load_query(qr) : D3{0.0, 0.0, 0.0}, a.up, a.absmax);
+    const CpQueryRef qr{a.P, a.n, qi, a.sigma};
+    lane_init(L, X, valid ? load_query(qr) : D3{0.0, 0.0, 0.0}, a.up, a.absmax, a.sigma);
     if (!valid || a.low > a.up) { L.best_ub = -INFINITY; L.thr2 = -1.f; }
     uint32_t nvis = 0, ntri = 0;
     int sp = 0; uint32_t cur = 0; bool have = true;
@@ -318,12 +321,17 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       { float4 c4, p4;
         ld256(&np->cx, n.cx, n.cy); ld256(&np->cz, n.cz, n.nx); ld256(&np->ny, n.ny, n.nz); ld256(&np->R, n.R, n.t); ld256(&np->child, c4, p4);
         n.child = make_uint4(__float_as_uint(c4.x), __float_as_uint(c4.y), __float_as_uint(c4.z), __float_as_uint(c4.w));
-        n.pad = make_uint4(__float_as_uint(p4.x), __float_as_uint(p4.y), 0u, 0u); }
+        n.pad = make_uint4(__float_as_uint(p4.x), __float_as_uint(p4.y), __float_as_uint(p4.z), 0u); }
       const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
       const uint32_t imask = n.pad.x, tmask = n.pad.y;
       float d2[4];
+      if (n.pad.z == 0u) {   // warp-uniform: the common node has cylinders only
 #pragma unroll
-      for (int i = 0; i < 4; ++i) d2[i] = lane_pill_d2(n, i, L);
+        for (int i = 0; i < 4; ++i) d2[i] = lane_pill_d2(n, i, L, 0u);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d2[i] = lane_pill_d2(n, i, L, n.pad.z);
+      }
       // faces first: they tighten the bounds the internal children are judged by
       if (tmask) {   // warp-uniform
         // two face records in flight where two neighbouring lanes are wanted: one load round trip instead of two
@@ -334,13 +342,13 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
 #define CP_FACE1(i) { const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i]; \
           float4 T0, T1, T2, T3; CP_LOADQ(tq, T0, T1, T2, T3); if (COUNT) ++ntri; \
           float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err); \
-          if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); }
+          if (!(d32 - err > L.best_ub)) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); }
 #define CP_FACE2(i, j) { const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)ch[i], *tr = a.triq + TRIQ_STRIDE * (size_t)ch[j]; \
           float4 T0, T1, T2, T3, U0, U1, U2, U3; CP_LOADQ(tq, T0, T1, T2, T3); CP_LOADQ(tr, U0, U1, U2, U3); if (COUNT) ntri += 2; \
           float err, erq; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err); \
           const float e32 = tri_dist_f32(U0, U1, U2, U3, L.px, L.py, L.pz, L.u, erq); \
-          if (d32 - err <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); \
-          if (e32 - erq <= L.best_ub) lane_offer(L, X, a.tri64, qr, ch[j], e32, erq); }
+          if (!(d32 - err > L.best_ub)) lane_offer(L, X, a.tri64, qr, ch[i], d32, err); \
+          if (!(e32 - erq > L.best_ub)) lane_offer(L, X, a.tri64, qr, ch[j], e32, erq); }
         if (w[0] && w[1]) CP_FACE2(0, 1) else if (w[0]) CP_FACE1(0) else if (w[1]) CP_FACE1(1)
         if (w[2] && w[3]) CP_FACE2(2, 3) else if (w[2]) CP_FACE1(2) else if (w[3]) CP_FACE1(3)
 #undef CP_FACE1
@@ -628,6 +636,13 @@ const uint32_t *morton_perm(const iglb200_mesh *m, const double *P, int64_t n, v
   return sc.perm;
 }
 
+ClosestArgs closest_args(const iglb200_mesh *m, const double *P, int64_t n, const uint32_t *perm, double up, double low,
+                         double *sqrD, int32_t *I, double *C, uint32_t *counters, unsigned long long *sched) {
+  ClosestArgs a{m->pnodes(), m->tri64(), m->triq(), P, n, perm, up, low, (float)((double)m->h.absmax * m->h.sigma), sqrD, I, C, counters, sched};
+  a.sigma = m->h.sigma;
+  return a;
+}
+
 void check_mesh(const iglb200_mesh *m) {
   if (!m || m->h.magic != IGLB200_ARENA_MAGIC) throw std::invalid_argument("invalid mesh handle");
 }
@@ -678,8 +693,7 @@ void run_signed_distance(const iglb200_mesh *m, const double *P, int64_t n, int 
   bounds_to_sqr(lower, upper, low, up);
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   { plat::Span sp("closest", s);
-    launch_closest(ClosestArgs{m->pnodes(), m->tri64(), m->triq(), P, n, perm, up, low, m->h.absmax, S, I, C, nullptr,
-                               scratch ? carve(scratch, n).sched : nullptr}, s); }
+    launch_closest(closest_args(m, P, n, perm, up, low, S, I, C, nullptr, scratch ? carve(scratch, n).sched : nullptr), s); }
   if (sign_type == IGLB200_SIGN_PSEUDONORMAL) {
     plat::Span sp("pseudonormal", s);
     plat::for_n(n, PseudonormalQuery{m->tri64(), m->pn(), P, n, up, low, (int32_t)m->h.nF, S, I, C, N}, s);
@@ -717,8 +731,7 @@ void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, dou
   }
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   plat::Span sp("closest", s);
-  launch_closest(ClosestArgs{m->pnodes(), m->tri64(), m->triq(), P, n, perm, INFINITY, 0.0, m->h.absmax, sqrD, I, C, nullptr,
-                             scratch ? carve(scratch, n).sched : nullptr}, s);
+  launch_closest(closest_args(m, P, n, perm, INFINITY, 0.0, sqrD, I, C, nullptr, scratch ? carve(scratch, n).sched : nullptr), s);
 }
 
 void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_scale, double *W, void *scratch,
@@ -872,7 +885,7 @@ void shard_run(const iglb200_mesh *m, char *scratch, int64_t n, int mode, int si
   if (mode == 0 && !fwn_sign && sign_type != IGLB200_SIGN_UNSIGNED) throw std::domain_error("sharded queries support the FAST_WINDING_NUMBER and UNSIGNED sign types");
   if (mode != 2) {
     plat::Span sp("closest", s);
-    ClosestArgs a{m->pnodes(), m->tri64(), m->triq(), Ps, n, nullptr, up, low, m->h.absmax, D, Is, Cs, nullptr, ws.sched.p};
+    ClosestArgs a = closest_args(m, Ps, n, nullptr, up, low, D, Is, Cs, nullptr, ws.sched.p);
     a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
     launch_closest(a, s);
   }
@@ -1630,8 +1643,7 @@ int iglb200_debug_visit_counts(const iglb200_mesh *m, const double *P_host_colma
   plat::h2d(dP.p, P_host_colmajor, (size_t)24 * n, nullptr);
   plat::dev_memset(acc.p, 0, 16, nullptr);
   const uint32_t *perm = morton_perm(m, dP.p, n, scratch.p, 1, nullptr);
-  launch_closest(ClosestArgs{m->pnodes(), m->tri64(), m->triq(), dP.p, n, perm, INFINITY, 0.0, m->h.absmax, dD.p, dI.p, dC.p, acc.p,
-                             carve(scratch.p, n).sched}, nullptr);
+  launch_closest(closest_args(m, dP.p, n, perm, INFINITY, 0.0, dD.p, dI.p, dC.p, acc.p, carve(scratch.p, n).sched), nullptr);
   plat::for_n(n, CountWinding{m->fnodes(), m->tri32(), dP.p, n, m->h.order, acc.p + 2, overflow_flag()}, nullptr);
   uint32_t h[4];
   plat::d2h(h, acc.p, 16, nullptr);

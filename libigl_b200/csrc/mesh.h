@@ -26,6 +26,8 @@ struct ArenaHeader {
   // exact winding number (wn.h), 0 = absent: per cluster (4 per node) face count, first leaf slot, first chain
   // entry (4*nnodes+1 entries); chain entries; faces in depth-first leaf order
   uint64_t off_wn_cnt, off_wn_start, off_wn_bstart, off_wn_bent, off_wn_leafface, n_wn_bent;
+  double sigma;          // power of two: the fp32 stage of the closest-triangle search (triq, pnodes) is stored in coordinates x sigma,
+                         // chosen so that absmax * sigma lies in [0.5, 1)
   uint64_t off_pnodes;   // PillNode (160 B / node): the closest-triangle search walks these; off_cnodes (boxes) serve the exact winding number
 };
 

@@ -46,7 +46,8 @@ struct alignas(128) CpNode {  // 128 B = one L2 line: child boxes SoA over the 4
 struct alignas(32) PillNode {
   float4 cx, cy, cz, nx, ny, nz, R, t;
   uint4 child;
-  uint4 pad;  // .x = bitmask of lanes that are internal nodes, .y = lanes that are faces
+  uint4 pad;  // .x = bitmask of lanes that are internal nodes, .y = lanes that are faces, .z = lanes bounded by an axis-aligned
+              // box instead (rows cx,cy,cz = lo, nx,ny,nz = hi): whichever has the smaller surface area (pill.h)
 };
 static_assert(sizeof(PillNode) == 160, "PillNode layout");
 

@@ -10,6 +10,8 @@
 //   1. normal sum, area sum, axis-aligned extent       -> axis (fp32, re-normalised in fp64)
 //   2. extent in an orthonormal frame (u, v, axis)      -> centre (fp32)
 //   3. max distance from the axis line, max |height|    -> R, t (rounded up)
+// All of it in the mesh's SCALED coordinates (x sigma, a power of two with max |coordinate| * sigma in [0.5, 1): the fp32
+// stage can neither overflow nor go denormal whatever the units of the mesh).
 // Everything is exact min/max arithmetic in fp64 against the fp32 values the kernel will read, so the cylinder
 // contains the fp64 geometry; the kernel's own fp32 rounding is covered by the slack in traverse.h: lane_init.
 #pragma once
@@ -27,7 +29,9 @@ struct Acc3 { double lat2, zabs; };
 struct Frame { double a[3], u[3], v[3]; float af[3]; };
 
 DEVFN void acc1_init(Acc1 &A) { for (int d = 0; d < 3; ++d) { A.n[d] = 0.0; A.lo[d] = INFINITY; A.hi[d] = -INFINITY; } A.area = 0.0; }
-DEVFN void acc1_face(Acc1 &A, const double *t) {
+DEVFN void acc1_face(Acc1 &A, const double *tt, double sg) {
+  double t[9];
+  for (int k = 0; k < 9; ++k) t[k] = tt[k] * sg;
   const double e1[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, e2[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
   const double c[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
   const double l = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
@@ -63,7 +67,9 @@ DEVFN Frame make_frame(const Acc1 &A) {
   return f;
 }
 DEVFN void acc2_init(Acc2 &A) { for (int d = 0; d < 3; ++d) { A.lo[d] = INFINITY; A.hi[d] = -INFINITY; } }
-DEVFN void acc2_face(Acc2 &A, const Frame &f, const double *t) {
+DEVFN void acc2_face(Acc2 &A, const Frame &f, const double *tt, double sg) {
+  double t[9];
+  for (int k = 0; k < 9; ++k) t[k] = tt[k] * sg;
   for (int k = 0; k < 3; ++k) {
     const double *x = t + 3 * k;
     const double p[3] = {x[0] * f.u[0] + x[1] * f.u[1] + x[2] * f.u[2], x[0] * f.v[0] + x[1] * f.v[1] + x[2] * f.v[2],
@@ -76,7 +82,9 @@ DEVFN void centre_of(const Frame &f, const Acc2 &A, float cf[3]) {
   const double m[3] = {0.5 * (A.lo[0] + A.hi[0]), 0.5 * (A.lo[1] + A.hi[1]), 0.5 * (A.lo[2] + A.hi[2])};
   for (int d = 0; d < 3; ++d) cf[d] = (float)(m[0] * f.u[d] + m[1] * f.v[d] + m[2] * f.a[d]);
 }
-DEVFN void acc3_face(Acc3 &A, const Frame &f, const float cf[3], const double *t) {
+DEVFN void acc3_face(Acc3 &A, const Frame &f, const float cf[3], const double *tt, double sg) {
+  double t[9];
+  for (int k = 0; k < 9; ++k) t[k] = tt[k] * sg;
   for (int k = 0; k < 3; ++k) {
     const double w[3] = {t[3 * k] - (double)cf[0], t[3 * k + 1] - (double)cf[1], t[3 * k + 2] - (double)cf[2]};
     const double z = w[0] * f.a[0] + w[1] * f.a[1] + w[2] * f.a[2];
@@ -92,9 +100,42 @@ DEVFN float extent_up(double x, double scale) {
   if ((double)f < y) f = plat::u2f(plat::f2u(f) + 1u);   // next float up (y >= 0)
   return f;
 }
-DEVFN void store_lane(PillNode *nodes, uint32_t cluster, const Frame &f, const float cf[3], const Acc3 &A, double scale) {
+DEVFN float f_dn(double d) { float f = (float)d; if ((double)f > d) f = plat::u2f(f > 0.f ? plat::f2u(f) - 1u : (f < 0.f ? plat::f2u(f) + 1u : 0x80000001u)); return f; }
+DEVFN float f_upw(double d) { float f = (float)d; if ((double)f < d) f = plat::u2f(f > 0.f ? plat::f2u(f) + 1u : (f < 0.f ? plat::f2u(f) - 1u : 0x00000001u)); return f; }
+// A lane keeps whichever bound has the smaller surface area — the measure of how often a far query's sphere reaches a
+// convex body (mean shadow = area / 4): the cylinder for clusters that are flat in SOME direction (smooth surfaces, single
+// faces), the axis-aligned box for needle-like faces and for clusters as thick as they are wide (noise, the top of the tree).
+DEVFN void store_lane(PillNode *nodes, uint32_t cluster, const Frame &f, const float cf[3], const Acc3 &A, double scale, const Acc1 &ext,
+                      uint32_t *kinds) {
   PillNode &n = nodes[cluster >> 2];
   const int l = (int)(cluster & 3u);
+  {
+    const double e[3] = {ext.hi[0] - ext.lo[0], ext.hi[1] - ext.lo[1], ext.hi[2] - ext.lo[2]};
+    double sbox = 2.0 * (e[0] * e[1] + e[1] * e[2] + e[2] * e[0]);
+    const double R0 = sqrt(A.lat2), t0 = A.zabs;
+    double spill = 6.283185307179586 * R0 * (R0 + 2.0 * t0);
+    const int mode = (int)scale;
+    if (mode == 0) sbox = INFINITY;
+    if (mode == 3) sbox = -1.0;
+    if (mode == 2) {
+      // far-field measure: a body of lateral radius R and half-thickness t about the surface is reached by the sphere of a
+      // query at distance D when it lies within R + sqrt(2 D t) of the foot point; D = a quarter of the scene (scaled: 0.5)
+      const double D = 0.5;
+      const double tb = 0.5 * (fabs(f.a[0]) * e[0] + fabs(f.a[1]) * e[1] + fabs(f.a[2]) * e[2]);
+      const double rb2 = 0.25 * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) - tb * tb;
+      const double rb = sqrt(rb2 > 0.0 ? rb2 : 0.0);
+      sbox = (rb + sqrt(2.0 * D * tb)); sbox *= sbox;
+      spill = (R0 + sqrt(2.0 * D * t0)); spill *= spill;
+    }
+    if (sbox < spill && e[0] == e[0] && e[1] == e[1] && e[2] == e[2]) {
+      ((float *)&n.cx)[l] = f_dn(ext.lo[0]); ((float *)&n.cy)[l] = f_dn(ext.lo[1]); ((float *)&n.cz)[l] = f_dn(ext.lo[2]);
+      ((float *)&n.nx)[l] = f_upw(ext.hi[0]); ((float *)&n.ny)[l] = f_upw(ext.hi[1]); ((float *)&n.nz)[l] = f_upw(ext.hi[2]);
+      ((float *)&n.R)[l] = 0.f; ((float *)&n.t)[l] = 0.f;
+      kinds[cluster] = 1u;
+      return;
+    }
+  }
+  kinds[cluster] = 0u;
   ((float *)&n.cx)[l] = cf[0]; ((float *)&n.cy)[l] = cf[1]; ((float *)&n.cz)[l] = cf[2];
   ((float *)&n.nx)[l] = f.af[0]; ((float *)&n.ny)[l] = f.af[1]; ((float *)&n.nz)[l] = f.af[2];
   float R = extent_up(sqrt(A.lat2), scale), t = extent_up(A.zabs, scale);
@@ -120,40 +161,47 @@ struct InitNodes {   // children, lane masks, absent lanes
   }
 };
 
+struct SetKinds {   // pad.z = lanes bounded by a box
+  const uint32_t *kinds; PillNode *out;
+  DEVFN void operator()(int64_t i) const {
+    out[i].pad.z = (kinds[4 * i] & 1u) | ((kinds[4 * i + 1] & 1u) << 1) | ((kinds[4 * i + 2] & 1u) << 2) | ((kinds[4 * i + 3] & 1u) << 3);
+  }
+};
+
 struct SmallClusters {   // one thread per cluster of <= BIG faces
-  const double *tri64; const uint32_t *leafface, *start, *cnt; PillNode *out; double scale;
+  const double *tri64; const uint32_t *leafface, *start, *cnt; PillNode *out; double sigma; uint32_t *kinds; int mode;
   DEVFN void operator()(int64_t c) const {
     const uint32_t n = cnt[c];
     if (n == 0 || n > BIG) return;
     const uint32_t s = start[c];
     Acc1 a1; acc1_init(a1);
-    for (uint32_t k = 0; k < n; ++k) acc1_face(a1, tri64 + 9 * (size_t)leafface[s + k]);
+    for (uint32_t k = 0; k < n; ++k) acc1_face(a1, tri64 + 9 * (size_t)leafface[s + k], sigma);
     const Frame f = make_frame(a1);
     Acc2 a2; acc2_init(a2);
-    for (uint32_t k = 0; k < n; ++k) acc2_face(a2, f, tri64 + 9 * (size_t)leafface[s + k]);
+    for (uint32_t k = 0; k < n; ++k) acc2_face(a2, f, tri64 + 9 * (size_t)leafface[s + k], sigma);
     float cf[3]; centre_of(f, a2, cf);
     Acc3 a3{0.0, 0.0};
-    for (uint32_t k = 0; k < n; ++k) acc3_face(a3, f, cf, tri64 + 9 * (size_t)leafface[s + k]);
-    store_lane(out, (uint32_t)c, f, cf, a3, scale);
+    for (uint32_t k = 0; k < n; ++k) acc3_face(a3, f, cf, tri64 + 9 * (size_t)leafface[s + k], sigma);
+    store_lane(out, (uint32_t)c, f, cf, a3, (double)mode, a1, kinds);
   }
 };
 struct FlagBig { const uint32_t *cnt; uint32_t *flag; int64_t nc; DEVFN void operator()(int64_t c) const { flag[c] = (c < nc && cnt[c] > BIG) ? 1u : 0u; } };
 struct ListBig { const uint32_t *flag, *scan; uint32_t *list; DEVFN void operator()(int64_t c) const { if (flag[c]) list[scan[c]] = (uint32_t)c; } };
 
 struct BigClusters {   // one block per cluster of > BIG faces (fixed reduction tree: deterministic)
-  const double *tri64; const uint32_t *leafface, *start, *cnt, *list; PillNode *out; double scale;
+  const double *tri64; const uint32_t *leafface, *start, *cnt, *list; PillNode *out; double sigma; uint32_t *kinds; int mode;
 #ifdef IGLB200_EMUL
   DEVFN void tile(uint32_t k) const {
     const uint32_t c = list[k], n = cnt[c], s = start[c];
     Acc1 a1; acc1_init(a1);
-    for (uint32_t e = 0; e < n; ++e) acc1_face(a1, tri64 + 9 * (size_t)leafface[s + e]);
+    for (uint32_t e = 0; e < n; ++e) acc1_face(a1, tri64 + 9 * (size_t)leafface[s + e], sigma);
     const Frame f = make_frame(a1);
     Acc2 a2; acc2_init(a2);
-    for (uint32_t e = 0; e < n; ++e) acc2_face(a2, f, tri64 + 9 * (size_t)leafface[s + e]);
+    for (uint32_t e = 0; e < n; ++e) acc2_face(a2, f, tri64 + 9 * (size_t)leafface[s + e], sigma);
     float cf[3]; centre_of(f, a2, cf);
     Acc3 a3{0.0, 0.0};
-    for (uint32_t e = 0; e < n; ++e) acc3_face(a3, f, cf, tri64 + 9 * (size_t)leafface[s + e]);
-    store_lane(out, c, f, cf, a3, scale);
+    for (uint32_t e = 0; e < n; ++e) acc3_face(a3, f, cf, tri64 + 9 * (size_t)leafface[s + e], sigma);
+    store_lane(out, c, f, cf, a3, (double)mode, a1, kinds);
   }
 #else
   template <class A, class M> static __device__ A block_reduce(A v, A *sh, M merge) {
@@ -172,34 +220,39 @@ struct BigClusters {   // one block per cluster of > BIG faces (fixed reduction 
     Acc2 *sh2 = (Acc2 *)sh1; Acc3 *sh3 = (Acc3 *)sh1;
     const uint32_t c = list[k], n = cnt[c], s = start[c];
     Acc1 a1; acc1_init(a1);
-    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) acc1_face(a1, tri64 + 9 * (size_t)leafface[s + e]);
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) acc1_face(a1, tri64 + 9 * (size_t)leafface[s + e], sigma);
     a1 = block_reduce(a1, sh1, [](Acc1 &x, const Acc1 &y) { acc1_merge(x, y); });
     const Frame f = make_frame(a1);
     Acc2 a2; acc2_init(a2);
-    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) acc2_face(a2, f, tri64 + 9 * (size_t)leafface[s + e]);
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) acc2_face(a2, f, tri64 + 9 * (size_t)leafface[s + e], sigma);
     a2 = block_reduce(a2, sh2, [](Acc2 &x, const Acc2 &y) { acc2_merge(x, y); });
     float cf[3]; centre_of(f, a2, cf);
     Acc3 a3{0.0, 0.0};
-    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) acc3_face(a3, f, cf, tri64 + 9 * (size_t)leafface[s + e]);
+    for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) acc3_face(a3, f, cf, tri64 + 9 * (size_t)leafface[s + e], sigma);
     a3 = block_reduce(a3, sh3, [](Acc3 &x, const Acc3 &y) { x.lat2 = fmax(x.lat2, y.lat2); x.zabs = fmax(x.zabs, y.zabs); });
-    if (threadIdx.x == 0) store_lane(out, c, f, cf, a3, scale);
+    if (threadIdx.x == 0) store_lane(out, c, f, cf, a3, (double)mode, a1, kinds);
   }
 #endif
 };
 
 // `cnt`, `start`, `leafface`: the cluster ranges (4 per node) in depth-first leaf order
 inline void build(const fwn::Tree &tree, const double *tri64, const uint32_t *cnt, const uint32_t *start, const uint32_t *leafface,
-                  double scale, PillNode *out, stream_t s) {
+                  double sigma, PillNode *out, stream_t s) {
   using plat::DevBuf;
   const int64_t nn = tree.nnodes, nc = 4 * nn;
   if (nn == 0) return;
+  const char *mode_env = std::getenv("IGLB200_BOUND_MODE");   // tuning aid: 0 cylinders only, 1 smaller surface area (default), 2 far-field measure, 3 boxes only
+  const int mode = mode_env ? std::atoi(mode_env) : 1;
+  DevBuf<uint32_t> kinds((size_t)nc);
+  plat::dev_memset(kinds.p, 0, (size_t)4 * nc, s);
   plat::for_n(nn, InitNodes{tree.nodes.p, out}, s);
-  plat::for_n(nc, SmallClusters{tri64, leafface, start, cnt, out, scale}, s);
+  plat::for_n(nc, SmallClusters{tri64, leafface, start, cnt, out, sigma, kinds.p, mode}, s);
   DevBuf<uint32_t> flag((size_t)nc + 1), scan((size_t)nc + 1), list((size_t)nc + 1);
   plat::for_n(nc + 1, FlagBig{cnt, flag.p, nc}, s);
   plat::exclusive_scan_u32(flag.p, scan.p, nc + 1, s);
   plat::for_n(nc, ListBig{flag.p, scan.p, list.p}, s);
-  plat::tiles_dyn(scan.p + nc, BigClusters{tri64, leafface, start, cnt, list.p, out, scale}, s);
+  plat::tiles_dyn(scan.p + nc, BigClusters{tri64, leafface, start, cnt, list.p, out, sigma, kinds.p, mode}, s);
+  plat::for_n(nn, SetKinds{kinds.p, out}, s);
   plat::sync(s);
 }
 

@@ -163,7 +163,7 @@ struct CpExact {
   float cl[CP_NCAND];       // their lower bounds
 };
 // where the query itself can be re-read by the fp64 stage
-struct CpQueryRef { const double *P; int64_t n, qi; };
+struct CpQueryRef { const double *P; int64_t n, qi; double sigma; };
 DEVFN D3 load_query(const CpQueryRef &q) { return D3{q.P[q.qi], q.P[q.n + q.qi], q.P[2 * q.n + q.qi]}; }
 
 DEVFN void lane_set_ub(CpLane &L, float ub) {
@@ -172,18 +172,24 @@ DEVFN void lane_set_ub(CpLane &L, float ub) {
   L.thr2 = t * t * 1.000001f;  // rounded up; absorbs the rounding of a box test (slack3) and of its sum of squares
 }
 
-DEVFN void lane_init(CpLane &L, CpExact &X, D3 p, double up_sqr_d, float absmax) {
-  L.px = (float)p.x; L.py = (float)p.y; L.pz = (float)p.z;
+// `absmax` and the lane's whole fp32 state are in the mesh's SCALED coordinates (x sigma, a power of two: exact)
+DEVFN void lane_init(CpLane &L, CpExact &X, D3 p, double up_sqr_d, float absmax, double sigma) {
+  L.px = (float)(p.x * sigma); L.py = (float)(p.y * sigma); L.pz = (float)(p.z * sigma);
   const float M = fmaxf(fmaxf(fabsf(L.px), fabsf(L.py)), fmaxf(fabsf(L.pz), absmax));
   // rounding allowance of one bound test (pill_lb2: < 64 * 2^-24 M); twice as much is added to the pruning threshold
   // instead of widening the query
   L.slack3 = M * 7.6293945e-6f;   // 128 * 2^-24
   L.u = M * 5.9604645e-8f * 1.0000002f;
+  // a query astronomically far from the mesh (its squares overflow fp32): the fp32 stage is blind, every face is a
+  // candidate of the fp64 stage (brute force: what the exact answer takes when all faces tie to within 1e-16)
+  if (!(M < 1.0e18f)) L.u = INFINITY;
   X.ncand = 0; X.min_lb = INFINITY;
   X.d2 = up_sqr_d; X.face = -1;
-  const float ub = (up_sqr_d < 3.0e38) ? f_up(sqrt(up_sqr_d)) * 1.0000002f : INFINITY;
+  const double ups = sqrt(up_sqr_d) * sigma;
+  const bool bounded = ups < 1.0e18;   // its square must stay finite in fp32
+  const float ub = bounded ? f_up(ups) * 1.0000002f : INFINITY;
   L.best_ub = ub;
-  if (up_sqr_d < 3.0e38) lane_set_ub(L, ub); else L.thr2 = INFINITY;
+  if (bounded) lane_set_ub(L, ub); else L.thr2 = INFINITY;
 }
 
 DEVFN double face_sqr_distance(const double *tri64, D3 p, uint32_t f, D3 &cc) {
@@ -209,28 +215,29 @@ inline
 #else
 static __device__ __noinline__
 #endif
-float lane_flush_ub(float best_ub, CpExact &X, const double *tri64, const double *P, int64_t n, int64_t qi) {
-  const CpQueryRef q{P, n, qi};
+float lane_flush_ub(float best_ub, CpExact &X, const double *tri64, const double *P, int64_t n, int64_t qi, double sigma) {
+  const CpQueryRef q{P, n, qi, sigma};
   const D3 p = load_query(q);
   const int nc = X.ncand;
   for (int k = 0; k < nc; ++k)
-    if (X.cl[k] <= best_ub) lane_exact(X, tri64, p, X.cf[k]);
+    if (!(X.cl[k] > best_ub)) lane_exact(X, tri64, p, X.cf[k]);
   X.ncand = 0; X.min_lb = INFINITY;
   if (X.face >= 0) {
-    const float ub = f_up(sqrt(X.d2)) * 1.0000002f;
+    const float ub = f_up(sqrt(X.d2) * sigma) * 1.0000002f;   // the exact distance in the scaled units of the fp32 stage
     if (ub < best_ub) return ub;
   }
   return best_ub;
 }
 DEVFN void lane_flush(CpLane &L, CpExact &X, const double *tri64, const CpQueryRef &q) {
-  const float ub = lane_flush_ub(L.best_ub, X, tri64, q.P, q.n, q.qi);
+  const float ub = lane_flush_ub(L.best_ub, X, tri64, q.P, q.n, q.qi, q.sigma);
   if (ub < L.best_ub) lane_set_ub(L, ub);
 }
 
 // stage-1 result for face f (caller has already checked d32 - err <= best_ub)
 DEVFN void lane_offer(CpLane &L, CpExact &X, const double *tri64, const CpQueryRef &q, uint32_t f, float d32, float err) {
-  const float lb = d32 - err;
-  if (!(lb <= L.best_ub)) return;
+  float lb = d32 - err;
+  if (lb > L.best_ub) return;
+  if (!(lb == lb)) lb = 0.f;   // a non-finite fp32 distance (a query astronomically far from the mesh) proves nothing: keep the face
   const float ub = d32 + err;
   int nc = X.ncand;
   float mlb = X.min_lb;
@@ -238,7 +245,7 @@ DEVFN void lane_offer(CpLane &L, CpExact &X, const double *tri64, const CpQueryR
   if (nc == CP_NCAND) {
     X.ncand = nc;
     lane_flush(L, X, tri64, q);
-    if (!(lb <= L.best_ub)) return;
+    if (lb > L.best_ub) return;
     nc = 0; mlb = INFINITY;
   }
   X.cf[nc] = f; X.cl[nc] = lb;
@@ -254,19 +261,6 @@ DEVFN void lane_finish(CpLane &L, CpExact &X, const double *tri64, const CpQuery
   face_sqr_distance(tri64, load_query(q), (uint32_t)res.face, res.c);   // closest point of the winner
 }
 
-// Squared distance from the query to a box in plain fp32; its rounding (of the differences and of the sum) is
-// allowed for in the threshold it is compared with (thr2, lane_set_ub), so the comparison never prunes a box that
-// the exact distance would keep.
-DEVFN float box_lb2(float lx, float ly, float lz, float hx, float hy, float hz, const CpLane &L) {
-  const float dx = fmaxf(fmaxf(lx - L.px, L.px - hx), 0.f);
-  const float dy = fmaxf(fmaxf(ly - L.py, L.py - hy), 0.f);
-  const float dz = fmaxf(fmaxf(lz - L.pz, L.pz - hz), 0.f);
-  return dx * dx + dy * dy + dz * dz;
-}
-DEVFN float lane_box_d2(const CpNode &n, int i, const CpLane &L) {
-  return box_lb2(((const float *)&n.lox)[i], ((const float *)&n.loy)[i], ((const float *)&n.loz)[i],
-                 ((const float *)&n.hix)[i], ((const float *)&n.hiy)[i], ((const float *)&n.hiz)[i], L);
-}
 // Squared lower bound of the distance from the query to the oriented cylinder of child lane i (PillNode, moments.h) in
 // plain fp32.  With w = p - c:  z = w.n,  l = w - z n,  bound^2 = max(|z| - t, 0)^2 + max(|l| - R, 0)^2.
 // Rounding: the query is rounded to fp32 (<= u per coordinate, u = 2^-24 M, M = max |coordinate| of query and mesh), the
@@ -281,7 +275,17 @@ DEVFN float pill_lb2(float cx, float cy, float cz, float nx, float ny, float nz,
   const float a = fmaxf(fabsf(z) - t, 0.f), b = fmaxf(rho - R, 0.f);
   return a * a + b * b;
 }
-DEVFN float lane_pill_d2(const PillNode &n, int i, const CpLane &L) {
+DEVFN float box_lb2(float lx, float ly, float lz, float hx, float hy, float hz, const CpLane &L) {
+  const float dx = fmaxf(fmaxf(lx - L.px, L.px - hx), 0.f);
+  const float dy = fmaxf(fmaxf(ly - L.py, L.py - hy), 0.f);
+  const float dz = fmaxf(fmaxf(lz - L.pz, L.pz - hz), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+// kind: the node's box-lane mask (warp-uniform)
+DEVFN float lane_pill_d2(const PillNode &n, int i, const CpLane &L, uint32_t kind) {
+  if ((kind >> i) & 1u)
+    return box_lb2(((const float *)&n.cx)[i], ((const float *)&n.cy)[i], ((const float *)&n.cz)[i],
+                   ((const float *)&n.nx)[i], ((const float *)&n.ny)[i], ((const float *)&n.nz)[i], L);
   return pill_lb2(((const float *)&n.cx)[i], ((const float *)&n.cy)[i], ((const float *)&n.cz)[i],
                   ((const float *)&n.nx)[i], ((const float *)&n.ny)[i], ((const float *)&n.nz)[i],
                   ((const float *)&n.R)[i], ((const float *)&n.t)[i], L);

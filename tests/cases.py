@@ -101,6 +101,36 @@ def case_closest_vs_brute(api, V, F, P, what):
     m.close()
 
 
+def case_closest_extreme_scales(api):
+    """The fp32 stage of the search works in coordinates scaled by a power of two, so the result must equal the all-fp64
+    brute force whatever the units of the mesh: 3e19 (squares overflow fp32), 1e-20 (squares are denormal), queries far
+    outside the mesh, and a mesh far from the origin."""
+    V, F = synth.icosphere(2)
+    P = synth.random_points(600, -2.0, 2.0, 5)
+    for scale in (3e19, 1e-20, 7.0e-3, 1.0):
+        m = api.Mesh(V * scale, F, 0)
+        for Q in (P * scale, P * scale * 1e6, (P + 40.0) * scale):
+            D, I, C = m.squared_distance(Q)
+            Db, Ib, Cb = oracle.brute_closest(V * scale, F, Q)
+            assert np.array_equal(D, Db) and np.array_equal(I, Ib) and np.array_equal(C, Cb), scale
+        m.close()
+    # astronomically far queries (the fp32 distances are inf/NaN): still the exact answer
+    m = api.Mesh(V, F, 0)
+    Q = P * 1e25
+    D, I, C = m.squared_distance(Q)
+    Db, Ib, Cb = oracle.brute_closest(V, F, Q)
+    assert np.array_equal(D, Db) and np.array_equal(I, Ib) and np.array_equal(C, Cb)
+    m.close()
+    # a mesh far from the origin (offset 1e4 x its size)
+    Vo = V + np.array([1.0e4, -2.0e4, 3.0e4])
+    m = api.Mesh(Vo, F, 0)
+    Q = P + np.array([1.0e4, -2.0e4, 3.0e4])
+    D, I, C = m.squared_distance(Q)
+    Db, Ib, Cb = oracle.brute_closest(Vo, F, Q)
+    assert np.array_equal(D, Db) and np.array_equal(I, Ib) and np.array_equal(C, Cb)
+    m.close()
+
+
 def case_fwn_orders(api, V, F, Q):
     """Taylor orders 0 and 1 (fast_winding_number(V,F,order,bvh), order < 2) against the genuine core."""
     for order in (0, 1):

@@ -130,3 +130,7 @@ def test_signed_distance_winding_number_and_default(emul_api):
 
 def test_marching_cubes_sparse(emul_api):
     cases.case_marching_cubes_sparse(emul_api)
+
+
+def test_closest_extreme_scales(emul_api):
+    cases.case_closest_extreme_scales(emul_api)
