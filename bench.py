@@ -7,8 +7,8 @@ FAST_WINDING_NUMBER sign, 256^3 grid queries against a 1 M-face torus-knot mesh)
 A "step" is one pass of the hot path over ONE FIXED query set (strong scaling: the set does not grow with N).
   value : device-resident throughput.  The query set and the outputs live in rank 0's HBM.  Per step: rank 0
           Morton-sorts once; every rank (one process per GPU, torchrun) takes super-chunks of sorted queries off a
-          counter in rank 0's memory (atomics over NVLink), reads them from and writes its results to rank 0's
-          memory directly (CUDA-IPC-mapped peer memory: the gather is the kernels' own epilogue); rank 0 un-sorts.
+          counter in rank 0's memory (atomics over NVLink), reads the queries from and writes S/I/C/W to rank 0's
+          memory directly (CUDA-IPC-mapped peer memory: scatter and gather are the kernels' own loads and stores).
           Two tiny NCCL all-reduces per step order the streams.  CUDA events on the launching streams, max over ranks.
   e2e   : the same metric through the host-pointer C ABI call a libigl user makes, H2D + kernels + D2H inside the
           timed region, page-locked host arrays.  N > 1: the ranks call iglb200_signed_distance_coop on ONE query set in
@@ -342,25 +342,38 @@ def ours_mesh(args, cfg):
         bcast_ms = e0.elapsed_time(e1)
     info = mesh.info()
 
-    # --- rank 0 owns the device-resident query set, the outputs and the shard scratch (IPC-mapped by the others)
-    sbytes = int(L.iglb200_shard_scratch_bytes(nq))
-    scratch = vp()
+    # --- rank 0 owns the device-resident query set and the outputs: ONE allocation [scratch | P | S | I | C | W] that the
+    #     other ranks map with CUDA IPC (their kernels read P and write S/I/C/W in rank 0's HBM over NVLink)
+    al = lambda x: (x + 255) & ~255
+    sbytes = al(int(L.iglb200_shard_scratch_bytes(nq)))
+    offP = sbytes
+    offS = offP + al(24 * nq)
+    offI = offS + al(8 * nq)
+    offC = offI + al(4 * nq)
+    offW = offC + al(24 * nq)
+    total = offW + al(8 * nq)
+    base = vp()
     handle = ctypes.create_string_buffer(64)
     if rank == 0:
-        api.check(L.iglb200_ipc_alloc(sbytes, ctypes.byref(scratch), handle))
+        api.check(L.iglb200_ipc_alloc(total, ctypes.byref(base), handle))
     hb = job.bcast_obj(bytes(handle.raw) if rank == 0 else None)
     if rank != 0:
-        api.check(L.iglb200_ipc_open(hb, ctypes.byref(scratch)))
+        api.check(L.iglb200_ipc_open(hb, ctypes.byref(base)))
+    b0 = base.value
+    scratch, pP, pS, pI, pC, pW = vp(b0), vp(b0 + offP), vp(b0 + offS), vp(b0 + offI), vp(b0 + offC), vp(b0 + offW)
     super_rows = int(args.super_rows or L.iglb200_shard_super_rows(nq, world))
     dP = dS = dI = dC = dW = None
     hP = None
     if rank == 0:
+        from libigl_b200.dist import _arena_tensor
+        whole = _arena_tensor(api, b0, total, dev)                 # zero-copy torch view of the IPC allocation
         hP = torch.from_numpy(np.ascontiguousarray(P.T)).pin_memory()      # [3, n] == column-major n x 3
-        dP = hP.to(dev, non_blocking=True)
-        dS = torch.empty(nq, dtype=torch.float64, device=dev)
-        dI = torch.empty(nq, dtype=torch.int32, device=dev)
-        dC = torch.empty((3, nq), dtype=torch.float64, device=dev)
-        dW = torch.empty(nq, dtype=torch.float64, device=dev)
+        dP = whole[offP:offP + 24 * nq].view(torch.float64).view(3, nq)
+        dP.copy_(hP, non_blocking=True)
+        dS = whole[offS:offS + 8 * nq].view(torch.float64)
+        dI = whole[offI:offI + 4 * nq].view(torch.int32)
+        dC = whole[offC:offC + 24 * nq].view(torch.float64).view(3, nq)
+        dW = whole[offW:offW + 8 * nq].view(torch.float64)
     stream = torch.cuda.Stream(device=dev)
     sp = lambda: vp(stream.cuda_stream)
     launches = [0]
@@ -368,15 +381,15 @@ def ours_mesh(args, cfg):
     def step():
         n_l = 0
         if rank == 0:
-            api.check(L.iglb200_shard_begin_dev(mesh.h, dP.data_ptr(), nq, scratch, int(args.sort), sp()))
+            api.check(L.iglb200_shard_begin_dev(mesh.h, pP, nq, scratch, int(args.sort), sp()))
             n_l += api.last_launch_count()
         job.stream_fence()
-        api.check(L.iglb200_shard_run_dev(mesh.h, scratch, nq, mode, sign, lower, upper, 2.0, super_rows, 0, sp()))
+        api.check(L.iglb200_shard_run_dev(mesh.h, pP, nq, scratch, mode, sign, lower, upper, 2.0, int(args.sort), pS, pI, pC, pW,
+                                          super_rows, 0, sp()))
         n_l += api.last_launch_count()
         job.stream_fence()
         if rank == 0:
-            api.check(L.iglb200_shard_finish_dev(mesh.h, nq, scratch, mode, sign, lower, upper, int(args.sort),
-                                                 dS.data_ptr(), dI.data_ptr(), dC.data_ptr(), dW.data_ptr(), sp()))
+            api.check(L.iglb200_shard_finish_dev(mesh.h, nq, mode, pS, pI, pC, pW, sp()))
             n_l += api.last_launch_count()
         launches[0] = n_l
 
@@ -441,10 +454,11 @@ def ours_mesh(args, cfg):
         print(json.dumps(line), flush=True)
     job.host_barrier()
     if rank != 0:
-        L.iglb200_ipc_close(scratch)
+        L.iglb200_ipc_close(base)
     job.host_barrier()
     if rank == 0:
-        L.iglb200_ipc_free(scratch)
+        del dP, dS, dI, dC, dW
+        L.iglb200_ipc_free(base)
     job.close()
 
 

@@ -177,16 +177,17 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
                          double *W, void *scratch, int sort_queries, void *stream);
 
 /* ---- SEVERAL GPUs on ONE device-resident query set (the loop of signed_distance.cpp:90-138 sharded).
- * The query set lives on one device, the OWNER; every GPU holds a copy of the mesh (iglb200_init in one process;
- * iglb200_mesh_from_arena after an NCCL broadcast between processes).
- *   begin  (owner)   Morton-sorts the queries once and gathers them in sorted order into `shard_scratch`
- *                    (iglb200_shard_scratch_bytes(nP) bytes of the owner's memory), zeroes the work counter in it.
- *   run    (each GPU, after begin) takes super-chunks of `super_rows` consecutive sorted queries off that counter —
- *                    an atomic over NVLink when the owner is a peer — until they run out, reads the queries from and
- *                    writes d2/I/C/W to the owner's scratch directly (peer loads/stores: no separate scatter/gather).
- *                    `shard_scratch` is the owner's buffer as seen from the calling device (peer-enabled pointer in one
+ * The query set P and the outputs S, I, C, W live on one device, the OWNER; every GPU holds a copy of the mesh
+ * (iglb200_init in one process; iglb200_mesh_from_arena after an NCCL broadcast between processes).
+ *   begin  (owner)   Morton-sorts the queries once: keys and permutation go to `shard_scratch`
+ *                    (iglb200_shard_scratch_bytes(nP) bytes of the owner's memory), the work counter in it is zeroed.
+ *   run    (each GPU, after begin) runs the same kernels as the single-GPU call over the super-chunks of `super_rows`
+ *                    consecutive sorted queries it takes off that counter — an atomic over NVLink when the owner is a
+ *                    peer — until they run out.  P, the permutation and S/I/C/W are read from / written to the OWNER's
+ *                    memory directly (peer loads and stores): no separate scatter, gather or un-sort pass.  All
+ *                    pointers are the owner's buffers as seen from the calling device (peer-enabled pointers in one
  *                    process, iglb200_ipc_open between processes).  max_supers > 0 caps what this GPU takes.
- *   finish (owner, after every run) un-sorts and applies the epilogue of signed_distance.cpp:99-135 into S, I, C, W.
+ *   finish (owner, after every run) writes the sentinel rows of a degenerate mesh (#F == 0); otherwise nothing.
  * Ordering between the phases is the caller's: events between streams in one process, a tiny collective on the
  * streams between processes.  mode 0: signed distance (sign_type FAST_WINDING_NUMBER or UNSIGNED; S,I,C[,W]),
  * 1: squared distance (S=sqrD,I,C), 2: fast winding number (W; rows are claimed 2048 at a time, super_rows unused).
@@ -194,12 +195,11 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
 uint64_t iglb200_shard_scratch_bytes(int64_t nP);
 int64_t iglb200_shard_super_rows(int64_t nP, int n_shards);   /* the library's choice; a multiple of 512 */
 int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int sort_queries, void *stream);
-int iglb200_shard_run_dev(const iglb200_mesh *m, void *shard_scratch, int64_t nP, int mode, int sign_type,
-                          double lower_bound, double upper_bound, float accuracy_scale,
+int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int mode, int sign_type,
+                          double lower_bound, double upper_bound, float accuracy_scale, int sort_queries,
+                          double *S, int32_t *I, double *C, double *W,
                           int64_t super_rows, int64_t max_supers, void *stream);
-int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, void *shard_scratch, int mode, int sign_type,
-                             double lower_bound, double upper_bound, int sort_queries,
-                             double *S, int32_t *I, double *C, double *W, void *stream);
+int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, int mode, double *S, int32_t *I, double *C, double *W, void *stream);
 /* device memory that other processes on the node can map (cudaIpcGetMemHandle / cudaIpcOpenMemHandle): the
  * owner allocates and publishes the 64-byte handle (e.g. torch.distributed broadcast), the others open it. */
 int iglb200_ipc_alloc(uint64_t bytes, void **device_ptr, unsigned char handle[64]);

@@ -70,6 +70,7 @@ struct MortonKeys {  // 30-bit Morton code of each query inside the doubled scen
   const double *P; int64_t n;
   double lo[3], inv[3];
   uint32_t *keys, *vals;
+  int shift;   // 10 - bits per axis
   static DEVFN uint32_t spread(uint32_t v) {
     v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu;
     v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
@@ -81,7 +82,7 @@ struct MortonKeys {  // 30-bit Morton code of each query inside the doubled scen
       double t = (P[d * n + i] - lo[d]) * inv[d];
       t = t < 0.0 ? 0.0 : (t > 1023.0 ? 1023.0 : t);
       if (!(t == t)) t = 0.0;
-      c[d] = (uint32_t)t;
+      c[d] = (uint32_t)t >> shift;
     }
     keys[i] = spread(c[0]) | (spread(c[1]) << 1) | (spread(c[2]) << 2);
     vals[i] = (uint32_t)i;
@@ -437,25 +438,33 @@ struct WindingQuery {
   double up, low; int32_t nF;
   double *W; double *S; int32_t *I; double *C;  // S holds sqrD on entry when mode!=0
   uint32_t *overflow;
-  DEVFN void operator()(int64_t t) const {
-    const int64_t i = perm ? (int64_t)perm[t] : t;
-    const double FOUR_PI = 4.0 * 3.1415926535897932384626433832795;
+  // rows that need no winding number are finished here; returns whether the walk must run for row i
+  DEVFN bool prelude(int64_t i) const {
     if (mode != 0) {
       const double sqrd = S[i];
       if (sqrd >= up || sqrd < low) {
         S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
         if (W) W[i] = NAN;
-        return;
+        return false;
       }
-      if (mode == 2) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return; }
+      if (mode == 2) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return false; }
     }
-    uint32_t stack[fwn::FWN_STACK];
-    const float om = fwn::winding_solid_angle(nodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], acc2, order, stack, nullptr, overflow);
+    return true;
+  }
+  DEVFN void epilogue(int64_t i, float om) const {
+    const double FOUR_PI = 4.0 * 3.1415926535897932384626433832795;
     const double w = (double)om / FOUR_PI;
     if (mode == 0) { W[i] = w; return; }
     const double wf = (double)(float)w;  // narrowed to float by fast_winding_number.cpp:452
     if (W) W[i] = wf;
     S[i] = (1.0 - 2.0 * fabs(wf)) * sqrt(S[i]);
+  }
+  DEVFN int64_t row(int64_t t) const { return perm ? (int64_t)perm[t] : t; }
+  DEVFN void operator()(int64_t t) const {   // one thread, one query (host emulation; the device walks packets)
+    const int64_t i = row(t);
+    if (!prelude(i)) return;
+    uint32_t stack[fwn::FWN_STACK];
+    epilogue(i, fwn::winding_solid_angle(nodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], acc2, order, stack, nullptr, overflow));
   }
 };
 
@@ -582,8 +591,21 @@ template <class F> void launch_query(const char *, int64_t n, F f, stream_t s) {
 #ifndef WN_THREADS
 #define WN_THREADS 64
 #endif
+// one warp = one packet of 32 consecutive (Morton-adjacent) rows [t0, t0 + 32)
+template <class F> DEVFN void winding_packet(const F &f, int64_t t0, uint2 *stack) {
+  const int64_t t = t0 + (threadIdx.x & 31);
+  const bool valid = t < f.n;
+  const int64_t i = valid ? f.row(t) : 0;
+  const bool alive = valid && f.prelude(i);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (alive) { qx = (float)f.P[i]; qy = (float)f.P[f.n + i]; qz = (float)f.P[2 * f.n + i]; }
+  const float om = fwn::winding_solid_angle_packet(f.nodes, f.tri32, alive, qx, qy, qz, f.acc2, f.order, stack, f.overflow);
+  if (alive) f.epilogue(i, om);
+}
 __global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_number_kernel(int64_t n, WindingQuery f) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+  __shared__ uint2 stacks[WN_THREADS / 32][fwn::FWN_PSTACK];
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x; b < n; b += (int64_t)gridDim.x * blockDim.x)
+    winding_packet(f, b + (threadIdx.x & ~31), stacks[threadIdx.x >> 5]);
 }
 inline unsigned query_grid(int64_t n, int threads) {
   const int64_t blocks = (n + threads - 1) / threads;
@@ -630,9 +652,14 @@ const uint32_t *morton_perm(const iglb200_mesh *m, const double *P, int64_t n, v
     mk.lo[d] = c - ext;           // box doubled about its centre
     mk.inv[d] = 1024.0 / (2.0 * ext);
   }
+  // about one query per Morton cell: bits per axis = ceil(log2(n) / 3) in [6, 10].  The sort is stable, so the queries of
+  // a cell keep their order; fewer key bits are fewer radix passes (16.7 M queries: 24-bit keys, 3 passes instead of 4)
+  int bits = 6;
+  while (bits < 10 && (int64_t(1) << (3 * bits)) < n) ++bits;
+  mk.shift = 10 - bits;
   plat::Span sp("morton_sort", s);
   plat::for_n(n, mk, s);
-  plat::sort_pairs_u32(sc.temp, sc.temp_bytes, sc.kin, sc.kout, sc.vin, sc.perm, n, 30, s);
+  plat::sort_pairs_u32(sc.temp, sc.temp_bytes, sc.kin, sc.kout, sc.vin, sc.perm, n, 3 * bits, s);
   return sc.perm;
 }
 
@@ -746,42 +773,31 @@ void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_s
 
 // ---------------------------------------------------------------------------------------------------
 // Sharded device-resident queries: SEVERAL GPUs answer ONE query set that lives on one of them (the owner).
-//   begin  (owner)      Morton-sort the queries once, gather them in sorted order (Ps), zero the work counter
-//   run    (every GPU)  closest-triangle search + winding number over the super-chunks this GPU takes off the
-//                       owner's counter; queries are read from, and results written in sorted order to, the owner's
-//                       memory directly (peer loads/stores over NVLink: the "gather" is the kernels' own epilogue)
-//   finish (owner)      un-sort + the epilogue of signed_distance.cpp:99-135
+//   begin  (owner)      Morton-sort the queries once (keys + permutation in the owner's scratch), zero the work counter
+//   run    (every GPU)  the SAME kernels as the single-GPU call — closest-triangle search, then the winding number with
+//                       the fused epilogue of signed_distance.cpp:99-135 — over the super-chunks of sorted queries this
+//                       GPU takes off the owner's counter.  Queries and the permutation are read from, and S/I/C/W are
+//                       written to, the owner's memory directly (peer loads/stores over NVLink): there is no separate
+//                       scatter, gather or un-sort pass — the transfer is the kernels' own prologue and epilogue.
+//   finish (owner)      nothing but the sentinel rows of a degenerate mesh.
 // Between the phases the caller orders the devices' streams (events in one process, a tiny NCCL collective between
 // processes).  The owner's scratch has one layout, computed from nP alone, so that a peer only needs its base pointer.
 // ---------------------------------------------------------------------------------------------------
 struct ShardLayout {
-  size_t oCounter, oSort, oPs, oD, oI, oC, oW, total;
+  size_t oCounter, oSort, total;
   explicit ShardLayout(int64_t n) {
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-    oCounter = 0; oSort = 256; oPs = oSort + al(iglb200_query_scratch_bytes(n)); oD = oPs + al(24 * (size_t)n); oI = oD + al(8 * (size_t)n);
-    oC = oI + al(4 * (size_t)n); oW = oC + al(24 * (size_t)n); total = oW + al(8 * (size_t)n);
+    oCounter = 0; oSort = 256; total = oSort + al(iglb200_query_scratch_bytes(n));
   }
 };
-struct GatherSorted { const double *P; int64_t n; const uint32_t *perm; double *Ps;
-  DEVFN void operator()(int64_t t) const { const int64_t i = perm ? (int64_t)perm[t] : t; Ps[t] = P[i]; Ps[n + t] = P[n + i]; Ps[2 * n + t] = P[2 * n + i]; } };
 
-// winding number of the sorted queries of the super-chunks listed by the search kernel (or of all rows when list == null)
-struct WindingShard {
-  const fwn::FwnNode *nodes; const float4 *tri32;
-  const double *Ps; int64_t n; float acc2; int order;
-  const double *D; double up, low; int skip_oob;   // skip rows whose squared distance is out of bounds (their W is never read)
-  double *W; uint32_t *overflow;
-  DEVFN void operator()(int64_t t) const {
-    if (skip_oob) { const double sqrd = D[t]; if (sqrd >= up || sqrd < low) { W[t] = NAN; return; } }
-    uint32_t stack[fwn::FWN_STACK];
-    const float om = fwn::winding_solid_angle(nodes, tri32, (float)Ps[t], (float)Ps[n + t], (float)Ps[2 * n + t], acc2, order, stack, nullptr, overflow);
-    W[t] = (double)om / (4.0 * 3.1415926535897932384626433832795);
-  }
-};
 #ifndef IGLB200_EMUL
-__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_shard_kernel(WindingShard f, const uint32_t *my_supers, const uint32_t *my_count,
+// winding number (+ fused epilogue) of the rows of the super-chunks listed by the search kernel; blocks take tiles of
+// WN_THREADS rows off a local counter
+__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_shard_kernel(WindingQuery f, const uint32_t *my_supers, const uint32_t *my_count,
                                                                                   int64_t super_rows, unsigned long long *next) {
   __shared__ unsigned long long item_s;
+  __shared__ uint2 stacks[WN_THREADS / 32][fwn::FWN_PSTACK];
   const int64_t per = super_rows / WN_THREADS;           // blocks' worth of rows in a super-chunk
   const unsigned long long total = (unsigned long long)*my_count * (unsigned long long)per;
   while (true) {
@@ -790,15 +806,16 @@ __global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_shard_kerne
     const unsigned long long item = item_s;
     __syncthreads();
     if (item >= total) return;
-    const int64_t t = (int64_t)my_supers[item / per] * super_rows + (int64_t)(item % per) * WN_THREADS + threadIdx.x;
-    if (t < f.n) f(t);
+    const int64_t t0 = (int64_t)my_supers[item / per] * super_rows + (int64_t)(item % per) * WN_THREADS + (threadIdx.x & ~31);
+    winding_packet(f, t0, stacks[threadIdx.x >> 5]);
   }
 }
 // winding number only: blocks claim pieces of `piece_rows` rows off the owner's counter (system-scope atomic) until
 // the rows run out; `budget` >= 0 caps the pieces this device takes (my_count counts them)
-__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_claim_kernel(WindingShard f, unsigned long long *remote, int64_t piece_rows,
+__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_claim_kernel(WindingQuery f, unsigned long long *remote, int64_t piece_rows,
                                                                                   int64_t budget, uint32_t *my_count) {
   __shared__ unsigned long long piece_s;
+  __shared__ uint2 stacks[WN_THREADS / 32][fwn::FWN_PSTACK];
   while (true) {
     if (threadIdx.x == 0) {
       unsigned long long pc = ~0ull;
@@ -809,34 +826,11 @@ __global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_claim_kerne
     const unsigned long long pc = piece_s;
     __syncthreads();
     if (pc == ~0ull || (int64_t)pc * piece_rows >= f.n) return;
-    const int64_t lo = (int64_t)pc * piece_rows, hi = min(f.n, lo + piece_rows);
-    for (int64_t t = lo + threadIdx.x; t < hi; t += WN_THREADS) f(t);
+    const int64_t lo = (int64_t)pc * piece_rows;
+    for (int64_t t0 = lo + (threadIdx.x & ~31); t0 < lo + piece_rows; t0 += WN_THREADS) winding_packet(f, t0, stacks[threadIdx.x >> 5]);
   }
 }
 #endif
-
-// epilogue of signed_distance.cpp:99-135 on the sorted intermediate results, written back in the caller's order
-struct ShardFinish {
-  int mode; int sign_type; double up, low; int32_t nF; int64_t n; const uint32_t *perm;
-  const double *D; const int32_t *Is; const double *Cs; const double *Ws;
-  double *S; int32_t *I; double *C; double *W;
-  DEVFN void operator()(int64_t t) const {
-    const int64_t i = perm ? (int64_t)perm[t] : t;
-    if (mode == 2) { W[i] = Ws[t]; return; }
-    const double sqrd = D[t];
-    if (mode == 1) { S[i] = sqrd; I[i] = Is[t]; C[i] = Cs[t]; C[n + i] = Cs[n + t]; C[2 * n + i] = Cs[2 * n + t]; return; }
-    if (sqrd >= up || sqrd < low) {
-      S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
-      if (W) W[i] = NAN;
-      return;
-    }
-    I[i] = Is[t]; C[i] = Cs[t]; C[n + i] = Cs[n + t]; C[2 * n + i] = Cs[2 * n + t];
-    if (sign_type == IGLB200_SIGN_UNSIGNED) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return; }
-    const double wf = (double)(float)Ws[t];   // narrowed to float by fast_winding_number.cpp:452
-    if (W) W[i] = wf;
-    S[i] = (1.0 - 2.0 * fabs(wf)) * sqrt(sqrd);
-  }
-};
 
 static constexpr int64_t FWN_PIECE_ROWS = 2048;   // winding-number-only shards: rows per claim
 struct ShardWs {   // per (thread, device) state of shard_run: schedule words, the list of super-chunks taken
@@ -860,20 +854,21 @@ void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratc
   const ShardLayout L(n);
   plat::dev_memset(scratch + L.oCounter, 0, 256, s);
   if (n == 0) return;
-  const uint32_t *perm = morton_perm(m, P, n, scratch + L.oSort, sort_queries, s);
-  plat::for_n(n, GatherSorted{P, n, perm, (double *)(scratch + L.oPs)}, s);
+  morton_perm(m, P, n, scratch + L.oSort, sort_queries, s);
 }
 
-void shard_run(const iglb200_mesh *m, char *scratch, int64_t n, int mode, int sign_type, double lower, double upper, float accuracy_scale,
-               int64_t super_rows, int64_t max_supers, stream_t s) {
-  if (n == 0 || m->h.nF == 0 || m->h.nnodes == 0) return;   // finish fills the sentinels
+bool shard_degenerate(const iglb200_mesh *m, int mode) { return (mode != 2 && m->h.nF == 0) || m->h.nnodes == 0; }
+
+// P, S, I, C, W: the owner's arrays as seen from the calling device
+void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int mode, int sign_type, double lower, double upper,
+               float accuracy_scale, int sort_queries, double *S, int32_t *I, double *C, double *W, int64_t super_rows, int64_t max_supers,
+               stream_t s) {
+  if (n == 0 || shard_degenerate(m, mode)) return;   // finish fills the sentinels
   const int64_t unit = (int64_t)CP_CHUNK * 32;
   if (super_rows <= 0 || super_rows % unit) throw std::invalid_argument("super_rows must be a positive multiple of 512");
   const ShardLayout L(n);
-  const double *Ps = (const double *)(scratch + L.oPs);
-  double *D = (double *)(scratch + L.oD), *Cs = (double *)(scratch + L.oC), *Ws = (double *)(scratch + L.oW);
-  int32_t *Is = (int32_t *)(scratch + L.oI);
   unsigned long long *remote = (unsigned long long *)(scratch + L.oCounter);
+  const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;
   const int64_t nsup = (n + super_rows - 1) / super_rows;
   ShardWs &ws = plat::per_device<ShardWs>();
   ws.ensure((size_t)nsup, s);
@@ -881,61 +876,50 @@ void shard_run(const iglb200_mesh *m, char *scratch, int64_t n, int mode, int si
   uint32_t *my_count = ws.supers.p, *my_supers = ws.supers.p + 1;
   double low = 0.0, up = INFINITY;
   if (mode == 0) bounds_to_sqr(lower, upper, low, up);
-  const bool fwn_sign = mode == 0 && sign_type == IGLB200_SIGN_FAST_WINDING_NUMBER;
-  if (mode == 0 && !fwn_sign && sign_type != IGLB200_SIGN_UNSIGNED) throw std::domain_error("sharded queries support the FAST_WINDING_NUMBER and UNSIGNED sign types");
+  if (mode == 0 && sign_type != IGLB200_SIGN_FAST_WINDING_NUMBER && sign_type != IGLB200_SIGN_UNSIGNED)
+    throw std::domain_error("sharded queries support the FAST_WINDING_NUMBER and UNSIGNED sign types");
   if (mode != 2) {
     plat::Span sp("closest", s);
-    ClosestArgs a = closest_args(m, Ps, n, nullptr, up, low, D, Is, Cs, nullptr, ws.sched.p);
+    ClosestArgs a = closest_args(m, P, n, perm, up, low, S, I, C, nullptr, ws.sched.p);
     a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
     launch_closest(a, s);
   }
-  if (mode == 2 || fwn_sign) {
-    plat::Span sp("winding", s);
-    const float acc = mode == 2 ? accuracy_scale : 2.0f;
-    WindingShard f{m->fnodes(), m->tri32(), Ps, n, acc * acc, m->h.order, D, up, low, mode == 0 ? 1 : 0, Ws, overflow_flag()};
+  if (mode == 1) return;
+  plat::Span sp("winding", s);
+  const float acc = mode == 2 ? accuracy_scale : 2.0f;
+  const WindingQuery f{m->fnodes(), m->tri32(), P, n, perm, acc * acc, m->h.order,
+                       mode == 2 ? 0 : (sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1), up, low, (int32_t)m->h.nF, W, S, I, C, overflow_flag()};
 #ifdef IGLB200_EMUL
-    if (mode == 2) {   // no search ran: pieces straight off the owner's counter
-      for (int64_t took = 0; max_supers <= 0 || took < max_supers; ++took) {
-        const unsigned long long pc = __atomic_fetch_add(remote, 1ull, __ATOMIC_RELAXED);
-        if ((int64_t)pc * FWN_PIECE_ROWS >= n) break;
-        for (int64_t t = (int64_t)pc * FWN_PIECE_ROWS; t < std::min(n, ((int64_t)pc + 1) * FWN_PIECE_ROWS); ++t) f(t);
-      }
-    } else {
-      for (uint32_t k = 0; k < *my_count; ++k)
-        for (int64_t t = (int64_t)my_supers[k] * super_rows; t < std::min(n, ((int64_t)my_supers[k] + 1) * super_rows); ++t) f(t);
+  if (mode == 2) {   // no search ran: pieces straight off the owner's counter
+    for (int64_t took = 0; max_supers <= 0 || took < max_supers; ++took) {
+      const unsigned long long pc = __atomic_fetch_add(remote, 1ull, __ATOMIC_RELAXED);
+      if ((int64_t)pc * FWN_PIECE_ROWS >= n) break;
+      for (int64_t t = (int64_t)pc * FWN_PIECE_ROWS; t < std::min(n, ((int64_t)pc + 1) * FWN_PIECE_ROWS); ++t) f(t);
     }
-#else
-    if (mode == 2) {
-      // winding number only (uniform cost per row): every block claims pieces of the rows straight off the owner's counter
-      winding_claim_kernel<<<plat::sm_count() * WN_MIN_BLOCKS, WN_THREADS, 0, s>>>(f, remote, FWN_PIECE_ROWS, max_supers > 0 ? max_supers : -1, my_count);
-    } else {
-      unsigned long long *next = ws.sched.p + 1 + 2 * 1024 + 1;
-      plat::dev_memset(next, 0, 8, s);
-      winding_shard_kernel<<<plat::sm_count() * WN_MIN_BLOCKS, WN_THREADS, 0, s>>>(f, my_supers, my_count, super_rows, next);
-    }
-    plat::launch_counter()++;
-    PLAT_CHECK(cudaGetLastError());
-#endif
+  } else {
+    for (uint32_t k = 0; k < *my_count; ++k)
+      for (int64_t t = (int64_t)my_supers[k] * super_rows; t < std::min(n, ((int64_t)my_supers[k] + 1) * super_rows); ++t) f(t);
   }
+#else
+  if (mode == 2) {
+    // winding number only (uniform cost per row): every block claims pieces of the rows straight off the owner's counter
+    winding_claim_kernel<<<plat::sm_count() * WN_MIN_BLOCKS, WN_THREADS, 0, s>>>(f, remote, FWN_PIECE_ROWS, max_supers > 0 ? max_supers : -1, my_count);
+  } else {
+    unsigned long long *next = ws.sched.p + 1 + 2 * 1024 + 1;
+    plat::dev_memset(next, 0, 8, s);
+    winding_shard_kernel<<<plat::sm_count() * WN_MIN_BLOCKS, WN_THREADS, 0, s>>>(f, my_supers, my_count, super_rows, next);
+  }
+  plat::launch_counter()++;
+  PLAT_CHECK(cudaGetLastError());
+#endif
 }
 
-void shard_finish(const iglb200_mesh *m, int64_t n, char *scratch, int mode, int sign_type, double lower, double upper, int sort_queries,
-                  double *S, int32_t *I, double *C, double *W, stream_t s) {
-  if (n == 0) return;
+void shard_finish(const iglb200_mesh *m, int64_t n, int mode, double *S, int32_t *I, double *C, double *W, stream_t s) {
+  if (n == 0 || !shard_degenerate(m, mode)) return;
   if (mode != 2 && m->h.nF == 0) { plat::for_n(n, FillConst{S, I, C, mode == 0 ? W : nullptr, n, NAN, -1, NAN}, s); return; }
-  if (m->h.nnodes == 0) {
-    if (mode == 2) plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, 0.0, 0, 0.0}, s);
-    else if (mode == 1) plat::for_n(n, FillConst{S, I, C, nullptr, n, INFINITY, -1, 0.0}, s);
-    else plat::for_n(n, FillConst{S, I, C, W, n, NAN, (int32_t)m->h.nF + 1, 0.0}, s);
-    return;
-  }
-  const ShardLayout L(n);
-  double low = 0.0, up = INFINITY;
-  if (mode == 0) bounds_to_sqr(lower, upper, low, up);
-  const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;
-  plat::Span sp("finish", s);
-  plat::for_n(n, ShardFinish{mode, sign_type, up, low, (int32_t)m->h.nF, n, perm, (const double *)(scratch + L.oD), (const int32_t *)(scratch + L.oI),
-                             (const double *)(scratch + L.oC), (const double *)(scratch + L.oW), S, I, C, W}, s);
+  if (mode == 2) plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, 0.0, 0, 0.0}, s);
+  else if (mode == 1) plat::for_n(n, FillConst{S, I, C, nullptr, n, INFINITY, -1, 0.0}, s);
+  else plat::for_n(n, FillConst{S, I, C, W, n, NAN, (int32_t)m->h.nF + 1, 0.0}, s);
 }
 
 // upload a strided host matrix n x 3 as canonical column-major doubles
@@ -1507,30 +1491,31 @@ int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, 
   return IGLB200_OK;
   API_END
 }
-int iglb200_shard_run_dev(const iglb200_mesh *m, void *shard_scratch, int64_t nP, int mode, int sign_type, double lower, double upper,
-                          float accuracy_scale, int64_t super_rows, int64_t max_supers, void *stream) {
+int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int mode, int sign_type, double lower,
+                          double upper, float accuracy_scale, int sort_queries, double *S, int32_t *I, double *C, double *W,
+                          int64_t super_rows, int64_t max_supers, void *stream) {
   API_BEGIN
   m = mesh_here(m);
-  if (nP < 0 || !shard_scratch) throw std::invalid_argument("null pointer");
+  if (nP < 0 || !shard_scratch || (nP > 0 && !P)) throw std::invalid_argument("null pointer");
   if (mode < 0 || mode > 2) throw std::invalid_argument("mode must be 0 (signed distance), 1 (squared distance) or 2 (fast winding number)");
-  require_device();
-  check_count(nP);
-  plat::launch_counter() = 0;
-  shard_run(m, (char *)shard_scratch, nP, mode, sign_type, lower, upper, accuracy_scale, super_rows, max_supers, (stream_t)stream);
-  return IGLB200_OK;
-  API_END
-}
-int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, void *shard_scratch, int mode, int sign_type, double lower, double upper,
-                             int sort_queries, double *S, int32_t *I, double *C, double *W, void *stream) {
-  API_BEGIN
-  m = mesh_here(m);
-  if (nP < 0 || !shard_scratch) throw std::invalid_argument("null pointer");
-  if (mode < 0 || mode > 2) throw std::invalid_argument("mode must be 0, 1 or 2");
   if (nP > 0 && ((mode != 2 && (!S || !I || !C)) || (mode == 2 && !W))) throw std::invalid_argument("null output");
   require_device();
   check_count(nP);
   plat::launch_counter() = 0;
-  shard_finish(m, nP, (char *)shard_scratch, mode, sign_type, lower, upper, sort_queries, S, I, C, W, (stream_t)stream);
+  shard_run(m, P, nP, (char *)shard_scratch, mode, sign_type, lower, upper, accuracy_scale, sort_queries, S, I, C, W, super_rows, max_supers,
+            (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, int mode, double *S, int32_t *I, double *C, double *W, void *stream) {
+  API_BEGIN
+  m = mesh_here(m);
+  if (nP < 0) throw std::invalid_argument("negative size");
+  if (mode < 0 || mode > 2) throw std::invalid_argument("mode must be 0, 1 or 2");
+  if (nP > 0 && ((mode != 2 && (!S || !I || !C)) || (mode == 2 && !W))) throw std::invalid_argument("null output");
+  require_device();
+  plat::launch_counter() = 0;
+  shard_finish(m, nP, mode, S, I, C, W, (stream_t)stream);
   return IGLB200_OK;
   API_END
 }

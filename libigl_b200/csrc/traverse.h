@@ -451,4 +451,74 @@ DEVFN float winding_solid_angle(const FwnNode *nodes, const float4 *tri32, float
   return sum;
 }
 
+#ifndef IGLB200_EMUL
+// The same evaluation for a PACKET: the 32 queries of a warp (neighbours in Morton order) walk the union of their
+// nodes with one shared stack of (node, lanes that descend into it).  Every node row is then one warp-uniform load —
+// the per-thread walk is bound by the L1 data pipe (each thread fetching its own copy of a 384-byte node: 92 % of the
+// LSU wavefront peak on c2) — and no thread keeps a stack in local memory.  Per query the arithmetic and its ORDER are
+// exactly those of winding_solid_angle (the far-field sum of a node, then its leaf triangles from lane 3 down to 0,
+// children visited from lane 0 up), so the result is bit-identical to the per-thread walk.
+static constexpr int FWN_PSTACK = 112;   // (node, mask) entries per warp: 3 pushes per level
+DEVFN float winding_solid_angle_packet(const FwnNode *nodes, const float4 *tri32, bool alive, float qx, float qy, float qz, float acc2,
+                                       int order, uint2 *stack, uint32_t *overflow) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31u;
+  float sum = 0.f;
+  int sp = 0;
+  const unsigned m0 = __ballot_sync(FULL, alive);
+  if (m0 == 0u) return 0.f;
+  if (lane == 0) stack[0] = make_uint2(0u, m0);
+  sp = 1;
+  __syncwarp();
+  while (sp > 0) {
+    const uint2 e = stack[--sp];
+    __syncwarp();
+    const bool me = (e.y >> lane) & 1u;
+    const FwnNode &n = nodes[e.x];
+    Lanes4 CH, R2, PX, PY, PZ, NX;
+    rows2((const float4 *)&n.child, CH, R2); rows2(&n.d[R_PX], PX, PY); rows2(&n.d[R_PZ], PZ, NX);
+    const uint32_t ch[4] = {plat::f2u(CH.v[0]), plat::f2u(CH.v[1]), plat::f2u(CH.v[2]), plat::f2u(CH.v[3])};
+    uint32_t descend = 0;
+    Lanes4 q0, q1, q2, ql2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q0.v[i] = fsub(qx, PX.v[i]); q1.v[i] = fsub(qy, PY.v[i]); q2.v[i] = fsub(qz, PZ.v[i]);
+      ql2.v[i] = plat::fadd(plat::fadd(plat::fmul(q0.v[i], q0.v[i]), plat::fmul(q1.v[i], q1.v[i])), plat::fmul(q2.v[i], q2.v[i]));
+      if (ql2.v[i] <= plat::fmul(R2.v[i], acc2)) descend |= 1u << i;   // absent lanes have R2 = +inf
+    }
+    if (!me) descend = 0u;
+    if (__any_sync(FULL, me && descend != 0xFu)) {   // :7194-7198: nothing to approximate when all four descend
+      Lanes4 om;
+      node_omega4(n, NX, q0, q1, q2, ql2, order, om);
+      if (me && descend != 0xFu) {
+        float node_sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if ((descend >> i) & 1u) continue;
+          if (!finite_f(om.v[i])) descend |= 1u << i;   // :7249-7251
+          else node_sum += om.v[i];
+        }
+        sum += node_sum;
+      }
+    }
+    // children in lane order; push in reverse so that lane 0 pops first
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      const unsigned dm = __ballot_sync(FULL, (descend >> i) & 1u);
+      if (dm == 0u) continue;
+      const uint32_t c = ch[i];
+      if (c == EMPTY) continue;
+      if (c & INTERNAL_BIT) {
+        if (sp < FWN_PSTACK) { if (lane == 0) stack[sp] = make_uint2(c & ~INTERNAL_BIT, dm); ++sp; }
+        else if (lane == 0) *overflow = 1u;
+      } else if ((dm >> lane) & 1u) {
+        sum += tri_solid_angle(tri32, c, qx, qy, qz);
+      }
+    }
+    __syncwarp();
+  }
+  return sum;
+}
+#endif
+
 }  // namespace fwn
