@@ -153,6 +153,16 @@ int iglb200_squared_distance(const iglb200_mesh *m,
                              void *sqrD, int d_is_f64, int32_t *I,
                              void *C, int c_is_f64, int64_t c_row_stride, int64_t c_col_stride);
 
+/* AABB::squared_distance(V,Ele,p,low_sqr_d,up_sqr_d,i,c) for a batch (AABB.h:575-614, AABB.cpp:1135-1218): only primitives
+ * closer than up_sqr_d count — a row without any gets sqrD = up_sqr_d, I = -1, C = 0 (the reference leaves i and c
+ * untouched) — and low_sqr_d > up_sqr_d returns low_sqr_d.  low_sqr_d is otherwise the reference's licence to stop early
+ * at ANY primitive below it; this search always returns the closest one. */
+int iglb200_squared_distance_bounded(const iglb200_mesh *m,
+                                     const void *P, int p_is_f64, int64_t nP, int64_t p_row_stride, int64_t p_col_stride,
+                                     double low_sqr_d, double up_sqr_d,
+                                     void *sqrD, int d_is_f64, int32_t *I,
+                                     void *C, int c_is_f64, int64_t c_row_stride, int64_t c_col_stride);
+
 /* ---- fast_winding_number(fwn_bvh, accuracy_scale, Q, W)
  *      fast_winding_number.h:172-187, fast_winding_number.cpp:421-437. */
 int iglb200_fwn_eval(const iglb200_mesh *m,

@@ -119,6 +119,23 @@ inline void signed_distance_fast_winding_number(const DerivedP &P, const Derived
                                                          (double)std::numeric_limits<Scalar>::max(), S, I, C, nullptr);
 }
 
+// signed_distance_fast_winding_number(q,V,F,tree,fwn_bvh) -> s, one query (signed_distance.h:300-312,
+// signed_distance.cpp:689-713).  Functional but a whole device round trip per point: batch wherever possible.
+template <class Derivedq, class DerivedV, class DerivedF>
+inline typename DerivedV::Scalar signed_distance_fast_winding_number(const Derivedq &q, const DerivedV & /*V*/, const DerivedF & /*F*/,
+                                                                     const AABB<DerivedV, 3> &tree, const FastWindingNumberBVH &fwn_bvh) {
+  const iglb200_mesh *m = fwn_bvh.mesh ? fwn_bvh.mesh : tree.mesh;
+  if (!m) throw Error(IGLB200_ERR_ARG, "iglb200: neither tree nor fwn_bvh has been built");
+  if ((int64_t)q.rows() * (int64_t)q.cols() != 3) throw Error(IGLB200_ERR_ARG, "iglb200: q must have 3 entries");
+  const double p[3] = {(double)q(0), (double)q(1), (double)q(2)};
+  double s = 0.0, c[3];
+  int32_t i = -1;
+  // unbounded, as the reference's single-query form (tree.squared_distance(V,F,q,i,c))
+  check(iglb200_signed_distance(m, p, 1, 1, 3, 1, (int)SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, 0.0, std::numeric_limits<double>::max(),
+                                &s, 1, &i, c, 1, 3, 1, nullptr, 1, nullptr, 1, 3, 1));
+  return (typename DerivedV::Scalar)s;
+}
+
 // signed_distance_pseudonormal(P,V,F,tree,FN,VN,EN,EMAP,S,I,C,N): batch overload with prebuilt structures
 // (signed_distance.h:135-147, signed_distance.cpp:468-512).  The device keeps its own copy of the angle-weighted
 // vertex, uniform edge and face normals, computed from V and F exactly as per_face_normals / per_vertex_normals /

@@ -62,7 +62,7 @@ class Api:
         "iglb200_host_alloc", "iglb200_host_free", "iglb200_host_register", "iglb200_host_unregister",
         "iglb200_mesh_create", "iglb200_mesh_create_ex", "iglb200_mesh_destroy", "iglb200_mesh_info", "iglb200_mesh_build_ms",
         "iglb200_mesh_arena", "iglb200_mesh_arena_download", "iglb200_mesh_from_arena",
-        "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_fwn_eval",
+        "iglb200_signed_distance", "iglb200_squared_distance", "iglb200_squared_distance_bounded", "iglb200_fwn_eval",
         "iglb200_query_scratch_bytes", "iglb200_signed_distance_dev", "iglb200_squared_distance_dev",
         "iglb200_fwn_eval_dev", "iglb200_last_launch_count", "iglb200_profile_enable", "iglb200_profile_collect",
         "iglb200_debug_visit_counts", "iglb200_poll_device_error", "iglb200_debug_fp32_peak_tflops",
@@ -115,6 +115,7 @@ class Api:
         L.iglb200_group_info.argtypes = [C.POINTER(_i64), C.c_char_p, C.c_uint64]
         L.iglb200_mesh_replicate.argtypes = [_vp]
         L.iglb200_squared_distance.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp, _int, _i64, _i64]
+        L.iglb200_squared_distance_bounded.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _dbl, _dbl, _vp, _int, _vp, _vp, _int, _i64, _i64]
         L.iglb200_fwn_eval.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, C.c_float, _vp, _int]
         L.iglb200_query_scratch_bytes.argtypes = [_i64]
         L.iglb200_query_scratch_bytes.restype = C.c_uint64
@@ -453,14 +454,14 @@ class Mesh:
     def signed_distance_fast_winding_number(self, P):
         return self.signed_distance(P)[0]
 
-    # AABB::squared_distance(V,Ele,P,sqrD,I,C)
-    def squared_distance(self, P):
+    # AABB::squared_distance(V,Ele,P,sqrD,I,C); with bounds: the batch form of AABB.h:575-614
+    def squared_distance(self, P, low_sqr_d=0.0, up_sqr_d=np.inf):
         Pk, pp, pf64, n, prs, pcs = _mat(P, "P")
         D = np.empty(n, np.float64)
         I = np.empty(n, np.int32)
         Cc = np.empty((n, 3), np.float64, order="F")
-        self.api.check(self.api.lib.iglb200_squared_distance(
-            self.h, pp, pf64, n, prs, pcs, D.ctypes.data_as(_vp), 1, I.ctypes.data_as(_vp),
+        self.api.check(self.api.lib.iglb200_squared_distance_bounded(
+            self.h, pp, pf64, n, prs, pcs, float(low_sqr_d), float(up_sqr_d), D.ctypes.data_as(_vp), 1, I.ctypes.data_as(_vp),
             Cc.ctypes.data_as(_vp), 1, 1, max(n, 1)))
         return D, I, Cc
 

@@ -749,16 +749,18 @@ void run_exact_winding(const iglb200_mesh *m, const double *O, int64_t n, double
                                                      W, nullptr, nullptr, nullptr, overflow_flag()}, s);
 }
 
+// low_sqr_d / up_sqr_d: AABB.cpp:1135-1148 — only primitives closer than up_sqr_d count (none: the result is up_sqr_d,
+// I = -1); low_sqr_d > up_sqr_d returns low_sqr_d
 void run_squared_distance(const iglb200_mesh *m, const double *P, int64_t n, double *sqrD, int32_t *I, double *C,
-                          void *scratch, int sort_queries, stream_t s) {
+                          void *scratch, int sort_queries, stream_t s, double low_sqr_d = 0.0, double up_sqr_d = INFINITY) {
   if (n == 0) return;
-  if (m->h.nnodes == 0) {  // empty tree: the reference returns the initial bound (+inf) and leaves I/C unset
-    plat::for_n(n, FillConst{sqrD, I, C, nullptr, n, INFINITY, -1, 0.0}, s);
+  if (m->h.nnodes == 0) {  // empty tree: the reference returns the initial bound and leaves I/C unset
+    plat::for_n(n, FillConst{sqrD, I, C, nullptr, n, low_sqr_d > up_sqr_d ? low_sqr_d : up_sqr_d, -1, 0.0}, s);
     return;
   }
   const uint32_t *perm = morton_perm(m, P, n, scratch, sort_queries, s);
   plat::Span sp("closest", s);
-  launch_closest(closest_args(m, P, n, perm, INFINITY, 0.0, sqrD, I, C, nullptr, scratch ? carve(scratch, n).sched : nullptr), s);
+  launch_closest(closest_args(m, P, n, perm, up_sqr_d, low_sqr_d, sqrD, I, C, nullptr, scratch ? carve(scratch, n).sched : nullptr), s);
 }
 
 void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_scale, double *W, void *scratch,
@@ -1111,7 +1113,7 @@ void host_worker(WorkerCtx &w, HostQuery &q) {
     char *draw = base + B.oRaw;
     chunk_upload(w, q.P, lo, c, dP, draw, hb + H.oIn);
     if (q.mode == 0) run_signed_distance(m, dP, c, q.sign_type, q.lower, q.upper, dS, dI, dC, q.W.p ? dW : nullptr, dN, base + B.oX, 1, w.s);
-    else if (q.mode == 1) run_squared_distance(m, dP, c, dS, dI, dC, base + B.oX, 1, w.s);
+    else if (q.mode == 1) run_squared_distance(m, dP, c, dS, dI, dC, base + B.oX, 1, w.s, q.lower, q.upper);
     else if (q.mode == 2) run_fwn(m, dP, c, q.acc, dW, base + B.oX, 1, w.s);
     else run_exact_winding(m, dP, c, dW, base + B.oX, 1, w.s);
     // downloads (each layout shim reuses `draw`: stream order keeps them apart)
@@ -1746,14 +1748,20 @@ int64_t iglb200_host_chunk_rows(int64_t nP, int n_devices) { return host_chunk_r
 
 int iglb200_squared_distance(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
                              void *sqrD, int d_is_f64, int32_t *I, void *C, int c_is_f64, int64_t c_rs, int64_t c_cs) {
+  return iglb200_squared_distance_bounded(m, P, p_is_f64, nP, p_rs, p_cs, 0.0, INFINITY, sqrD, d_is_f64, I, C, c_is_f64, c_rs, c_cs);
+}
+int iglb200_squared_distance_bounded(const iglb200_mesh *m, const void *P, int p_is_f64, int64_t nP, int64_t p_rs, int64_t p_cs,
+                                     double low_sqr_d, double up_sqr_d, void *sqrD, int d_is_f64, int32_t *I, void *C, int c_is_f64,
+                                     int64_t c_rs, int64_t c_cs) {
   API_BEGIN
   check_mesh(m);
   if (nP < 0 || (nP > 0 && (!P || !sqrD || !I || !C))) throw std::invalid_argument("null pointer");
   if (nP > 0 && (c_rs <= 0 || c_cs <= 0 || p_rs <= 0 || p_cs <= 0)) throw std::invalid_argument("strides must be positive");
   require_device();
   plat::launch_counter() = 0;
+  if (low_sqr_d != low_sqr_d || up_sqr_d != up_sqr_d) throw std::invalid_argument("NaN bound");
   HostQuery q;
-  q.m = m; q.mode = 1; q.n = nP;
+  q.m = m; q.mode = 1; q.n = nP; q.lower = low_sqr_d; q.upper = up_sqr_d;   // squared bounds in mode 1
   q.P = host_mat(P, p_is_f64, nP, p_rs, p_cs); q.C = host_mat(C, c_is_f64, nP, c_rs, c_cs);
   q.S = host_vec(sqrD, d_is_f64); q.I = I; q.i_pinned = nP > 0 && plat::host_is_pinned(I);
   if (nP > 0 && (q.P.kind == MAT_OTHER || q.C.kind == MAT_OTHER)) {
@@ -1764,7 +1772,7 @@ int iglb200_squared_distance(const iglb200_mesh *m, const void *P, int p_is_f64,
     DevBuf<int32_t> dI((size_t)nP);
     DevBuf<char> scratch(iglb200_query_scratch_bytes(nP));
     upload_points(P, p_is_f64, nP, p_rs, p_cs, dP, s);
-    run_squared_distance(m, dP.p, nP, dS.p, dI.p, dC.p, scratch.p, 1, s);
+    run_squared_distance(m, dP.p, nP, dS.p, dI.p, dC.p, scratch.p, 1, s, low_sqr_d, up_sqr_d);
     download_scalar(dS, nP, sqrD, d_is_f64, s);
     plat::d2h(I, dI.p, (size_t)4 * nP, s);
     download_points(dC, nP, C, c_is_f64, c_rs, c_cs, s);

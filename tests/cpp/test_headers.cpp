@@ -194,6 +194,39 @@ int main() {
     REQUIRE(SV2.rows() > 50 && SF2.rows() == 2 * SV2.rows() - 4 && GV2.rows() == S2.rows());
     for (int64_t i = 0; i < S2.rows(); ++i) REQUIRE(S2(i) == S2(i));
   }
+  // single-query and bounded overloads (fast_winding_number.h:196-206, signed_distance.h:300-312, AABB.h:575-614)
+  {
+    iglb200::AABB<MatrixXd, 3> tree; tree.init(V, F);
+    iglb200::FastWindingNumberBVH bvh;
+    iglb200::fast_winding_number(V, F, 2, bvh);
+    MatrixXd q(1, 3);
+    q(0, 0) = q(0, 1) = q(0, 2) = 0.1;                       // inside the tet
+    REQUIRE(std::fabs(iglb200::fast_winding_number(bvh, 2.0f, q) - 1.0) < 1e-6);
+    q(0, 0) = q(0, 1) = q(0, 2) = 0.5;                       // outside, sqrt(1/12) from face 3
+    REQUIRE(std::fabs(iglb200::fast_winding_number(bvh, 2.0f, q)) < 1e-6);
+    REQUIRE(std::fabs(iglb200::signed_distance_fast_winding_number(q, V, F, tree, bvh) - std::sqrt(1. / 12.)) < 1e-7);
+    int i = -7; MatrixXd c(1, 3); c(0, 0) = c(0, 1) = c(0, 2) = -7.0;
+    REQUIRE(std::fabs(tree.squared_distance(V, F, q, 1.0, i, c) - 1. / 12.) < 1e-15 && i == 3);        // found below the bound
+    i = -7; c(0, 0) = -7.0;
+    REQUIRE(tree.squared_distance(V, F, q, 0.0, 0.05, i, c) == 0.05 && i == -7 && c(0, 0) == -7.0);       // nothing nearer than up_sqr_d: untouched
+    REQUIRE(tree.squared_distance(V, F, q, 2.0, 1.0, i, c) == 2.0 && i == -7);                           // low > up returns low (AABB.cpp:1145-1148)
+  }
+  // cached point-cloud evaluation: one precompute, many evaluations (fast_winding_number.h:44-53, 88-100 as an opaque handle)
+  {
+    MatrixXd Pp(1, 3), Np(1, 3), Q(4, 3); VectorXd Ap(1, 1), W1, W2;
+    Pp(0, 0) = 0.1; Pp(0, 1) = 0.2; Pp(0, 2) = 0.3;
+    const double nl = std::sqrt(16. + 25. + 36.);
+    Np(0, 0) = 4 / nl; Np(0, 1) = 5 / nl; Np(0, 2) = 6 / nl;
+    Ap(0) = 0.7;
+    const double qs[4][3] = {{0, 0, 0}, {4, -3, 2}, {-1, 1, 3}, {0, 5, -2}};
+    for (int r = 0; r < 4; ++r) for (int d = 0; d < 3; ++d) Q(r, d) = qs[r][d];
+    iglb200::FastWindingNumberCloud cloud;
+    iglb200::fast_winding_number(Pp, Np, Ap, 2, cloud);
+    iglb200::fast_winding_number(cloud, Q, 2.0, W1);
+    iglb200::fast_winding_number(cloud, Q, 2.0, W2);
+    const double gold[4] = {0.38779369004261133, -0.00041235296362485, -0.00362978253577090, -0.00041235296362485};
+    for (int r = 0; r < 4; ++r) REQUIRE(std::fabs(W1(r) - gold[r]) < 1e-15 && W1(r) == W2(r));
+  }
   std::printf("OK\n");
   return 0;
 }

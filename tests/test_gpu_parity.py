@@ -133,6 +133,73 @@ def test_c3_noisy_sphere_random_queries(gpu_api):
     m.close()
 
 
+def test_c3_full_size(gpu_api):
+    """BASELINE config c3 at full size: 5.2 M-face noisy sphere, 10 M random queries, AABB::squared_distance.
+    Oracle (restated f64 AABB) on a strided 100 k-row sample: d2 and C bit-identical; properties on all rows."""
+    V, F = synth.noisy_sphere(9, 0.01, 0)
+    assert F.shape[0] == 5_242_880
+    P = synth.random_points(10_000_000, -1.5, 1.5, 1)
+    m = gpu_api.Mesh(V, F, 0)
+    D, I, C = m.squared_distance(np.asfortranarray(P))
+    m.close()
+    assert (I >= 0).all() and (I < F.shape[0]).all()
+    assert np.abs(((P - C) ** 2).sum(1) - D).max() < 1e-12
+    k = np.arange(0, P.shape[0], 100)
+    Do, Io, Co = oracle.PortAABB(V, F).squared_distance(P[k])
+    parity.check_closest(V, F, P[k], D[k], I[k], C[k], Do, Io, Co, "c3 full size")
+    k2 = np.arange(7, P.shape[0], 997)
+    assert np.array_equal(oracle.face_distance(V, F, P[k2], I[k2]), D[k2])   # the reported face attains the reported distance
+
+
+def test_c4_full_size(gpu_api):
+    """BASELINE config c4 at full size: 2 M oriented points, 20 M queries, order 2, beta 2.  Oracle (restated octree +
+    expansion, pinned against the Taylor series in test_oracle.py) on a strided 40 k-row sample."""
+    V, F = synth.icosphere(7)
+    Pc, N, A = synth.oriented_cloud(V, F, 2_000_000, 2)
+    Q = synth.random_points(20_000_000, -1.5, 1.5, 2)
+    c = gpu_api.Cloud(Pc, N, A, 2)
+    W = c.eval(np.asfortranarray(Q), 2.0)
+    o = oracle.PortCloud(Pc, N, A, 2)
+    assert c.info()["n_cells"] == o.num_cells()
+    c.close()
+    k = np.arange(0, Q.shape[0], 500)
+    Wo = o.eval(Q[k], 2.0)
+    d = np.abs(W[k] - Wo)
+    assert (d <= 1e-5 * np.maximum(1.0, np.abs(Wo))).all() and d.max() < 1e-10, d.max()
+    r = np.linalg.norm(Q, axis=1)
+    assert (W[r < 0.9] > 0.9).all() and (np.abs(W[r > 1.2]) < 0.1).all()          # inside / outside the unit sphere
+    assert np.isfinite(W).all()
+
+
+def test_c5_full_size(gpu_api):
+    """BASELINE config c5 at full size: 10 M-face torus knot, 512^3 = 134 M grid queries, FAST_WINDING_NUMBER sign.
+    Oracle (genuine FWN core + restated AABB) on a strided ~33 k-row sample; size-independent properties on all rows."""
+    V, F = synth.torus_knot(*synth.knot_dims(10_000_000))
+    assert F.shape[0] == 10_000_000
+    m = gpu_api.Mesh(V, F, 2)
+    P = synth.grid_points(*synth.bbox(V), 512, 1.1)
+    n = P.shape[0]
+    assert n == 512 ** 3
+    Pf = np.asfortranarray(P)
+    S, I, C, W = m.signed_distance(Pf, return_W=True)
+    m.close()
+    assert not np.isnan(S).any()
+    assert (I >= 0).all() and (I < F.shape[0]).all()
+    d2 = np.zeros(n)
+    for j in range(3):                                   # column by column: 134 M rows
+        d2 += (Pf[:, j] - C[:, j]) ** 2
+    assert np.abs(np.abs(S) - np.sqrt(d2) * np.abs(1 - 2 * np.abs(W))).max() < 1e-12      # S = (1-2|w|) sqrt(d2)
+    inside = W > 0.5
+    assert (S[inside] <= 0).all() and (S[~inside] >= 0).all()
+    assert 0.001 < inside.mean() < 0.2
+    k = np.arange(0, n, 4099)
+    Pk = np.ascontiguousarray(P[k])
+    assert np.abs(oracle.face_distance(V, F, Pk, I[k]) - d2[k]).max() < 1e-12
+    r = parity.check_signed_distance(V, F, Pk, S[k], I[k], np.ascontiguousarray(C[k]), W[k], what="c5 sample",
+                                     fwn=oracle.RefFwn(V, F), tree=oracle.PortAABB(V, F))
+    assert r["n"] == len(k)
+
+
 def test_adversarial_triangles(gpu_api):
     cases.case_adversarial_triangles(gpu_api)
 

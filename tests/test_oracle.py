@@ -158,3 +158,131 @@ def test_exact_winding_number_known_values():
     assert abs(abs(w[0]) - 0.125) < 1e-15
     S, I, C, Wd = oracle.signed_distance_winding_number(np.array([[0.5, 0.5, 0.5]]), V, F)
     assert abs(S[0] - np.sqrt(1. / 12.)) < 1e-15 and I[0] == 3        # tests/include/igl/signed_distance.cpp:4-43
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pinning the CLOUD oracle beyond the dipole term.  The only vector the reference's tests hold for the point-cloud
+# fast winding number (tests/include/igl/fast_winding_number.cpp:17-53) is a one-point cloud: a leaf, direct_eval only.
+# The order-1/2 Taylor terms (fast_winding_number.cpp:94-110 precompute, :190-224 evaluation) are pinned here against
+# mathematics instead: (a) the brute-force dipole sum, (b) finite differences of the dipole kernel, (c) the coefficient
+# sums written as plain tensor contractions, (d) the evaluation as the Taylor polynomial of (b) contracted with (c).
+def _dipole_K(x):
+    """K(x) = x / (4 pi |x|^3): the dipole at p with strength m = a*n contributes K(p - q) . m  (:159-172)."""
+    r = np.linalg.norm(x, axis=-1, keepdims=True)
+    return x / (4.0 * np.pi * r ** 3)
+
+
+def _dK(L):
+    """dK[i, j] = d_i K_j at L (SecondDerivative, :190-197)."""
+    r = np.linalg.norm(L)
+    return (np.eye(3) / r ** 3 - 3.0 * np.outer(L, L) / r ** 5) / (4.0 * np.pi)
+
+
+def _ddK(L):
+    """ddK[k, i, j] = d_k d_i K_j at L (ThirdDerivative, :203-222)."""
+    r = np.linalg.norm(L)
+    e = np.eye(3)
+    t = 15.0 * np.einsum("k,i,j->kij", L, L, L) / r ** 7
+    t -= 3.0 * (np.einsum("ij,k->kij", e, L) + np.einsum("ik,j->kij", e, L) + np.einsum("jk,i->kij", e, L)) / r ** 5
+    return t / (4.0 * np.pi)
+
+
+def _cloud(n, seed=3):
+    rng = np.random.default_rng(seed)
+    P = rng.normal(size=(n, 3))
+    P /= np.linalg.norm(P, axis=1)[:, None]
+    P *= 1.0 + 0.05 * rng.normal(size=(n, 1))
+    N = P / np.linalg.norm(P, axis=1)[:, None]
+    A = np.full(n, 4.0 * np.pi / n) * (1.0 + 0.3 * rng.random(n))
+    return P, N, A
+
+
+def _members(cells, P):
+    """Points of every octree cell, re-derived from the cell centres with the reference's octant rule (octree.cpp:43-51)."""
+    CH, CN = cells["CH"], cells["CN"]
+    mem = {0: np.arange(P.shape[0])}
+    todo = [0]
+    while todo:
+        c = todo.pop()
+        if CH[c, 0] == -1:
+            continue
+        idx = mem[c]
+        octant = (P[idx, 0] >= CN[c, 0]) * 1 + (P[idx, 1] >= CN[c, 1]) * 2 + (P[idx, 2] >= CN[c, 2]) * 4
+        for o in range(8):
+            mem[int(CH[c, o])] = idx[octant == o]
+            todo.append(int(CH[c, o]))
+    return mem
+
+
+def test_cloud_oracle_brute_force_dipole_sum():
+    P, N, A = _cloud(1500)
+    Q = synth.random_points(300, -2.0, 2.0, 9)
+    M = A[:, None] * N
+    brute = np.array([np.einsum("ij,ij->", _dipole_K(P - q), M) for q in Q])
+    for order in (0, 1, 2):
+        o = oracle.PortCloud(P, N, A, order)
+        assert np.abs(o.eval(Q, 0.0) - brute).max() < 1e-12            # beta <= 0: the plain sum (:300-309)
+        assert np.abs(o.eval(Q, 1e12) - brute).max() < 1e-12           # beta -> inf: every cell descends to its leaves
+    # the expansion converges to it with the order
+    errs = [np.abs(oracle.PortCloud(P, N, A, k).eval(Q, 2.0) - brute).max() for k in (0, 1, 2)]
+    assert errs[2] < errs[1] < errs[0] and errs[2] < 0.1 and np.median(np.abs(oracle.PortCloud(P, N, A, 2).eval(Q, 2.0) - brute)) < 2e-3
+
+
+def test_cloud_kernel_derivatives_by_finite_differences():
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        L = rng.normal(size=3) * 2.0
+        h = 1e-4
+        e = np.eye(3)
+        fd1 = np.array([(_dipole_K(L + h * e[i]) - _dipole_K(L - h * e[i])) / (2 * h) for i in range(3)])
+        assert np.abs(fd1 - _dK(L)).max() < 1e-7 * np.abs(_dK(L)).max() + 1e-9
+        fd2 = np.array([(_dK(L + h * e[k]) - _dK(L - h * e[k])) / (2 * h) for k in range(3)])
+        assert np.abs(fd2 - _ddK(L)).max() < 1e-7 * np.abs(_ddK(L)).max() + 1e-9
+
+
+def test_cloud_oracle_coefficients_and_expansion_are_the_taylor_series():
+    P, N, A = _cloud(1200, seed=5)
+    o = oracle.PortCloud(P, N, A, 2)
+    cells = o.cells()
+    mem = _members(cells, P)
+    assert all(len(mem[c]) == cells["counts"][c] for c in mem)
+    internal = [c for c in mem if cells["CH"][c, 0] != -1 and len(mem[c]) > 1]
+    assert len(internal) > 50
+    for c in internal[:200]:
+        idx = mem[c]
+        a, p, n = A[idx], P[idx], N[idx]
+        cm = (a[:, None] * p).sum(0) / a.sum()
+        d = p - cm
+        assert np.abs(cells["CM"][c] - cm).max() < 1e-13
+        assert abs(cells["R"][c] - np.linalg.norm(d, axis=1).max()) < 1e-13
+        ec = cells["EC"][c]
+        assert np.abs(ec[:3] - (a[:, None] * n).sum(0)).max() < 1e-13
+        T1 = np.einsum("p,pi,pj->ij", a, d, n)                      # sum a * delta (x) n
+        assert np.abs(ec[3:12].reshape(3, 3).T - T1).max() < 1e-13    # Eigen::Map of a column-major 3x3 (:98-101)
+        T2 = 0.5 * np.einsum("p,pk,pi,pj->kij", a, d, d, n)
+        for k in range(3):
+            assert np.abs(ec[12 + 9 * k:21 + 9 * k].reshape(3, 3).T - T2[k]).max() < 1e-13
+    # evaluation: a query far from every child of the root takes expansion_eval for each of them (:262-282)
+    q = np.array([[30.0, -20.0, 25.0]])
+    kids = [int(k) for k in cells["CH"][0] if cells["counts"][int(k)] > 0]
+    assert all(cells["CH"][k, 0] != -1 for k in kids)
+    assert all(np.linalg.norm(cells["CM"][k] - q[0]) > 2.0 * cells["R"][k] for k in kids)
+    for order, nterms in ((0, 3), (1, 12), (2, 39)):
+        oo = oracle.PortCloud(P, N, A, order)
+        cc = oo.cells()
+        want = 0.0
+        for k in kids:
+            L = cc["CM"][k] - q[0]
+            ec = cc["EC"][k]
+            w = _dipole_K(L) @ ec[:3]
+            if order >= 1:
+                w += np.einsum("ij,ij->", _dK(L), ec[3:12].reshape(3, 3).T)
+            if order >= 2:
+                w += sum(np.einsum("ij,ij->", _ddK(L)[kk], ec[12 + 9 * kk:21 + 9 * kk].reshape(3, 3).T) for kk in range(3))
+            want += w
+        got = oo.eval(q, 2.0)[0]
+        assert abs(got - want) < 1e-15 + 1e-12 * abs(want), (order, got, want)
+    # ... and the truncated series approaches the exact sum of the cell like (R/r)^(order+1)
+    exact = np.einsum("ij,ij->", _dipole_K(P - q[0]), A[:, None] * N)
+    errs = [abs(oracle.PortCloud(P, N, A, k).eval(q, 2.0)[0] - exact) for k in (0, 1, 2)]
+    assert errs[2] < 0.2 * errs[1] < 0.04 * errs[0] or errs[2] < 1e-12
