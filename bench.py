@@ -381,7 +381,7 @@ def ours_mesh(args, cfg):
     def step():
         n_l = 0
         if rank == 0:
-            api.check(L.iglb200_shard_begin_dev(mesh.h, pP, nq, scratch, int(args.sort), sp()))
+            api.check(L.iglb200_shard_begin_dev(mesh.h, pP, nq, scratch, int(args.sort), super_rows, sp()))
             n_l += api.last_launch_count()
         job.stream_fence()
         api.check(L.iglb200_shard_run_dev(mesh.h, pP, nq, scratch, mode, sign, lower, upper, 2.0, int(args.sort), pS, pI, pC, pW,

@@ -190,7 +190,9 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
  * The query set P and the outputs S, I, C, W live on one device, the OWNER; every GPU holds a copy of the mesh
  * (iglb200_init in one process; iglb200_mesh_from_arena after an NCCL broadcast between processes).
  *   begin  (owner)   Morton-sorts the queries once: keys and permutation go to `shard_scratch`
- *                    (iglb200_shard_scratch_bytes(nP) bytes of the owner's memory), the work counter in it is zeroed.
+ *                    (iglb200_shard_scratch_bytes(nP) bytes of the owner's memory), the work counter in it is zeroed, and
+ *                    the super-chunks are ranked farthest-from-the-mesh first (the costliest searches are handed out
+ *                    first, so that a launch does not end on them).  `super_rows` >= 8192, the same in begin and run.
  *   run    (each GPU, after begin) runs the same kernels as the single-GPU call over the super-chunks of `super_rows`
  *                    consecutive sorted queries it takes off that counter — an atomic over NVLink when the owner is a
  *                    peer — until they run out.  P, the permutation and S/I/C/W are read from / written to the OWNER's
@@ -204,7 +206,8 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
  * All asynchronous on `stream` of the calling thread's current device. */
 uint64_t iglb200_shard_scratch_bytes(int64_t nP);
 int64_t iglb200_shard_super_rows(int64_t nP, int n_shards);   /* the library's choice; a multiple of 512 */
-int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int sort_queries, void *stream);
+int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int sort_queries,
+                            int64_t super_rows, void *stream);
 int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int mode, int sign_type,
                           double lower_bound, double upper_bound, float accuracy_scale, int sort_queries,
                           double *S, int32_t *I, double *C, double *W,

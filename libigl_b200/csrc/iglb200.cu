@@ -103,6 +103,8 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   uint32_t super_chunks = 0;
   uint32_t *my_supers = nullptr, *my_count = nullptr;
   int64_t max_supers = 0;   // > 0: take at most this many (static partition / tests)
+  const uint32_t *super_order = nullptr;   // the k-th super-chunk handed out is super_order[k]: costliest (farthest) first
+  uint32_t nnodes = 0;
   // the fp32 stage works in coordinates scaled by a power of two so that the mesh's max |coordinate| lies in [0.5, 1):
   // exact, and squares can neither overflow nor go denormal whatever the units of the mesh (absmax above is scaled too)
   double sigma = 1.0;
@@ -200,8 +202,9 @@ void launch_closest(const ClosestArgs &a, stream_t) {
   // sharded: super-chunks off the owner's counter, listed for the kernels that follow
   const int64_t super_rows = (int64_t)a.super_chunks * CP_CHUNK * 32;
   while (a.max_supers <= 0 || (int64_t)*a.my_count < a.max_supers) {
-    const unsigned long long sc = __atomic_fetch_add(a.remote, 1ull, __ATOMIC_RELAXED);
+    unsigned long long sc = __atomic_fetch_add(a.remote, 1ull, __ATOMIC_RELAXED);
     if ((int64_t)sc * super_rows >= a.n) break;
+    if (a.super_order) sc = a.super_order[sc];
     a.my_supers[(*a.my_count)++] = (uint32_t)sc;
     for (int64_t base = (int64_t)sc * super_rows; base < std::min(a.n, ((int64_t)sc + 1) * super_rows); base += 32) closest_packet_emul(a, base);
   }
@@ -225,6 +228,9 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
+#ifndef CP_TOP
+#define CP_TOP 0           // > 0: stage that many top nodes in shared memory (needs CP_WARPS > 1 to pay for the copy; measured: see profiles/)
+#endif
 #ifndef CP_WARPS
 #define CP_WARPS 1         // a block is one packet: a finished packet frees its slot at once (4 warps/block: 94.6 ms)
 #endif
@@ -234,7 +240,7 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // Sharded schedule, one level above the per-SM chunks: sched[0] = (super-chunk << 32 | chunks of it handed out).  When a
 // super-chunk is used up, one thread of the device takes the next one off the owner's counter (atomicAdd over NVLink when
 // the owner is a peer) and notes it in my_supers.  Returns a chunk index; chunks past the last packet end the caller's warp.
-struct ShardSched { unsigned long long *sched, *remote; uint32_t super_chunks; uint32_t *my_supers, *my_count; int64_t max_supers; };
+struct ShardSched { unsigned long long *sched, *remote; uint32_t super_chunks; uint32_t *my_supers, *my_count; int64_t max_supers; const uint32_t *order; };
 static __device__ __noinline__ unsigned long long next_chunk_sharded(const ShardSched a, uint32_t npackets) {
   unsigned long long *G = a.sched, *glock = a.sched + 1 + 2 * 1024;
   while (true) {
@@ -250,8 +256,10 @@ static __device__ __noinline__ unsigned long long next_chunk_sharded(const Shard
         const uint32_t have = *(volatile uint32_t *)a.my_count;
         if (a.max_supers <= 0 || (int64_t)have < a.max_supers) {
           sc = atomicAdd_system(a.remote, 1ull);
-          if (sc > 0xFFFFFFFFull) sc = 0xFFFFFFFFull;
-          if (sc * a.super_chunks * CP_CHUNK < (unsigned long long)npackets) { a.my_supers[have] = (uint32_t)sc; *(volatile uint32_t *)a.my_count = have + 1; }
+          if (sc * a.super_chunks * CP_CHUNK < (unsigned long long)npackets) {
+            if (a.order) sc = a.order[sc];
+            a.my_supers[have] = (uint32_t)sc; *(volatile uint32_t *)a.my_count = have + 1;
+          } else sc = 0xFFFFFFFFull;
         }
         __threadfence();
         atomicExch(G, sc << 32);
@@ -270,6 +278,14 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   CpExact &X = exact[threadIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *stack = stacks[warp];
+#if CP_TOP > 0
+  // experiment (north_star subsystem 2): the top CP_TOP nodes of the tree (breadth-first: levels are contiguous) staged in
+  // shared memory, one copy per block of CP_WARPS packets
+  __shared__ __align__(32) PillNode top[CP_TOP];
+  const uint32_t ntop = min((uint32_t)CP_TOP, a.nnodes);
+  for (uint32_t k = threadIdx.x; k < ntop * (sizeof(PillNode) / 16); k += blockDim.x) ((uint4 *)top)[k] = ((const uint4 *)a.nodes)[k];
+  __syncthreads();
+#endif
   // Persistent schedule: every SM hands out the packets of one chunk of CP_CHUNK Morton-consecutive packets to its
   // resident warps, so the packets that share an L1 are neighbours; chunks are taken from a global counter, so the
   // chunks in flight still form one window of the query set (L2).  sched[0] = next chunk, sched[1 + 2*smid] =
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         if ((uint32_t)old < CP_CHUNK) { packet = (uint32_t)(old >> 32) * CP_CHUNK + (uint32_t)old; break; }
         if (atomicCAS(lock, 0ull, 1ull) == 0ull) {   // this warp refills the SM's chunk
           if ((uint32_t)(*(volatile unsigned long long *)st) >= CP_CHUNK) {
-            const unsigned long long nc = a.remote ? next_chunk_sharded(ShardSched{a.sched, a.remote, a.super_chunks, a.my_supers, a.my_count, a.max_supers}, npackets)
+            const unsigned long long nc = a.remote ? next_chunk_sharded(ShardSched{a.sched, a.remote, a.super_chunks, a.my_supers, a.my_count, a.max_supers, a.super_order}, npackets)
                                                                : atomicAdd(a.sched, 1ull);
             atomicExch(st, nc << 32);
           }
@@ -319,6 +335,10 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       if (COUNT) ++nvis;
       const PillNode *np = a.nodes + cur;
       PillNode n;
+#if CP_TOP > 0
+      if (cur < ntop) n = top[cur];
+      else
+#endif
       { float4 c4, p4;
         ld256(&np->cx, n.cx, n.cy); ld256(&np->cz, n.cz, n.nx); ld256(&np->ny, n.ny, n.nz); ld256(&np->R, n.R, n.t); ld256(&np->child, c4, p4);
         n.child = make_uint4(__float_as_uint(c4.x), __float_as_uint(c4.y), __float_as_uint(c4.z), __float_as_uint(c4.w));
@@ -414,15 +434,17 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   // one packet per warp, blocks in Morton order: the packets in flight form one sliding window of the
   // query set, so the tree region they touch stays L2-resident (a grid-stride loop spreads it over ~14 regions)
   int64_t blocks = std::min<int64_t>((warps + CP_WARPS - 1) / CP_WARPS, (int64_t)0x7FFFFFFF);
+#if CP_TOP == 0
   static_assert(CP_WARPS == 1, "the persistent schedule hands out packets to one-warp blocks");
+#endif
   if (warps > (int64_t)0xFFF00000) throw std::invalid_argument("too many queries in one call (packet index is 32 bits)");
   DevBuf<unsigned long long> own;
   ClosestArgs b = a;
   if (!b.sched) { own.alloc(SCHED_WORDS); b.sched = own.p; }   // no caller scratch: a private state for this launch
   plat::for_n(SCHED_WORDS, InitSched{b.sched, b.remote ? 1 : 0}, s);
   blocks = std::min<int64_t>(blocks, (int64_t)plat::sm_count() * CP_MIN_BLOCKS);
-  if (b.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
-  else closest_packet_kernel<false><<<(unsigned)blocks, 32, 0, s>>>(b, overflow_flag());
+  if (b.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(b, overflow_flag());
+  else closest_packet_kernel<false><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(b, overflow_flag());
   if (own.p) plat::sync(s);
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
@@ -667,6 +689,7 @@ ClosestArgs closest_args(const iglb200_mesh *m, const double *P, int64_t n, cons
                          double *sqrD, int32_t *I, double *C, uint32_t *counters, unsigned long long *sched) {
   ClosestArgs a{m->pnodes(), m->tri64(), m->triq(), P, n, perm, up, low, (float)((double)m->h.absmax * m->h.sigma), sqrD, I, C, counters, sched};
   a.sigma = m->h.sigma;
+  a.nnodes = (uint32_t)m->h.nnodes;
   return a;
 }
 
@@ -786,10 +809,28 @@ void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_s
 // processes).  The owner's scratch has one layout, computed from nP alone, so that a peer only needs its base pointer.
 // ---------------------------------------------------------------------------------------------------
 struct ShardLayout {
-  size_t oCounter, oSort, total;
+  size_t oCounter, oOrder, oSort, total;
+  static constexpr int64_t MIN_SUPER = int64_t(8) << 10;
   explicit ShardLayout(int64_t n) {
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-    oCounter = 0; oSort = 256; total = oSort + al(iglb200_query_scratch_bytes(n));
+    const size_t nsup_max = (size_t)(n / MIN_SUPER + 2);
+    oCounter = 0; oOrder = 256; oSort = oOrder + al(4 * 4 * nsup_max);   // keys in/out, ids in/out (the order)
+    total = oSort + al(iglb200_query_scratch_bytes(n));
+  }
+  uint32_t *order(char *scratch, int64_t n) const { return (uint32_t *)(scratch + oOrder) + 3 * (size_t)(n / MIN_SUPER + 2); }
+};
+// cost proxy of a super-chunk: the farther its queries are from the mesh, the longer their search — hand those out first,
+// so that what is left for the end of the launch is cheap (the tail of a launch is its slowest last packet)
+struct SuperKeys {
+  const double *P; int64_t n; const uint32_t *perm; int64_t super_rows; double c[3]; uint32_t *keys, *ids;
+  DEVFN void operator()(int64_t sc) const {
+    int64_t t = sc * super_rows + super_rows / 2;
+    if (t >= n) t = n - 1;
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    const double x = P[i] - c[0], y = P[n + i] - c[1], z = P[2 * n + i] - c[2];
+    const float d2 = (float)(x * x + y * y + z * z);
+    keys[sc] = ~plat::f2ord(d2 == d2 ? d2 : 0.f);   // descending distance
+    ids[sc] = (uint32_t)sc;
   }
 };
 
@@ -852,11 +893,21 @@ int64_t shard_super_rows(int64_t n, int n_shards) {
   return (r + unit - 1) / unit * unit;
 }
 
-void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int sort_queries, stream_t s) {
+void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int sort_queries, int64_t super_rows, stream_t s) {
   const ShardLayout L(n);
   plat::dev_memset(scratch + L.oCounter, 0, 256, s);
   if (n == 0) return;
-  morton_perm(m, P, n, scratch + L.oSort, sort_queries, s);
+  if (super_rows < ShardLayout::MIN_SUPER) throw std::invalid_argument("super_rows must be at least 8192");
+  const uint32_t *perm = morton_perm(m, P, n, scratch + L.oSort, sort_queries, s);
+  // hand-out order of the super-chunks (the cub temp area of the query sort is free again: same stream)
+  const int64_t nsup = (n + super_rows - 1) / super_rows;
+  const size_t cap = (size_t)(n / ShardLayout::MIN_SUPER + 2);
+  uint32_t *kin = (uint32_t *)(scratch + L.oOrder), *kout = kin + cap, *vin = kout + cap, *vout = vin + cap;
+  SuperKeys sk{P, n, perm, super_rows, {0.5 * (m->h.bbox_lo[0] + m->h.bbox_hi[0]), 0.5 * (m->h.bbox_lo[1] + m->h.bbox_hi[1]),
+                                          0.5 * (m->h.bbox_lo[2] + m->h.bbox_hi[2])}, kin, vin};
+  plat::for_n(nsup, sk, s);
+  Scratch sc = carve(scratch + L.oSort, n);
+  plat::sort_pairs_u32(sc.temp, sc.temp_bytes, kin, kout, vin, vout, nsup, 32, s);
 }
 
 bool shard_degenerate(const iglb200_mesh *m, int mode) { return (mode != 2 && m->h.nF == 0) || m->h.nnodes == 0; }
@@ -884,6 +935,7 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
     plat::Span sp("closest", s);
     ClosestArgs a = closest_args(m, P, n, perm, up, low, S, I, C, nullptr, ws.sched.p);
     a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
+    a.super_order = L.order(scratch, n);
     launch_closest(a, s);
   }
   if (mode == 1) return;
@@ -1482,14 +1534,15 @@ uint64_t iglb200_query_scratch_bytes(int64_t nP) {
 // ---- sharded device-resident queries + inter-process memory
 uint64_t iglb200_shard_scratch_bytes(int64_t nP) { return ShardLayout(nP < 0 ? 0 : nP).total; }
 int64_t iglb200_shard_super_rows(int64_t nP, int n_shards) { return shard_super_rows(nP, n_shards); }
-int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int sort_queries, void *stream) {
+int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int sort_queries, int64_t super_rows,
+                            void *stream) {
   API_BEGIN
   m = mesh_here(m);
   if (nP < 0 || !shard_scratch || (nP > 0 && !P)) throw std::invalid_argument("null pointer");
   require_device();
   check_count(nP);
   plat::launch_counter() = 0;
-  shard_begin(m, P, nP, (char *)shard_scratch, sort_queries, (stream_t)stream);
+  shard_begin(m, P, nP, (char *)shard_scratch, sort_queries, super_rows, (stream_t)stream);
   return IGLB200_OK;
   API_END
 }

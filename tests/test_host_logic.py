@@ -269,7 +269,7 @@ def test_sharded_device_queries_match_the_fused_path(emul_api):
     api, L = emul_api, emul_api.lib
     vp = C.c_void_p
     V, F = synth.icosphere(3)
-    P = synth.grid_points(*synth.bbox(V), 28, 1.6)
+    P = synth.grid_points(*synth.bbox(V), 40, 1.6)
     n = P.shape[0]
     Pc = np.ascontiguousarray(P.T)           # [3, n] = column-major n x 3
     tiny, huge = float(np.finfo(float).tiny), float(np.finfo(float).max)
@@ -281,16 +281,16 @@ def test_sharded_device_queries_match_the_fused_path(emul_api):
         qs = np.zeros(int(L.iglb200_query_scratch_bytes(n)), np.uint8)
         sup = int(L.iglb200_shard_super_rows(n, 2))
         assert sup % 512 == 0 and sup >= 8192
-        sup = 1024                                    # small super-chunks so that both devices get several
+        sup = 8192                                    # the smallest super-chunk: 64 000 rows make eight
         for mode, sign, lo, hi in ((0, 4, tiny, huge), (0, 4, 0.05, 0.4), (0, 3, tiny, huge), (1, 0, 0, 0), (2, 0, 0, 0)):
             S, I, Cc, W = np.full(n, -5.0), np.full(n, -5, np.int32), np.full((3, n), -5.0), np.full(n, -5.0)
             api.set_device(0)
-            api.check(L.iglb200_shard_begin_dev(m.h, ptr(Pc), n, ptr(scratch), 1, None))
+            api.check(L.iglb200_shard_begin_dev(m.h, ptr(Pc), n, ptr(scratch), 1, sup, None))
             outs = (ptr(S), ptr(I), ptr(Cc), ptr(W))
-            api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 5, None))   # device 0: 5 pieces
+            api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 3, None))   # device 0: 3 pieces
             api.set_device(1)
             api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 0, None))   # device 1: the rest
-            assert int(scratch[:8].view(np.uint64)[0]) > 5
+            assert int(scratch[:8].view(np.uint64)[0]) >= 8
             api.set_device(0)
             api.check(L.iglb200_shard_finish_dev(m.h, n, mode, *outs, None))
             S1, I1, C1, W1 = np.empty(n), np.empty(n, np.int32), np.empty((3, n)), np.empty(n)
