@@ -305,11 +305,13 @@ def timed_steps(job, stream, step, warmup, steps):
     return job.max_over_ranks(e0.elapsed_time(e1))
 
 
-def ours_mesh(args, cfg):
-    """configs c1, c2, c3, c5: queries against a triangle mesh (signed distance or squared distance)."""
+def ours_mesh(args, cfg, job, light=False):
+    """configs c1, c2, c3, c5: queries against a triangle mesh (signed distance or squared distance).
+    light: the device-resident leg only (no e2e, no CPU arm, no rooflines).  Returns the result on rank 0."""
     import libigl_b200
-    job = Job()
     torch = job.torch
+    steps = min(args.steps, 3) if light else args.steps
+    warmup = min(args.warmup, 2) if light else args.warmup
     rank, world, dev = job.rank, job.world, job.dev
     api = libigl_b200.lib()
     api.set_device(job.local)
@@ -394,23 +396,23 @@ def ours_mesh(args, cfg):
         launches[0] = n_l
 
     # warm-up, then the timed region
-    timed_steps(job, stream, step, args.warmup, 0)
+    timed_steps(job, stream, step, warmup, 0)
     sampler = ClockSampler(job.local)
     if rank == 0:
         sampler.start()
     api.profile_enable(True)
-    ms = timed_steps(job, stream, step, 0, args.steps)
+    ms = timed_steps(job, stream, step, 0, steps)
     api.check(L.iglb200_poll_device_error())
     prof = api.profile_collect()
     api.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    value = nq * args.steps / (ms * 1e-3)
-    kernel_ms = {k: v / args.steps for k, v in prof.items()}
+    value = nq * steps / (ms * 1e-3)
+    kernel_ms = {k: v / steps for k, v in prof.items()}
     per_rank = job.gather_floats([kernel_ms.get("closest", 0.0), kernel_ms.get("winding", 0.0)])
 
     # N = 1: the fused single-GPU entry point on the same data must give the same bits (and its time is reported)
     fused_ms = None
-    if world == 1:
+    if world == 1 and not light:
         qs = torch.empty(int(L.iglb200_query_scratch_bytes(nq)), dtype=torch.uint8, device=dev)
         S2, I2, C2, W2 = torch.empty_like(dS), torch.empty_like(dI), torch.empty_like(dC), torch.empty_like(dW)
 
@@ -427,16 +429,17 @@ def ours_mesh(args, cfg):
         del qs, S2, I2, C2, W2
 
     # --- end to end through the host-pointer C ABI
-    e2e = run_e2e_mesh(job, api, mesh, cfg, args, hP, nq, mode, sign, lower, upper, dS, dI)
+    e2e = None if light else run_e2e_mesh(job, api, mesh, cfg, args, hP, nq, mode, sign, lower, upper, dS, dI)
 
+    line = None
     if rank == 0:
         line = {
-            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 distance + f32 winding number" if mode == 0 else "f64", "data": "synthetic",
             "config": config_dict(cfg, args, nF, nq, grid, world),
             "e2e": e2e,
-            "gpu_launches": int(launches[0] * args.steps),
+            "gpu_launches": int(launches[0] * steps),
             "kernel_ms_per_step": kernel_ms,
             "per_rank_kernel_ms": {"closest": [r[0] for r in per_rank], "winding": [r[1] for r in per_rank]},
             "super_rows": super_rows,
@@ -446,20 +449,24 @@ def ours_mesh(args, cfg):
         }
         if fused_ms is not None:
             line["fused_single_call_ms_per_step"] = fused_ms
-        add_rooflines(line, api, mesh, cfg, args, kernel_ms, info, nq, value, P, grid, world)
-        if world == 1 and not args.no_cpu:
+        if not light:
+            add_rooflines(line, api, mesh, cfg, args, kernel_ms, info, nq, value, P, grid, world)
+        if world == 1 and not args.no_cpu and not light:
             r = run_cpu(cfg, args, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                                     "build_s": r["build_s"]}
-        print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
     job.host_barrier()
     if rank != 0:
         L.iglb200_ipc_close(base)
     job.host_barrier()
     if rank == 0:
-        del dP, dS, dI, dC, dW
+        del dP, dS, dI, dC, dW, whole
         L.iglb200_ipc_free(base)
-    job.close()
+    mesh.close()
+    del keep
+    torch.cuda.empty_cache()
+    return line
 
 
 def run_e2e_mesh(job, api, mesh, cfg, args, hP, nq, mode, sign, lower, upper, dS, dI):
@@ -731,6 +738,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single-process", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="default run: skip the config-5 leg that rides along with c2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = CONFIGS[args.config]
@@ -739,7 +747,22 @@ def main():
     elif cfg["kind"] == "cloud":
         ours_cloud(args, cfg)
     else:
-        ours_mesh(args, cfg)
+        job = Job()
+        line = ours_mesh(args, cfg, job)
+        if args.config == "c2" and not args.no_c5 and not args.faces and not args.grid:
+            # BASELINE config 5 rides along in the same JSON line: 512^3 vs 10 M faces, query-sharded over the same N GPUs
+            # (device-resident leg only; `--config c5` runs it in full)
+            try:
+                c5 = ours_mesh(args, CONFIGS["c5"], job, light=True)
+                if line is not None and c5 is not None:
+                    line["c5"] = {k: c5[k] for k in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config",
+                                                     "kernel_ms_per_step", "per_rank_kernel_ms", "super_rows", "tree")}
+            except Exception as ex:   # the headline line stands on its own
+                if line is not None:
+                    line["c5"] = {"error": str(ex)[:300]}
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        job.close()
 
 
 if __name__ == "__main__":

@@ -1069,6 +1069,7 @@ struct HostQuery {
   int64_t n = 0;
   int sign_type = 0; double lower = 0, upper = 0; float acc = 2.0f;
   int64_t chunk = 0;
+  int64_t edge = 0;                 // that many quarter-size chunks open and close the batch (0: uniform chunks)
   int64_t *counter = nullptr;       // chunks handed out so far (process-local or shared between processes)
   std::atomic<int> failed{0};
   std::atomic<long long> launches{0};
@@ -1143,11 +1144,29 @@ void chunk_unstage3(const HostMat &M, int64_t lo, int64_t c, const char *hst) {
 
 int64_t take_chunk(int64_t *counter) { return __atomic_fetch_add(counter, (int64_t)1, __ATOMIC_RELAXED); }
 
+// Chunk k of a batch of n rows.  The first upload and the last kernels + download of a batch overlap with nothing, so
+// the batch opens and closes with `edge` chunks of a quarter of the size (one per worker): [small x edge | big ... | small x edge]
+struct ChunkPlan {
+  int64_t n, big, small, edge, mid, total;
+  ChunkPlan(int64_t n_, int64_t chunk, int64_t edge_) : n(n_), big(chunk), small(std::max<int64_t>(((chunk / 4) + 31) & ~int64_t(31), 32)), edge(edge_) {
+    if (edge <= 0 || n < 2 * edge * small + big) { edge = 0; mid = (n + big - 1) / big; }
+    else mid = (n - 2 * edge * small + big - 1) / big;
+    total = 2 * edge + mid;
+  }
+  bool range(int64_t k, int64_t &lo, int64_t &hi) const {
+    if (k >= total) return false;
+    if (k < edge) { lo = k * small; hi = lo + small; }
+    else if (k < edge + mid) { lo = edge * small + (k - edge) * big; hi = std::min(lo + big, n - edge * small); }
+    else { lo = n - (total - k) * small; hi = lo + small; }
+    return true;
+  }
+};
+
 // One worker's share of a host query: chunks until the counter runs past the end.
 void host_worker(WorkerCtx &w, HostQuery &q) {
   const iglb200_mesh *m = q.m->on(w.device);
   if (!m) return;
-  const int64_t nchunks = (q.n + q.chunk - 1) / q.chunk;
+  const ChunkPlan plan(q.n, q.chunk, q.edge);
   const ChunkBufs B = chunk_bufs(q, q.chunk);
   const StageBufs H = stage_bufs(q.chunk);
   plat::launch_counter() = 0;
@@ -1155,9 +1174,10 @@ void host_worker(WorkerCtx &w, HostQuery &q) {
   // three device scratch areas for layout shims are needed at most (C, N raw at once are sequenced on one stream, so one suffices)
   while (!q.failed.load(std::memory_order_relaxed)) {
     const int64_t k = take_chunk(q.counter);
-    if (k >= nchunks) break;
+    int64_t lo = 0, hi = 0;
+    if (!plan.range(k, lo, hi)) break;
     if (!sized) { w.ensure(B.total, H.total); sized = true; }
-    const int64_t lo = k * q.chunk, c = std::min(q.chunk, q.n - lo);
+    const int64_t c = hi - lo;
     char *base = w.dbuf, *hb = w.hbuf;
     double *dP = (double *)(base + B.oP), *dS = (double *)(base + B.oS), *dC = (double *)(base + B.oC), *dW = (double *)(base + B.oW);
     double *dN = q.N.p ? (double *)(base + B.oN) : nullptr;
@@ -1206,12 +1226,13 @@ struct Pool {
   uint64_t gen = 0;
   int pending = 0;
   HostQuery *job = nullptr;
-  int per_dev = 3;
+  int per_dev = 0;   // 0: by the size of the group (measured on c2: pageable arrays want 6 copy threads on one GPU)
   Pool() {
     const char *e = std::getenv("IGLB200_HOST_WORKERS");
     const int v = e ? std::atoi(e) : 0;
     if (v > 0 && v <= 16) per_dev = v;
   }
+  int workers_for(int ndev) const { return per_dev ? per_dev : (ndev <= 1 ? 6 : (ndev <= 2 ? 4 : 3)); }
   void loop(W *w) {
     try { plat::set_device(w->ctx.device); plat::pin_thread_near_device(w->ctx.device); } catch (...) {}
     std::unique_lock<std::mutex> lk(mu);
@@ -1246,7 +1267,8 @@ struct Pool {
       if (!q.m->on(d)) continue;
       int have = 0;
       for (W *w : ws) have += w->ctx.device == d;
-      for (; have < per_dev; ++have) {
+      const int want = workers_for(q.m->n_devices());
+      for (; have < want; ++have) {
         W *w = new W; w->ctx.device = d; w->seen = gen;
         ws.push_back(w);
         w->t = std::thread([this, w] { loop(w); });
@@ -1287,6 +1309,8 @@ void run_host_query(HostQuery &q, int64_t *shared_counter, int64_t shared_chunk)
     q.counter = shared_counter; q.chunk = std::min<int64_t>(shared_chunk, int64_t(1) << 24);
   } else {
     q.counter = &local_counter; q.chunk = host_chunk_rows(q.n, ndev);
+    static const int64_t edge_off = env_i64("IGLB200_STREAM_EDGE_OFF", 0);
+    q.edge = edge_off ? 0 : (int64_t)ndev * pool().workers_for(ndev);
   }
   static const int64_t inline_rows = env_i64("IGLB200_INLINE_ROWS", 1 << 15);
   if (!shared_counter && ndev == 1 && q.n <= inline_rows) {

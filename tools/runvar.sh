@@ -1,6 +1,6 @@
 #!/bin/bash
 # on the GPU box: bench.py (short) against the default build and every variant in build/variants/
-ARGS="${@:---steps 4 --warmup 2 --no-cpu --e2e-steps 1}"
+ARGS="${@:---steps 4 --warmup 2 --no-cpu --no-c5 --e2e-steps 1}"
 summ() { python -c "
 import json,sys
 for l in open(sys.argv[1]):
