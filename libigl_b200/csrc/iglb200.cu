@@ -1309,8 +1309,8 @@ void run_host_query(HostQuery &q, int64_t *shared_counter, int64_t shared_chunk)
     q.counter = shared_counter; q.chunk = std::min<int64_t>(shared_chunk, int64_t(1) << 24);
   } else {
     q.counter = &local_counter; q.chunk = host_chunk_rows(q.n, ndev);
-    static const int64_t edge_off = env_i64("IGLB200_STREAM_EDGE_OFF", 0);
-    q.edge = edge_off ? 0 : (int64_t)ndev * pool().workers_for(ndev);
+    static const int64_t edge_off = env_i64("IGLB200_STREAM_EDGE_OFF", 0), edge_cfg = env_i64("IGLB200_STREAM_EDGE", 0);
+    q.edge = edge_off ? 0 : (edge_cfg ? edge_cfg : (int64_t)ndev * pool().workers_for(ndev));
   }
   static const int64_t inline_rows = env_i64("IGLB200_INLINE_ROWS", 1 << 15);
   if (!shared_counter && ndev == 1 && q.n <= inline_rows) {
