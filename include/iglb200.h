@@ -190,9 +190,9 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
  * The query set P and the outputs S, I, C, W live on one device, the OWNER; every GPU holds a copy of the mesh
  * (iglb200_init in one process; iglb200_mesh_from_arena after an NCCL broadcast between processes).
  *   begin  (owner)   Morton-sorts the queries once: keys and permutation go to `shard_scratch`
- *                    (iglb200_shard_scratch_bytes(nP) bytes of the owner's memory), the work counter in it is zeroed, and
- *                    the super-chunks are ranked farthest-from-the-mesh first (the costliest searches are handed out
- *                    first, so that a launch does not end on them).  `super_rows` >= 8192, the same in begin and run.
+ *                    (iglb200_shard_scratch_bytes(nP) bytes of the owner's memory), the work counter in it is zeroed and
+ *                    the hand-out order of the super-chunks is fixed (Morton order).  `super_rows` >= 8192, the same in
+ *                    begin and run.
  *   run    (each GPU, after begin) runs the same kernels as the single-GPU call over the super-chunks of `super_rows`
  *                    consecutive sorted queries it takes off that counter — an atomic over NVLink when the owner is a
  *                    peer — until they run out.  P, the permutation and S/I/C/W are read from / written to the OWNER's

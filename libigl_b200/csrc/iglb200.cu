@@ -89,6 +89,12 @@ struct MortonKeys {  // 30-bit Morton code of each query inside the doubled scen
   }
 };
 
+// What the winding-number kernel of a SHARDED query needs about row t of the sorted order, left by the search kernel in the
+// memory of the GPU that ran it: reading it back is local and coalesced, where S[perm[t]] and P[perm[t]] are scattered
+// reads of the owner's memory over NVLink (measured on c5, 8 GPUs: the winding kernel took 19 ms on the peers, 11 on the owner)
+struct ShardStash { float qx, qy, qz; uint32_t row; double sqrd; };
+static_assert(sizeof(ShardStash) == 24, "stash layout");
+
 struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   const fwn::PillNode *nodes; const double *tri64; const float4 *triq;
   const double *P; int64_t n; const uint32_t *perm;
@@ -103,7 +109,8 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   uint32_t super_chunks = 0;
   uint32_t *my_supers = nullptr, *my_count = nullptr;
   int64_t max_supers = 0;   // > 0: take at most this many (static partition / tests)
-  const uint32_t *super_order = nullptr;   // the k-th super-chunk handed out is super_order[k]: costliest (farthest) first
+  const uint32_t *super_order = nullptr;   // the k-th super-chunk handed out is super_order[k]
+  ShardStash *stash = nullptr;             // [n], indexed by sorted position
   uint32_t nnodes = 0;
   // the fp32 stage works in coordinates scaled by a power of two so that the mesh's max |coordinate| lies in [0.5, 1):
   // exact, and squares can neither overflow nor go denormal whatever the units of the mesh (absmax above is scaled too)
@@ -193,6 +200,10 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
     else lane_finish(L[l], X[l], a.tri64, qr[l], a.up, r);
     closest_store(a, qi[l], r);
+    if (a.stash) {
+      const D3 p = load_query(qr[l]);
+      a.stash[base + l] = ShardStash{(float)p.x, (float)p.y, (float)p.z, (uint32_t)qi[l], r.sqr_d};
+    }
   }
   if (a.counters) { a.counters[0] += nvis; a.counters[1] += ntri; }
 }
@@ -408,6 +419,10 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
       else lane_finish(L, X, a.tri64, qr, a.up, r);
       closest_store(a, qi, r);
+      if (a.stash) {
+        const D3 p = load_query(qr);
+        a.stash[t] = ShardStash{(float)p.x, (float)p.y, (float)p.z, (uint32_t)qi, r.sqr_d};
+      }
     }
     if (COUNT && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
     __syncwarp();
@@ -460,10 +475,17 @@ struct WindingQuery {
   double up, low; int32_t nF;
   double *W; double *S; int32_t *I; double *C;  // S holds sqrD on entry when mode!=0
   uint32_t *overflow;
-  // rows that need no winding number are finished here; returns whether the walk must run for row i
-  DEVFN bool prelude(int64_t i) const {
+  const ShardStash *stash = nullptr;   // sharded: row, query and squared distance of sorted position t come from here
+  // Row of sorted position t, its query and (mode != 0) its squared distance.  Rows that need no winding number are
+  // finished here; returns whether the walk must run.
+  DEVFN bool begin(int64_t t, int64_t &i, float &qx, float &qy, float &qz, double &sqrd) const {
+    sqrd = 0.0;
+    if (stash) { const ShardStash st = stash[t]; i = st.row; qx = st.qx; qy = st.qy; qz = st.qz; sqrd = st.sqrd; }
+    else {
+      i = perm ? (int64_t)perm[t] : t;
+      if (mode != 0) sqrd = S[i];
+    }
     if (mode != 0) {
-      const double sqrd = S[i];
       if (sqrd >= up || sqrd < low) {
         S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
         if (W) W[i] = NAN;
@@ -471,22 +493,22 @@ struct WindingQuery {
       }
       if (mode == 2) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return false; }
     }
+    if (!stash) { qx = (float)P[i]; qy = (float)P[n + i]; qz = (float)P[2 * n + i]; }
     return true;
   }
-  DEVFN void epilogue(int64_t i, float om) const {
+  DEVFN void epilogue(int64_t i, float om, double sqrd) const {
     const double FOUR_PI = 4.0 * 3.1415926535897932384626433832795;
     const double w = (double)om / FOUR_PI;
     if (mode == 0) { W[i] = w; return; }
     const double wf = (double)(float)w;  // narrowed to float by fast_winding_number.cpp:452
     if (W) W[i] = wf;
-    S[i] = (1.0 - 2.0 * fabs(wf)) * sqrt(S[i]);
+    S[i] = (1.0 - 2.0 * fabs(wf)) * sqrt(sqrd);
   }
-  DEVFN int64_t row(int64_t t) const { return perm ? (int64_t)perm[t] : t; }
   DEVFN void operator()(int64_t t) const {   // one thread, one query (host emulation; the device walks packets)
-    const int64_t i = row(t);
-    if (!prelude(i)) return;
+    int64_t i; float qx, qy, qz; double sqrd;
+    if (!begin(t, i, qx, qy, qz, sqrd)) return;
     uint32_t stack[fwn::FWN_STACK];
-    epilogue(i, fwn::winding_solid_angle(nodes, tri32, (float)P[i], (float)P[n + i], (float)P[2 * n + i], acc2, order, stack, nullptr, overflow));
+    epilogue(i, fwn::winding_solid_angle(nodes, tri32, qx, qy, qz, acc2, order, stack, nullptr, overflow), sqrd);
   }
 };
 
@@ -616,13 +638,12 @@ template <class F> void launch_query(const char *, int64_t n, F f, stream_t s) {
 // one warp = one packet of 32 consecutive (Morton-adjacent) rows [t0, t0 + 32)
 template <class F> DEVFN void winding_packet(const F &f, int64_t t0, uint2 *stack) {
   const int64_t t = t0 + (threadIdx.x & 31);
-  const bool valid = t < f.n;
-  const int64_t i = valid ? f.row(t) : 0;
-  const bool alive = valid && f.prelude(i);
+  int64_t i = 0;
   float qx = 0.f, qy = 0.f, qz = 0.f;
-  if (alive) { qx = (float)f.P[i]; qy = (float)f.P[f.n + i]; qz = (float)f.P[2 * f.n + i]; }
+  double sqrd = 0.0;
+  const bool alive = t < f.n && f.begin(t, i, qx, qy, qz, sqrd);
   const float om = fwn::winding_solid_angle_packet(f.nodes, f.tri32, alive, qx, qy, qz, f.acc2, f.order, stack, f.overflow);
-  if (alive) f.epilogue(i, om);
+  if (alive) f.epilogue(i, om, sqrd);
 }
 __global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_number_kernel(int64_t n, WindingQuery f) {
   __shared__ uint2 stacks[WN_THREADS / 32][fwn::FWN_PSTACK];
@@ -819,17 +840,16 @@ struct ShardLayout {
   }
   uint32_t *order(char *scratch, int64_t n) const { return (uint32_t *)(scratch + oOrder) + 3 * (size_t)(n / MIN_SUPER + 2); }
 };
-// cost proxy of a super-chunk: the farther its queries are from the mesh, the longer their search — hand those out first,
-// so that what is left for the end of the launch is cheap (the tail of a launch is its slowest last packet)
+// hand-out key of a super-chunk: its index (Morton order) or, as an experiment, its distance from the mesh (see shard_begin)
 struct SuperKeys {
-  const double *P; int64_t n; const uint32_t *perm; int64_t super_rows; double c[3]; uint32_t *keys, *ids;
+  const double *P; int64_t n; const uint32_t *perm; int64_t super_rows; double c[3]; uint32_t *keys, *ids; int far_first;
   DEVFN void operator()(int64_t sc) const {
     int64_t t = sc * super_rows + super_rows / 2;
     if (t >= n) t = n - 1;
     const int64_t i = perm ? (int64_t)perm[t] : t;
     const double x = P[i] - c[0], y = P[n + i] - c[1], z = P[2 * n + i] - c[2];
     const float d2 = (float)(x * x + y * y + z * z);
-    keys[sc] = ~plat::f2ord(d2 == d2 ? d2 : 0.f);   // descending distance
+    keys[sc] = far_first ? ~plat::f2ord(d2 == d2 ? d2 : 0.f) : (uint32_t)sc;   // descending distance, or Morton order
     ids[sc] = (uint32_t)sc;
   }
 };
@@ -878,9 +898,11 @@ __global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_claim_kerne
 static constexpr int64_t FWN_PIECE_ROWS = 2048;   // winding-number-only shards: rows per claim
 struct ShardWs {   // per (thread, device) state of shard_run: schedule words, the list of super-chunks taken
   DevBuf<unsigned long long> sched; DevBuf<uint32_t> supers; size_t cap = 0;
-  void ensure(size_t nsup, stream_t s) {
+  DevBuf<ShardStash> stash;
+  void ensure(size_t nsup, size_t nstash, stream_t s) {
     if (!sched.p) sched.alloc(SCHED_WORDS);
     if (nsup + 1 > cap) { plat::sync(s); supers.alloc(nsup + 1); cap = nsup + 1; }
+    if (nstash > stash.n) { plat::sync(s); stash.alloc(nstash); }
   }
 };
 
@@ -899,12 +921,16 @@ void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratc
   if (n == 0) return;
   if (super_rows < ShardLayout::MIN_SUPER) throw std::invalid_argument("super_rows must be at least 8192");
   const uint32_t *perm = morton_perm(m, P, n, scratch + L.oSort, sort_queries, s);
-  // hand-out order of the super-chunks (the cub temp area of the query sort is free again: same stream)
+  // Hand-out order of the super-chunks (the cub temp area of the query sort is free again: same stream).  Morton order by
+  // default: consecutive super-chunks share tree nodes in L2.  IGLB200_SHARD_ORDER=far hands out the farthest first — the
+  // idea being that a launch should not END on its costliest packets — but with cylinder bounds the far field is the cheap
+  // part and the jumps cost L2 locality: measured slower (c2, 8 GPUs: search 7.0 vs 6.4 ms per rank).
+  static const int far_first = [] { const char *e = std::getenv("IGLB200_SHARD_ORDER"); return (e && std::string(e) == "far") ? 1 : 0; }();
   const int64_t nsup = (n + super_rows - 1) / super_rows;
   const size_t cap = (size_t)(n / ShardLayout::MIN_SUPER + 2);
   uint32_t *kin = (uint32_t *)(scratch + L.oOrder), *kout = kin + cap, *vin = kout + cap, *vout = vin + cap;
   SuperKeys sk{P, n, perm, super_rows, {0.5 * (m->h.bbox_lo[0] + m->h.bbox_hi[0]), 0.5 * (m->h.bbox_lo[1] + m->h.bbox_hi[1]),
-                                          0.5 * (m->h.bbox_lo[2] + m->h.bbox_hi[2])}, kin, vin};
+                                          0.5 * (m->h.bbox_lo[2] + m->h.bbox_hi[2])}, kin, vin, far_first};
   plat::for_n(nsup, sk, s);
   Scratch sc = carve(scratch + L.oSort, n);
   plat::sort_pairs_u32(sc.temp, sc.temp_bytes, kin, kout, vin, vout, nsup, 32, s);
@@ -924,7 +950,7 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
   const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;
   const int64_t nsup = (n + super_rows - 1) / super_rows;
   ShardWs &ws = plat::per_device<ShardWs>();
-  ws.ensure((size_t)nsup, s);
+  ws.ensure((size_t)nsup, mode == 0 ? (size_t)n : 0, s);
   plat::dev_memset(ws.supers.p, 0, 4, s);              // [0] = count, [1..] = list
   uint32_t *my_count = ws.supers.p, *my_supers = ws.supers.p + 1;
   double low = 0.0, up = INFINITY;
@@ -936,13 +962,15 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
     ClosestArgs a = closest_args(m, P, n, perm, up, low, S, I, C, nullptr, ws.sched.p);
     a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
     a.super_order = L.order(scratch, n);
+    a.stash = mode == 0 ? ws.stash.p : nullptr;
     launch_closest(a, s);
   }
   if (mode == 1) return;
   plat::Span sp("winding", s);
   const float acc = mode == 2 ? accuracy_scale : 2.0f;
   const WindingQuery f{m->fnodes(), m->tri32(), P, n, perm, acc * acc, m->h.order,
-                       mode == 2 ? 0 : (sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1), up, low, (int32_t)m->h.nF, W, S, I, C, overflow_flag()};
+                       mode == 2 ? 0 : (sign_type == IGLB200_SIGN_UNSIGNED ? 2 : 1), up, low, (int32_t)m->h.nF, W, S, I, C, overflow_flag(),
+                       mode == 0 ? ws.stash.p : nullptr};
 #ifdef IGLB200_EMUL
   if (mode == 2) {   // no search ran: pieces straight off the owner's counter
     for (int64_t took = 0; max_supers <= 0 || took < max_supers; ++took) {
@@ -1149,7 +1177,7 @@ int64_t take_chunk(int64_t *counter) { return __atomic_fetch_add(counter, (int64
 struct ChunkPlan {
   int64_t n, big, small, edge, mid, total;
   ChunkPlan(int64_t n_, int64_t chunk, int64_t edge_) : n(n_), big(chunk), small(std::max<int64_t>(((chunk / 4) + 31) & ~int64_t(31), 32)), edge(edge_) {
-    if (edge <= 0 || n < 2 * edge * small + big) { edge = 0; mid = (n + big - 1) / big; }
+    if (edge <= 0 || 8 * 2 * edge * small > n) { edge = 0; mid = (n + big - 1) / big; }   // shape only when the edges are < 1/8 of the batch
     else mid = (n - 2 * edge * small + big - 1) / big;
     total = 2 * edge + mid;
   }
@@ -1291,8 +1319,10 @@ static int64_t env_i64(const char *name, int64_t dflt) { const char *e = std::ge
 int64_t host_chunk_rows(int64_t n, int ndev) {
   static const int64_t cfg = env_i64("IGLB200_STREAM_CHUNK", 0);
   if (cfg) return std::min(cfg, std::max<int64_t>(n, 1));
-  const int64_t want = (n + (int64_t)ndev * 12 - 1) / ((int64_t)ndev * 12);    // >= 4 chunks per worker
-  int64_t c = std::min<int64_t>(int64_t(1) << 20, std::max<int64_t>(int64_t(1) << 16, want));
+  // large enough for the persistent search kernel to run full (>= 256 Ki rows), small enough that a device sees at
+  // least four chunks so that uploads, kernels and downloads overlap
+  const int64_t want = (n + (int64_t)ndev * 4 - 1) / ((int64_t)ndev * 4);
+  int64_t c = std::min<int64_t>(int64_t(1) << 20, std::max<int64_t>(int64_t(1) << 18, want));
   c = (c + 31) & ~int64_t(31);
   return std::min(c, std::max<int64_t>(n, 1));
 }
