@@ -391,7 +391,7 @@ def ours_mesh(args, cfg, job, light=False):
         n_l += api.last_launch_count()
         job.stream_fence()
         if rank == 0:
-            api.check(L.iglb200_shard_finish_dev(mesh.h, nq, mode, pS, pI, pC, pW, sp()))
+            api.check(L.iglb200_shard_finish_dev(mesh.h, nq, scratch, mode, sign, lower, upper, int(args.sort), pS, pI, pC, pW, sp()))
             n_l += api.last_launch_count()
         launches[0] = n_l
 
@@ -541,7 +541,8 @@ def run_e2e_mesh(job, api, mesh, cfg, args, hP, nq, mode, sign, lower, upper, dS
         if rank != 0:
             sh = SharedArrays(name, nq, create=False)
         sh.register(api)
-        chunk = int(args.chunk_rows or L.iglb200_host_chunk_rows(nq, world))
+        # every rank runs its own workers: enough chunks that all of them draw several
+        chunk = int(args.chunk_rows or max(1 << 16, min(1 << 20, -(-nq // (world * 12)))))
         base = sh.counter.ctypes.data
 
         def coop_step(i):

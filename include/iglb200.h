@@ -199,7 +199,10 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
  *                    memory directly (peer loads and stores): no separate scatter, gather or un-sort pass.  All
  *                    pointers are the owner's buffers as seen from the calling device (peer-enabled pointers in one
  *                    process, iglb200_ipc_open between processes).  max_supers > 0 caps what this GPU takes.
- *   finish (owner, after every run) writes the sentinel rows of a degenerate mesh (#F == 0); otherwise nothing.
+ *                    For the signed distance the winding number runs BESIDE the search on every GPU (a second stream
+ *                    and work counter): its blocks fill the tail of the search kernel.
+ *   finish (owner, after every run) signed distance: one pass that combines each row's squared distance and solid angle
+ *                    into S and W (signed_distance.cpp:99-135); writes the sentinel rows of a degenerate mesh.
  * Ordering between the phases is the caller's: events between streams in one process, a tiny collective on the
  * streams between processes.  mode 0: signed distance (sign_type FAST_WINDING_NUMBER or UNSIGNED; S,I,C[,W]),
  * 1: squared distance (S=sqrD,I,C), 2: fast winding number (W; rows are claimed 2048 at a time, super_rows unused).
@@ -212,7 +215,9 @@ int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, vo
                           double lower_bound, double upper_bound, float accuracy_scale, int sort_queries,
                           double *S, int32_t *I, double *C, double *W,
                           int64_t super_rows, int64_t max_supers, void *stream);
-int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, int mode, double *S, int32_t *I, double *C, double *W, void *stream);
+int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, void *shard_scratch, int mode, int sign_type,
+                             double lower_bound, double upper_bound, int sort_queries,
+                             double *S, int32_t *I, double *C, double *W, void *stream);
 /* device memory that other processes on the node can map (cudaIpcGetMemHandle / cudaIpcOpenMemHandle): the
  * owner allocates and publishes the 64-byte handle (e.g. torch.distributed broadcast), the others open it. */
 int iglb200_ipc_alloc(uint64_t bytes, void **device_ptr, unsigned char handle[64]);

@@ -830,13 +830,15 @@ void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_s
 // processes).  The owner's scratch has one layout, computed from nP alone, so that a peer only needs its base pointer.
 // ---------------------------------------------------------------------------------------------------
 struct ShardLayout {
-  size_t oCounter, oOrder, oSort, total;
+  size_t oCounter, oOrder, oSort, oPsf, oWs, total;
   static constexpr int64_t MIN_SUPER = int64_t(8) << 10;
   explicit ShardLayout(int64_t n) {
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t nsup_max = (size_t)(n / MIN_SUPER + 2);
     oCounter = 0; oOrder = 256; oSort = oOrder + al(4 * 4 * nsup_max);   // keys in/out, ids in/out (the order)
-    total = oSort + al(iglb200_query_scratch_bytes(n));
+    oPsf = oSort + al(iglb200_query_scratch_bytes(n));                    // sorted queries as floats, x[n] y[n] z[n]
+    oWs = oPsf + al(12 * (size_t)n);                                      // solid angle of sorted row t
+    total = oWs + al(4 * (size_t)n);
   }
   uint32_t *order(char *scratch, int64_t n) const { return (uint32_t *)(scratch + oOrder) + 3 * (size_t)(n / MIN_SUPER + 2); }
 };
@@ -851,6 +853,47 @@ struct SuperKeys {
     const float d2 = (float)(x * x + y * y + z * z);
     keys[sc] = far_first ? ~plat::f2ord(d2 == d2 ? d2 : 0.f) : (uint32_t)sc;   // descending distance, or Morton order
     ids[sc] = (uint32_t)sc;
+  }
+};
+
+// Overlapped sharded signed distance: the winding number does not depend on the search, so it runs BESIDE it (second
+// stream, its own work counter) over the sorted queries as floats and leaves the solid angle of sorted row t in the owner's
+// scratch; its blocks become resident as the search kernel's warps run out of packets, i.e. they fill the search's tail
+// (whose length is set by a few packets near the medial axis, 7x the mean).  The owner combines afterwards.
+struct GatherSortedF { const double *P; int64_t n; const uint32_t *perm; float *Psf;
+  DEVFN void operator()(int64_t t) const {
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    Psf[t] = (float)P[i]; Psf[n + t] = (float)P[n + i]; Psf[2 * n + t] = (float)P[2 * n + i];
+  } };
+struct WindingSorted {
+  const fwn::FwnNode *nodes; const float4 *tri32; const float *Psf; int64_t n; float acc2; int order; float *Ws; uint32_t *overflow;
+  DEVFN bool begin(int64_t t, int64_t &i, float &qx, float &qy, float &qz, double &) const {
+    i = t; qx = Psf[t]; qy = Psf[n + t]; qz = Psf[2 * n + t];
+    return true;
+  }
+  DEVFN void epilogue(int64_t t, float om, double) const { Ws[t] = om; }
+  DEVFN void operator()(int64_t t) const {
+    uint32_t stack[fwn::FWN_STACK];
+    Ws[t] = fwn::winding_solid_angle(nodes, tri32, Psf[t], Psf[n + t], Psf[2 * n + t], acc2, order, stack, nullptr, overflow);
+  }
+};
+// owner: S, W of every row from its squared distance (left in S by the search) and its solid angle; out-of-bounds rows
+struct ShardCombine {
+  int sign_type; double up, low; int32_t nF; int64_t n; const uint32_t *perm; const float *Ws;
+  double *S; int32_t *I; double *C; double *W;
+  DEVFN void operator()(int64_t t) const {
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    const double sqrd = S[i];
+    if (sqrd >= up || sqrd < low) {
+      S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
+      if (W) W[i] = NAN;
+      return;
+    }
+    if (sign_type == IGLB200_SIGN_UNSIGNED) { S[i] = sqrt(sqrd); if (W) W[i] = NAN; return; }
+    const double w = (double)Ws[t] / (4.0 * 3.1415926535897932384626433832795);
+    const double wf = (double)(float)w;  // narrowed to float by fast_winding_number.cpp:452
+    if (W) W[i] = wf;
+    S[i] = (1.0 - 2.0 * fabs(wf)) * sqrt(sqrd);
   }
 };
 
@@ -875,7 +918,8 @@ __global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_shard_kerne
 }
 // winding number only: blocks claim pieces of `piece_rows` rows off the owner's counter (system-scope atomic) until
 // the rows run out; `budget` >= 0 caps the pieces this device takes (my_count counts them)
-__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_claim_kernel(WindingQuery f, unsigned long long *remote, int64_t piece_rows,
+template <class F>
+__global__ void __launch_bounds__(WN_THREADS, WN_MIN_BLOCKS) winding_claim_kernel(F f, unsigned long long *remote, int64_t piece_rows,
                                                                                   int64_t budget, uint32_t *my_count) {
   __shared__ unsigned long long piece_s;
   __shared__ uint2 stacks[WN_THREADS / 32][fwn::FWN_PSTACK];
@@ -899,6 +943,12 @@ static constexpr int64_t FWN_PIECE_ROWS = 2048;   // winding-number-only shards:
 struct ShardWs {   // per (thread, device) state of shard_run: schedule words, the list of super-chunks taken
   DevBuf<unsigned long long> sched; DevBuf<uint32_t> supers; size_t cap = 0;
   DevBuf<ShardStash> stash;
+  stream_t aux = nullptr; plat::event_t e0 = nullptr, e1 = nullptr; bool have_aux = false;
+  DevBuf<uint32_t> aux_count;
+  void ensure_aux() {
+    if (have_aux) return;
+    aux = plat::stream_create(); e0 = plat::event_create(); e1 = plat::event_create(); aux_count.alloc(1); have_aux = true;
+  }
   void ensure(size_t nsup, size_t nstash, stream_t s) {
     if (!sched.p) sched.alloc(SCHED_WORDS);
     if (nsup + 1 > cap) { plat::sync(s); supers.alloc(nsup + 1); cap = nsup + 1; }
@@ -914,6 +964,9 @@ int64_t shard_super_rows(int64_t n, int n_shards) {
   r = std::max<int64_t>(int64_t(8) << 10, std::min<int64_t>(int64_t(256) << 10, r));
   return (r + unit - 1) / unit * unit;
 }
+
+// IGLB200_SHARD_OVERLAP=0 runs the winding kernel AFTER the search on each GPU (over the rows it took, from its local stash)
+bool shard_overlap() { static const bool on = [] { const char *e = std::getenv("IGLB200_SHARD_OVERLAP"); return !(e && e[0] == '0'); }(); return on; }
 
 void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int sort_queries, int64_t super_rows, stream_t s) {
   const ShardLayout L(n);
@@ -934,6 +987,7 @@ void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratc
   plat::for_n(nsup, sk, s);
   Scratch sc = carve(scratch + L.oSort, n);
   plat::sort_pairs_u32(sc.temp, sc.temp_bytes, kin, kout, vin, vout, nsup, 32, s);
+  if (shard_overlap()) plat::for_n(n, GatherSortedF{P, n, perm, (float *)(scratch + L.oPsf)}, s);
 }
 
 bool shard_degenerate(const iglb200_mesh *m, int mode) { return (mode != 2 && m->h.nF == 0) || m->h.nnodes == 0; }
@@ -950,20 +1004,49 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
   const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;
   const int64_t nsup = (n + super_rows - 1) / super_rows;
   ShardWs &ws = plat::per_device<ShardWs>();
-  ws.ensure((size_t)nsup, mode == 0 ? (size_t)n : 0, s);
+  ws.ensure((size_t)nsup, (mode == 0 && !shard_overlap()) ? (size_t)n : 0, s);
   plat::dev_memset(ws.supers.p, 0, 4, s);              // [0] = count, [1..] = list
   uint32_t *my_count = ws.supers.p, *my_supers = ws.supers.p + 1;
   double low = 0.0, up = INFINITY;
   if (mode == 0) bounds_to_sqr(lower, upper, low, up);
   if (mode == 0 && sign_type != IGLB200_SIGN_FAST_WINDING_NUMBER && sign_type != IGLB200_SIGN_UNSIGNED)
     throw std::domain_error("sharded queries support the FAST_WINDING_NUMBER and UNSIGNED sign types");
+  const bool overlap = mode == 0 && shard_overlap();
+  if (overlap && sign_type == IGLB200_SIGN_FAST_WINDING_NUMBER) {
+    ws.ensure_aux();
+    plat::event_record(ws.e0, s);
+    plat::stream_wait(ws.aux, ws.e0);
+  }
   if (mode != 2) {
     plat::Span sp("closest", s);
     ClosestArgs a = closest_args(m, P, n, perm, up, low, S, I, C, nullptr, ws.sched.p);
     a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
     a.super_order = L.order(scratch, n);
-    a.stash = mode == 0 ? ws.stash.p : nullptr;
+    a.stash = (mode == 0 && !overlap) ? ws.stash.p : nullptr;
     launch_closest(a, s);
+  }
+  if (overlap && sign_type == IGLB200_SIGN_FAST_WINDING_NUMBER) {
+    // the winding number beside the search: second stream, second counter (remote + 1), pieces of sorted rows
+    // (launched after the search so that the search's blocks are dispatched first)
+    plat::Span sp("winding", ws.aux);
+    const WindingSorted f{m->fnodes(), m->tri32(), (const float *)(scratch + L.oPsf), n, 4.0f, m->h.order, (float *)(scratch + L.oWs), overflow_flag()};
+#ifdef IGLB200_EMUL
+    for (int64_t took = 0; max_supers <= 0 || took < max_supers * (super_rows / FWN_PIECE_ROWS); ++took) {
+      const unsigned long long pc = __atomic_fetch_add(remote + 1, 1ull, __ATOMIC_RELAXED);
+      if ((int64_t)pc * FWN_PIECE_ROWS >= n) break;
+      for (int64_t t = (int64_t)pc * FWN_PIECE_ROWS; t < std::min(n, ((int64_t)pc + 1) * FWN_PIECE_ROWS); ++t) f(t);
+    }
+#else
+    plat::dev_memset(ws.aux_count.p, 0, 4, ws.aux);
+    winding_claim_kernel<<<plat::sm_count() * WN_MIN_BLOCKS, WN_THREADS, 0, ws.aux>>>(
+        f, remote + 1, FWN_PIECE_ROWS, max_supers > 0 ? max_supers * (super_rows / FWN_PIECE_ROWS) : -1, ws.aux_count.p);
+    plat::launch_counter()++;
+    PLAT_CHECK(cudaGetLastError());
+#endif
+  }
+  if (overlap) {
+    if (sign_type == IGLB200_SIGN_FAST_WINDING_NUMBER) { plat::event_record(ws.e1, ws.aux); plat::stream_wait(s, ws.e1); }
+    return;   // the owner combines in finish
   }
   if (mode == 1) return;
   plat::Span sp("winding", s);
@@ -996,8 +1079,20 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
 #endif
 }
 
-void shard_finish(const iglb200_mesh *m, int64_t n, int mode, double *S, int32_t *I, double *C, double *W, stream_t s) {
-  if (n == 0 || !shard_degenerate(m, mode)) return;
+void shard_finish(const iglb200_mesh *m, int64_t n, char *scratch, int mode, int sign_type, double lower, double upper, int sort_queries,
+                  double *S, int32_t *I, double *C, double *W, stream_t s) {
+  if (n == 0) return;
+  if (!shard_degenerate(m, mode)) {
+    if (mode == 0 && shard_overlap()) {
+      const ShardLayout L(n);
+      double low = 0.0, up = INFINITY;
+      bounds_to_sqr(lower, upper, low, up);
+      const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;
+      plat::Span sp("combine", s);
+      plat::for_n(n, ShardCombine{sign_type, up, low, (int32_t)m->h.nF, n, perm, (const float *)(scratch + L.oWs), S, I, C, W}, s);
+    }
+    return;
+  }
   if (mode != 2 && m->h.nF == 0) { plat::for_n(n, FillConst{S, I, C, mode == 0 ? W : nullptr, n, NAN, -1, NAN}, s); return; }
   if (mode == 2) plat::for_n(n, FillConst{W, nullptr, nullptr, nullptr, n, 0.0, 0, 0.0}, s);
   else if (mode == 1) plat::for_n(n, FillConst{S, I, C, nullptr, n, INFINITY, -1, 0.0}, s);
@@ -1616,15 +1711,16 @@ int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, vo
   return IGLB200_OK;
   API_END
 }
-int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, int mode, double *S, int32_t *I, double *C, double *W, void *stream) {
+int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, void *shard_scratch, int mode, int sign_type, double lower, double upper,
+                             int sort_queries, double *S, int32_t *I, double *C, double *W, void *stream) {
   API_BEGIN
   m = mesh_here(m);
-  if (nP < 0) throw std::invalid_argument("negative size");
+  if (nP < 0 || !shard_scratch) throw std::invalid_argument("null pointer or negative size");
   if (mode < 0 || mode > 2) throw std::invalid_argument("mode must be 0, 1 or 2");
   if (nP > 0 && ((mode != 2 && (!S || !I || !C)) || (mode == 2 && !W))) throw std::invalid_argument("null output");
   require_device();
   plat::launch_counter() = 0;
-  shard_finish(m, nP, mode, S, I, C, W, (stream_t)stream);
+  shard_finish(m, nP, (char *)shard_scratch, mode, sign_type, lower, upper, sort_queries, S, I, C, W, (stream_t)stream);
   return IGLB200_OK;
   API_END
 }

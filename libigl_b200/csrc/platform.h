@@ -66,6 +66,10 @@ inline stream_t stream_create() { return nullptr; }
 inline void stream_destroy(stream_t) {}
 inline void peer_copy(void *d, int, const void *s_, int, size_t n, stream_t) { std::memcpy(d, s_, n); }
 inline void pin_thread_near_device(int) {}
+typedef void *event_t;
+inline event_t event_create() { return nullptr; }
+inline void event_record(event_t, stream_t) {}
+inline void stream_wait(stream_t, event_t) {}
 // f(i) for i in [0,n)
 template <class F> void for_n(int64_t n, F f, stream_t) { for (int64_t i = 0; i < n; ++i) f(i); }
 // f(i) for i in [0,*count) with the count living in "device" memory
@@ -156,6 +160,10 @@ inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
 inline void peer_copy(void *d, int ddev, const void *s_, int sdev, size_t n, stream_t s) {
   if (n) PLAT_CHECK(cudaMemcpyPeerAsync(d, ddev, s_, sdev, n, s));
 }
+typedef cudaEvent_t event_t;
+inline event_t event_create() { cudaEvent_t e = nullptr; PLAT_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return e; }
+inline void event_record(event_t e, stream_t s) { PLAT_CHECK(cudaEventRecord(e, s)); }
+inline void stream_wait(stream_t s, event_t e) { PLAT_CHECK(cudaStreamWaitEvent(s, e, 0)); }
 // run the calling thread on the CPUs next to the GPU (pinned staging buffers are then first-touched on that NUMA node)
 inline void pin_thread_near_device(int dev) {
   char bus[32] = {0};

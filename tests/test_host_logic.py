@@ -292,7 +292,7 @@ def test_sharded_device_queries_match_the_fused_path(emul_api):
             api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 0, None))   # device 1: the rest
             assert int(scratch[:8].view(np.uint64)[0]) >= 8
             api.set_device(0)
-            api.check(L.iglb200_shard_finish_dev(m.h, n, mode, *outs, None))
+            api.check(L.iglb200_shard_finish_dev(m.h, n, ptr(scratch), mode, sign, lo, hi, 1, *outs, None))
             S1, I1, C1, W1 = np.empty(n), np.empty(n, np.int32), np.empty((3, n)), np.empty(n)
             if mode == 0:
                 api.check(L.iglb200_signed_distance_dev(m.h, ptr(Pc), n, sign, lo, hi, ptr(S1), ptr(I1), ptr(C1), ptr(W1), None, ptr(qs), 1, None))
