@@ -199,10 +199,9 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
  *                    memory directly (peer loads and stores): no separate scatter, gather or un-sort pass.  All
  *                    pointers are the owner's buffers as seen from the calling device (peer-enabled pointers in one
  *                    process, iglb200_ipc_open between processes).  max_supers > 0 caps what this GPU takes.
- *                    For the signed distance the winding number runs BESIDE the search on every GPU (a second stream
- *                    and work counter): its blocks fill the tail of the search kernel.
- *   finish (owner, after every run) signed distance: one pass that combines each row's squared distance and solid angle
- *                    into S and W (signed_distance.cpp:99-135); writes the sentinel rows of a degenerate mesh.
+ *                    The winding kernel then runs over the rows this GPU took, from a stash the search left in its
+ *                    own memory (no scattered peer reads).
+ *   finish (owner, after every run) writes the sentinel rows of a degenerate mesh (#F == 0); otherwise nothing.
  * Ordering between the phases is the caller's: events between streams in one process, a tiny collective on the
  * streams between processes.  mode 0: signed distance (sign_type FAST_WINDING_NUMBER or UNSIGNED; S,I,C[,W]),
  * 1: squared distance (S=sqrD,I,C), 2: fast winding number (W; rows are claimed 2048 at a time, super_rows unused).
@@ -233,6 +232,16 @@ int iglb200_winding_number(const iglb200_mesh *m,
                            void *W, int w_is_f64);
 int iglb200_winding_number_dev(const iglb200_mesh *m, const double *O, int64_t nO, double *W, void *scratch,
                                int sort_queries, void *stream);
+/* igl::iterative_closest_point(VX,FX,VY,FY,num_samples,max_iters,R,t) (iterative_closest_point.h, iterative_closest_point.cpp:40-130):
+ * `meshY` is the handle of (VY,FY); per iteration num_samples area-weighted random points of X*R+t, their closest points
+ * on Y (the hot path's search), Y's face normals there and the point-to-plane fit of rigid_alignment.cpp:24-108 run on the
+ * device; only the 6x6 normal equations are solved on the host.  R is 3x3 ROW-major with VX*R + t ~ Y (row vectors), t 1x3.
+ * The reference seeds its sampler from std::rand(); here the samples are a counter-based hash of `seed`. */
+int iglb200_iterative_closest_point(const iglb200_mesh *meshY,
+                                    const void *VX, int vx_is_f64, int64_t nVX, int64_t vx_row_stride, int64_t vx_col_stride,
+                                    const int32_t *FX, int64_t nFX, int64_t fx_row_stride, int64_t fx_col_stride,
+                                    int num_samples, int max_iters, uint64_t seed, double R[9], double t[3]);
+
 /* After synchronising a stream that ran *_dev calls: 0, or an error if a device-side
  * condition (traversal stack overflow) invalidated their results.  The host-pointer
  * entry points check this themselves. */

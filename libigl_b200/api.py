@@ -68,7 +68,7 @@ class Api:
         "iglb200_debug_visit_counts", "iglb200_poll_device_error", "iglb200_debug_fp32_peak_tflops",
         "iglb200_cloud_create", "iglb200_cloud_destroy", "iglb200_cloud_info", "iglb200_cloud_eval",
         "iglb200_cloud_eval_dev",
-        "iglb200_winding_number", "iglb200_winding_number_dev",
+        "iglb200_winding_number", "iglb200_winding_number_dev", "iglb200_iterative_closest_point",
         "iglb200_grid_create", "iglb200_grid_create_from", "iglb200_grid_destroy", "iglb200_grid_info", "iglb200_grid_device",
         "iglb200_grid_get_gv", "iglb200_grid_set_s", "iglb200_grid_get_s", "iglb200_grid_signed_distance",
         "iglb200_grid_flood_fill", "iglb200_grid_marching_cubes", "iglb200_surface_info", "iglb200_surface_get",
@@ -134,6 +134,7 @@ class Api:
         L.iglb200_cloud_eval_dev.argtypes = [_vp, _vp, _i64, _dbl, _vp, _vp]
         L.iglb200_winding_number.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _vp, _int]
         L.iglb200_winding_number_dev.argtypes = [_vp, _vp, _i64, _vp, _vp, _int, _vp]
+        L.iglb200_iterative_closest_point.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, _int, C.c_uint64, _vp, _vp]
         L.iglb200_grid_create.argtypes = [_vp, _vp, _int, _int, C.POINTER(_vp)]
         L.iglb200_grid_create_from.argtypes = [_vp, _i64, _i64, _int, _int, _int, C.POINTER(_vp)]
         L.iglb200_grid_destroy.argtypes = [_vp]
@@ -472,6 +473,18 @@ class Mesh:
         W = np.empty(n, np.float64)
         self.api.check(self.api.lib.iglb200_winding_number(self.h, op, of64, n, ors, ocs, W.ctypes.data_as(_vp), 1))
         return W
+
+    def iterative_closest_point(self, VX, FX, num_samples, max_iters, seed=0):
+        """igl::iterative_closest_point(VX,FX,VY,FY,num_samples,max_iters,R,t) with this mesh as Y: returns R (3x3), t (3)
+        such that VX @ R + t ~ Y."""
+        Vk, vp, vf64, nV, vrs, vcs = _mat(VX, "VX")
+        FX = np.ascontiguousarray(FX, dtype=np.int32)
+        R = np.empty((3, 3))
+        t = np.empty(3)
+        self.api.check(self.api.lib.iglb200_iterative_closest_point(self.h, vp, vf64, nV, vrs, vcs, FX.ctypes.data_as(_vp), FX.shape[0], 3, 1,
+                                                                    int(num_samples), int(max_iters), int(seed),
+                                                                    R.ctypes.data_as(_vp), t.ctypes.data_as(_vp)))
+        return R, t
 
     def fast_winding_number(self, Q, accuracy_scale=2.0):
         Qk, qp, qf64, n, qrs, qcs = _mat(Q, "Q")

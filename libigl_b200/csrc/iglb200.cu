@@ -4,6 +4,7 @@
 #include "cloud.h"
 #include "grid.h"
 #include "wn.h"
+#include "icp.h"
 #include "group.h"
 #include <atomic>
 #include <chrono>
@@ -856,10 +857,9 @@ struct SuperKeys {
   }
 };
 
-// Overlapped sharded signed distance: the winding number does not depend on the search, so it runs BESIDE it (second
-// stream, its own work counter) over the sorted queries as floats and leaves the solid angle of sorted row t in the owner's
-// scratch; its blocks become resident as the search kernel's warps run out of packets, i.e. they fill the search's tail
-// (whose length is set by a few packets near the medial axis, 7x the mean).  The owner combines afterwards.
+// Overlapped sharded signed distance (experiment, off by default — see shard_overlap): the winding number does not depend
+// on the search, so it can run BESIDE it (second stream, its own work counter) over the sorted queries as floats, leaving
+// the solid angle of sorted row t in the owner's scratch; the owner combines afterwards.
 struct GatherSortedF { const double *P; int64_t n; const uint32_t *perm; float *Psf;
   DEVFN void operator()(int64_t t) const {
     const int64_t i = perm ? (int64_t)perm[t] : t;
@@ -965,8 +965,11 @@ int64_t shard_super_rows(int64_t n, int n_shards) {
   return (r + unit - 1) / unit * unit;
 }
 
-// IGLB200_SHARD_OVERLAP=0 runs the winding kernel AFTER the search on each GPU (over the rows it took, from its local stash)
-bool shard_overlap() { static const bool on = [] { const char *e = std::getenv("IGLB200_SHARD_OVERLAP"); return !(e && e[0] == '0'); }(); return on; }
+// Default: the winding kernel runs AFTER the search on each GPU, over the rows that GPU took, from its local stash.
+// IGLB200_SHARD_OVERLAP=1 (experiment, measured SLOWER: c2 57.7 vs 53.7 ms on one GPU, 14.0 vs 9.7 ms on eight) runs it
+// BESIDE the search on a second stream with its own work counter, hoping to fill the search's tail: both kernels are
+// persistent, so whichever gets its blocks resident first keeps the register file and the other one waits or thrashes.
+bool shard_overlap() { static const bool on = [] { const char *e = std::getenv("IGLB200_SHARD_OVERLAP"); return e && e[0] == '1'; }(); return on; }
 
 void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int sort_queries, int64_t super_rows, stream_t s) {
   const ShardLayout L(n);
@@ -2065,6 +2068,60 @@ int iglb200_winding_number_dev(const iglb200_mesh *m, const double *O, int64_t n
   check_count(nO);
   plat::launch_counter() = 0;
   run_exact_winding(m, O, nO, W, scratch, sort_queries, (stream_t)stream);
+  return IGLB200_OK;
+  API_END
+}
+
+// igl::iterative_closest_point(VX,FX,VY,FY,num_samples,max_iters,R,t) (iterative_closest_point.cpp:40-130); Y is the mesh handle
+int iglb200_iterative_closest_point(const iglb200_mesh *meshY, const void *VX, int vx_is_f64, int64_t nVX, int64_t vx_rs, int64_t vx_cs,
+                                    const int32_t *FX, int64_t nFX, int64_t fx_rs, int64_t fx_cs, int num_samples, int max_iters,
+                                    uint64_t seed, double R[9], double t[3]) {
+  API_BEGIN
+  check_mesh(meshY);
+  if (!VX || !FX || !R || !t || nVX <= 0 || nFX <= 0) throw std::invalid_argument("null pointer or empty mesh X");
+  if (vx_rs <= 0 || vx_cs <= 0 || fx_rs <= 0 || fx_cs <= 0) throw std::invalid_argument("strides must be positive");
+  if (num_samples < 1 || max_iters < 0) throw std::invalid_argument("num_samples must be >= 1 and max_iters >= 0");
+  if (meshY->h.nnodes == 0) throw std::invalid_argument("mesh Y has no (finite) faces");
+  require_device();
+  plat::DeviceGuard dg(meshY->device);
+  plat::launch_counter() = 0;
+  stream_t s = nullptr;
+  const int64_t ns = num_samples;
+  DevBuf<double> dVX, dVXRT((size_t)3 * nVX), dblA((size_t)nFX), cum((size_t)nFX), X((size_t)3 * ns), Pc((size_t)3 * ns), N((size_t)3 * ns),
+      sqrD((size_t)ns), sys(icp::NSYS);
+  DevBuf<int32_t> dF((size_t)3 * nFX), I((size_t)ns);
+  DevBuf<char> scratch(iglb200_query_scratch_bytes(ns));
+  upload_points(VX, vx_is_f64, nVX, vx_rs, vx_cs, dVX, s);
+  {
+    std::vector<int32_t> hf((size_t)3 * nFX);
+    for (int64_t f = 0; f < nFX; ++f) for (int k = 0; k < 3; ++k) {
+      const int32_t v = FX[f * fx_rs + k * fx_cs];
+      if (v < 0 || v >= nVX) throw std::invalid_argument("FX contains a vertex index outside [0, #VX)");
+      hf[(size_t)3 * f + k] = v;
+    }
+    plat::h2d(dF.p, hf.data(), hf.size() * 4, s);
+    plat::sync(s);
+  }
+  double Rr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tt[3] = {0, 0, 0};
+  for (int iter = 0; iter < max_iters; ++iter) {
+    icp::Transform tf{dVX.p, nVX, {Rr[0], Rr[1], Rr[2], Rr[3], Rr[4], Rr[5], Rr[6], Rr[7], Rr[8]}, {tt[0], tt[1], tt[2]}, dVXRT.p};
+    plat::for_n(nVX, tf, s);
+    plat::for_n(nFX, icp::FaceAreas{dVXRT.p, nVX, dF.p, nFX, dblA.p}, s);
+    plat::inclusive_scan_f64(dblA.p, cum.p, nFX, s);
+    plat::for_n(ns, icp::Sample{dVXRT.p, nVX, dF.p, nFX, cum.p, seed, (uint64_t)iter, ns, X.p}, s);
+    run_squared_distance(meshY, X.p, ns, sqrD.p, I.p, Pc.p, scratch.p, 1, s);
+    plat::for_n(ns, icp::Normals{meshY->tri64(), I.p, ns, N.p}, s);
+    double Rup[9], tup[3];
+    icp::rigid_alignment(X.p, Pc.p, N.p, ns, sys.p, Rup, tup, s);
+    const double tn[3] = {tt[0] * Rup[0] + tt[1] * Rup[3] + tt[2] * Rup[6] + tup[0], tt[0] * Rup[1] + tt[1] * Rup[4] + tt[2] * Rup[7] + tup[1],
+                          tt[0] * Rup[2] + tt[1] * Rup[5] + tt[2] * Rup[8] + tup[2]};
+    icp::mat3_mul(Rr, Rup, Rr);
+    tt[0] = tn[0]; tt[1] = tn[1]; tt[2] = tn[2];
+  }
+  plat::sync(s);
+  throw_if_overflow(s);
+  for (int k = 0; k < 9; ++k) R[k] = Rr[k];
+  for (int k = 0; k < 3; ++k) t[k] = tt[k];
   return IGLB200_OK;
   API_END
 }

@@ -80,6 +80,10 @@ inline void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, str
   uint32_t s = 0;
   for (int64_t i = 0; i < n; ++i) { uint32_t v = in[i]; out[i] = s; s += v; }
 }
+inline void inclusive_scan_f64(const double *in, double *out, int64_t n, stream_t) {
+  double acc = 0.0;
+  for (int64_t i = 0; i < n; ++i) { acc += in[i]; out[i] = acc; }
+}
 inline size_t sort_pairs_temp_bytes(int64_t) { return 16; }
 // stable sort of (key,val) by key
 inline void sort_pairs_u32(void *, size_t, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int, stream_t) {
@@ -207,6 +211,7 @@ template <class F> __global__ void __launch_bounds__(256) k_tiles_dyn(const uint
   const uint32_t n = *ntiles;
   for (uint32_t t = blockIdx.x; t < n; t += gridDim.x) { f.tile(t); __syncthreads(); }
 }
+template <class F> __global__ void __launch_bounds__(256) k_tiles_one(F f) { f.tile(0); }
 template <class F> void for_n(int64_t n, F f, stream_t s) {
   if (n <= 0) return;
   int64_t blocks = (n + 255) / 256;
@@ -237,6 +242,17 @@ inline void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, str
   PLAT_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n, s));
   if (need > tmp.cap) { sync(s); dev_free(tmp.p); tmp.p = dev_alloc(need); tmp.cap = need; }
   PLAT_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, need, in, out, (int)n, s));
+  launch_counter()++;
+}
+inline void inclusive_scan_f64(const double *in, double *out, int64_t n, stream_t s) {
+  if (n <= 0) return;
+  if (n > 0x7FFFFFFF) throw std::invalid_argument("scan of more than 2^31-1 items");
+  static thread_local ScanTemp tmps[MAX_DEVICES];
+  ScanTemp &tmp = tmps[current_device() % MAX_DEVICES];
+  size_t need = 0;
+  PLAT_CHECK(cub::DeviceScan::InclusiveSum(nullptr, need, in, out, (int)n, s));
+  if (need > tmp.cap) { sync(s); dev_free(tmp.p); tmp.p = dev_alloc(need); tmp.cap = need; }
+  PLAT_CHECK(cub::DeviceScan::InclusiveSum(tmp.p, need, in, out, (int)n, s));
   launch_counter()++;
 }
 inline size_t sort_pairs_temp_bytes(int64_t n) {

@@ -131,6 +131,84 @@ def case_closest_extreme_scales(api):
     m.close()
 
 
+def _icp_numpy(VX, FX, VY, FY, num_samples, max_iters, seed):
+    """igl::iterative_closest_point restated (iterative_closest_point.cpp:40-130, random_points_on_mesh_intrinsic.cpp:21-45,
+    rigid_alignment.cpp:24-108) with the device's sample stream (csrc/icp.h: u01) and the oracle's closest points."""
+    M = (1 << 64) - 1
+
+    def mix(z):
+        z = (z + 0x9E3779B97F4A7C15) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+
+    def u01(it, k, j):
+        h = mix(mix(mix(seed) ^ ((it * 0x632BE59BD9B4E019) & M)) ^ ((k * 3 + j) & M))
+        return (h >> 11) / 9007199254740992.0
+
+    tree = oracle.PortAABB(VY, FY)
+    NY = np.cross(VY[FY[:, 1]] - VY[FY[:, 0]], VY[FY[:, 2]] - VY[FY[:, 0]])
+    NY /= np.linalg.norm(NY, axis=1)[:, None]
+    R, t = np.eye(3), np.zeros(3)
+    for it in range(max_iters):
+        V = VX @ R + t
+        r_, s_ = V[FX[:, 0]] - V[FX[:, 2]], V[FX[:, 1]] - V[FX[:, 2]]
+        dblA = np.sqrt(sum((r_[:, d] * s_[:, (d + 1) % 3] - r_[:, (d + 1) % 3] * s_[:, d]) ** 2 for d in range(3)))
+        C = np.cumsum(dblA)
+        Cn = C / C[-1]
+        X = np.empty((num_samples, 3))
+        for k in range(num_samples):
+            r, s, tt = u01(it, k, 0), u01(it, k, 1), u01(it, k, 2)
+            f = min(int(np.searchsorted(Cn, r, side="right")), FX.shape[0] - 1)
+            st = np.sqrt(tt)
+            X[k] = (1 - st) * V[FX[f, 0]] + (1 - s) * st * V[FX[f, 1]] + s * st * V[FX[f, 2]]
+        _, I, P = tree.squared_distance(X)
+        N = NY[I]
+        Rr, tr, w = np.eye(3), np.zeros(3), 1e-5
+        for _ in range(5):
+            Xc = X @ Rr + tr
+            NA = np.hstack([np.cross(Xc, N), N])
+            NB = np.einsum("ij,ij->i", N, P - Xc)
+            Z, O = np.zeros(len(Xc)), np.ones(len(Xc))
+            A = np.vstack([np.column_stack([Z, Xc[:, 2], -Xc[:, 1], O, Z, Z]), np.column_stack([-Xc[:, 2], Z, Xc[:, 0], Z, O, Z]),
+                           np.column_stack([Xc[:, 1], -Xc[:, 0], Z, Z, Z, O])])
+            B = np.concatenate([P[:, 0] - Xc[:, 0], P[:, 1] - Xc[:, 1], P[:, 2] - Xc[:, 2]])
+            Q = (1 - w) * NA.T @ NA + w * A.T @ A
+            f = (1 - w) * NA.T @ NB + w * A.T @ B
+            if np.linalg.matrix_rank(Q, tol=np.abs(np.linalg.eigvalsh(Q)).max() * 6 * np.finfo(float).eps) < 6:
+                w = 1 - (1 - w) / 2
+            u = np.linalg.pinv(Q, rcond=6 * np.finfo(float).eps, hermitian=True) @ f
+            W = np.array([[0, u[2], -u[1]], [-u[2], 0, u[0]], [u[1], -u[0], 0]])
+            x = np.linalg.norm(u[:3])
+            Ri = np.eye(3) if x == 0 else np.eye(3) + np.sin(x) / x * W + (1 - np.cos(x)) / (x * x) * W @ W
+            Rr, tr = Rr @ Ri, tr @ Ri + u[3:]
+        R, t = R @ Rr, t @ Rr + tr
+    return R, t
+
+
+def case_icp(api):
+    """iterative_closest_point: the device run equals the numpy restatement on the same sample stream, and it registers a
+    rotated, shifted copy of a mesh back onto the original."""
+    VY, FY = synth.torus_knot(160, 14)
+    ax = np.array([0.3, -0.5, 0.8]); ax /= np.linalg.norm(ax)
+    ang = 0.12
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    Rt = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    VX = VY @ Rt + np.array([0.05, -0.03, 0.04])
+    my = api.Mesh(VY, FY, 0)
+    R, t = my.iterative_closest_point(VX, FY, 400, 6, seed=12345)
+    Rn, tn = _icp_numpy(VX, FY, VY, FY, 400, 6, 12345)
+    assert np.abs(R - Rn).max() < 1e-8 and np.abs(t - tn).max() < 1e-8, (np.abs(R - Rn).max(), np.abs(t - tn).max())
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-12 and np.linalg.det(R) > 0.999
+    d0 = np.sqrt(my.squared_distance(VX)[0]).mean()
+    d1 = np.sqrt(my.squared_distance(VX @ R + t)[0]).mean()
+    assert d1 < 0.05 * d0, (d0, d1)
+    # zero iterations: identity
+    R0, t0 = my.iterative_closest_point(VX, FY, 10, 0)
+    assert np.array_equal(R0, np.eye(3)) and np.array_equal(t0, np.zeros(3))
+    my.close()
+
+
 def case_fwn_orders(api, V, F, Q):
     """Taylor orders 0 and 1 (fast_winding_number(V,F,order,bvh), order < 2) against the genuine core."""
     for order in (0, 1):

@@ -13,6 +13,7 @@
 #include "iglb200/hausdorff.h"
 #include "iglb200/offset_surface.h"
 #include "iglb200/winding_number.h"
+#include "iglb200/iterative_closest_point.h"
 
 using namespace mini;
 #define REQUIRE(x) do { if (!(x)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #x); std::exit(1); } } while (0)
@@ -226,6 +227,23 @@ int main() {
     iglb200::fast_winding_number(cloud, Q, 2.0, W2);
     const double gold[4] = {0.38779369004261133, -0.00041235296362485, -0.00362978253577090, -0.00041235296362485};
     for (int r = 0; r < 4; ++r) REQUIRE(std::fabs(W1(r) - gold[r]) < 1e-15 && W1(r) == W2(r));
+  }
+  // iterative_closest_point (iterative_closest_point.h:36-82): a shifted copy of the tet is pulled back onto it
+  {
+    MatrixXd VX(V.rows(), 3), R; MatrixXd t;
+    for (int64_t i = 0; i < V.rows(); ++i) { VX(i, 0) = V(i, 0) + 0.02; VX(i, 1) = V(i, 1) - 0.01; VX(i, 2) = V(i, 2) + 0.015; }
+    iglb200::iterative_closest_point(VX, F, V, F, 200, 8, R, t);
+    REQUIRE(R.rows() == 3 && R.cols() == 3 && t.rows() == 1 && t.cols() == 3);
+    double worst = 0;
+    for (int64_t i = 0; i < V.rows(); ++i) for (int d = 0; d < 3; ++d) {
+      const double y = VX(i, 0) * R(0, d) + VX(i, 1) * R(1, d) + VX(i, 2) * R(2, d) + t(0, d);
+      worst = std::fmax(worst, std::fabs(y - V(i, d)));
+    }
+    REQUIRE(worst < 5e-3);
+    iglb200::AABB<MatrixXd, 3> Ytree; Ytree.init(V, F);
+    MatrixXd NY, R2, t2;
+    iglb200::iterative_closest_point(VX, F, V, F, Ytree, NY, 200, 8, R2, t2);
+    REQUIRE(R2.rows() == 3 && t2.cols() == 3);
   }
   std::printf("OK\n");
   return 0;

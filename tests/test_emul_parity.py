@@ -134,3 +134,7 @@ def test_marching_cubes_sparse(emul_api):
 
 def test_closest_extreme_scales(emul_api):
     cases.case_closest_extreme_scales(emul_api)
+
+
+def test_iterative_closest_point(emul_api):
+    cases.case_icp(emul_api)

@@ -56,6 +56,10 @@ def test_closest_extreme_scales(gpu_api):
     cases.case_closest_extreme_scales(gpu_api)
 
 
+def test_iterative_closest_point(gpu_api):
+    cases.case_icp(gpu_api)
+
+
 def test_fwn(gpu_api):
     V, F = synth.noisy_sphere(4, 0.02, 7)
     cases.case_fwn(gpu_api, V, F, synth.random_points(50000, -1.5, 1.5, 2), "noisy")
