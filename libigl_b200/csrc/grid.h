@@ -325,6 +325,30 @@ struct McFaces {      // march_cube.cpp:126-141: ids of the three edges' vertice
   }
 };
 
+// 64-bit totals of the per-cube counts: the 32-bit scans below must not wrap silently
+struct Sum64 {
+  const uint32_t *a, *b; int64_t n; unsigned long long *out;   // out[0] += sum a, out[1] += sum b; 1024 entries per call
+  DEVFN void operator()(int64_t k) const {
+    unsigned long long sa = 0, sb = 0;
+    const int64_t hi = (k + 1) * 1024 < n ? (k + 1) * 1024 : n;
+    for (int64_t i = k * 1024; i < hi; ++i) { sa += a[i]; sb += b[i]; }
+#ifdef IGLB200_EMUL
+    out[0] += sa; out[1] += sb;
+#else
+    atomicAdd(&out[0], sa); atomicAdd(&out[1], sb);
+#endif
+  }
+};
+inline void check_totals(const uint32_t *vcount, const uint32_t *fcount, int64_t nc, stream_t st) {
+  plat::DevBuf<unsigned long long> tot(2);
+  plat::dev_memset(tot.p, 0, 16, st);
+  plat::for_n((nc + 1023) / 1024, Sum64{vcount, fcount, nc, tot.p}, st);
+  unsigned long long h[2];
+  plat::d2h(h, tot.p, 16, st);
+  plat::sync(st);
+  if (h[0] > 0x7FFFFFFFull || h[1] > 0x7FFFFFFFull) throw std::invalid_argument("marching_cubes: more than 2^31-1 vertices or faces");
+}
+
 // S: n values (x fastest); GV: column-major 3 x n; the iso-surface of (S - shift) at `iso`
 inline iglb200_surface *marching_cubes(const double *S, const double *GV, int nx, int ny, int nz, double shift, double iso, stream_t st) {
   if (nx < 1 || ny < 1 || nz < 1) throw std::invalid_argument("marching_cubes: empty grid");
@@ -340,6 +364,7 @@ inline iglb200_surface *marching_cubes(const double *S, const double *GV, int nx
       plat::for_n(nc, McClassify{d, S, shift, iso, info.p, vcount.p, fcount.p}, st);
       plat::dev_memset(vcount.p + nc, 0, 4, st);
       plat::dev_memset(fcount.p + nc, 0, 4, st);
+      check_totals(vcount.p, fcount.p, nc, st);
       plat::exclusive_scan_u32(vcount.p, vbase.p, nc + 1, st);   // entry nc = total
       plat::exclusive_scan_u32(fcount.p, fbase.p, nc + 1, st);
       uint32_t tot[2];
