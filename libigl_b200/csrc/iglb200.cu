@@ -240,6 +240,9 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
+#ifndef CP_SKIP_ABSENT
+#define CP_SKIP_ABSENT 0   // measured: see profiles/README_r2.md
+#endif
 #ifndef CP_TOP
 #define CP_TOP 0           // > 0: stage that many top nodes in shared memory (needs CP_WARPS > 1 to pay for the copy; measured: see profiles/)
 #endif
@@ -359,8 +362,19 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       const uint32_t imask = n.pad.x, tmask = n.pad.y;
       float d2[4];
       if (n.pad.z == 0u) {   // warp-uniform: the common node has cylinders only
+#if CP_SKIP_ABSENT
+        // children fill the lanes from 0 up: a node with two or three children skips the tests of its absent lanes
+        const uint32_t present = imask | tmask;
+        d2[0] = lane_pill_d2(n, 0, L, 0u); d2[1] = lane_pill_d2(n, 1, L, 0u);
+        d2[2] = INFINITY; d2[3] = INFINITY;
+        if (present & 4u) {
+          d2[2] = lane_pill_d2(n, 2, L, 0u);
+          if (present & 8u) d2[3] = lane_pill_d2(n, 3, L, 0u);
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 4; ++i) d2[i] = lane_pill_d2(n, i, L, 0u);
+#endif
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) d2[i] = lane_pill_d2(n, i, L, n.pad.z);

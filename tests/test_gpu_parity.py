@@ -327,3 +327,71 @@ def test_signed_distance_winding_number_and_default(gpu_api):
 
 def test_marching_cubes_sparse(gpu_api):
     cases.case_marching_cubes_sparse(gpu_api)
+
+
+def test_sharded_device_path_equals_the_single_call(gpu_api):
+    """iglb200_shard_begin/run/finish (what bench.py's `value` times, here with one shard) == the single-call device entry
+    points, bit for bit, for signed distance (FWN, UNSIGNED, bounded), squared distance and the winding number alone."""
+    import ctypes as C
+    import torch
+    api, L = gpu_api, gpu_api.lib
+    V, F = synth.torus_knot(600, 24)
+    P = synth.grid_points(*synth.bbox(V), 64, 1.1)
+    n = P.shape[0]
+    dev = torch.device("cuda", 0)
+    dP = torch.from_numpy(np.ascontiguousarray(P.T)).to(dev)
+    m = api.Mesh(V, F, 2)
+    scratch = torch.empty(int(L.iglb200_shard_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+    qs = torch.empty(int(L.iglb200_query_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+    tiny, huge = float(np.finfo(float).tiny), float(np.finfo(float).max)
+    sup = int(L.iglb200_shard_super_rows(n, 1))
+    vp = C.c_void_p
+    for mode, sign, lo, hi in ((0, 4, tiny, huge), (0, 4, 0.02, 0.3), (0, 3, tiny, huge), (1, 0, 0.0, 0.0), (2, 0, 0.0, 0.0)):
+        out = [torch.full((n,), -5.0, dtype=torch.float64, device=dev), torch.full((n,), -5, dtype=torch.int32, device=dev),
+               torch.full((3, n), -5.0, dtype=torch.float64, device=dev), torch.full((n,), -5.0, dtype=torch.float64, device=dev)]
+        ref = [torch.empty_like(t) for t in out]
+        po, pr = [vp(t.data_ptr()) for t in out], [vp(t.data_ptr()) for t in ref]
+        api.check(L.iglb200_shard_begin_dev(m.h, vp(dP.data_ptr()), n, vp(scratch.data_ptr()), 1, sup, None))
+        api.check(L.iglb200_shard_run_dev(m.h, vp(dP.data_ptr()), n, vp(scratch.data_ptr()), mode, sign, lo, hi, 2.0, 1, *po, sup, 0, None))
+        api.check(L.iglb200_shard_finish_dev(m.h, n, vp(scratch.data_ptr()), mode, sign, lo, hi, 1, *po, None))
+        if mode == 0:
+            api.check(L.iglb200_signed_distance_dev(m.h, vp(dP.data_ptr()), n, sign, lo, hi, *pr, None, vp(qs.data_ptr()), 1, None))
+        elif mode == 1:
+            api.check(L.iglb200_squared_distance_dev(m.h, vp(dP.data_ptr()), n, pr[0], pr[1], pr[2], vp(qs.data_ptr()), 1, None))
+        else:
+            api.check(L.iglb200_fwn_eval_dev(m.h, vp(dP.data_ptr()), n, 2.0, pr[3], vp(qs.data_ptr()), 1, None))
+        torch.cuda.synchronize()
+        api.check(L.iglb200_poll_device_error())
+        eq = lambda a, b: bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+        if mode != 2:
+            assert eq(out[0], ref[0]) and torch.equal(out[1], ref[1]) and eq(out[2], ref[2]), (mode, sign)
+        if mode != 1:
+            assert eq(out[3], ref[3]), (mode, sign)
+    m.close()
+
+
+def test_device_group_on_gpu(gpu_api):
+    """iglb200_init(n) with every GPU of the box (one on the driver's test box, eight under `gpurun --gpus 8`): meshes are
+    replicated, host queries dealt to all devices, results identical to single-device operation."""
+    api = gpu_api
+    V, F = synth.torus_knot(600, 24)
+    P = synth.grid_points(*synth.bbox(V), 72, 1.1)
+    api.init(1)
+    m1 = api.Mesh(V, F, 2)
+    ref = m1.signed_distance(P, return_W=True)
+    m1.close()
+    n = min(api.device_count(), 8)
+    try:
+        api.init(n)
+        g = api.group_info()
+        assert g["devices"] == n
+        m = api.Mesh(V, F, 2)
+        assert m.info()["n_devices"] == n
+        out = m.signed_distance(np.asfortranarray(P), return_W=True)
+        for a, b in zip(out, ref):
+            assert np.array_equal(a, b, equal_nan=True)
+        D, I, Cc = m.squared_distance(P.astype(np.float32))
+        assert np.array_equal(I, m.squared_distance(P.astype(np.float32).astype(np.float64))[1])
+        m.close()
+    finally:
+        api.init(1)
