@@ -241,7 +241,7 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
 #ifndef CP_SKIP_ABSENT
-#define CP_SKIP_ABSENT 0   // measured: see profiles/README_r2.md
+#define CP_SKIP_ABSENT 1   // 41.0 -> 40.8 ms on c2 (with boxes it was +2 %: a cylinder test is dearer than the branch)
 #endif
 #ifndef CP_TOP
 #define CP_TOP 0           // > 0: stage that many top nodes in shared memory (needs CP_WARPS > 1 to pay for the copy; measured: see profiles/)
@@ -644,11 +644,13 @@ struct FillConst { double *S; int32_t *I; double *C; double *W; int64_t n; doubl
 #ifdef IGLB200_EMUL
 template <class F> void launch_query(const char *, int64_t n, F f, stream_t s) { plat::for_n(n, f, s); }
 #else
-#ifndef WN_MIN_BLOCKS
-#define WN_MIN_BLOCKS 10   // 96 registers, 20 warps per SM: 15.9 ms on c2 (113 regs/16 warps 17.0, 80 regs/25 warps 18.6)
-#endif
+// packet walk: one-warp blocks (no block barrier in the dynamic fetch), 96 registers, 20 warps per SM.  c2: 32 threads x 20 blocks
+// 11.5 ms; 64 x 10: 12.0; 64 x 12 (80 regs): 12.6; 64 x 8: 12.8; 128 x 5: 12.9
 #ifndef WN_THREADS
-#define WN_THREADS 64
+#define WN_THREADS 32
+#endif
+#ifndef WN_MIN_BLOCKS
+#define WN_MIN_BLOCKS (640 / WN_THREADS)
 #endif
 // one warp = one packet of 32 consecutive (Morton-adjacent) rows [t0, t0 + 32)
 template <class F> DEVFN void winding_packet(const F &f, int64_t t0, uint2 *stack) {
