@@ -630,8 +630,9 @@ def add_rooflines(line, api, mesh, cfg, args, kernel_ms, info, nq, value, P, gri
         ncu_flops = None
         if os.path.exists(fj):
             j = json.load(open(fj))
-            if j.get("kernel") == dom and j.get("queries") == nq and world == 1:
-                ncu_flops = j["fp32_flops_per_launch"]    # smsp__sass_thread_inst_executed_op_{ffma x2, fadd, fmul}_pred_on
+            if j.get("kernel") == dom and j.get("queries") == nq and j.get("faces") == int(info["n_faces"]):
+                # smsp__sass_thread_inst_executed_op_{ffma x2, fadd, fmul}_pred_on of the whole query set; a rank's launch does 1/N of it
+                ncu_flops = j["fp32_flops_per_launch"] / world
         used = ncu_flops if ncu_flops else flops_launch
         ach_t = used / t_dom
         line["roofline"] = {"bound": "fp32", "kernel": dom, "achieved": ach_t / 1e12, "peak": theo / 1e12, "unit": "TFLOP/s",
