@@ -135,7 +135,7 @@ DEVFN void closest_store(const ClosestArgs &a, int64_t i, const fwn::CpResult &r
 
 #ifdef IGLB200_EMUL
 // Host emulation of one warp: identical control flow, lanes looped.
-void closest_packet_emul(const ClosestArgs &a, int64_t base) {
+void closest_packet_emul(const ClosestArgs &a, int64_t base, int32_t &seed_face) {
   using namespace fwn;
   static thread_local uint32_t stack[CP_STACK];
   CpLane L[32]; CpExact X[32]; CpQueryRef qr[32]; bool valid[32]; int64_t qi[32];
@@ -146,6 +146,12 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     qr[l] = CpQueryRef{a.P, a.n, qi[l], a.sigma};
     lane_init(L[l], X[l], valid[l] ? load_query(qr[l]) : D3{0.0, 0.0, 0.0}, a.up, a.absmax, a.sigma);
     if (!valid[l] || a.low > a.up) { L[l].best_ub = -INFINITY; L[l].thr2 = -1.f; }
+    else if (seed_face >= 0) {
+      const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)seed_face;
+      float err; const float d32 = tri_dist_f32(tq[0], tq[1], tq[2], tq[3], L[l].px, L[l].py, L[l].pz, L[l].u, err);
+      const float ub = d32 + err;
+      if (ub < L[l].best_ub) lane_set_ub(L[l], ub);
+    }
   }
   uint32_t nvis = 0, ntri = 0;
   int sp = 0; uint32_t cur = 0; bool have = true;
@@ -201,6 +207,7 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
     if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
     else lane_finish(L[l], X[l], a.tri64, qr[l], a.up, r);
     closest_store(a, qi[l], r);
+    if (l == 0) seed_face = r.face;
     if (a.stash) {
       const D3 p = load_query(qr[l]);
       a.stash[base + l] = ShardStash{(float)p.x, (float)p.y, (float)p.z, (uint32_t)qi[l], r.sqr_d};
@@ -208,9 +215,11 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base) {
   }
   if (a.counters) { a.counters[0] += nvis; a.counters[1] += ntri; }
 }
-static constexpr int CP_CHUNK = 16;
+static constexpr int CP_CHUNK = 64;
+static constexpr int CP_GROUP = 8;
 void launch_closest(const ClosestArgs &a, stream_t) {
-  if (!a.remote) { for (int64_t base = 0; base < a.n; base += 32) closest_packet_emul(a, base); return; }
+  int32_t seed = -1;   // groups of CP_GROUP packets: the first of a group starts unseeded
+  if (!a.remote) { for (int64_t base = 0; base < a.n; base += 32) { if ((base / 32) % CP_GROUP == 0) seed = -1; closest_packet_emul(a, base, seed); } return; }
   // sharded: super-chunks off the owner's counter, listed for the kernels that follow
   const int64_t super_rows = (int64_t)a.super_chunks * CP_CHUNK * 32;
   while (a.max_supers <= 0 || (int64_t)*a.my_count < a.max_supers) {
@@ -218,7 +227,10 @@ void launch_closest(const ClosestArgs &a, stream_t) {
     if ((int64_t)sc * super_rows >= a.n) break;
     if (a.super_order) sc = a.super_order[sc];
     a.my_supers[(*a.my_count)++] = (uint32_t)sc;
-    for (int64_t base = (int64_t)sc * super_rows; base < std::min(a.n, ((int64_t)sc + 1) * super_rows); base += 32) closest_packet_emul(a, base);
+    for (int64_t base = (int64_t)sc * super_rows; base < std::min(a.n, ((int64_t)sc + 1) * super_rows); base += 32) {
+      if ((base / 32) % CP_GROUP == 0) seed = -1;
+      closest_packet_emul(a, base, seed);
+    }
   }
 }
 uint32_t *overflow_flag() { static thread_local uint32_t f = 0; return &f; }
@@ -240,6 +252,18 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // One warp = one packet of 32 Morton-adjacent queries sharing a stack (shared memory).
 // Per node: 4 box tests per lane, two warp reductions (which children does anybody still
 // need; which of them is nearest), faces tested by all lanes at once.
+// A warp takes CP_GROUP consecutive packets at a time and carries lane 0's winning face from one to the next: the distance to
+// ANY face is an upper bound, and the winner of the Morton-adjacent packet is a close one — a search otherwise spends about
+// half of its node visits before its bounds are tight (emulation, c2: -18 % node visits, -14 % face tests when every packet
+// is seeded by its predecessor).  The last chunks of a launch are handed out packet by packet (short tail).
+// Measured on c2 (search kernel, ms): no groups 40.9; chunk 16: groups of 2 38.7, 4 39.4, 8 41.1; chunk 32 / 4: 38.3;
+// chunk 64 / 4: 38.1; **chunk 64 / 8: 37.9**.  c5: 683 -> 607 ms with 16 / 4.
+#ifndef CP_GROUP
+#define CP_GROUP 8
+#endif
+#ifndef CP_ENDZONE_PACKETS
+#define CP_ENDZONE_PACKETS (148 * 128)   // at most; and at most an eighth of the launch
+#endif
 #ifndef CP_SKIP_ABSENT
 #define CP_SKIP_ABSENT 1   // 41.0 -> 40.8 ms on c2 (with boxes it was +2 %: a cylinder test is dearer than the branch)
 #endif
@@ -250,7 +274,7 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 #define CP_WARPS 1         // a block is one packet: a finished packet frees its slot at once (4 warps/block: 94.6 ms)
 #endif
 #ifndef CP_CHUNK
-#define CP_CHUNK 16   // measured: 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2
+#define CP_CHUNK 64   // round 1 (boxes, no groups): 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2; with groups see CP_GROUP
 #endif
 // Sharded schedule, one level above the per-SM chunks: sched[0] = (super-chunk << 32 | chunks of it handed out).  When a
 // super-chunk is used up, one thread of the device takes the next one off the owner's counter (atomicAdd over NVLink when
@@ -308,13 +332,23 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
   smid &= 1023u;   // the state array has 1024 slots
   const uint32_t npackets = (uint32_t)((a.n + 31) / 32);
+  const uint32_t nchunks = (npackets + CP_CHUNK - 1) / CP_CHUNK;
+  const uint32_t endzone = (min((uint32_t)CP_ENDZONE_PACKETS, npackets / 8u) + CP_CHUNK - 1) / CP_CHUNK;   // chunks handed out packet by packet
+  int32_t seed_face = -1;
   while (true) {
-    uint32_t packet = 0xFFFFFFFFu;
+    uint32_t first = 0xFFFFFFFFu, cnt = 1;
     if (lane == 0) {
       unsigned long long *st = a.sched + 1 + 2 * smid, *lock = st + 1;
       while (true) {
-        const unsigned long long old = atomicAdd(st, 1ull);
-        if ((uint32_t)old < CP_CHUNK) { packet = (uint32_t)(old >> 32) * CP_CHUNK + (uint32_t)old; break; }
+        // groups of CP_GROUP packets, single packets in the end zone (decided on a peek: a stale one only mis-sizes one group)
+        const uint32_t peek = (uint32_t)(*(volatile unsigned long long *)st >> 32);
+        const uint32_t g = (peek + endzone >= nchunks) ? 1u : (uint32_t)CP_GROUP;
+        const unsigned long long old = atomicAdd(st, (unsigned long long)g);
+        if ((uint32_t)old < CP_CHUNK) {
+          first = (uint32_t)(old >> 32) * CP_CHUNK + (uint32_t)old;
+          cnt = min(g, (uint32_t)CP_CHUNK - (uint32_t)old);
+          break;
+        }
         if (atomicCAS(lock, 0ull, 1ull) == 0ull) {   // this warp refills the SM's chunk
           if ((uint32_t)(*(volatile unsigned long long *)st) >= CP_CHUNK) {
             const unsigned long long nc = a.remote ? next_chunk_sharded(ShardSched{a.sched, a.remote, a.super_chunks, a.my_supers, a.my_count, a.max_supers, a.super_order}, npackets)
@@ -326,8 +360,13 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         }
       }
     }
-    packet = __shfl_sync(FULL, packet, 0);
-    if (packet >= npackets) break;   // the SM's chunk lies past the last packet: this warp is done
+    first = __shfl_sync(FULL, first, 0);
+    cnt = __shfl_sync(FULL, cnt, 0);
+    if (first >= npackets) break;   // the SM's chunk lies past the last packet: this warp is done
+    if (cnt == 1) seed_face = -1;   // a single packet has no predecessor of its own
+   for (uint32_t gi = 0; gi < cnt; ++gi) {
+    const uint32_t packet = first + gi;
+    if (packet >= npackets) break;
     const int64_t base = (int64_t)packet * 32;
     const int64_t t = base + lane;
     const bool valid = t < a.n;
@@ -336,6 +375,13 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     const CpQueryRef qr{a.P, a.n, qi, a.sigma};
     lane_init(L, X, valid ? load_query(qr) : D3{0.0, 0.0, 0.0}, a.up, a.absmax, a.sigma);
     if (!valid || a.low > a.up) { L.best_ub = -INFINITY; L.thr2 = -1.f; }
+    else if (seed_face >= 0) {   // warp-uniform
+      const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)seed_face;
+      float4 T0, T1, T2, T3; ld256(tq, T0, T1); ld256(tq + 2, T2, T3);
+      float err; const float d32 = tri_dist_f32(T0, T1, T2, T3, L.px, L.py, L.pz, L.u, err);
+      const float ub = d32 + err;
+      if (ub < L.best_ub) lane_set_ub(L, ub);
+    }
     uint32_t nvis = 0, ntri = 0;
     int sp = 0; uint32_t cur = 0; bool have = true;
     while (true) {
@@ -429,18 +475,22 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       }
       __syncwarp();
     }
+    int32_t won = -1;
     if (valid) {
       CpResult r;
       if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
       else lane_finish(L, X, a.tri64, qr, a.up, r);
       closest_store(a, qi, r);
+      won = r.face;
       if (a.stash) {
         const D3 p = load_query(qr);
         a.stash[t] = ShardStash{(float)p.x, (float)p.y, (float)p.z, (uint32_t)qi, r.sqr_d};
       }
     }
+    seed_face = __shfl_sync(FULL, won, 0);   // lane 0's winner seeds the next packet of the group
     if (COUNT && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
     __syncwarp();
+   }
   }
 }
 // one flag per (host thread, device); zeroed before any kernel of any stream can see it
@@ -974,7 +1024,7 @@ struct ShardWs {   // per (thread, device) state of shard_run: schedule words, t
 
 int64_t shard_super_rows(int64_t n, int n_shards) {
   // >= 64 super-chunks per device so that the last ones even out the load, each large enough to keep a device's L2
-  // on one region of the tree: [8 Ki, 256 Ki] rows, a multiple of a chunk (16 packets of 32)
+  // on one region of the tree: [8 Ki, 256 Ki] rows, a multiple of a chunk (CP_CHUNK packets of 32)
   const int64_t unit = (int64_t)CP_CHUNK * 32;
   int64_t r = n / ((int64_t)std::max(n_shards, 1) * 64);
   r = std::max<int64_t>(int64_t(8) << 10, std::min<int64_t>(int64_t(256) << 10, r));
@@ -1017,7 +1067,7 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
                stream_t s) {
   if (n == 0 || shard_degenerate(m, mode)) return;   // finish fills the sentinels
   const int64_t unit = (int64_t)CP_CHUNK * 32;
-  if (super_rows <= 0 || super_rows % unit) throw std::invalid_argument("super_rows must be a positive multiple of 512");
+  if (super_rows <= 0 || super_rows % unit) throw std::invalid_argument("super_rows must be a positive multiple of 2048");
   const ShardLayout L(n);
   unsigned long long *remote = (unsigned long long *)(scratch + L.oCounter);
   const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;
