@@ -207,7 +207,7 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
  * 1: squared distance (S=sqrD,I,C), 2: fast winding number (W; rows are claimed 2048 at a time, super_rows unused).
  * All asynchronous on `stream` of the calling thread's current device. */
 uint64_t iglb200_shard_scratch_bytes(int64_t nP);
-int64_t iglb200_shard_super_rows(int64_t nP, int n_shards);   /* the library's choice; a multiple of 2048 */
+int64_t iglb200_shard_super_rows(int64_t nP, int n_shards);   /* the library's choice; a multiple of 1024 */
 int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int sort_queries,
                             int64_t super_rows, void *stream);
 int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int mode, int sign_type,

@@ -215,8 +215,8 @@ void closest_packet_emul(const ClosestArgs &a, int64_t base, int32_t &seed_face)
   }
   if (a.counters) { a.counters[0] += nvis; a.counters[1] += ntri; }
 }
-static constexpr int CP_CHUNK = 64;
-static constexpr int CP_GROUP = 8;
+static constexpr int CP_CHUNK = 32;
+static constexpr int CP_GROUP = 2;
 void launch_closest(const ClosestArgs &a, stream_t) {
   int32_t seed = -1;   // groups of CP_GROUP packets: the first of a group starts unseeded
   if (!a.remote) { for (int64_t base = 0; base < a.n; base += 32) { if ((base / 32) % CP_GROUP == 0) seed = -1; closest_packet_emul(a, base, seed); } return; }
@@ -256,13 +256,14 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // ANY face is an upper bound, and the winner of the Morton-adjacent packet is a close one — a search otherwise spends about
 // half of its node visits before its bounds are tight (emulation, c2: -18 % node visits, -14 % face tests when every packet
 // is seeded by its predecessor).  The last chunks of a launch are handed out packet by packet (short tail).
-// Measured on c2 (search kernel, ms): no groups 40.9; chunk 16: groups of 2 38.7, 4 39.4, 8 41.1; chunk 32 / 4: 38.3;
-// chunk 64 / 4: 38.1; **chunk 64 / 8: 37.9**.  c5: 683 -> 607 ms with 16 / 4.
+// Measured (search kernel, ms; c2 / c3 / c5): no groups 40.9 / 21.8 / 688; chunk 16, groups of 2: 39.4 / 22.0 / 631;
+// **chunk 32, groups of 2: 38.6 / 21.9 / 624**; chunk 32 / 4: 38.9 / 24.5 / 615; chunk 64 / 4: 38.5 / 24.6 / 613;
+// chunk 64 / 8: 38.7 / 27.1 / 628 (random queries — c3 — dislike long groups).
 #ifndef CP_GROUP
-#define CP_GROUP 8
+#define CP_GROUP 2
 #endif
 #ifndef CP_ENDZONE_PACKETS
-#define CP_ENDZONE_PACKETS (148 * 128)   // at most; and at most an eighth of the launch
+#define CP_ENDZONE_PACKETS (148 * 256)   // at most; and at most half of the launch.  Too short an end zone and the launch ends on whole groups
 #endif
 #ifndef CP_SKIP_ABSENT
 #define CP_SKIP_ABSENT 1   // 41.0 -> 40.8 ms on c2 (with boxes it was +2 %: a cylinder test is dearer than the branch)
@@ -274,7 +275,7 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 #define CP_WARPS 1         // a block is one packet: a finished packet frees its slot at once (4 warps/block: 94.6 ms)
 #endif
 #ifndef CP_CHUNK
-#define CP_CHUNK 64   // round 1 (boxes, no groups): 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2; with groups see CP_GROUP
+#define CP_CHUNK 32   // round 1 (boxes, no groups): 1 -> 85.9 ms, 4 -> 83.1, 8 -> 82.3, 16 -> 81.5, 32 -> 82.5, 128 -> 86.2; with groups see CP_GROUP
 #endif
 // Sharded schedule, one level above the per-SM chunks: sched[0] = (super-chunk << 32 | chunks of it handed out).  When a
 // super-chunk is used up, one thread of the device takes the next one off the owner's counter (atomicAdd over NVLink when
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   smid &= 1023u;   // the state array has 1024 slots
   const uint32_t npackets = (uint32_t)((a.n + 31) / 32);
   const uint32_t nchunks = (npackets + CP_CHUNK - 1) / CP_CHUNK;
-  const uint32_t endzone = (min((uint32_t)CP_ENDZONE_PACKETS, npackets / 8u) + CP_CHUNK - 1) / CP_CHUNK;   // chunks handed out packet by packet
+  const uint32_t endzone = (min((uint32_t)CP_ENDZONE_PACKETS, npackets / 2u) + CP_CHUNK - 1) / CP_CHUNK;   // chunks handed out packet by packet
   int32_t seed_face = -1;
   while (true) {
     uint32_t first = 0xFFFFFFFFu, cnt = 1;
@@ -1067,7 +1068,7 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
                stream_t s) {
   if (n == 0 || shard_degenerate(m, mode)) return;   // finish fills the sentinels
   const int64_t unit = (int64_t)CP_CHUNK * 32;
-  if (super_rows <= 0 || super_rows % unit) throw std::invalid_argument("super_rows must be a positive multiple of 2048");
+  if (super_rows <= 0 || super_rows % unit) throw std::invalid_argument("super_rows must be a positive multiple of 1024");
   const ShardLayout L(n);
   unsigned long long *remote = (unsigned long long *)(scratch + L.oCounter);
   const uint32_t *perm = (sort_queries && n >= 2) ? carve(scratch + L.oSort, n).perm : nullptr;

@@ -280,7 +280,7 @@ def test_sharded_device_queries_match_the_fused_path(emul_api):
         scratch = np.zeros(int(L.iglb200_shard_scratch_bytes(n)), np.uint8)
         qs = np.zeros(int(L.iglb200_query_scratch_bytes(n)), np.uint8)
         sup = int(L.iglb200_shard_super_rows(n, 2))
-        assert sup % 2048 == 0 and sup >= 8192
+        assert sup % 1024 == 0 and sup >= 8192
         sup = 8192                                    # the smallest super-chunk: 64 000 rows make eight
         for mode, sign, lo, hi in ((0, 4, tiny, huge), (0, 4, 0.05, 0.4), (0, 3, tiny, huge), (1, 0, 0, 0), (2, 0, 0, 0)):
             S, I, Cc, W = np.full(n, -5.0), np.full(n, -5, np.int32), np.full((3, n), -5.0), np.full(n, -5.0)
