@@ -66,11 +66,12 @@ inline void signed_distance(const DerivedP &P, const DerivedV &V, const DerivedF
                             const typename DerivedV::Scalar lower_bound, const typename DerivedV::Scalar upper_bound, DerivedS &S,
                             DerivedI &I, DerivedC &C, DerivedN &N) {
   if (F.rows() == 0) {  // signed_distance.cpp:398-405
-    S.resize(P.rows(), 1); I.resize(P.rows(), 1); C.resize(P.rows(), 3);
+    S.resize(P.rows(), 1); I.resize(P.rows(), 1); C.resize(P.rows(), 3); N.resize(P.rows(), 3);   // N too: :403
     for (int64_t i = 0; i < (int64_t)P.rows(); ++i) {
       S(i, 0) = std::numeric_limits<typename DerivedS::Scalar>::quiet_NaN();
       I(i, 0) = -1;
       for (int d = 0; d < 3; ++d) C(i, d) = std::numeric_limits<typename DerivedC::Scalar>::quiet_NaN();
+      for (int d = 0; d < 3; ++d) N(i, d) = std::numeric_limits<typename DerivedN::Scalar>::quiet_NaN();
     }
     return;
   }

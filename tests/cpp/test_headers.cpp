@@ -195,6 +195,12 @@ int main() {
     REQUIRE(SV2.rows() > 50 && SF2.rows() == 2 * SV2.rows() - 4 && GV2.rows() == S2.rows());
     for (int64_t i = 0; i < S2.rows(); ++i) REQUIRE(S2(i) == S2(i));
   }
+  // #F == 0: S = NaN, I = -1, C = NaN and N = NaN (signed_distance.cpp:398-405)
+  {
+    MatrixXi F0(0, 3); VectorXd S; VectorXi I; MatrixXd C, N;
+    iglb200::signed_distance(P, V, F0, iglb200::SIGNED_DISTANCE_TYPE_FAST_WINDING_NUMBER, S, I, C, N);
+    REQUIRE(S(0) != S(0) && I(0) == -1 && C(0, 1) != C(0, 1) && N.rows() == 1 && N.cols() == 3 && N(0, 2) != N(0, 2));
+  }
   // single-query and bounded overloads (fast_winding_number.h:196-206, signed_distance.h:300-312, AABB.h:575-614)
   {
     iglb200::AABB<MatrixXd, 3> tree; tree.init(V, F);
