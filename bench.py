@@ -227,7 +227,7 @@ def reference_arm(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -387,7 +387,7 @@ def ours_mesh(args, cfg, job, light=False):
             n_l += api.last_launch_count()
         job.stream_fence()
         api.check(L.iglb200_shard_run_dev(mesh.h, pP, nq, scratch, mode, sign, lower, upper, 2.0, int(args.sort), pS, pI, pC, pW,
-                                          super_rows, 0, sp()))
+                                          super_rows, 0, rank, world, sp()))
         n_l += api.last_launch_count()
         job.stream_fence()
         if rank == 0:
@@ -717,13 +717,35 @@ def ours_cloud(args, cfg):
             r = run_cpu(cfg, args, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                                     "build_s": r["build_s"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     job.host_barrier()
     cl.close()
     job.close()
 
 
+_RESULT_FD = None
+
+
+def keep_stdout_clean():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when the
+    box sets NCCL_DEBUG), so fd 1 is pointed at stderr for the run and the result line goes to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(text.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text)
+
+
 def main():
+    keep_stdout_clean()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -763,7 +785,7 @@ def main():
                 if line is not None:
                     line["c5"] = {"error": str(ex)[:300]}
         if line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
         job.close()
 
 

@@ -199,6 +199,11 @@ int iglb200_fwn_eval_dev(const iglb200_mesh *m, const double *Q, int64_t nQ, flo
  *                    memory directly (peer loads and stores): no separate scatter, gather or un-sort pass.  All
  *                    pointers are the owner's buffers as seen from the calling device (peer-enabled pointers in one
  *                    process, iglb200_ipc_open between processes).  max_supers > 0 caps what this GPU takes.
+ *                    The super-chunks form n_shards (<= 64) contiguous slices of the sorted order with a counter each:
+ *                    the caller with shard_index k works through slice k first — one region of space, hence one part of
+ *                    the tree in its L2 — and then helps with whichever slice has the most left, so the slices need
+ *                    not cost the same.  Every participant passes the same n_shards and its own shard_index; a single
+ *                    caller passes (0, 1).
  *                    The winding kernel then runs over the rows this GPU took, from a stash the search left in its
  *                    own memory (no scattered peer reads).
  *   finish (owner, after every run) writes the sentinel rows of a degenerate mesh (#F == 0); otherwise nothing.
@@ -213,7 +218,7 @@ int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, 
 int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int mode, int sign_type,
                           double lower_bound, double upper_bound, float accuracy_scale, int sort_queries,
                           double *S, int32_t *I, double *C, double *W,
-                          int64_t super_rows, int64_t max_supers, void *stream);
+                          int64_t super_rows, int64_t max_supers, int shard_index, int n_shards, void *stream);
 int iglb200_shard_finish_dev(const iglb200_mesh *m, int64_t nP, void *shard_scratch, int mode, int sign_type,
                              double lower_bound, double upper_bound, int sort_queries,
                              double *S, int32_t *I, double *C, double *W, void *stream);

@@ -104,7 +104,7 @@ class Api:
         L.iglb200_shard_super_rows.argtypes = [_i64, _int]
         L.iglb200_shard_super_rows.restype = _i64
         L.iglb200_shard_begin_dev.argtypes = [_vp, _vp, _i64, _vp, _int, _i64, _vp]
-        L.iglb200_shard_run_dev.argtypes = [_vp, _vp, _i64, _vp, _int, _int, _dbl, _dbl, C.c_float, _int, _vp, _vp, _vp, _vp, _i64, _i64, _vp]
+        L.iglb200_shard_run_dev.argtypes = [_vp, _vp, _i64, _vp, _int, _int, _dbl, _dbl, C.c_float, _int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]
         L.iglb200_shard_finish_dev.argtypes = [_vp, _i64, _vp, _int, _int, _dbl, _dbl, _int, _vp, _vp, _vp, _vp, _vp]
         L.iglb200_ipc_alloc.argtypes = [C.c_uint64, C.POINTER(_vp), C.c_char_p]
         L.iglb200_ipc_open.argtypes = [C.c_char_p, C.POINTER(_vp)]

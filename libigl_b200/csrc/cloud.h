@@ -280,20 +280,24 @@ struct EvalQuery {  // helper() of fast_winding_number.cpp:233-292, depth-first
     }
     return wn;
   }
-  DEVFN void operator()(int64_t t) const {
+  // the cases without a walk: an empty cloud, or brute force (:302-309)
+  DEVFN bool no_walk() const { return ncloud == 0 || !(beta > 0); }
+  DEVFN void direct(int64_t t) const {
     const int64_t i = perm ? (int64_t)perm[t] : t;
     const double q[3] = {Q[i], Q[nq + i], Q[2 * nq + i]};
     double wn = 0;
-    if (ncloud == 0) { WN[i] = 0.0; return; }
-    if (!(beta > 0)) {  // brute force (:302-309)
-      for (int64_t j = 0; j < ncloud; ++j) {
-        double loc[3];
-        for (int d = 0; d < 3; ++d) loc[d] = P[3 * j + d] - q[d];
-        wn += direct_eval(loc, AN + 3 * j);
-      }
-      WN[i] = wn;
-      return;
+    for (int64_t j = 0; j < ncloud; ++j) {
+      double loc[3];
+      for (int d = 0; d < 3; ++d) loc[d] = P[3 * j + d] - q[d];
+      wn += direct_eval(loc, AN + 3 * j);
     }
+    WN[i] = wn;
+  }
+  DEVFN void operator()(int64_t t) const {
+    if (no_walk()) { direct(t); return; }
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    const double q[3] = {Q[i], Q[nq + i], Q[2 * nq + i]};
+    double wn = 0;
     if (cchild[0] < 0) { WN[i] = leaf_sum(0, q); return; }
     uint32_t scell[MAX_LEVELS + 2];
     uint8_t snext[MAX_LEVELS + 2];
@@ -475,8 +479,64 @@ struct QueryKeys {   // 30-bit Morton code of a query inside the cloud's box dou
 #ifndef CLOUD_MIN_BLOCKS
 #define CLOUD_MIN_BLOCKS 12   // 80 registers, 24 warps per SM: 36.8 ms on c4 (112 regs 47.7, 96 regs 39.6)
 #endif
+// The walk of EvalQuery for a PACKET: the 32 queries of a warp (neighbours in Morton order) descend the octree together,
+// depth-first as each of them would alone, with one shared stack of (cell, next octant, lanes that opened the cell).  A
+// lane that did not open a cell waits while the others walk it — as it would in a diverged warp — but cell centres, radii,
+// expansion coefficients and leaf points are now warp-uniform loads.  Every lane adds exactly the terms of its own walk in
+// the same order, so the result is bit-identical to the per-thread form.
+static __device__ double cloud_eval_packet(const EvalQuery &f, bool alive, const double *q, uint4 *stack) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31u;
+  double wn = 0;
+  const unsigned m0 = __ballot_sync(FULL, alive);
+  if (m0 == 0u) return 0.0;
+  if (f.cchild[0] < 0) return alive ? f.leaf_sum(0, q) : 0.0;
+  uint32_t cell = 0, mask = m0, next = 0;
+  int sp = 0;
+  while (true) {
+    if (next == 8) {
+      if (sp == 0) break;
+      const uint4 e = stack[--sp];
+      __syncwarp();
+      cell = e.x; mask = e.y; next = e.z;
+      continue;
+    }
+    const uint32_t ch = (uint32_t)f.cchild[cell] + next;
+    ++next;
+    if (f.ccount[ch] == 0) continue;
+    const bool me = (mask >> lane) & 1u;
+    double loc[3];
+    for (int d = 0; d < 3; ++d) loc[d] = f.CM[3 * (size_t)ch + d] - q[d];
+    const double nrm = sqrt(loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2]);
+    if (f.cchild[ch] < 0) {   // a leaf is summed directly, near or far (warp-uniform)
+      if (me) wn += f.leaf_sum(ch, q);
+      continue;
+    }
+    const bool far = nrm > f.beta * f.R[ch];
+    if (me && far) wn += expansion_eval(loc, f.EC + (size_t)ch * f.nterms, f.nterms);
+    const unsigned open = __ballot_sync(FULL, me && !far);
+    if (open) {
+      if (lane == 0) stack[sp] = make_uint4(cell, mask, next, 0u);
+      ++sp;
+      __syncwarp();
+      cell = ch; mask = open; next = 0;
+    }
+  }
+  return wn;
+}
 static __global__ void __launch_bounds__(CLOUD_THREADS, CLOUD_MIN_BLOCKS) cloud_eval_kernel(int64_t n, EvalQuery f) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+  __shared__ uint4 stacks[CLOUD_THREADS / 32][MAX_LEVELS + 2];
+  const bool walk = !f.no_walk();   // otherwise: nothing to sum, or brute force (uniform loads as it is)
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x; b < n; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = b + threadIdx.x;
+    if (!walk) { if (t < n) f.direct(t); continue; }
+    const bool alive = t < n;
+    const int64_t i = alive ? (f.perm ? (int64_t)f.perm[t] : t) : 0;
+    double q[3] = {0.0, 0.0, 0.0};
+    if (alive) { q[0] = f.Q[i]; q[1] = f.Q[f.nq + i]; q[2] = f.Q[2 * f.nq + i]; }
+    const double wn = cloud_eval_packet(f, alive, q, stacks[threadIdx.x >> 5]);
+    if (alive) f.WN[i] = wn;
+  }
 }
 #endif
 

@@ -106,8 +106,13 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   // Sharded operation (several GPUs on ONE query set): chunks are not numbered from this launch's own counter but come
   // in SUPER-chunks of `super_chunks` consecutive chunks taken off a counter in the memory of the device that owns the
   // query set (a system-scope atomic over NVLink); the super-chunks this device took are listed for the kernels that follow.
+  // The super-chunks are cut into `nshards` contiguous SLICES of the Morton order, one counter each (remote[2 + slice]): a
+  // device works through its own slice first — one region of space, so it pulls one part of the tree through its L2
+  // instead of all of it — and then helps with whichever slice has the most left.
   unsigned long long *remote = nullptr;
   uint32_t super_chunks = 0;
+  uint32_t nsup = 0;            // super-chunks in the query set
+  int shard = 0, nshards = 1;   // this device's slice, number of slices
   uint32_t *my_supers = nullptr, *my_count = nullptr;
   int64_t max_supers = 0;   // > 0: take at most this many (static partition / tests)
   const uint32_t *super_order = nullptr;   // the k-th super-chunk handed out is super_order[k]
@@ -222,9 +227,21 @@ void launch_closest(const ClosestArgs &a, stream_t) {
   if (!a.remote) { for (int64_t base = 0; base < a.n; base += 32) { if ((base / 32) % CP_GROUP == 0) seed = -1; closest_packet_emul(a, base, seed); } return; }
   // sharded: super-chunks off the owner's counter, listed for the kernels that follow
   const int64_t super_rows = (int64_t)a.super_chunks * CP_CHUNK * 32;
+  // its own slice of the super-chunks first, then whichever slice has the most left (as next_chunk_sharded does)
+  auto slice_lo = [&](int k) { return (uint32_t)((unsigned long long)a.nsup * (unsigned)k / (unsigned)a.nshards); };
+  int cur = a.shard;
   while (a.max_supers <= 0 || (int64_t)*a.my_count < a.max_supers) {
-    unsigned long long sc = __atomic_fetch_add(a.remote, 1ull, __ATOMIC_RELAXED);
-    if ((int64_t)sc * super_rows >= a.n) break;
+    const unsigned long long k = __atomic_fetch_add(a.remote + 2 + cur, 1ull, __ATOMIC_RELAXED);
+    if (slice_lo(cur) + k >= slice_lo(cur + 1)) {
+      unsigned long long most = 0;
+      for (int j = 0; j < a.nshards; ++j) {
+        const unsigned long long size = slice_lo(j + 1) - slice_lo(j), taken = __atomic_load_n(a.remote + 2 + j, __ATOMIC_RELAXED);
+        if (size > taken && size - taken > most) { most = size - taken; cur = j; }
+      }
+      if (most == 0) break;
+      continue;
+    }
+    unsigned long long sc = slice_lo(cur) + k;
     if (a.super_order) sc = a.super_order[sc];
     a.my_supers[(*a.my_count)++] = (uint32_t)sc;
     for (int64_t base = (int64_t)sc * super_rows; base < std::min(a.n, ((int64_t)sc + 1) * super_rows); base += 32) {
@@ -280,29 +297,64 @@ DEVFN void ld256(const void *p, float4 &a, float4 &b) {
 // Sharded schedule, one level above the per-SM chunks: sched[0] = (super-chunk << 32 | chunks of it handed out).  When a
 // super-chunk is used up, one thread of the device takes the next one off the owner's counter (atomicAdd over NVLink when
 // the owner is a peer) and notes it in my_supers.  Returns a chunk index; chunks past the last packet end the caller's warp.
-struct ShardSched { unsigned long long *sched, *remote; uint32_t super_chunks; uint32_t *my_supers, *my_count; int64_t max_supers; const uint32_t *order; };
-static __device__ __noinline__ unsigned long long next_chunk_sharded(const ShardSched a, uint32_t npackets) {
-  unsigned long long *G = a.sched, *glock = a.sched + 1 + 2 * 1024;
+// The chunk index carries CP_SINGLE when the device is close to the end of its work (packets are then handed out one by
+// one instead of in groups, so that the launch does not end on a few warps with a group each).
+struct ShardSched {
+  unsigned long long *sched, *remote; uint32_t super_chunks; uint32_t *my_supers, *my_count; int64_t max_supers; const uint32_t *order;
+  uint32_t nsup; int shard, nshards; uint32_t endzone;   // endzone: packets per device handed out singly at the end
+  DEVFN uint32_t slice_lo(int k) const { return (uint32_t)((unsigned long long)nsup * (unsigned)k / (unsigned)nshards); }
+};
+static constexpr unsigned long long CP_SINGLE = 0x80000000ull, CP_PAST_END = 0x0FFFFFFFull;
+// super-chunks not yet handed out: in slice `best` (the one with the most left), and in all of them
+static __device__ unsigned long long shard_left(const ShardSched &a, int &best) {
+  unsigned long long total = 0, most = 0;
+  for (int j = 0; j < a.nshards; ++j) {
+    const unsigned long long size = a.slice_lo(j + 1) - a.slice_lo(j), taken = *(volatile unsigned long long *)(a.remote + 2 + j);
+    const unsigned long long left = size > taken ? size - taken : 0ull;
+    total += left;
+    if (left > most) { most = left; best = j; }
+  }
+  return total;
+}
+static __device__ __noinline__ unsigned long long next_chunk_sharded(const ShardSched a) {
+  unsigned long long *G = a.sched, *glock = a.sched + 1 + 2 * 1024, *curw = glock + 2;
   while (true) {
     const unsigned long long old = atomicAdd(G, 1ull);
     if ((uint32_t)old < a.super_chunks) {
-      const unsigned long long sc = old >> 32;
+      const unsigned long long hi = old >> 32, sc = hi & 0x7FFFFFFFull;
       const unsigned long long chunk = sc * a.super_chunks + (uint32_t)old;
-      return (sc == 0xFFFFFFFFull || chunk > 0x0FFFFFFFull) ? 0x0FFFFFFFull : chunk;   // sentinel: its packets lie past the end
+      return (sc == 0x7FFFFFFFull || chunk > CP_PAST_END) ? CP_PAST_END : (chunk | (hi & CP_SINGLE));   // sentinel: its packets lie past the end
     }
     if (atomicCAS(glock, 0ull, 1ull) == 0ull) {
       if ((uint32_t)(*(volatile unsigned long long *)G) >= a.super_chunks) {
-        unsigned long long sc = 0xFFFFFFFFull;   // "past the end"
+        unsigned long long word = 0x7FFFFFFFull;   // "past the end"
         const uint32_t have = *(volatile uint32_t *)a.my_count;
         if (a.max_supers <= 0 || (int64_t)have < a.max_supers) {
-          sc = atomicAdd_system(a.remote, 1ull);
-          if (sc * a.super_chunks * CP_CHUNK < (unsigned long long)npackets) {
-            if (a.order) sc = a.order[sc];
-            a.my_supers[have] = (uint32_t)sc; *(volatile uint32_t *)a.my_count = have + 1;
-          } else sc = 0xFFFFFFFFull;
+          const unsigned long long super_packets = (unsigned long long)a.super_chunks * CP_CHUNK;
+          int cur = *curw ? (int)*curw - 1 : a.shard;
+          while (true) {
+            const uint32_t lo = a.slice_lo(cur), hi = a.slice_lo(cur + 1);
+            const unsigned long long k = atomicAdd_system(a.remote + 2 + cur, 1ull);
+            if (lo + k < hi) {
+              uint32_t sc = lo + (uint32_t)k;
+              bool single = false;
+              if (cur != a.shard || (hi - sc - 1) * super_packets <= a.endzone) {   // not deep inside its own slice
+                int best = cur;
+                single = shard_left(a, best) * super_packets <= (unsigned long long)a.endzone * (unsigned)a.nshards;
+              }
+              if (a.order) sc = a.order[sc];
+              a.my_supers[have] = sc; *(volatile uint32_t *)a.my_count = have + 1;
+              word = sc | (single ? CP_SINGLE : 0ull);
+              break;
+            }
+            int best = -1;   // this slice is used up: help with the one that has the most left
+            if (shard_left(a, best) == 0ull) break;
+            cur = best;
+          }
+          *curw = (unsigned long long)cur + 1;
         }
         __threadfence();
-        atomicExch(G, sc << 32);
+        atomicExch(G, word << 32);
       }
       __threadfence();
       atomicExch(glock, 0ull);
@@ -334,7 +386,8 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   smid &= 1023u;   // the state array has 1024 slots
   const uint32_t npackets = (uint32_t)((a.n + 31) / 32);
   const uint32_t nchunks = (npackets + CP_CHUNK - 1) / CP_CHUNK;
-  const uint32_t endzone = (min((uint32_t)CP_ENDZONE_PACKETS, npackets / 2u) + CP_CHUNK - 1) / CP_CHUNK;   // chunks handed out packet by packet
+  const uint32_t endzone_packets = min((uint32_t)CP_ENDZONE_PACKETS, npackets / (2u * (uint32_t)a.nshards));
+  const uint32_t endzone = (endzone_packets + CP_CHUNK - 1) / CP_CHUNK;   // chunks handed out packet by packet
   int32_t seed_face = -1;
   while (true) {
     uint32_t first = 0xFFFFFFFFu, cnt = 1;
@@ -343,17 +396,19 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       while (true) {
         // groups of CP_GROUP packets, single packets in the end zone (decided on a peek: a stale one only mis-sizes one group)
         const uint32_t peek = (uint32_t)(*(volatile unsigned long long *)st >> 32);
-        const uint32_t g = (peek + endzone >= nchunks) ? 1u : (uint32_t)CP_GROUP;
+        const uint32_t g = (peek & (uint32_t)CP_SINGLE) ? 1u : (uint32_t)CP_GROUP;
         const unsigned long long old = atomicAdd(st, (unsigned long long)g);
         if ((uint32_t)old < CP_CHUNK) {
-          first = (uint32_t)(old >> 32) * CP_CHUNK + (uint32_t)old;
+          first = ((uint32_t)(old >> 32) & ~(uint32_t)CP_SINGLE) * CP_CHUNK + (uint32_t)old;
           cnt = min(g, (uint32_t)CP_CHUNK - (uint32_t)old);
           break;
         }
         if (atomicCAS(lock, 0ull, 1ull) == 0ull) {   // this warp refills the SM's chunk
           if ((uint32_t)(*(volatile unsigned long long *)st) >= CP_CHUNK) {
-            const unsigned long long nc = a.remote ? next_chunk_sharded(ShardSched{a.sched, a.remote, a.super_chunks, a.my_supers, a.my_count, a.max_supers, a.super_order}, npackets)
-                                                               : atomicAdd(a.sched, 1ull);
+            unsigned long long nc;
+            if (a.remote) nc = next_chunk_sharded(ShardSched{a.sched, a.remote, a.super_chunks, a.my_supers, a.my_count, a.max_supers, a.super_order,
+                                                             a.nsup, a.shard, a.nshards, endzone_packets});
+            else { nc = atomicAdd(a.sched, 1ull); if (nc + endzone >= nchunks) nc |= CP_SINGLE; }
             atomicExch(st, nc << 32);
           }
           __threadfence();
@@ -601,22 +656,30 @@ struct ExactWindingQuery {
   double up, low; int32_t nF;
   double *W; double *S; int32_t *I; double *C;   // S holds sqrD on entry when mode 1
   uint32_t *overflow;
-  DEVFN void operator()(int64_t t) const {
-    const int64_t i = perm ? (int64_t)perm[t] : t;
+  // rows that need no winding number are finished here; returns whether the walk must run for row i
+  DEVFN bool prelude(int64_t i) const {
     if (mode == 1) {
       const double sqrd = S[i];
       if (sqrd >= up || sqrd < low) {
         S[i] = NAN; I[i] = nF + 1; C[i] = 0.0; C[n + i] = 0.0; C[2 * n + i] = 0.0;
         if (W) W[i] = NAN;
-        return;
+        return false;
       }
     }
+    return true;
+  }
+  DEVFN void epilogue(int64_t i, double w) const {
+    if (W) W[i] = w;
+    if (mode == 1) S[i] = fwn::dmul(fwn::dsub(1.0, fwn::dmul(2.0, w)), sqrt(S[i]));
+  }
+  DEVFN void operator()(int64_t t) const {   // one thread, one query (host emulation; the device walks packets)
+    const int64_t i = perm ? (int64_t)perm[t] : t;
+    if (!prelude(i)) return;
     uint32_t stack[wn::STACK];
     bool ovf = false;
     const double w = wn::winding_number(nodes, tri64, v, P[i], P[n + i], P[2 * n + i], stack, ovf);
     if (ovf) plat::atomic_max(overflow, 1u);
-    if (W) W[i] = w;
-    if (mode == 1) S[i] = fwn::dmul(fwn::dsub(1.0, fwn::dmul(2.0, w)), sqrt(S[i]));
+    epilogue(i, w);
   }
 };
 
@@ -727,11 +790,22 @@ void launch_query(const char *, int64_t n, WindingQuery f, stream_t s) {
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }
-__global__ void __launch_bounds__(128) exact_winding_kernel(int64_t n, ExactWindingQuery f) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+// one warp = one packet of 32 consecutive (Morton-adjacent) rows
+__global__ void __launch_bounds__(64) exact_winding_kernel(int64_t n, ExactWindingQuery f) {
+  __shared__ uint2 stacks[2][wn::PSTACK];
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x; b < n; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = b + threadIdx.x;
+    const bool valid = t < n;
+    const int64_t i = valid ? (f.perm ? (int64_t)f.perm[t] : t) : 0;
+    const bool alive = valid && f.prelude(i);
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (alive) { px = f.P[i]; py = f.P[n + i]; pz = f.P[2 * n + i]; }
+    const double w = wn::winding_number_packet(f.nodes, f.tri64, f.v, alive, px, py, pz, stacks[threadIdx.x >> 5], f.overflow);
+    if (alive) f.epilogue(i, w);
+  }
 }
 void launch_query(const char *, int64_t n, ExactWindingQuery f, stream_t s) {
-  exact_winding_kernel<<<query_grid(n, 128), 128, 0, s>>>(n, f);
+  exact_winding_kernel<<<query_grid(n, 64), 64, 0, s>>>(n, f);
   plat::launch_counter()++;
   PLAT_CHECK(cudaGetLastError());
 }
@@ -900,10 +974,12 @@ void run_fwn(const iglb200_mesh *m, const double *Q, int64_t n, float accuracy_s
 struct ShardLayout {
   size_t oCounter, oOrder, oSort, oPsf, oWs, total;
   static constexpr int64_t MIN_SUPER = int64_t(8) << 10;
+  static constexpr int MAX_SHARDS = 64;
+  static constexpr size_t COUNTER_BYTES = 1024;   // [0] pieces (winding number only), [1] overlap experiment, [2 + k] slice k
   explicit ShardLayout(int64_t n) {
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t nsup_max = (size_t)(n / MIN_SUPER + 2);
-    oCounter = 0; oOrder = 256; oSort = oOrder + al(4 * 4 * nsup_max);   // keys in/out, ids in/out (the order)
+    oCounter = 0; oOrder = COUNTER_BYTES; oSort = oOrder + al(4 * 4 * nsup_max);   // keys in/out, ids in/out (the order)
     oPsf = oSort + al(iglb200_query_scratch_bytes(n));                    // sorted queries as floats, x[n] y[n] z[n]
     oWs = oPsf + al(12 * (size_t)n);                                      // solid angle of sorted row t
     total = oWs + al(4 * (size_t)n);
@@ -1040,7 +1116,7 @@ bool shard_overlap() { static const bool on = [] { const char *e = std::getenv("
 
 void shard_begin(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int sort_queries, int64_t super_rows, stream_t s) {
   const ShardLayout L(n);
-  plat::dev_memset(scratch + L.oCounter, 0, 256, s);
+  plat::dev_memset(scratch + L.oCounter, 0, ShardLayout::COUNTER_BYTES, s);
   if (n == 0) return;
   if (super_rows < ShardLayout::MIN_SUPER) throw std::invalid_argument("super_rows must be at least 8192");
   const uint32_t *perm = morton_perm(m, P, n, scratch + L.oSort, sort_queries, s);
@@ -1065,7 +1141,9 @@ bool shard_degenerate(const iglb200_mesh *m, int mode) { return (mode != 2 && m-
 // P, S, I, C, W: the owner's arrays as seen from the calling device
 void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch, int mode, int sign_type, double lower, double upper,
                float accuracy_scale, int sort_queries, double *S, int32_t *I, double *C, double *W, int64_t super_rows, int64_t max_supers,
-               stream_t s) {
+               int shard, int nshards, stream_t s) {
+  if (nshards < 1 || nshards > ShardLayout::MAX_SHARDS || shard < 0 || shard >= nshards)
+    throw std::invalid_argument("shard_index must lie in [0, n_shards), n_shards in [1, 64]");
   if (n == 0 || shard_degenerate(m, mode)) return;   // finish fills the sentinels
   const int64_t unit = (int64_t)CP_CHUNK * 32;
   if (super_rows <= 0 || super_rows % unit) throw std::invalid_argument("super_rows must be a positive multiple of 1024");
@@ -1092,6 +1170,7 @@ void shard_run(const iglb200_mesh *m, const double *P, int64_t n, char *scratch,
     ClosestArgs a = closest_args(m, P, n, perm, up, low, S, I, C, nullptr, ws.sched.p);
     a.remote = remote; a.super_chunks = (uint32_t)(super_rows / unit); a.my_supers = my_supers; a.my_count = my_count; a.max_supers = max_supers;
     a.super_order = L.order(scratch, n);
+    a.nsup = (uint32_t)nsup; a.shard = shard; a.nshards = nshards;
     a.stash = (mode == 0 && !overlap) ? ws.stash.p : nullptr;
     launch_closest(a, s);
   }
@@ -1767,7 +1846,7 @@ int iglb200_shard_begin_dev(const iglb200_mesh *m, const double *P, int64_t nP, 
 }
 int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, void *shard_scratch, int mode, int sign_type, double lower,
                           double upper, float accuracy_scale, int sort_queries, double *S, int32_t *I, double *C, double *W,
-                          int64_t super_rows, int64_t max_supers, void *stream) {
+                          int64_t super_rows, int64_t max_supers, int shard_index, int n_shards, void *stream) {
   API_BEGIN
   m = mesh_here(m);
   if (nP < 0 || !shard_scratch || (nP > 0 && !P)) throw std::invalid_argument("null pointer");
@@ -1777,7 +1856,7 @@ int iglb200_shard_run_dev(const iglb200_mesh *m, const double *P, int64_t nP, vo
   check_count(nP);
   plat::launch_counter() = 0;
   shard_run(m, P, nP, (char *)shard_scratch, mode, sign_type, lower, upper, accuracy_scale, sort_queries, S, I, C, W, super_rows, max_supers,
-            (stream_t)stream);
+            shard_index, n_shards, (stream_t)stream);
   return IGLB200_OK;
   API_END
 }

@@ -260,4 +260,76 @@ DEVFN double winding_number(const fwn::CpNode *nodes, const double *tri64, const
   return w;
 }
 
+#ifndef IGLB200_EMUL
+// The same evaluation for a PACKET: the 32 queries of a warp (neighbours in Morton order) walk the union of their nodes
+// with one shared stack of (node, lanes inside its box).  Triangles, boxes and boundary-chain entries are then
+// warp-uniform loads, and the chain / face loops of a cluster run once for all the lanes outside its box instead of once
+// per thread at its own pace.  Per query the terms and their ORDER are exactly those of winding_number above, so the result
+// is bit-identical to the per-thread walk.
+static constexpr int PSTACK = 112;
+DEVFN double winding_number_packet(const fwn::CpNode *nodes, const double *tri64, const View &v, bool alive, double px, double py, double pz,
+                                   uint2 *stack, uint32_t *overflow) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31u;
+  double w = 0.0;
+  const unsigned m0 = __ballot_sync(FULL, alive);
+  if (m0 == 0u) return 0.0;
+  int sp = 1;
+  if (lane == 0) stack[0] = make_uint2(0u, m0);
+  __syncwarp();
+  while (sp > 0) {
+    const uint2 e = stack[--sp];
+    __syncwarp();
+    const bool me = (e.y >> lane) & 1u;
+    const uint32_t ni = e.x;
+    const fwn::CpNode &n = nodes[ni];
+    const uint32_t ch[4] = {n.child.x, n.child.y, n.child.z, n.child.w};
+    const uint32_t imask = n.pad.x, tmask = n.pad.y;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      if ((tmask >> l) & 1u) {   // warp-uniform
+        const double *t = tri64 + 9 * (size_t)ch[l];
+        if (me) w += tri_winding(t, t + 3, t + 6, px, py, pz);
+      } else if ((imask >> l) & 1u) {
+        const double lx = ((const float *)&n.lox)[l], ly = ((const float *)&n.loy)[l], lz = ((const float *)&n.loz)[l];
+        const double hx = ((const float *)&n.hix)[l], hy = ((const float *)&n.hiy)[l], hz = ((const float *)&n.hiz)[l];
+        const bool inside = px >= lx && px <= hx && py >= ly && py <= hy && pz >= lz && pz <= hz;
+        const unsigned min_ = __ballot_sync(FULL, me && inside), mout = __ballot_sync(FULL, me && !inside);
+        if (min_) {
+          if (sp < PSTACK) { if (lane == 0) stack[sp] = make_uint2(ch[l] & ~INTERNAL_BIT, min_); ++sp; }
+          else if (lane == 0) *overflow = 1u;
+        }
+        if (mout) {
+          const uint32_t c = 4 * ni + l;
+          const uint32_t b0 = v.bstart[c], b1 = v.bstart[c + 1], nf = v.cnt[c];
+          const bool mine = (mout >> lane) & 1u;
+          double acc = 0.0;
+          if (b1 - b0 < nf) {
+            // outside the cluster's box: its faces and the fan over its boundary chain bound a closed surface
+            const double apex[3] = {0.5 * (lx + hx), 0.5 * (ly + hy), 0.5 * (lz + hz)};
+            for (uint32_t k = b0; k < b1; ++k) {
+              const uint64_t en = v.bent[k];
+              const uint32_t slot = (uint32_t)en;
+              const int mult = (int)(uint32_t)(en >> 32);
+              const uint32_t f = slot / 3, k0 = slot % 3, k1 = (k0 + 1) % 3;
+              const double *t = tri64 + 9 * (size_t)f;
+              if (mine) acc += (double)mult * tri_winding(apex, t + 3 * k0, t + 3 * k1, px, py, pz);
+            }
+          } else {   // a chain as long as the face list: sum the faces (WindingNumberTree.h:292, 326-330)
+            const uint32_t s0 = v.start[c];
+            for (uint32_t k = 0; k < nf; ++k) {
+              const double *t = tri64 + 9 * (size_t)v.leafface[s0 + k];
+              if (mine) acc += tri_winding(t, t + 3, t + 6, px, py, pz);
+            }
+          }
+          if (mine) w += acc;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  return w;
+}
+#endif
+
 }  // namespace wn

@@ -352,7 +352,7 @@ def test_sharded_device_path_equals_the_single_call(gpu_api):
         ref = [torch.empty_like(t) for t in out]
         po, pr = [vp(t.data_ptr()) for t in out], [vp(t.data_ptr()) for t in ref]
         api.check(L.iglb200_shard_begin_dev(m.h, vp(dP.data_ptr()), n, vp(scratch.data_ptr()), 1, sup, None))
-        api.check(L.iglb200_shard_run_dev(m.h, vp(dP.data_ptr()), n, vp(scratch.data_ptr()), mode, sign, lo, hi, 2.0, 1, *po, sup, 0, None))
+        api.check(L.iglb200_shard_run_dev(m.h, vp(dP.data_ptr()), n, vp(scratch.data_ptr()), mode, sign, lo, hi, 2.0, 1, *po, sup, 0, 0, 1, None))
         api.check(L.iglb200_shard_finish_dev(m.h, n, vp(scratch.data_ptr()), mode, sign, lo, hi, 1, *po, None))
         if mode == 0:
             api.check(L.iglb200_signed_distance_dev(m.h, vp(dP.data_ptr()), n, sign, lo, hi, *pr, None, vp(qs.data_ptr()), 1, None))

@@ -287,10 +287,11 @@ def test_sharded_device_queries_match_the_fused_path(emul_api):
             api.set_device(0)
             api.check(L.iglb200_shard_begin_dev(m.h, ptr(Pc), n, ptr(scratch), 1, sup, None))
             outs = (ptr(S), ptr(I), ptr(Cc), ptr(W))
-            api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 3, None))   # device 0: 3 pieces
+            api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 3, 0, 2, None))   # device 0: 3 pieces of its slice
             api.set_device(1)
-            api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 0, None))   # device 1: the rest
-            assert int(scratch[:8].view(np.uint64)[0]) >= 8
+            api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), mode, sign, lo, hi, 2.0, 1, *outs, sup, 0, 1, 2, None))   # device 1: its slice, then the rest of the other
+            counters = scratch[:1024].view(np.uint64)   # [0] winding-number pieces, [2 + k] super-chunks of slice k
+            assert int(counters[0] + counters[2:4].sum()) >= 8
             api.set_device(0)
             api.check(L.iglb200_shard_finish_dev(m.h, n, ptr(scratch), mode, sign, lo, hi, 1, *outs, None))
             S1, I1, C1, W1 = np.empty(n), np.empty(n, np.int32), np.empty((3, n)), np.empty(n)

@@ -62,7 +62,7 @@ ptr = [vp(base.value + o) for o in offs[:5]]
 tiny, huge = float(np.finfo(float).tiny), float(np.finfo(float).max)
 for mode in (0, 1, 2):
     api.check(L.iglb200_shard_begin_dev(ms.h, ptr[0], nq, base, 1, 8192, None))
-    api.check(L.iglb200_shard_run_dev(ms.h, ptr[0], nq, base, mode, 4, tiny, huge, 2.0, 1, ptr[1], ptr[2], ptr[3], ptr[4], 8192, 0, None))
+    api.check(L.iglb200_shard_run_dev(ms.h, ptr[0], nq, base, mode, 4, tiny, huge, 2.0, 1, ptr[1], ptr[2], ptr[3], ptr[4], 8192, 0, 0, 1, None))
     api.check(L.iglb200_shard_finish_dev(ms.h, nq, base, mode, 4, tiny, huge, 1, ptr[1], ptr[2], ptr[3], ptr[4], None))
     torch.cuda.synchronize()
     api.check(L.iglb200_poll_device_error())
