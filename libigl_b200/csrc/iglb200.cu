@@ -113,6 +113,9 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   uint32_t super_chunks = 0;
   uint32_t nsup = 0;            // super-chunks in the query set
   int shard = 0, nshards = 1;   // this device's slice, number of slices
+  // Warps that run out of packets stay and take over parts of the walks still going on (work donation).  Off when
+  // several launches share the device on purpose (the host path: the next chunk's kernel fills this one's tail).
+  int donate = 1;
   uint32_t *my_supers = nullptr, *my_count = nullptr;
   int64_t max_supers = 0;   // > 0: take at most this many (static partition / tests)
   const uint32_t *super_order = nullptr;   // the k-th super-chunk handed out is super_order[k]
@@ -123,7 +126,19 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   double sigma = 1.0;
 };
 
-static constexpr int64_t SCHED_WORDS = 1 + 2 * 1024 + 3;   // next chunk; per SM id: state, refill lock; sharded: lock, block counter, spare
+// Work donation (the tail of a launch): a warp that walks an unusually heavy packet while other warps have run out of
+// work hands them the older half of its stack as a task (packet, sub-trees, the lanes' current upper bounds); the
+// results of the pieces of a packet are merged under a lock (smaller squared distance, lower face index on a tie).
+// Every warp of the launch owns a mailbox (a state word and a task record): no shared queue, hence no shared lock.
+static constexpr int CP_TASK_NODES = 14, CP_MAILBOXES = 4096, CP_NLOCKS = 256;
+struct CpTask { uint32_t packet, nn; uint32_t node[CP_TASK_NODES]; float ub[32]; };   // 192 bytes
+static constexpr uint32_t BOX_CLOSED = 0u, BOX_WAITING = 1u, BOX_CLAIMED = 2u, BOX_FILLED = 3u;
+// state words of a launch: next chunk; per SM id: state, refill lock; sharded: lock, block counter, current slice;
+// donation: idle warps, warps holding work, two spare; packet locks; mailbox states (32 bits each); the task records
+static constexpr int64_t SCHED_DONATE = 1 + 2 * 1024 + 3, SCHED_LOCKS = SCHED_DONATE + 4, SCHED_BOX_STATE = SCHED_LOCKS + CP_NLOCKS;
+static constexpr int64_t SCHED_TASKS = SCHED_BOX_STATE + CP_MAILBOXES / 2;
+static constexpr int64_t SCHED_INIT_WORDS = SCHED_TASKS;
+static constexpr int64_t SCHED_WORDS = SCHED_TASKS + CP_MAILBOXES * (int64_t)(sizeof(CpTask) / 8);
 struct InitSched {   // every SM starts with an exhausted chunk (and, sharded, the device with an exhausted super-chunk)
   unsigned long long *w; int sharded;
   DEVFN void operator()(int64_t i) const {
@@ -361,6 +376,111 @@ static __device__ __noinline__ unsigned long long next_chunk_sharded(const Shard
     }
   }
 }
+#ifndef CP_DONATE_EVERY
+#define CP_DONATE_EVERY 32   // pops between two looks at the idle counter
+#endif
+// donor: hand the older half of the stack (at most CP_TASK_NODES sub-trees) to a warp that waits at its mailbox (four
+// mailboxes are tried at random: in the tail of a launch most warps wait); returns the new height of the stack
+static __device__ __noinline__ int cp_donate(unsigned long long *sched, uint32_t *stack, int sp, uint32_t packet, float best_ub, uint32_t salt) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  uint32_t *state = (uint32_t *)(sched + SCHED_BOX_STATE);
+  const uint32_t h = ((blockIdx.x * 2654435761u + salt * 40503u + (uint32_t)lane * 0x9E3779B9u) >> 7) % gridDim.x;
+  bool claimed = false;
+  if (lane < 4 && h != blockIdx.x) claimed = atomicCAS(&state[h], BOX_WAITING, BOX_CLAIMED) == BOX_WAITING;
+  const unsigned won = __ballot_sync(FULL, claimed);
+  if (!won) return sp;
+  const int w = __ffs(won) - 1;
+  if (claimed && lane != w) atomicExch(&state[h], BOX_WAITING);   // one is enough
+  const uint32_t box = __shfl_sync(FULL, h, w);
+  const int nd = min(sp / 2, CP_TASK_NODES);
+  CpTask *tk = (CpTask *)(sched + SCHED_TASKS) + box;
+  tk->ub[lane] = best_ub;
+  if (lane < nd) tk->node[lane] = stack[lane];
+  if (lane == 0) { tk->packet = packet; tk->nn = (uint32_t)nd; }
+  __syncwarp();
+  for (int k0 = 0; k0 < sp - nd; k0 += 32) {   // close the gap
+    const int k = k0 + lane;
+    uint32_t v = 0;
+    if (k < sp - nd) v = stack[k + nd];
+    __syncwarp();
+    if (k < sp - nd) stack[k] = v;
+    __syncwarp();
+  }
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(&state[box], BOX_FILLED);
+  return sp - nd;
+}
+// a warp out of packets waits at its mailbox for a task: false when nobody is left who could send one
+static __device__ __noinline__ bool cp_take_task(unsigned long long *sched, uint32_t *stack, uint32_t &packet, int &sp, float &ub, bool &counted) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  uint32_t *idle = (uint32_t *)(sched + SCHED_DONATE), *active = (uint32_t *)(sched + SCHED_DONATE + 1);
+  uint32_t *state = (uint32_t *)(sched + SCHED_BOX_STATE) + blockIdx.x;
+  int got = 0;
+  if (lane == 0) {
+    if (counted) atomicSub(active, 1u);
+    atomicAdd(idle, 1u);
+    atomicExch(state, BOX_WAITING);
+    unsigned ns = 250, polls = 0;
+    while (true) {   // (capping the waiting warps at a quarter of the launch was measured: slices 5.66 instead of 5.41 ms)
+      const uint32_t st = *(volatile uint32_t *)state;
+      if (st == BOX_FILLED) { got = 1; break; }
+      // nobody holds work any more: withdraw — unless a donor has just claimed this mailbox, then its task is on the way
+      if (st == BOX_WAITING && (++polls & 3u) == 0u && *(volatile uint32_t *)active == 0u &&
+          atomicCAS(state, BOX_WAITING, BOX_CLOSED) == BOX_WAITING) break;
+      __nanosleep(ns);
+      if (ns < 4000u) ns *= 2u;
+    }
+    atomicSub(idle, 1u);
+    if (got) atomicAdd(active, 1u);
+  }
+  got = __shfl_sync(FULL, got, 0);
+  if (!got) { counted = false; return false; }
+  counted = true;
+  const CpTask *tk = (const CpTask *)(sched + SCHED_TASKS) + blockIdx.x;
+  ub = ((const volatile float *)tk->ub)[lane];
+  const uint32_t nn = *(const volatile uint32_t *)&tk->nn;
+  packet = *(const volatile uint32_t *)&tk->packet;
+  if ((uint32_t)lane < nn) stack[lane] = ((const volatile uint32_t *)tk->node)[lane];
+  __syncwarp();
+  if (lane == 0) atomicExch(state, BOX_CLOSED);
+  sp = (int)nn;
+  return true;
+}
+// a packet about to be shared starts from "nothing found" in the outputs; its pieces then merge into them
+static __device__ __noinline__ void cp_begin_shared(const ClosestArgs a, int64_t qi, int64_t t, bool valid) {
+  if (valid) {
+    fwn::CpResult r; r.sqr_d = a.up; r.face = -1; r.c = {0.0, 0.0, 0.0};
+    closest_store(a, qi, r);
+    if (a.stash) a.stash[t] = ShardStash{(float)a.P[qi], (float)a.P[a.n + qi], (float)a.P[2 * a.n + qi], (uint32_t)qi, a.up};
+  }
+  __threadfence_system();
+  __syncwarp();
+}
+static __device__ __noinline__ void cp_store_merged(const ClosestArgs a, int64_t qi, int64_t t, bool valid, double sqr_d, int32_t face, double cx,
+                                                    double cy, double cz, uint32_t packet) {
+  const int lane = threadIdx.x & 31;
+  uint32_t *lock = (uint32_t *)(a.sched + SCHED_LOCKS + (packet & (uint32_t)(CP_NLOCKS - 1)));
+  if (lane == 0) while (atomicCAS(lock, 0u, 1u) != 0u) __nanosleep(100);
+  __syncwarp();
+  if (valid && face >= 0) {
+    const double cur = *(volatile double *)&a.sqrD[qi];
+    const int32_t cf = *(volatile int32_t *)&a.I[qi];
+    if (cf < 0 || sqr_d < cur || (sqr_d == cur && face < cf)) {
+      fwn::CpResult r; r.sqr_d = sqr_d; r.face = face; r.c = {cx, cy, cz};
+      closest_store(a, qi, r);
+      if (a.stash) a.stash[t].sqrd = sqr_d;
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) atomicExch(lock, 0u);
+}
+#ifdef CP_TIMELINE
+__device__ unsigned long long *g_timeline = nullptr;   // [8 * blocks]: first request, last request that got work, exit (globaltimer, ns); visits and duration of the longest walk, donations, tasks
+#endif
 template <bool COUNT>
 __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_kernel(ClosestArgs a, uint32_t *overflow) {
   using namespace fwn;
@@ -389,8 +509,11 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   const uint32_t endzone_packets = min((uint32_t)CP_ENDZONE_PACKETS, npackets / (2u * (uint32_t)a.nshards));
   const uint32_t endzone = (endzone_packets + CP_CHUNK - 1) / CP_CHUNK;   // chunks handed out packet by packet
   int32_t seed_face = -1;
+  bool drained = false, counted = false;   // no packets left for this warp; it is counted among the warps holding work
   while (true) {
     uint32_t first = 0xFFFFFFFFu, cnt = 1;
+    int task_sp = 0; float task_ub = 0.f;
+    if (!drained) {
     if (lane == 0) {
       unsigned long long *st = a.sched + 1 + 2 * smid, *lock = st + 1;
       while (true) {
@@ -418,7 +541,23 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     }
     first = __shfl_sync(FULL, first, 0);
     cnt = __shfl_sync(FULL, cnt, 0);
-    if (first >= npackets) break;   // the SM's chunk lies past the last packet: this warp is done
+    if (first >= npackets) drained = true;   // the SM's chunk lies past the last packet
+    else if (!counted) { counted = true; if (lane == 0) atomicAdd((uint32_t *)(a.sched + SCHED_DONATE + 1), 1u); }
+    }
+#ifdef CP_TIMELINE
+    if (lane == 0 && g_timeline) {   // tuning aid: when each warp took its first / last piece of work and when it left
+      unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (g_timeline[8 * blockIdx.x] == 0ull) g_timeline[8 * blockIdx.x] = now;
+      if (first < npackets) g_timeline[8 * blockIdx.x + 1] = now; else g_timeline[8 * blockIdx.x + 2] = now;
+    }
+#endif
+    // out of packets: help with the heavy packets still being walked, until none is left
+    const bool is_task = drained;
+    if (drained) {
+      if (!a.donate) break;
+      if (!cp_take_task(a.sched, stack, first, task_sp, task_ub, counted)) break;
+      cnt = 1;
+    }
     if (cnt == 1) seed_face = -1;   // a single packet has no predecessor of its own
    for (uint32_t gi = 0; gi < cnt; ++gi) {
     const uint32_t packet = first + gi;
@@ -431,6 +570,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     const CpQueryRef qr{a.P, a.n, qi, a.sigma};
     lane_init(L, X, valid ? load_query(qr) : D3{0.0, 0.0, 0.0}, a.up, a.absmax, a.sigma);
     if (!valid || a.low > a.up) { L.best_ub = -INFINITY; L.thr2 = -1.f; }
+    else if (is_task) { if (task_ub < L.best_ub) lane_set_ub(L, task_ub); }
     else if (seed_face >= 0) {   // warp-uniform
       const float4 *tq = a.triq + TRIQ_STRIDE * (size_t)seed_face;
       float4 T0, T1, T2, T3; ld256(tq, T0, T1); ld256(tq + 2, T2, T3);
@@ -438,8 +578,13 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       const float ub = d32 + err;
       if (ub < L.best_ub) lane_set_ub(L, ub);
     }
-    uint32_t nvis = 0, ntri = 0;
+    uint32_t nvis = 0, ntri = 0, npop = 0;
     int sp = 0; uint32_t cur = 0; bool have = true;
+    bool shared = is_task;   // the packet is (or becomes) walked by several warps
+#ifdef CP_TIMELINE
+    unsigned long long tl_walk0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_walk0));
+#endif
+    if (is_task) { sp = task_sp - 1; cur = stack[sp]; }
     while (true) {
       if (!have) {
         if (sp == 0) break;
@@ -447,6 +592,15 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         // no re-test against the tightened bounds here: for a packet (smallest bound any lane had at the push against the
         // largest threshold any lane still has) it rejects next to nothing; the node's own tests do it
         cur = stack[sp];
+        // a long walk (counted in pops: off the descending path): is anybody out of work?
+        if ((++npop & (uint32_t)(CP_DONATE_EVERY - 1)) == 0u && sp >= 2 && a.donate) {
+          uint32_t idle = lane == 0 ? *(volatile uint32_t *)(a.sched + SCHED_DONATE) : 0u;
+          idle = __shfl_sync(FULL, idle, 0);
+          if (idle) {
+            if (!shared) { cp_begin_shared(a, qi, t, valid); shared = true; }
+            sp = cp_donate(a.sched, stack, sp, packet, L.best_ub, npop);
+          }
+        }
       }
       have = false;
       if (COUNT) ++nvis;
@@ -531,18 +685,29 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       }
       __syncwarp();
     }
+#ifdef CP_TIMELINE
+    if (lane == 0 && g_timeline) {
+      unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      unsigned long long *tl = g_timeline + 8 * blockIdx.x;
+      if (now - tl_walk0 > tl[4]) { tl[3] = npop; tl[4] = now - tl_walk0; tl[7] = packet; }
+      if (is_task) tl[6]++;
+    }
+#endif
     int32_t won = -1;
+    CpResult r; r.sqr_d = 0.0; r.face = -1; r.c = {0.0, 0.0, 0.0};
     if (valid) {
-      CpResult r;
-      if (a.low > a.up) { r.sqr_d = a.low; r.face = -1; r.c = {0.0, 0.0, 0.0}; }  // AABB.cpp:1145-1148
+      if (a.low > a.up) r.sqr_d = a.low;  // AABB.cpp:1145-1148
       else lane_finish(L, X, a.tri64, qr, a.up, r);
-      closest_store(a, qi, r);
       won = r.face;
-      if (a.stash) {
-        const D3 p = load_query(qr);
-        a.stash[t] = ShardStash{(float)p.x, (float)p.y, (float)p.z, (uint32_t)qi, r.sqr_d};
+      if (!shared) {
+        closest_store(a, qi, r);
+        if (a.stash) {
+          const D3 p = load_query(qr);
+          a.stash[t] = ShardStash{(float)p.x, (float)p.y, (float)p.z, (uint32_t)qi, r.sqr_d};
+        }
       }
     }
+    if (shared) cp_store_merged(a, qi, t, valid, r.sqr_d, r.face, r.c.x, r.c.y, r.c.z, packet);   // warp-uniform
     seed_face = __shfl_sync(FULL, won, 0);   // lane 0's winner seeds the next packet of the group
     if (COUNT && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
     __syncwarp();
@@ -577,8 +742,8 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   DevBuf<unsigned long long> own;
   ClosestArgs b = a;
   if (!b.sched) { own.alloc(SCHED_WORDS); b.sched = own.p; }   // no caller scratch: a private state for this launch
-  plat::for_n(SCHED_WORDS, InitSched{b.sched, b.remote ? 1 : 0}, s);
-  blocks = std::min<int64_t>(blocks, (int64_t)plat::sm_count() * CP_MIN_BLOCKS);
+  plat::for_n(SCHED_INIT_WORDS, InitSched{b.sched, b.remote ? 1 : 0}, s);
+  blocks = std::min<int64_t>(std::min<int64_t>(blocks, (int64_t)plat::sm_count() * CP_MIN_BLOCKS), CP_MAILBOXES);
   if (b.counters) closest_packet_kernel<true><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(b, overflow_flag());
   else closest_packet_kernel<false><<<(unsigned)blocks, 32 * CP_WARPS, 0, s>>>(b, overflow_flag());
   if (own.p) plat::sync(s);
@@ -848,11 +1013,19 @@ const uint32_t *morton_perm(const iglb200_mesh *m, const double *P, int64_t n, v
   return sc.perm;
 }
 
+// set while a host-path worker drives its chunks: other workers' kernels run beside this thread's on the same device
+bool &launches_share_device() { static thread_local bool f = false; return f; }
+struct ShareDeviceScope {
+  bool old;
+  ShareDeviceScope() : old(launches_share_device()) { launches_share_device() = true; }
+  ~ShareDeviceScope() { launches_share_device() = old; }
+};
 ClosestArgs closest_args(const iglb200_mesh *m, const double *P, int64_t n, const uint32_t *perm, double up, double low,
                          double *sqrD, int32_t *I, double *C, uint32_t *counters, unsigned long long *sched) {
   ClosestArgs a{m->pnodes(), m->tri64(), m->triq(), P, n, perm, up, low, (float)((double)m->h.absmax * m->h.sigma), sqrD, I, C, counters, sched};
   a.sigma = m->h.sigma;
   a.nnodes = (uint32_t)m->h.nnodes;
+  a.donate = launches_share_device() ? 0 : 1;
   return a;
 }
 
@@ -1438,6 +1611,7 @@ struct ChunkPlan {
 void host_worker(WorkerCtx &w, HostQuery &q) {
   const iglb200_mesh *m = q.m->on(w.device);
   if (!m) return;
+  const ShareDeviceScope share;
   const ChunkPlan plan(q.n, q.chunk, q.edge);
   const ChunkBufs B = chunk_bufs(q, q.chunk);
   const StageBufs H = stage_bufs(q.chunk);
@@ -1962,6 +2136,11 @@ double iglb200_debug_fp32_peak_tflops(void) {
   } catch (...) { return -1.0; }
 #endif
 }
+#ifdef CP_TIMELINE
+int iglb200_debug_timeline(unsigned long long *buf) {
+  return (int)cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf));
+}
+#endif
 int iglb200_poll_device_error(void) {
   API_BEGIN
   require_device();

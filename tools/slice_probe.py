@@ -16,14 +16,16 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from libigl_b200 import api, synth  # noqa: E402
+import libigl_b200  # noqa: E402
+from libigl_b200 import synth  # noqa: E402
 
 
 def main():
     K = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     faces = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
     grid = int(sys.argv[3]) if len(sys.argv) > 3 else 256
-    L = api.lib()
+    api = libigl_b200.lib()
+    L = api.lib
     V, F = synth.torus_knot(*synth.knot_dims(faces))
     lo, hi = synth.bbox(V)
     P = synth.grid_points(lo, hi, grid, 1.1)
@@ -54,6 +56,33 @@ def main():
                 ts.append(e0.elapsed_time(e1))
         return float(np.median(ts))
 
+    if hasattr(L, "iglb200_debug_timeline"):   # a -DCP_TIMELINE build: when do the warps of the search kernel run dry?
+        nb = 148 * 32
+        tl = torch.zeros(8 * nb + 8, dtype=torch.int64, device=dev)
+        L.iglb200_debug_timeline.argtypes = [vp]
+        for k, nk, cap in ((0, 1, 0), (0, K, nsup // K), (K // 2, K, nsup // K)):
+            api.check(L.iglb200_shard_begin_dev(m.h, vp(dP.data_ptr()), n, vp(scratch.data_ptr()), 1, sup, None))
+            tl.zero_()
+            assert L.iglb200_debug_timeline(vp(tl.data_ptr())) == 0
+            torch.cuda.synchronize()
+            api.check(L.iglb200_shard_run_dev(m.h, vp(dP.data_ptr()), n, vp(scratch.data_ptr()), 1, 4, tiny, huge, 2.0, 1, *po, sup, cap, k, nk, None))
+            torch.cuda.synchronize()
+            extra = tl.cpu().numpy()[8 * 2960:8 * 2960 + 5]
+            t = tl.cpu().numpy()[:8 * 2960].reshape(2960, 8).astype(np.float64)
+            t = t[t[:, 0] > 0]
+            t0 = t[:, 0].min()
+            first, last, exit_ = (t[:, 0] - t0) / 1e6, (t[:, 1] - t0) / 1e6, (t[:, 2] - t0) / 1e6
+            end = exit_.max()
+            busy = (exit_ - first).sum() / (len(t) * end)
+            pct = lambda x: " ".join("%.2f" % v for v in np.percentile(x, [0, 10, 50, 90, 99, 100]))
+            print(f"timeline shard {k}/{nk}: warps {len(t)}, kernel {end:.2f} ms, warp-time in use {100 * busy:.1f}%\n"
+                  f"   first request at (ms, pct 0/10/50/90/99/100): {pct(first)}\n"
+                  f"   last work taken at: {pct(last)}\n   exit at: {pct(exit_)}\n"
+                  f"   duration of the last piece of work (exit - last taken): {pct(exit_ - last)}\n"
+                  f"   longest walk of each warp: visits {pct(t[:, 3])}, ms {pct(t[:, 4] / 1e6)}; donations {int(t[:, 5].sum())}, tasks run {int(t[:, 6].sum())}\n"
+                  f"   checks: {extra[2]}, with idle warps and stack < 2: {extra[0]}, with idle warps and stack >= 2: {extra[1]}, stack max {extra[3]} mean {extra[4] / max(extra[2], 1):.1f}\n"
+                  f"   slowest walks (ms, visits, packet): " + " ".join("(%.2f, %d, %d)" % (t[j, 4] / 1e6, t[j, 3], t[j, 7]) for j in np.argsort(-t[:, 4])[:8]), flush=True)
+        L.iglb200_debug_timeline(vp(0))
     for mode, name in ((1, "search"), (0, "search+winding")):
         whole = run(mode, 0, 1, 0)
         parts = [run(mode, k, K, nsup * (k + 1) // K - nsup * k // K) for k in range(K)]
