@@ -130,15 +130,21 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
 // work hands them the older half of its stack as a task (packet, sub-trees, the lanes' current upper bounds); the
 // results of the pieces of a packet are merged under a lock (smaller squared distance, lower face index on a tie).
 // Every warp of the launch owns a mailbox (a state word and a task record): no shared queue, hence no shared lock.
-static constexpr int CP_TASK_NODES = 14, CP_MAILBOXES = 4096, CP_NLOCKS = 256;
-struct CpTask { uint32_t packet, nn; uint32_t node[CP_TASK_NODES]; float ub[32]; };   // 192 bytes
+// A packet walked in pieces owns a SLOT in the launching device's memory where the pieces merge (squared distance, face)
+// per query; the piece that finishes last writes the packet's results — so a sharded launch does its merging locally and
+// touches the owner's arrays once, as for any other packet.
+static constexpr int CP_TASK_NODES = 13, CP_MAILBOXES = 4096, CP_SLOTS = 8192;
+struct CpTask { uint32_t packet, nn, slot; uint32_t node[CP_TASK_NODES]; float ub[32]; };   // 192 bytes
+struct CpSlot { double d2[32]; int32_t face[32]; uint32_t pending, lock; uint32_t pad[30]; };   // 512 bytes
+static_assert(sizeof(CpTask) == 192 && sizeof(CpSlot) == 512, "record sizes");
 static constexpr uint32_t BOX_CLOSED = 0u, BOX_WAITING = 1u, BOX_CLAIMED = 2u, BOX_FILLED = 3u;
 // state words of a launch: next chunk; per SM id: state, refill lock; sharded: lock, block counter, current slice;
-// donation: idle warps, warps holding work, two spare; packet locks; mailbox states (32 bits each); the task records
-static constexpr int64_t SCHED_DONATE = 1 + 2 * 1024 + 3, SCHED_LOCKS = SCHED_DONATE + 4, SCHED_BOX_STATE = SCHED_LOCKS + CP_NLOCKS;
+// donation: idle warps, warps holding work, slots handed out, spare; mailbox states (32 bits each); task records; slots
+static constexpr int64_t SCHED_DONATE = 1 + 2 * 1024 + 3, SCHED_BOX_STATE = SCHED_DONATE + 4;
 static constexpr int64_t SCHED_TASKS = SCHED_BOX_STATE + CP_MAILBOXES / 2;
 static constexpr int64_t SCHED_INIT_WORDS = SCHED_TASKS;
-static constexpr int64_t SCHED_WORDS = SCHED_TASKS + CP_MAILBOXES * (int64_t)(sizeof(CpTask) / 8);
+static constexpr int64_t SCHED_SLOTS = SCHED_TASKS + CP_MAILBOXES * (int64_t)(sizeof(CpTask) / 8);
+static constexpr int64_t SCHED_WORDS = SCHED_SLOTS + CP_SLOTS * (int64_t)(sizeof(CpSlot) / 8);
 struct InitSched {   // every SM starts with an exhausted chunk (and, sharded, the device with an exhausted super-chunk)
   unsigned long long *w; int sharded;
   DEVFN void operator()(int64_t i) const {
@@ -381,7 +387,8 @@ static __device__ __noinline__ unsigned long long next_chunk_sharded(const Shard
 #endif
 // donor: hand the older half of the stack (at most CP_TASK_NODES sub-trees) to a warp that waits at its mailbox (four
 // mailboxes are tried at random: in the tail of a launch most warps wait); returns the new height of the stack
-static __device__ __noinline__ int cp_donate(unsigned long long *sched, uint32_t *stack, int sp, uint32_t packet, float best_ub, uint32_t salt) {
+static __device__ __noinline__ int cp_donate(unsigned long long *sched, uint32_t *stack, int sp, uint32_t packet, float best_ub, uint32_t salt,
+                                             int32_t slot) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   uint32_t *state = (uint32_t *)(sched + SCHED_BOX_STATE);
@@ -397,7 +404,10 @@ static __device__ __noinline__ int cp_donate(unsigned long long *sched, uint32_t
   CpTask *tk = (CpTask *)(sched + SCHED_TASKS) + box;
   tk->ub[lane] = best_ub;
   if (lane < nd) tk->node[lane] = stack[lane];
-  if (lane == 0) { tk->packet = packet; tk->nn = (uint32_t)nd; }
+  if (lane == 0) {
+    tk->packet = packet; tk->nn = (uint32_t)nd; tk->slot = (uint32_t)slot;
+    atomicAdd(&((CpSlot *)(sched + SCHED_SLOTS) + slot)->pending, 1u);   // one more piece, before anybody can finish it
+  }
   __syncwarp();
   for (int k0 = 0; k0 < sp - nd; k0 += 32) {   // close the gap
     const int k = k0 + lane;
@@ -413,7 +423,8 @@ static __device__ __noinline__ int cp_donate(unsigned long long *sched, uint32_t
   return sp - nd;
 }
 // a warp out of packets waits at its mailbox for a task: false when nobody is left who could send one
-static __device__ __noinline__ bool cp_take_task(unsigned long long *sched, uint32_t *stack, uint32_t &packet, int &sp, float &ub, bool &counted) {
+static __device__ __noinline__ bool cp_take_task(unsigned long long *sched, uint32_t *stack, uint32_t &packet, int &sp, float &ub, bool &counted,
+                                                 int32_t &slot) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   uint32_t *idle = (uint32_t *)(sched + SCHED_DONATE), *active = (uint32_t *)(sched + SCHED_DONATE + 1);
@@ -443,40 +454,59 @@ static __device__ __noinline__ bool cp_take_task(unsigned long long *sched, uint
   ub = ((const volatile float *)tk->ub)[lane];
   const uint32_t nn = *(const volatile uint32_t *)&tk->nn;
   packet = *(const volatile uint32_t *)&tk->packet;
+  slot = (int32_t)*(const volatile uint32_t *)&tk->slot;
   if ((uint32_t)lane < nn) stack[lane] = ((const volatile uint32_t *)tk->node)[lane];
   __syncwarp();
   if (lane == 0) atomicExch(state, BOX_CLOSED);
   sp = (int)nn;
   return true;
 }
-// a packet about to be shared starts from "nothing found" in the outputs; its pieces then merge into them
-static __device__ __noinline__ void cp_begin_shared(const ClosestArgs a, int64_t qi, int64_t t, bool valid) {
-  if (valid) {
-    fwn::CpResult r; r.sqr_d = a.up; r.face = -1; r.c = {0.0, 0.0, 0.0};
-    closest_store(a, qi, r);
-    if (a.stash) a.stash[t] = ShardStash{(float)a.P[qi], (float)a.P[a.n + qi], (float)a.P[2 * a.n + qi], (uint32_t)qi, a.up};
-  }
-  __threadfence_system();
-  __syncwarp();
-}
-static __device__ __noinline__ void cp_store_merged(const ClosestArgs a, int64_t qi, int64_t t, bool valid, double sqr_d, int32_t face, double cx,
-                                                    double cy, double cz, uint32_t packet) {
+// a packet about to be walked in pieces takes a slot ("nothing found yet", one piece: the caller); -1 when none is left
+static __device__ __noinline__ int32_t cp_begin_shared(unsigned long long *sched, double up) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  uint32_t *lock = (uint32_t *)(a.sched + SCHED_LOCKS + (packet & (uint32_t)(CP_NLOCKS - 1)));
-  if (lane == 0) while (atomicCAS(lock, 0u, 1u) != 0u) __nanosleep(100);
+  uint32_t k = 0;
+  if (lane == 0) k = atomicAdd((uint32_t *)(sched + SCHED_DONATE + 2), 1u);
+  k = __shfl_sync(FULL, k, 0);
+  if (k >= (uint32_t)CP_SLOTS) return -1;
+  CpSlot *sl = (CpSlot *)(sched + SCHED_SLOTS) + k;
+  sl->d2[lane] = up; sl->face[lane] = -1;
+  if (lane == 0) { sl->pending = 1u; sl->lock = 0u; }
+  __threadfence();
   __syncwarp();
-  if (valid && face >= 0) {
-    const double cur = *(volatile double *)&a.sqrD[qi];
-    const int32_t cf = *(volatile int32_t *)&a.I[qi];
-    if (cf < 0 || sqr_d < cur || (sqr_d == cur && face < cf)) {
-      fwn::CpResult r; r.sqr_d = sqr_d; r.face = face; r.c = {cx, cy, cz};
-      closest_store(a, qi, r);
-      if (a.stash) a.stash[t].sqrd = sqr_d;
-    }
+  return (int32_t)k;
+}
+// a piece of a packet is done: merge its result into the slot (smaller squared distance; lower face index on a tie).  The
+// piece that finishes last writes the packet's results (and its row of the stash) like any other packet's.
+static __device__ __noinline__ void cp_finish_shared(const ClosestArgs a, int32_t slot, int64_t qi, int64_t t, bool valid, double sqr_d, int32_t face) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  CpSlot *sl = (CpSlot *)(a.sched + SCHED_SLOTS) + slot;
+  if (lane == 0) while (atomicCAS(&sl->lock, 0u, 1u) != 0u) __nanosleep(100);
+  __syncwarp();
+  double d2 = *(volatile double *)&sl->d2[lane];
+  int32_t f = *(volatile int32_t *)&sl->face[lane];
+  if (valid && face >= 0 && (f < 0 || sqr_d < d2 || (sqr_d == d2 && face < f))) {
+    d2 = sqr_d; f = face;
+    *(volatile double *)&sl->d2[lane] = d2; *(volatile int32_t *)&sl->face[lane] = f;
   }
-  __threadfence_system();
+  __threadfence();
   __syncwarp();
-  if (lane == 0) atomicExch(lock, 0u);
+  uint32_t left = 0;
+  if (lane == 0) { atomicExch(&sl->lock, 0u); left = atomicSub(&sl->pending, 1u) - 1u; }
+  left = __shfl_sync(FULL, left, 0);
+  if (left != 0u || !valid) return;
+  // every piece has merged (each one before it counted itself out): read the final pair
+  __threadfence();
+  d2 = *(volatile double *)&sl->d2[lane];
+  f = *(volatile int32_t *)&sl->face[lane];
+  fwn::CpResult r; r.sqr_d = d2; r.face = f; r.c = {0.0, 0.0, 0.0};
+  const fwn::CpQueryRef qr{a.P, a.n, qi, a.sigma};
+  const fwn::D3 p = fwn::load_query(qr);
+  if (!(r.sqr_d < a.up) || r.face < 0) { r.sqr_d = a.up; r.face = -1; }
+  else fwn::face_sqr_distance(a.tri64, p, (uint32_t)r.face, r.c);   // closest point of the winner
+  closest_store(a, qi, r);
+  if (a.stash) a.stash[t] = ShardStash{(float)p.x, (float)p.y, (float)p.z, (uint32_t)qi, r.sqr_d};
 }
 #ifdef CP_TIMELINE
 __device__ unsigned long long *g_timeline = nullptr;   // [8 * blocks]: first request, last request that got work, exit (globaltimer, ns); visits and duration of the longest walk, donations, tasks
@@ -512,7 +542,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   bool drained = false, counted = false;   // no packets left for this warp; it is counted among the warps holding work
   while (true) {
     uint32_t first = 0xFFFFFFFFu, cnt = 1;
-    int task_sp = 0; float task_ub = 0.f;
+    int task_sp = 0; float task_ub = 0.f; int32_t slot = -1;   // slot >= 0: the packet is walked in pieces
     if (!drained) {
     if (lane == 0) {
       unsigned long long *st = a.sched + 1 + 2 * smid, *lock = st + 1;
@@ -555,7 +585,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     const bool is_task = drained;
     if (drained) {
       if (!a.donate) break;
-      if (!cp_take_task(a.sched, stack, first, task_sp, task_ub, counted)) break;
+      if (!cp_take_task(a.sched, stack, first, task_sp, task_ub, counted, slot)) break;
       cnt = 1;
     }
     if (cnt == 1) seed_face = -1;   // a single packet has no predecessor of its own
@@ -580,7 +610,6 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
     }
     uint32_t nvis = 0, ntri = 0, npop = 0;
     int sp = 0; uint32_t cur = 0; bool have = true;
-    bool shared = is_task;   // the packet is (or becomes) walked by several warps
 #ifdef CP_TIMELINE
     unsigned long long tl_walk0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_walk0));
 #endif
@@ -597,8 +626,8 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
           uint32_t idle = lane == 0 ? *(volatile uint32_t *)(a.sched + SCHED_DONATE) : 0u;
           idle = __shfl_sync(FULL, idle, 0);
           if (idle) {
-            if (!shared) { cp_begin_shared(a, qi, t, valid); shared = true; }
-            sp = cp_donate(a.sched, stack, sp, packet, L.best_ub, npop);
+            if (slot < 0) slot = cp_begin_shared(a.sched, a.up);
+            if (slot >= 0) sp = cp_donate(a.sched, stack, sp, packet, L.best_ub, npop, slot);
           }
         }
       }
@@ -699,7 +728,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
       if (a.low > a.up) r.sqr_d = a.low;  // AABB.cpp:1145-1148
       else lane_finish(L, X, a.tri64, qr, a.up, r);
       won = r.face;
-      if (!shared) {
+      if (slot < 0) {
         closest_store(a, qi, r);
         if (a.stash) {
           const D3 p = load_query(qr);
@@ -707,7 +736,7 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         }
       }
     }
-    if (shared) cp_store_merged(a, qi, t, valid, r.sqr_d, r.face, r.c.x, r.c.y, r.c.z, packet);   // warp-uniform
+    if (slot >= 0) { cp_finish_shared(a, slot, qi, t, valid, r.sqr_d, r.face); slot = -1; }   // warp-uniform
     seed_face = __shfl_sync(FULL, won, 0);   // lane 0's winner seeds the next packet of the group
     if (COUNT && lane == 0) { atomicAdd(&a.counters[0], nvis); atomicAdd(&a.counters[1], ntri); }
     __syncwarp();
