@@ -116,6 +116,9 @@ struct ClosestArgs {  // AABB.cpp:1135-1218 semantics for a batch of queries
   // Warps that run out of packets stay and take over parts of the walks still going on (work donation).  Off when
   // several launches share the device on purpose (the host path: the next chunk's kernel fills this one's tail).
   int donate = 1;
+  // packets per chunk of the persistent schedule (a power of two, <= CP_CHUNK; launch_closest sizes it so that a small
+  // launch still has ~16 chunks per SM to even out; sharded launches use CP_CHUNK: super-chunks are made of those)
+  uint32_t chunk = 32;
   uint32_t *my_supers = nullptr, *my_count = nullptr;
   int64_t max_supers = 0;   // > 0: take at most this many (static partition / tests)
   const uint32_t *super_order = nullptr;   // the k-th super-chunk handed out is super_order[k]
@@ -535,9 +538,10 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
   unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
   smid &= 1023u;   // the state array has 1024 slots
   const uint32_t npackets = (uint32_t)((a.n + 31) / 32);
-  const uint32_t nchunks = (npackets + CP_CHUNK - 1) / CP_CHUNK;
+  const uint32_t chunk = a.chunk;
+  const uint32_t nchunks = (npackets + chunk - 1) / chunk;
   const uint32_t endzone_packets = min((uint32_t)CP_ENDZONE_PACKETS, npackets / (2u * (uint32_t)a.nshards));
-  const uint32_t endzone = (endzone_packets + CP_CHUNK - 1) / CP_CHUNK;   // chunks handed out packet by packet
+  const uint32_t endzone = (endzone_packets + chunk - 1) / chunk;   // chunks handed out packet by packet
   int32_t seed_face = -1;
   bool drained = false, counted = false;   // no packets left for this warp; it is counted among the warps holding work
   while (true) {
@@ -551,13 +555,13 @@ __global__ void __launch_bounds__(32 * CP_WARPS, CP_MIN_BLOCKS) closest_packet_k
         const uint32_t peek = (uint32_t)(*(volatile unsigned long long *)st >> 32);
         const uint32_t g = (peek & (uint32_t)CP_SINGLE) ? 1u : (uint32_t)CP_GROUP;
         const unsigned long long old = atomicAdd(st, (unsigned long long)g);
-        if ((uint32_t)old < CP_CHUNK) {
-          first = ((uint32_t)(old >> 32) & ~(uint32_t)CP_SINGLE) * CP_CHUNK + (uint32_t)old;
-          cnt = min(g, (uint32_t)CP_CHUNK - (uint32_t)old);
+        if ((uint32_t)old < chunk) {
+          first = ((uint32_t)(old >> 32) & ~(uint32_t)CP_SINGLE) * chunk + (uint32_t)old;
+          cnt = min(g, chunk - (uint32_t)old);
           break;
         }
         if (atomicCAS(lock, 0ull, 1ull) == 0ull) {   // this warp refills the SM's chunk
-          if ((uint32_t)(*(volatile unsigned long long *)st) >= CP_CHUNK) {
+          if ((uint32_t)(*(volatile unsigned long long *)st) >= chunk) {
             unsigned long long nc;
             if (a.remote) nc = next_chunk_sharded(ShardSched{a.sched, a.remote, a.super_chunks, a.my_supers, a.my_count, a.max_supers, a.super_order,
                                                              a.nsup, a.shard, a.nshards, endzone_packets});
@@ -770,6 +774,9 @@ void launch_closest(const ClosestArgs &a, stream_t s) {
   if (warps > (int64_t)0xFFF00000) throw std::invalid_argument("too many queries in one call (packet index is 32 bits)");
   DevBuf<unsigned long long> own;
   ClosestArgs b = a;
+  b.chunk = CP_CHUNK;
+  if (!b.remote)   // 32 packets per chunk from 2.4 M queries up; a 256 Ki-row chunk of the host path gets 2
+    while (b.chunk > 2u && (int64_t)b.chunk * 16 * plat::sm_count() > warps) b.chunk >>= 1;
   if (!b.sched) { own.alloc(SCHED_WORDS); b.sched = own.p; }   // no caller scratch: a private state for this launch
   plat::for_n(SCHED_INIT_WORDS, InitSched{b.sched, b.remote ? 1 : 0}, s);
   blocks = std::min<int64_t>(std::min<int64_t>(blocks, (int64_t)plat::sm_count() * CP_MIN_BLOCKS), CP_MAILBOXES);
