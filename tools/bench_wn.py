@@ -24,5 +24,7 @@ for nf, g in ((100_000, 96), (1_000_000, 128)):
     S, I, C = m.signed_distance(P, 2)
     prof2 = api.profile_collect()
     print(nf, g, "build_s", round(tb, 3), "arena_MB", info["device_bytes"] / 1e6, "wn wall_s", round(t1, 3), prof, "sd default", prof2,
-          "q/s", P.shape[0] / (prof["exact_winding"] / 1e3), "Wrange", W.min(), W.max(), flush=True)
+          "q/s (wall clock, host arrays in and out)", P.shape[0] / t1,
+          "q/s (kernel; spans are per thread, so only calls small enough to run on the calling thread report one)",
+          (P.shape[0] / (prof["exact_winding"] / 1e3)) if "exact_winding" in prof else None, "Wrange", W.min(), W.max(), flush=True)
     m.close()
