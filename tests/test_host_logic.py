@@ -310,3 +310,46 @@ def test_sharded_device_queries_match_the_fused_path(emul_api):
     finally:
         api.set_device(0)
         api.init(1)
+
+
+def test_sharded_slices_are_handed_out_once_whoever_comes_first(emul_api):
+    """Three slices of the sorted order, callers arriving in every order and with every mix of caps: each super-chunk is
+    taken exactly once (own slice first, then the slice with the most left), an unknown slice index is refused, and the
+    result is the single call's bit for bit."""
+    import ctypes as C
+    from libigl_b200 import synth
+    api, L = emul_api, emul_api.lib
+    vp = C.c_void_p
+    V, F = synth.icosphere(2)
+    P = synth.random_points(90_000, -1.4, 1.4, 5)
+    n = P.shape[0]
+    Pc = np.ascontiguousarray(P.T)
+    ptr = lambda a: a.ctypes.data_as(vp)
+    sup = 8192
+    nsup = -(-n // sup)                                # 11 super-chunks: slices of 3, 4 and 4
+    m = api.Mesh(V, F, 2)
+    scratch = np.zeros(int(L.iglb200_shard_scratch_bytes(n)), np.uint8)
+    qs = np.zeros(int(L.iglb200_query_scratch_bytes(n)), np.uint8)
+    S1, I1, C1 = np.empty(n), np.empty(n, np.int32), np.empty((3, n))
+    api.check(L.iglb200_squared_distance_dev(m.h, ptr(Pc), n, ptr(S1), ptr(I1), ptr(C1), ptr(qs), 1, None))
+    # (shard, cap) in calling order; cap 0 = no cap
+    plans = [[(2, 0), (0, 0), (1, 0)],                 # the last slice's owner comes first and takes everything
+             [(0, 1), (1, 1), (2, 1), (1, 0)],         # one each, then shard 1 finishes its slice and both others
+             [(1, 5), (1, 0)],                         # one caller past its own slice (4) into the fullest other one
+             [(0, 2), (2, 2), (0, 2), (2, 0), (1, 0)]]
+    for plan in plans:
+        S, I, Cc, W = np.full(n, -5.0), np.full(n, -5, np.int32), np.full((3, n), -5.0), np.full(n, -5.0)
+        outs = (ptr(S), ptr(I), ptr(Cc), ptr(W))
+        api.check(L.iglb200_shard_begin_dev(m.h, ptr(Pc), n, ptr(scratch), 1, sup, None))
+        for shard, cap in plan:
+            api.check(L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), 1, 0, 0.0, 0.0, 2.0, 1, *outs, sup, cap, shard, 3, None))
+        api.check(L.iglb200_shard_finish_dev(m.h, n, ptr(scratch), 1, 0, 0.0, 0.0, 1, *outs, None))
+        counters = scratch[:1024].view(np.uint64)[2:5]
+        sizes = [nsup * (k + 1) // 3 - nsup * k // 3 for k in range(3)]
+        assert all(int(c) >= sz for c, sz in zip(counters, sizes)), (plan, counters, sizes)
+        assert np.array_equal(S, S1) and np.array_equal(I, I1) and np.array_equal(Cc, C1), plan
+    for shard, nshards in ((3, 3), (-1, 3), (0, 0), (0, 65)):
+        rc = L.iglb200_shard_run_dev(m.h, ptr(Pc), n, ptr(scratch), 1, 0, 0.0, 0.0, 2.0, 1, ptr(S1), ptr(I1), ptr(C1), None, sup, 0, shard, nshards, None)
+        assert rc != 0
+    m.close()
+
