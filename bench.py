@@ -627,12 +627,13 @@ def add_rooflines(line, api, mesh, cfg, args, kernel_ms, info, nq, value, P, gri
             flops_launch = (vc["fwn_nodes"] * FLOP_NODE_FWN + vc["fwn_tris"] * FLOP_TRI_FWN) * nq / world
             src = "visit counters x 372 flop per node visit, 100 per exact triangle (the reference's own walk)"
         fj = os.path.join(ROOT, "profiles", "flops_r2.json")
-        ncu_flops = None
+        ncu_flops = ncu_note = None
         if os.path.exists(fj):
             j = json.load(open(fj))
             if j.get("kernel") == dom and j.get("queries") == nq and j.get("faces") == int(info["n_faces"]):
                 # smsp__sass_thread_inst_executed_op_{ffma x2, fadd, fmul}_pred_on of the whole query set; a rank's launch does 1/N of it
                 ncu_flops = j["fp32_flops_per_launch"] / world
+                ncu_note = j.get("note")
         used = ncu_flops if ncu_flops else flops_launch
         ach_t = used / t_dom
         line["roofline"] = {"bound": "fp32", "kernel": dom, "achieved": ach_t / 1e12, "peak": theo / 1e12, "unit": "TFLOP/s",
@@ -641,6 +642,7 @@ def add_rooflines(line, api, mesh, cfg, args, kernel_ms, info, nq, value, P, gri
                             "frac_of_microbenchmark": ach_t / measured if measured > 0 else None,
                             "executed_flops_per_launch": used,
                             "numerator": "ncu sass op counters (profiles/flops_r2.json)" if ncu_flops else src,
+                            "numerator_note": ncu_note if ncu_flops else None,
                             "launch_ms": kernel_ms[dom],
                             "counts": {"cp_nodes_per_packet": vc["cp_nodes_per_warp"], "cp_faces_per_packet": vc["cp_tris_per_warp"],
                                        "fwn_nodes_per_query": vc["fwn_nodes"], "fwn_tris_per_query": vc["fwn_tris"]}}
